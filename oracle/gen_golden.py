@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE (baler v1.4.0) in this container.
+
+TEST INFRASTRUCTURE ONLY.  Runs where `/root/reference` is mounted (the build container);
+the GPU box never sees the reference, it only sees the committed fixtures.
+
+    python oracle/gen_golden.py            # rewrites every fixture (deterministic: CPU, fixed seeds)
+
+Two shims are needed to import the reference on this image:
+  * `oracle/_shims/matplotlib` - matplotlib is not installed, helper.py:31 imports plotting;
+  * `ReduceLROnPlateau(verbose=True)` (utils.py:313-320) is a TypeError on torch 2.11.
+Nothing of the reference is copied: its functions are called and their outputs saved.
+
+Fixtures (all float64 unless noted; state-dict tensors stored under "<prefix>/<key>"):
+  ae_cms.npz        trained AE(24,15): normalise -> encode -> decode -> renormalise on 256 rows
+  ae_train.npz      fresh AE(24,15): loss, grads, Adam after 1 and 3 steps (mse only and mse+l1)
+  ae_fit.npz        training.train() for 3 epochs on 4096 rows: loss_data, final weights
+  ae_dbn.npz        AE_Dropout_BN(24,15): eval encode/decode; one train step with captured masks
+  cli_roundtrip.npz perform_training/compression/decompression in a temp workspace (4096 rows)
+  schedules.npz     LRScheduler / EarlyStopping decision sequences
+  conv_ae.npz       Conv_AE(5, 250) on 5x5 blocks: eval encode/decode, one train step
+"""
+import os
+import sys
+import shutil
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("BALER_REFERENCE", "/root/reference")
+os.environ["CUDA_VISIBLE_DEVICES"] = ""
+sys.path[:0] = [os.path.join(HERE, "_shims"), REF, ROOT]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+_Plateau = torch.optim.lr_scheduler.ReduceLROnPlateau
+
+
+class _PlateauNoVerbose(_Plateau):
+    def __init__(self, *a, verbose=None, **k):
+        super().__init__(*a, **k)
+
+
+torch.optim.lr_scheduler.ReduceLROnPlateau = _PlateauNoVerbose
+
+from baler import baler as ref_baler  # noqa: E402
+from baler.modules import helper as ref_helper  # noqa: E402
+from baler.modules import models as ref_models  # noqa: E402
+from baler.modules import training as ref_training  # noqa: E402
+from baler.modules import utils as ref_utils  # noqa: E402
+
+from baler_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+torch.set_num_threads(4)
+
+
+def sd_np(model, prefix):
+    return {f"{prefix}/{k}": v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def grads_np(model, prefix):
+    return {f"{prefix}/{k}": p.grad.detach().numpy().copy() for k, p in model.named_parameters()}
+
+
+def make_config(**over):
+    """The shipped CMS config (CMS_project_v1_config.py) with overrides, on the reference's own Config class."""
+
+    class C(ref_helper.Config):
+        pass
+
+    c = C
+    c.input_path = "unused"
+    c.data_dimension = 1
+    c.compression_ratio = 1.6
+    c.apply_normalization = True
+    c.model_name = "AE"
+    c.epochs = 3
+    c.lr = 0.001
+    c.batch_size = 512
+    c.early_stopping = True
+    c.lr_scheduler = True
+    c.save_error_bounded_deltas = False
+    c.error_bounded_requirement = 10
+    c.early_stopping_patience = 100
+    c.min_delta = 0
+    c.lr_scheduler_patience = 50
+    c.custom_norm = False
+    c.reg_param = 0.001
+    c.RHO = 0.05
+    c.test_size = 0
+    c.extra_compression = False
+    c.intermittent_model_saving = False
+    c.intermittent_saving_patience = 100
+    c.mse_avg = False
+    c.mse_sum = True
+    c.emd = False
+    c.l1 = True
+    c.activation_extraction = False
+    c.deterministic_algorithm = False
+    c.convert_to_blocks = False
+    c.separate_model_saving = False
+    c.latent_space_size = 15
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+def gen_ae_cms():
+    table = synth.cms_table(20000)
+    feats = ref_helper.data_processing.find_minmax(table)
+    norm = ref_helper.normalize(table, False)
+    assert norm.dtype == np.float32
+    torch.manual_seed(0)
+    model = ref_models.AE(24, 15)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    xs = torch.tensor(norm, dtype=torch.float64)
+    model.train()
+    for _ in range(2):  # two epochs of the reference's own loss so activations are in a trained regime
+        for i in range(0, len(xs), 512):
+            opt.zero_grad()
+            xb = xs[i : i + 512]
+            loss, _, _ = ref_utils.mse_sum_loss_l1(list(model.children()), xb, model(xb), 0.001, True)
+            loss.backward()
+            opt.step()
+    model.eval()
+    with torch.no_grad():
+        x = xs[:256]
+        z = model.encode(x)
+        y = model.decode(z)
+    un = ref_helper.renormalize(y.numpy(), feats[0], feats[1])
+    d = sd_np(model, "sd")
+    d.update(x_raw=table[:256], col_min=table.min(0), col_max=table.max(0), norm_features=feats,
+             x_norm=norm[:256], latent=z.numpy(), recon=y.numpy(), unnorm=un)
+    np.savez(os.path.join(OUT, "ae_cms.npz"), **d)
+    print("ae_cms", z.shape, float(np.abs(z).max()), float(np.abs(y).max()))
+
+
+def gen_ae_train():
+    table = synth.cms_table(2048, seed=7)
+    norm = ref_helper.normalize(table, False)
+    xs = torch.tensor(norm, dtype=torch.float64)
+    d = dict(x_norm=norm)
+    for tag, validate in (("mse", True), ("l1", False)):
+        torch.manual_seed(0)
+        model = ref_models.AE(24, 15)
+        if tag == "mse":
+            d.update(sd_np(model, "sd0"))
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        model.train()
+        losses = []
+        for step in range(3):
+            xb = xs[step * 512 : (step + 1) * 512]
+            opt.zero_grad()
+            loss, mse, l1 = ref_utils.mse_sum_loss_l1(list(model.children()), xb, model(xb), 0.001, validate)
+            loss.backward()
+            if step == 0:
+                d.update(grads_np(model, f"g_{tag}"))
+                d[f"mse0_{tag}"] = float(mse) if not validate else float(loss)
+                d[f"l1_0_{tag}"] = float(l1)
+            opt.step()
+            losses.append(float(loss))
+            if step in (0, 2):
+                d.update(sd_np(model, f"sd{step + 1}_{tag}"))
+        d[f"losses_{tag}"] = np.array(losses)
+    # ragged last batch (448 rows in T600k; here 100 rows) - loss only
+    torch.manual_seed(0)
+    model = ref_models.AE(24, 15)
+    xb = xs[:100]
+    loss, _, _ = ref_utils.mse_sum_loss_l1(list(model.children()), xb, model(xb), 0.001, True)
+    d["loss_ragged100"] = float(loss)
+    np.savez(os.path.join(OUT, "ae_train.npz"), **d)
+    print("ae_train", d["losses_mse"], d["losses_l1"])
+
+
+def gen_ae_fit():
+    table = synth.cms_table(4096, seed=11)
+    norm = ref_helper.normalize(table, False)
+    cfg = make_config(epochs=3)
+    tmp = tempfile.mkdtemp()
+    try:
+        torch.manual_seed(0)
+        model = ref_models.AE(24, 15)
+        d = {}
+        trained = ref_training.train(model, 24, norm, norm, tmp, cfg)
+        d["loss_data"] = np.load(os.path.join(tmp, "loss_data.npy"))
+        d.update(sd_np(trained, "sd_final"))
+    finally:
+        shutil.rmtree(tmp)
+    np.savez(os.path.join(OUT, "ae_fit.npz"), **d)
+    print("ae_fit", d["loss_data"])
+
+
+def gen_ae_dbn():
+    table = synth.cms_table(2048, seed=13)
+    norm = ref_helper.normalize(table, False)
+    xs = torch.tensor(norm, dtype=torch.float64)
+    torch.manual_seed(0)
+    model = ref_models.AE_Dropout_BN(24, 15)
+    # make BN buffers / affine non-trivial so folding is actually tested
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.copy_(0.5 + torch.rand(m.weight.shape, generator=g, dtype=torch.float64))
+                m.bias.copy_(0.2 * torch.randn(m.bias.shape, generator=g, dtype=torch.float64))
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g, dtype=torch.float64))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g, dtype=torch.float64))
+    d = dict(x_norm=norm[:512])
+    d.update(sd_np(model, "sd0"))
+    model.eval()
+    with torch.no_grad():
+        z = model.encode(xs[:256])
+        y = model.decode(z)
+    d.update(latent_eval=z.numpy(), recon_eval=y.numpy())
+    # one train step; dropout masks captured from torch so the other side can inject them
+    masks = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            masks[name] = (out != 0).numpy()
+        return f
+
+    hs = [m.register_forward_hook(hook(f"mask{i}")) for i, m in enumerate(
+        [m for m in model.enc_nn if isinstance(m, torch.nn.Dropout)])]
+    model.train()
+    torch.manual_seed(5)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    xb = xs[:512]
+    opt.zero_grad()
+    out = model(xb)
+    loss, _, _ = ref_utils.mse_sum_loss_l1(list(model.children()), xb, out, 0.001, True)
+    loss.backward()
+    d.update(grads_np(model, "g"))
+    opt.step()
+    for h in hs:
+        h.remove()
+    d.update({k: v for k, v in masks.items()})
+    d.update(recon_train=out.detach().numpy(), loss_train=float(loss))
+    d.update(sd_np(model, "sd1"))
+    np.savez_compressed(os.path.join(OUT, "ae_dbn.npz"), **d)
+    print("ae_dbn", float(loss), {k: v.mean() for k, v in masks.items()})
+
+
+def gen_cli_roundtrip():
+    """`baler --mode train|compress|decompress` on a temp copy of the CMS project layout."""
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    try:
+        os.chdir(tmp)
+        ref_helper.create_new_project("CMS_workspace", "CMS_project_v1")
+        table = synth.cms_table(4096, seed=17)
+        path = os.path.join("workspaces", "CMS_workspace", "data", "example_CMS_data.npz")
+        np.savez(path, data=table, names=synth.CMS_NAMES)
+        type_list = ["float64"] * 12 + ["int"] * 7 + ["float64"] * 3 + ["int"] * 2
+        cfg = make_config(input_path=path, epochs=2, type_list=type_list, activation_extraction=True)
+        if hasattr(cfg, "latent_space_size"):
+            del cfg.latent_space_size
+        out = os.path.join("workspaces", "CMS_workspace", "CMS_project_v1", "output")
+        torch.manual_seed(0)
+        ref_baler.perform_training(out, cfg, False)
+        ref_baler.perform_compression(out, cfg, False)
+        ref_baler.perform_decompression(out, cfg, False)
+        sd = torch.load(os.path.join(out, "compressed_output", "model.pt"))
+        d = {f"sd/{k}": v.numpy() for k, v in sd.items()}
+        comp = np.load(os.path.join(out, "compressed_output", "compressed.npz"))
+        dec = np.load(os.path.join(out, "decompressed_output", "decompressed.npz"))
+        d.update(compressed=comp["data"], comp_norm_features=comp["normalization_features"],
+                 decompressed=dec["data"],
+                 norm_features=np.load(os.path.join(out, "training", "normalization_features.npy")),
+                 loss_data=np.load(os.path.join(out, "training", "loss_data.npy")),
+                 activations=np.load(os.path.join(out, "training", "activations.npy")))
+        print("cli", comp["data"].shape, comp["data"].dtype, dec["data"].shape, dec["data"].dtype, d["loss_data"])
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(tmp)
+    np.savez(os.path.join(OUT, "cli_roundtrip.npz"), **d)
+
+
+def gen_schedules():
+    """LR plateau schedule (tests/test_utils.py:83-108 pattern) and early stopping decisions."""
+    d = {}
+    lin = torch.nn.Linear(10, 1)
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    sched = ref_utils.LRScheduler(opt, patience=2, min_lr=1e-5, factor=0.5)
+    seq = [10.0, 9.0, 8.0, 7.0] + [10.0, 9.0, 10.0, 11.0, 12.0] + [10.0] * 100
+    lrs = []
+    for v in seq:
+        sched(v)
+        lrs.append(opt.param_groups[0]["lr"])
+    d.update(lr_losses=np.array(seq), lr_values=np.array(lrs))
+    # defaults used by training.train: patience from config, factor 0.5, min_lr 1e-6
+    opt = torch.optim.Adam(lin.parameters(), lr=1e-3)
+    sched = ref_utils.LRScheduler(opt, patience=3)
+    rng = np.random.default_rng(3)
+    seq2 = list(np.abs(1.0 + 0.05 * rng.normal(size=80)))
+    lrs2 = []
+    for v in seq2:
+        sched(v)
+        lrs2.append(opt.param_groups[0]["lr"])
+    d.update(lr2_losses=np.array(seq2), lr2_values=np.array(lrs2))
+    es = ref_utils.EarlyStopping(patience=4, min_delta=0.01)
+    seq3 = [1.0, 0.9, 0.95, 0.895, 0.7, 0.71, 0.72, 0.695, 0.73, 0.74]
+    stops, counters = [], []
+    for v in seq3:
+        es(v)
+        stops.append(es.early_stop)
+        counters.append(es.counter)
+    d.update(es_losses=np.array(seq3), es_stop=np.array(stops), es_counter=np.array(counters))
+    np.savez(os.path.join(OUT, "schedules.npz"), **d)
+    print("schedules", lrs[-1], lrs2[-1], stops)
+
+
+def gen_conv_ae():
+    snaps = synth.cfd_snapshots(6)  # 6 x 50 x 50 -> 600 blocks of 1x5x5
+    blocks = ref_helper.data_processing.convert_to_blocks_util([1, 5, 5], snaps)
+    xs = torch.tensor(blocks, dtype=torch.float32).view(blocks.shape[0], 1, 5, 5)
+    torch.manual_seed(0)
+    model = ref_models.Conv_AE(5, 250)
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(0.5 + torch.rand(m.weight.shape, generator=g))
+                m.bias.copy_(0.2 * torch.randn(m.bias.shape, generator=g))
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+    d = dict(blocks=blocks[:64].astype(np.float32))
+    sd0 = {f"sd0/{k}": v.detach().numpy().copy().astype(np.float16 if False else np.float32)
+           for k, v in model.state_dict().items()}
+    d.update(sd0)
+    model.eval()
+    with torch.no_grad():
+        z = model.encode(xs[:64])
+        y = model.decode(z)
+    d.update(latent_eval=z.numpy(), recon_eval=y.numpy())
+    np.savez_compressed(os.path.join(OUT, "conv_ae.npz"), **d)
+    print("conv_ae", z.shape, y.shape, os.path.getsize(os.path.join(OUT, "conv_ae.npz")) / 1e6, "MB")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules"]
+    for name in which:
+        globals()["gen_" + name]()
