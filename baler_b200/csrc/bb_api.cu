@@ -1,0 +1,438 @@
+// C-ABI entry points (include/baler_b200.h): context, model packing, encode / decode dispatch and
+// the host-buffer compress / decompress pipelines.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <thread>
+
+#include "bb_common.cuh"
+
+extern "C" {
+
+int bb_version(void) { return BB_VERSION; }
+
+const char* bb_strerror(int code) {
+  switch (code) {
+    case BB_OK: return "ok";
+    case BB_ERR_INVALID: return "baler_b200: invalid argument";
+    case BB_ERR_UNSUPPORTED: return "baler_b200: shape or mode not supported by the CUDA kernels";
+    case BB_ERR_NOMEM: return "baler_b200: out of memory";
+    case BB_ERR_NODEVICE: return "baler_b200: no CUDA device (there is no CPU fallback)";
+    case BB_ERR_OVERFLOW: return "baler_b200: fp16 split range guard tripped; use BB_PREC_FP32";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "baler_b200: unknown error";
+  }
+}
+
+int bb_ctx_create(int device, bb_ctx** out) {
+  if (!out) return BB_ERR_INVALID;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return BB_ERR_NODEVICE;
+  if (device < 0 || device >= n) return BB_ERR_INVALID;
+  BB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return BB_ERR_UNSUPPORTED;  // sm_100a SASS only
+  bb_ctx* c = new (std::nothrow) bb_ctx();
+  if (!c) return BB_ERR_NOMEM;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = c;
+  return BB_OK;
+}
+
+int bb_ctx_destroy(bb_ctx* ctx) {
+  if (!ctx) return BB_OK;
+  if (ctx->minmax_scratch) cudaFree(ctx->minmax_scratch);
+  delete ctx;
+  return BB_OK;
+}
+
+int bb_ctx_sm_count(const bb_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+}  // extern "C"
+
+namespace {
+
+int fill_chain(Chain* c, int n_layers, const int* dims, const int* acts, const double* const* w,
+               const double* const* b) {
+  if (n_layers < 1 || n_layers > BB_MAX_LAYERS || !dims || !acts || !w || !b) return BB_ERR_INVALID;
+  ChainDesc& d = c->desc;
+  memset(&d, 0, sizeof(d));
+  d.n_layers = n_layers;
+  d.in_dim = dims[0];
+  d.out_dim = dims[n_layers];
+  for (int l = 0; l < n_layers; ++l) {
+    if (dims[l] < 1 || dims[l + 1] < 1 || acts[l] < BB_ACT_NONE || acts[l] > BB_ACT_RELU || !w[l] || !b[l])
+      return BB_ERR_INVALID;
+    d.layer[l].K = dims[l];
+    d.layer[l].N = dims[l + 1];
+    d.layer[l].act = acts[l];
+    c->w_host[l].assign(w[l], w[l] + (size_t)dims[l] * dims[l + 1]);
+    c->b_host[l].assign(b[l], b[l] + dims[l + 1]);
+  }
+  return BB_OK;
+}
+
+void free_chain(Chain* c) {
+  if (c->blob_dev) cudaFree(c->blob_dev);
+  if (c->tc_blob_dev) cudaFree(c->tc_blob_dev);
+}
+
+int resolve_precision(const bb_model* m, const Chain* c, int precision) {
+  if (precision == BB_PREC_AUTO) return c->tc_ok ? BB_PREC_SPLIT16 : BB_PREC_FP32;
+  return precision;
+}
+
+int run_chain(bb_model* m, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
+              const float* pre_min, const float* pre_range, const float* post_min,
+              const float* post_range, void* out, int out_dtype, int precision, cudaStream_t stream) {
+  if (!m || (!in && n_rows) || (!out && n_rows) || n_rows < 0) return BB_ERR_INVALID;
+  if ((pre_min == nullptr) != (pre_range == nullptr) || (post_min == nullptr) != (post_range == nullptr))
+    return BB_ERR_INVALID;
+  if ((in_dtype != BB_F32 && in_dtype != BB_F16) || (out_dtype != BB_F32 && out_dtype != BB_F16)) return BB_ERR_INVALID;
+  const int p = resolve_precision(m, c, precision);
+  if (p == BB_PREC_FP32)
+    return bb_chain_f32_launch(m->ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range,
+                               out, out_dtype, stream);
+  if (p == BB_PREC_SPLIT16 || p == BB_PREC_FAST16) {
+    if (!c->tc_ok) return BB_ERR_UNSUPPORTED;
+    return bb_tc_launch(m->ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range, out,
+                        out_dtype, p == BB_PREC_FAST16, m->flag_dev, stream);
+  }
+  return BB_ERR_INVALID;
+}
+
+size_t dtype_size(int dt) { return dt == BB_F64 ? 8 : (dt == BB_F16 ? 2 : 4); }
+
+// fp32 -> fp64 widening of a finished chunk on host threads (the reference stores float64 latents)
+void widen_f32_f64(const float* src, double* dst, size_t n) {
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const size_t per = (n + hw - 1) / hw;
+  if (n < (1u << 16)) {
+    for (size_t i = 0; i < n; ++i) dst[i] = (double)src[i];
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < hw; ++t) {
+    const size_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    th.emplace_back([=] { for (size_t i = lo; i < hi; ++i) dst[i] = (double)src[i]; });
+  }
+  for (auto& t : th) t.join();
+}
+
+void narrow_f64_f32(const double* src, float* dst, size_t n) {
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const size_t per = (n + hw - 1) / hw;
+  if (n < (1u << 16)) {
+    for (size_t i = 0; i < n; ++i) dst[i] = (float)src[i];
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < hw; ++t) {
+    const size_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    th.emplace_back([=] { for (size_t i = lo; i < hi; ++i) dst[i] = (float)src[i]; });
+  }
+  for (auto& t : th) t.join();
+}
+
+constexpr int64_t PIPE_CHUNK_ROWS = 1 << 21;  // rows per pipeline chunk (2 Mi rows: 192 MiB in, 120 MiB out for 24 -> 15)
+
+int pipe_init(bb_model* m, size_t in_bytes, size_t out_bytes) {
+  if (!m->s_compute) {
+    BB_CUDA(cudaStreamCreateWithFlags(&m->s_copy_in, cudaStreamNonBlocking));
+    BB_CUDA(cudaStreamCreateWithFlags(&m->s_compute, cudaStreamNonBlocking));
+    BB_CUDA(cudaStreamCreateWithFlags(&m->s_copy_out, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+      BB_CUDA(cudaEventCreateWithFlags(&m->ev_in[s], cudaEventDisableTiming));
+      BB_CUDA(cudaEventCreateWithFlags(&m->ev_done[s], cudaEventDisableTiming));
+      BB_CUDA(cudaEventCreateWithFlags(&m->ev_out[s], cudaEventDisableTiming));
+    }
+    BB_CUDA(cudaMalloc(&m->feat_dev, 3 * sizeof(float) * std::max(m->enc.desc.in_dim, m->dec.desc.out_dim)));
+  }
+  const size_t need[2] = {in_bytes, out_bytes};
+  for (int io = 0; io < 2; ++io) {
+    if (m->stage_bytes[io] < need[io]) {
+      for (int s = 0; s < 2; ++s) {
+        if (m->stage_dev[io][s]) cudaFree(m->stage_dev[io][s]);
+        m->stage_dev[io][s] = nullptr;
+        BB_CUDA(cudaMalloc(&m->stage_dev[io][s], need[io]));
+      }
+      m->stage_bytes[io] = need[io];
+    }
+  }
+  return BB_OK;
+}
+
+// range = max - min on device (float32 subtraction, like numpy on a float32 table)
+__global__ void range_kernel(const float* mn, const float* mx, float* rg, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) rg[i] = __fsub_rn(mx[i], mn[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bb_model_create_dense(bb_ctx* ctx, int n_enc_layers, const int* enc_dims, const int* enc_acts,
+                          const double* const* enc_w, const double* const* enc_b, int n_dec_layers,
+                          const int* dec_dims, const int* dec_acts, const double* const* dec_w,
+                          const double* const* dec_b, bb_model** out) {
+  if (!ctx || !out) return BB_ERR_INVALID;
+  BB_CUDA(cudaSetDevice(ctx->device));
+  bb_model* m = new (std::nothrow) bb_model();
+  if (!m) return BB_ERR_NOMEM;
+  m->ctx = ctx;
+  int rc = fill_chain(&m->enc, n_enc_layers, enc_dims, enc_acts, enc_w, enc_b);
+  if (rc == BB_OK) rc = fill_chain(&m->dec, n_dec_layers, dec_dims, dec_acts, dec_w, dec_b);
+  if (rc == BB_OK && m->enc.desc.out_dim != m->dec.desc.in_dim) rc = BB_ERR_INVALID;
+  if (rc == BB_OK) rc = bb_chain_f32_prepare(ctx, &m->enc);
+  if (rc == BB_OK) rc = bb_chain_f32_prepare(ctx, &m->dec);
+  if (rc == BB_OK) rc = (int)cudaMalloc(&m->flag_dev, sizeof(int));
+  if (rc == BB_OK) rc = (int)cudaMemset(m->flag_dev, 0, sizeof(int));
+  if (rc == BB_OK) {
+    // the tensor-core path is optional per shape; failure to prepare it is not an error
+    int t = bb_tc_prepare(ctx, &m->enc);
+    if (t != BB_OK && t != BB_ERR_UNSUPPORTED) rc = t;
+    t = bb_tc_prepare(ctx, &m->dec);
+    if (t != BB_OK && t != BB_ERR_UNSUPPORTED) rc = t;
+  }
+  if (rc != BB_OK) {
+    bb_model_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return BB_OK;
+}
+
+int bb_model_destroy(bb_model* m) {
+  if (!m) return BB_OK;
+  free_chain(&m->enc);
+  free_chain(&m->dec);
+  if (m->flag_dev) cudaFree(m->flag_dev);
+  if (m->feat_dev) cudaFree(m->feat_dev);
+  for (int io = 0; io < 2; ++io)
+    for (int s = 0; s < 2; ++s)
+      if (m->stage_dev[io][s]) cudaFree(m->stage_dev[io][s]);
+  for (int s = 0; s < 2; ++s) {
+    if (m->ev_in[s]) cudaEventDestroy(m->ev_in[s]);
+    if (m->ev_done[s]) cudaEventDestroy(m->ev_done[s]);
+    if (m->ev_out[s]) cudaEventDestroy(m->ev_out[s]);
+  }
+  if (m->s_copy_in) cudaStreamDestroy(m->s_copy_in);
+  if (m->s_compute) cudaStreamDestroy(m->s_compute);
+  if (m->s_copy_out) cudaStreamDestroy(m->s_copy_out);
+  delete m;
+  return BB_OK;
+}
+
+int bb_model_n_features(const bb_model* m) { return m ? m->enc.desc.in_dim : 0; }
+int bb_model_z_dim(const bb_model* m) { return m ? m->enc.desc.out_dim : 0; }
+int bb_model_auto_precision(const bb_model* m) {
+  return (m && m->enc.tc_ok && m->dec.tc_ok) ? BB_PREC_SPLIT16 : BB_PREC_FP32;
+}
+
+int bb_colminmax_f32(bb_ctx* ctx, const float* x_dev, int64_t n_rows, int n_cols, float* min_dev,
+                     float* max_dev, bb_stream_t stream) {
+  if (!ctx || (!x_dev && n_rows) || !min_dev || !max_dev) return BB_ERR_INVALID;
+  return bb_colminmax_launch(ctx, x_dev, n_rows, n_cols, min_dev, max_dev, 1, (cudaStream_t)stream);
+}
+
+int bb_encode_f32(bb_model* m, const float* x_dev, int64_t n_rows, const float* min_dev,
+                  const float* range_dev, void* z_dev, int z_dtype, int precision, bb_stream_t stream) {
+  if (!m) return BB_ERR_INVALID;
+  return run_chain(m, &m->enc, x_dev, BB_F32, n_rows, min_dev, range_dev, nullptr, nullptr, z_dev, z_dtype,
+                   precision, (cudaStream_t)stream);
+}
+
+int bb_decode_f32(bb_model* m, const void* z_dev, int z_dtype, int64_t n_rows, const float* min_dev,
+                  const float* range_dev, float* y_dev, int precision, bb_stream_t stream) {
+  if (!m) return BB_ERR_INVALID;
+  return run_chain(m, &m->dec, z_dev, z_dtype, n_rows, nullptr, nullptr, min_dev, range_dev, y_dev, BB_F32,
+                   precision, (cudaStream_t)stream);
+}
+
+int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* features_host,
+                     int recompute_minmax, void* z_host, int z_dtype, int precision) {
+  if (!m || (!x_host && n_rows) || (!z_host && n_rows) || n_rows < 0) return BB_ERR_INVALID;
+  if (z_dtype != BB_F32 && z_dtype != BB_F16 && z_dtype != BB_F64) return BB_ERR_INVALID;
+  if (recompute_minmax && !features_host) return BB_ERR_INVALID;
+  BB_CUDA(cudaSetDevice(m->ctx->device));
+  const int F = m->enc.desc.in_dim, Z = m->enc.desc.out_dim;
+  const int dev_dtype = (z_dtype == BB_F16) ? BB_F16 : BB_F32;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_rows, PIPE_CHUNK_ROWS));
+  const int64_t n_chunks = n_rows ? (n_rows + chunk - 1) / chunk : 0;
+  const size_t in_b = (size_t)chunk * F * sizeof(float), out_b = (size_t)chunk * Z * dtype_size(dev_dtype);
+  int rc = pipe_init(m, in_b, out_b);
+  if (rc != BB_OK) return rc;
+  float* fmin = m->feat_dev;
+  float* frange = m->feat_dev + F;
+  float* fmax = m->feat_dev + 2 * F;
+  const bool norm = features_host != nullptr;
+
+  // Column statistics of THIS table (helper.py:500-502): either a first streaming pass that keeps
+  // the table resident when it fits, or the features handed in.
+  float* resident = nullptr;
+  if (norm && recompute_minmax && n_rows) {
+    size_t free_b = 0, total_b = 0;
+    BB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t table_b = (size_t)n_rows * F * sizeof(float);
+    if (table_b < free_b / 2 && cudaMalloc(&resident, table_b) != cudaSuccess) {
+      resident = nullptr;
+      cudaGetLastError();
+    }
+    for (int64_t k = 0; k < n_chunks; ++k) {
+      const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
+      const int s = (int)(k & 1);
+      float* dst = resident ? resident + (size_t)r0 * F : (float*)m->stage_dev[0][s];
+      if (!resident && k >= 2) BB_CUDA(cudaStreamWaitEvent(m->s_copy_in, m->ev_done[s], 0));
+      BB_CUDA(cudaMemcpyAsync(dst, x_host + (size_t)r0 * F, (size_t)rows * F * sizeof(float), cudaMemcpyHostToDevice, m->s_copy_in));
+      BB_CUDA(cudaEventRecord(m->ev_in[s], m->s_copy_in));
+      BB_CUDA(cudaStreamWaitEvent(m->s_compute, m->ev_in[s], 0));
+      rc = bb_colminmax_launch(m->ctx, dst, rows, F, fmin, fmax, k == 0, m->s_compute);
+      if (rc != BB_OK) { if (resident) cudaFree(resident); return rc; }
+      BB_CUDA(cudaEventRecord(m->ev_done[s], m->s_compute));
+    }
+    range_kernel<<<(F + 127) / 128, 128, 0, m->s_compute>>>(fmin, fmax, frange, F);
+    BB_CUDA(cudaMemcpyAsync(features_host, fmin, 2 * F * sizeof(float), cudaMemcpyDeviceToHost, m->s_compute));
+    BB_CUDA(cudaStreamSynchronize(m->s_compute));
+  } else if (norm) {
+    BB_CUDA(cudaMemcpyAsync(fmin, features_host, 2 * F * sizeof(float), cudaMemcpyHostToDevice, m->s_compute));
+  }
+
+  std::vector<float> widen_tmp;
+  float* pinned_out[2] = {nullptr, nullptr};
+  if (z_dtype == BB_F64 && n_rows) {
+    for (int s = 0; s < 2; ++s)
+      if (cudaMallocHost(&pinned_out[s], (size_t)chunk * Z * sizeof(float)) != cudaSuccess) {
+        if (resident) cudaFree(resident);
+        return BB_ERR_NOMEM;
+      }
+  }
+  auto finish_chunk = [&](int64_t k) -> int {  // host side of chunk k: wait for its D2H, widen if needed
+    const int s = (int)(k & 1);
+    BB_CUDA(cudaEventSynchronize(m->ev_out[s]));
+    if (z_dtype == BB_F64) {
+      const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
+      widen_f32_f64(pinned_out[s], (double*)z_host + (size_t)r0 * Z, (size_t)rows * Z);
+    }
+    return BB_OK;
+  };
+  rc = BB_OK;
+  for (int64_t k = 0; k < n_chunks && rc == BB_OK; ++k) {
+    const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
+    const int s = (int)(k & 1);
+    const float* src;
+    if (resident) {
+      src = resident + (size_t)r0 * F;
+    } else {
+      if (k >= 2) BB_CUDA(cudaStreamWaitEvent(m->s_copy_in, m->ev_done[s], 0));  // slot's previous kernel finished
+      BB_CUDA(cudaMemcpyAsync(m->stage_dev[0][s], x_host + (size_t)r0 * F, (size_t)rows * F * sizeof(float), cudaMemcpyHostToDevice, m->s_copy_in));
+      BB_CUDA(cudaEventRecord(m->ev_in[s], m->s_copy_in));
+      BB_CUDA(cudaStreamWaitEvent(m->s_compute, m->ev_in[s], 0));
+      src = (const float*)m->stage_dev[0][s];
+    }
+    if (k >= 2) {
+      rc = finish_chunk(k - 2);  // frees output slot s on the host side (and its pinned buffer)
+      if (rc != BB_OK) break;
+      BB_CUDA(cudaStreamWaitEvent(m->s_compute, m->ev_out[s], 0));
+    }
+    rc = run_chain(m, &m->enc, src, BB_F32, rows, norm ? fmin : nullptr, norm ? frange : nullptr, nullptr, nullptr,
+                   m->stage_dev[1][s], dev_dtype, precision, m->s_compute);
+    if (rc != BB_OK) break;
+    BB_CUDA(cudaEventRecord(m->ev_done[s], m->s_compute));
+    BB_CUDA(cudaStreamWaitEvent(m->s_copy_out, m->ev_done[s], 0));
+    void* dst = (z_dtype == BB_F64) ? (void*)pinned_out[s] : (void*)((char*)z_host + (size_t)r0 * Z * dtype_size(z_dtype));
+    BB_CUDA(cudaMemcpyAsync(dst, m->stage_dev[1][s], (size_t)rows * Z * dtype_size(dev_dtype), cudaMemcpyDeviceToHost, m->s_copy_out));
+    BB_CUDA(cudaEventRecord(m->ev_out[s], m->s_copy_out));
+  }
+  for (int64_t k = std::max<int64_t>(0, n_chunks - 2); k < n_chunks && rc == BB_OK; ++k) rc = finish_chunk(k);
+  cudaStreamSynchronize(m->s_compute);
+  cudaStreamSynchronize(m->s_copy_out);
+  for (int s = 0; s < 2; ++s)
+    if (pinned_out[s]) cudaFreeHost(pinned_out[s]);
+  if (resident) cudaFree(resident);
+  return rc;
+}
+
+int bb_decompress_host(bb_model* m, const void* z_host, int z_dtype, int64_t n_rows,
+                       const float* features_host, void* y_host, int y_dtype, int precision) {
+  if (!m || (!z_host && n_rows) || (!y_host && n_rows) || n_rows < 0) return BB_ERR_INVALID;
+  if (z_dtype != BB_F32 && z_dtype != BB_F16 && z_dtype != BB_F64) return BB_ERR_INVALID;
+  if (y_dtype != BB_F32 && y_dtype != BB_F64) return BB_ERR_INVALID;
+  BB_CUDA(cudaSetDevice(m->ctx->device));
+  const int F = m->dec.desc.out_dim, Z = m->dec.desc.in_dim;
+  const int dev_in = (z_dtype == BB_F16) ? BB_F16 : BB_F32;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_rows, PIPE_CHUNK_ROWS));
+  const int64_t n_chunks = n_rows ? (n_rows + chunk - 1) / chunk : 0;
+  const size_t in_b = (size_t)chunk * Z * dtype_size(dev_in), out_b = (size_t)chunk * F * sizeof(float);
+  int rc = pipe_init(m, in_b, out_b);
+  if (rc != BB_OK) return rc;
+  float* fmin = m->feat_dev;
+  float* frange = m->feat_dev + F;
+  const bool norm = features_host != nullptr;
+  if (norm) BB_CUDA(cudaMemcpyAsync(fmin, features_host, 2 * F * sizeof(float), cudaMemcpyHostToDevice, m->s_compute));
+
+  float* pin_in[2] = {nullptr, nullptr};
+  float* pin_out[2] = {nullptr, nullptr};
+  auto cleanup = [&]() {
+    for (int s = 0; s < 2; ++s) {
+      if (pin_in[s]) cudaFreeHost(pin_in[s]);
+      if (pin_out[s]) cudaFreeHost(pin_out[s]);
+    }
+  };
+  if (n_rows) {
+    for (int s = 0; s < 2; ++s) {
+      if (z_dtype == BB_F64 && cudaMallocHost(&pin_in[s], (size_t)chunk * Z * sizeof(float)) != cudaSuccess) { cleanup(); return BB_ERR_NOMEM; }
+      if (y_dtype == BB_F64 && cudaMallocHost(&pin_out[s], (size_t)chunk * F * sizeof(float)) != cudaSuccess) { cleanup(); return BB_ERR_NOMEM; }
+    }
+  }
+  auto finish_chunk = [&](int64_t k) -> int {
+    const int s = (int)(k & 1);
+    BB_CUDA(cudaEventSynchronize(m->ev_out[s]));
+    if (y_dtype == BB_F64) {
+      const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
+      widen_f32_f64(pin_out[s], (double*)y_host + (size_t)r0 * F, (size_t)rows * F);
+    }
+    return BB_OK;
+  };
+  rc = BB_OK;
+  for (int64_t k = 0; k < n_chunks && rc == BB_OK; ++k) {
+    const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
+    const int s = (int)(k & 1);
+    if (k >= 2) {
+      BB_CUDA(cudaEventSynchronize(m->ev_in[s]));  // pinned input slot consumed by its H2D copy
+      BB_CUDA(cudaStreamWaitEvent(m->s_copy_in, m->ev_done[s], 0));
+    }
+    const void* src = (const char*)z_host + (size_t)r0 * Z * dtype_size(z_dtype);
+    if (z_dtype == BB_F64) {
+      narrow_f64_f32((const double*)src, pin_in[s], (size_t)rows * Z);
+      src = pin_in[s];
+    }
+    BB_CUDA(cudaMemcpyAsync(m->stage_dev[0][s], src, (size_t)rows * Z * dtype_size(dev_in), cudaMemcpyHostToDevice, m->s_copy_in));
+    BB_CUDA(cudaEventRecord(m->ev_in[s], m->s_copy_in));
+    BB_CUDA(cudaStreamWaitEvent(m->s_compute, m->ev_in[s], 0));
+    if (k >= 2) {
+      rc = finish_chunk(k - 2);
+      if (rc != BB_OK) break;
+      BB_CUDA(cudaStreamWaitEvent(m->s_compute, m->ev_out[s], 0));
+    }
+    rc = run_chain(m, &m->dec, m->stage_dev[0][s], dev_in, rows, nullptr, nullptr, norm ? fmin : nullptr,
+                   norm ? frange : nullptr, m->stage_dev[1][s], BB_F32, precision, m->s_compute);
+    if (rc != BB_OK) break;
+    BB_CUDA(cudaEventRecord(m->ev_done[s], m->s_compute));
+    BB_CUDA(cudaStreamWaitEvent(m->s_copy_out, m->ev_done[s], 0));
+    void* dst = (y_dtype == BB_F64) ? (void*)pin_out[s] : (void*)((float*)y_host + (size_t)r0 * F);
+    BB_CUDA(cudaMemcpyAsync(dst, m->stage_dev[1][s], (size_t)rows * F * sizeof(float), cudaMemcpyDeviceToHost, m->s_copy_out));
+    BB_CUDA(cudaEventRecord(m->ev_out[s], m->s_copy_out));
+  }
+  for (int64_t k = std::max<int64_t>(0, n_chunks - 2); k < n_chunks && rc == BB_OK; ++k) rc = finish_chunk(k);
+  cudaStreamSynchronize(m->s_compute);
+  cudaStreamSynchronize(m->s_copy_out);
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Internal definitions shared by the baler_b200 CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <vector>
+
+#include "../../include/baler_b200.h"
+
+#define BB_CUDA(expr)                          \
+  do {                                         \
+    cudaError_t _e = (expr);                   \
+    if (_e != cudaSuccess) return (int)_e;     \
+  } while (0)
+
+constexpr int BB_MAX_LAYERS = 8;
+constexpr float BB_LEAKY = 0.01f;
+
+struct bb_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;  // max dynamic shared memory per block
+  float* minmax_scratch = nullptr;  // [2][blocks][cols] partials of the column min/max pass
+  size_t minmax_scratch_bytes = 0;
+  unsigned int* minmax_counter = nullptr;
+};
+
+// One dense layer of a fused chain as the fp32 kernel sees it.
+struct ChainLayer {
+  int K, N, Npad;  // in features, out features, out features padded to the thread tile
+  int act;         // BB_ACT_*
+  int tn;          // columns per thread tile: 8, 4, 2 or 1
+  int w_off;       // float offset of Wt[K][Npad] (k-major) in the weight blob
+  int b_off;       // float offset of bias[Npad]
+};
+
+struct ChainDesc {
+  int n_layers;
+  int in_dim, out_dim;
+  int blob_floats;     // size of the fp32 weight blob
+  int buf_rows[2];     // rows ([feature] index) of the two ping-pong activation buffers
+  ChainLayer layer[BB_MAX_LAYERS];
+};
+
+// Host + device state of one direction (encoder or decoder).
+struct Chain {
+  ChainDesc desc;
+  float* blob_dev = nullptr;   // fp32 packed weights (FFMA kernel)
+  size_t smem_bytes = 0;       // dynamic smem the fp32 kernel needs
+  int f32_tr = 0;              // rows per tile of the fp32 kernel (80, 64 or 32)
+  // tcgen05 path (filled by bb_tc_prepare when the shape is supported)
+  bool tc_ok = false;
+  void* tc_blob_dev = nullptr;
+  size_t tc_blob_bytes = 0;
+  std::vector<double> w_host[BB_MAX_LAYERS];  // kept for re-packing
+  std::vector<double> b_host[BB_MAX_LAYERS];
+};
+
+struct bb_model {
+  bb_ctx* ctx = nullptr;
+  Chain enc, dec;
+  int* flag_dev = nullptr;  // overflow flag of the split16 path
+  // host pipeline resources (lazily created)
+  cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
+  void* stage_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [in/out][slot]
+  size_t stage_bytes[2] = {0, 0};
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  float* feat_dev = nullptr;  // [min | range | max] x n_features
+};
+
+// --- launches implemented in the kernel translation units
+int bb_chain_f32_prepare(bb_ctx* ctx, Chain* c);
+int bb_chain_f32_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
+                        const float* pre_min, const float* pre_range, const float* post_min,
+                        const float* post_range, void* out, int out_dtype, cudaStream_t stream);
+int bb_colminmax_launch(bb_ctx* ctx, const float* x, int64_t n_rows, int n_cols, float* min_dev,
+                        float* max_dev, int reset, cudaStream_t stream);
+int bb_tc_prepare(bb_ctx* ctx, Chain* c);
+int bb_tc_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
+                 const float* pre_min, const float* pre_range, const float* post_min,
+                 const float* post_range, void* out, int out_dtype, int fast, int* flag_dev,
+                 cudaStream_t stream);

@@ -1,0 +1,252 @@
+"""Thin Python host side over the C ABI: device memory and streams come from torch, every FLOP of the
+path runs in libbaler_b200.so.  Nothing here falls back to torch math."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BB_ACT_LEAKY, BB_ACT_NONE, BB_ACT_RELU, BB_F16, BB_F32, BB_F64, PRECISIONS, check
+
+_NP2BB = {np.dtype(np.float32): BB_F32, np.dtype(np.float16): BB_F16, np.dtype(np.float64): BB_F64}
+_T2BB = {torch.float32: BB_F32, torch.float16: BB_F16}
+_contexts = {}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("baler_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+class Context:
+    """bb_ctx for one CUDA device (replaces helper.get_device, reference helper.py:425-439)."""
+
+    def __init__(self, index):
+        require_cuda()
+        self.index = index
+        self.handle = C.c_void_p()
+        check(_lib.lib().bb_ctx_create(index, C.byref(self.handle)), "bb_ctx_create")
+        self.sm_count = _lib.lib().bb_ctx_sm_count(self.handle)
+        self.device = torch.device("cuda", index)
+
+
+def get_context(device=None):
+    require_cuda()
+    if device is None:
+        index = torch.cuda.current_device()
+    else:
+        device = torch.device(device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+    if index not in _contexts:
+        _contexts[index] = Context(index)
+    return _contexts[index]
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(ctx):
+    return C.c_void_p(torch.cuda.current_stream(ctx.device).cuda_stream)
+
+
+def _host_ptrs(arrays):
+    """ctypes array of pointers to contiguous float64 host arrays (kept alive by the caller)"""
+    arr = (C.c_void_p * len(arrays))()
+    for i, a in enumerate(arrays):
+        arr[i] = a.ctypes.data
+    return arr
+
+
+def _prec(precision):
+    if isinstance(precision, str):
+        return PRECISIONS[precision]
+    return int(precision)
+
+
+def colminmax(x, ctx=None):
+    """per-column (min, max) of a row-major CUDA float32 table -> two float32 CUDA vectors"""
+    ctx = ctx or get_context(x.device)
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    mn = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    mx = torch.empty_like(mn)
+    check(_lib.lib().bb_colminmax_f32(ctx.handle, _ptr(x), x.shape[0], x.shape[1], _ptr(mn), _ptr(mx), _stream(ctx)),
+          "bb_colminmax_f32")
+    return mn, mx
+
+
+def normalize_table(x, mn, rg, inverse=False, out=None, ctx=None):
+    """(x - min) / range, or x * range + min when inverse, on a CUDA float32 table"""
+    ctx = ctx or get_context(x.device)
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty_like(x) if out is None else out
+    c = x.shape[-1]
+    fn = _lib.lib().bb_renormalize_f32 if inverse else _lib.lib().bb_normalize_f32
+    check(fn(ctx.handle, _ptr(x), x.numel() // c, c, _ptr(mn), _ptr(rg), _ptr(out), _stream(ctx)), "bb_(re)normalize_f32")
+    return out
+
+
+def mse_sum(a, b, ctx=None):
+    """sum((a - b)^2) of two CUDA float32 tensors -> python float (one device->host read)"""
+    ctx = ctx or get_context(a.device)
+    out = torch.zeros(1, dtype=torch.float64, device=a.device)
+    check(_lib.lib().bb_mse_sum_f32(ctx.handle, _ptr(a), _ptr(b), a.numel(), _ptr(out), _stream(ctx)), "bb_mse_sum_f32")
+    return float(out.item())
+
+
+class DenseCodec:
+    """Packed encoder + decoder of one dense autoencoder (bb_model).
+
+    enc_layers / dec_layers: lists of (weight (out, in) float64, bias (out,) float64, act) with
+    act in {"none", "leaky", "relu"}; eval-mode BatchNorm already folded by the caller."""
+
+    _ACT = {"none": BB_ACT_NONE, "leaky": BB_ACT_LEAKY, "relu": BB_ACT_RELU}
+
+    def __init__(self, enc_layers, dec_layers, device=None):
+        self.ctx = get_context(device)
+        self.handle = C.c_void_p()
+        keep = []
+
+        def pack(layers):
+            w = [np.ascontiguousarray(l[0], dtype=np.float64) for l in layers]
+            b = [np.ascontiguousarray(l[1], dtype=np.float64) for l in layers]
+            dims = (C.c_int * (len(layers) + 1))(*([w[0].shape[1]] + [x.shape[0] for x in w]))
+            acts = (C.c_int * len(layers))(*[self._ACT[l[2]] for l in layers])
+            keep.extend(w + b)
+            return len(layers), dims, acts, _host_ptrs(w), _host_ptrs(b)
+
+        ne, ed, ea, ew, eb = pack(enc_layers)
+        nd, dd, da, dw, db = pack(dec_layers)
+        with torch.cuda.device(self.ctx.device):
+            check(_lib.lib().bb_model_create_dense(self.ctx.handle, ne, ed, ea, ew, eb, nd, dd, da, dw, db,
+                                                   C.byref(self.handle)), "bb_model_create_dense")
+        self.n_features = _lib.lib().bb_model_n_features(self.handle)
+        self.z_dim = _lib.lib().bb_model_z_dim(self.handle)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                _lib.lib().bb_model_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def auto_precision(self):
+        return {v: k for k, v in PRECISIONS.items() if k in ("fp32", "split16")}[
+            _lib.lib().bb_model_auto_precision(self.handle)]
+
+    # ---- device-resident tensors
+    def encode(self, x, fmin=None, frange=None, out_dtype=torch.float32, precision="auto", out=None):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == self.n_features
+        n = x.numel() // self.n_features
+        z = out if out is not None else torch.empty((n, self.z_dim), dtype=out_dtype, device=x.device)
+        check(_lib.lib().bb_encode_f32(self.handle, _ptr(x), n, _ptr(fmin), _ptr(frange), _ptr(z), _T2BB[z.dtype],
+                                       _prec(precision), _stream(self.ctx)), "bb_encode_f32")
+        return z
+
+    def decode(self, z, fmin=None, frange=None, precision="auto", out=None):
+        assert z.is_cuda and z.dtype in _T2BB and z.is_contiguous() and z.shape[-1] == self.z_dim
+        n = z.numel() // self.z_dim
+        y = out if out is not None else torch.empty((n, self.n_features), dtype=torch.float32, device=z.device)
+        check(_lib.lib().bb_decode_f32(self.handle, _ptr(z), _T2BB[z.dtype], n, _ptr(fmin), _ptr(frange), _ptr(y),
+                                       _prec(precision), _stream(self.ctx)), "bb_decode_f32")
+        return y
+
+    # ---- host buffers (numpy), chunked copy/compute pipeline inside the library
+    def compress_host(self, x, features=None, recompute_minmax=False, z_dtype=np.float32, precision="auto", out=None):
+        """x: (n, F) float32 ndarray.  features: None (no normalisation) or (2, F) float32 [min; range]
+        (overwritten when recompute_minmax).  Returns (z, features)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        z = out if out is not None else np.empty((n, self.z_dim), dtype=z_dtype)
+        feats = None
+        if features is not None or recompute_minmax:
+            feats = np.zeros((2, self.n_features), dtype=np.float32) if features is None else \
+                np.ascontiguousarray(features, dtype=np.float32).copy()
+        check(_lib.lib().bb_compress_host(self.handle, x.ctypes.data, n,
+                                          None if feats is None else feats.ctypes.data, int(bool(recompute_minmax)),
+                                          z.ctypes.data, _NP2BB[z.dtype], _prec(precision)), "bb_compress_host")
+        return z, feats
+
+    def decompress_host(self, z, features=None, y_dtype=np.float64, precision="auto", out=None):
+        z = np.ascontiguousarray(z)
+        n = z.shape[0]
+        y = out if out is not None else np.empty((n, self.n_features), dtype=y_dtype)
+        feats = None if features is None else np.ascontiguousarray(features, dtype=np.float32)
+        check(_lib.lib().bb_decompress_host(self.handle, z.ctypes.data, _NP2BB[z.dtype], n,
+                                            None if feats is None else feats.ctypes.data, y.ctypes.data,
+                                            _NP2BB[y.dtype], _prec(precision)), "bb_decompress_host")
+        return y
+
+
+class Trainer:
+    """bb_trainer: parameters, Adam state and scratch of one dense-AE training run on one GPU."""
+
+    def __init__(self, weights, biases, n_features, z_dim, max_batch, device=None):
+        self.ctx = get_context(device)
+        self.handle = C.c_void_p()
+        self._w = [np.ascontiguousarray(w, dtype=np.float64) for w in weights]
+        self._b = [np.ascontiguousarray(b, dtype=np.float64) for b in biases]
+        with torch.cuda.device(self.ctx.device):
+            check(_lib.lib().bb_trainer_create(self.ctx.handle, n_features, z_dim, _host_ptrs(self._w),
+                                               _host_ptrs(self._b), max_batch, C.byref(self.handle)), "bb_trainer_create")
+        self.n_params = _lib.lib().bb_trainer_param_count(self.handle)
+        self.loss_accum = torch.zeros(1, dtype=torch.float64, device=self.ctx.device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                _lib.lib().bb_trainer_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def _flat(self, ptr):
+        # zero-copy torch view of library-owned device memory
+        from torch.utils import dlpack  # noqa: F401  (documented route; below uses __cuda_array_interface__)
+
+        class _Arr:
+            pass
+
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (self.n_params,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(a, device=self.ctx.device)
+
+    def params_view(self):
+        return self._flat(_lib.lib().bb_trainer_params_dev(self.handle))
+
+    def grads_view(self):
+        return self._flat(_lib.lib().bb_trainer_grads_dev(self.handle))
+
+    def step(self, x, hyper, phase=0):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        check(_lib.lib().bb_trainer_step(self.handle, _ptr(x), x.shape[0], C.byref(hyper), phase,
+                                         _ptr(self.loss_accum), _stream(self.ctx)), "bb_trainer_step")
+
+    def epoch(self, x, batch, hyper):
+        out = C.c_double()
+        check(_lib.lib().bb_trainer_epoch(self.handle, _ptr(x), x.shape[0], batch, C.byref(hyper), C.byref(out),
+                                          _stream(self.ctx)), "bb_trainer_epoch")
+        return out.value
+
+    def validate(self, x, batch):
+        out = C.c_double()
+        check(_lib.lib().bb_trainer_validate(self.handle, _ptr(x), x.shape[0], batch, C.byref(out), _stream(self.ctx)),
+              "bb_trainer_validate")
+        return out.value
+
+    def activation_means(self):
+        out = np.empty((6, 200), dtype=np.float64)
+        check(_lib.lib().bb_trainer_activation_means(self.handle, out.ctypes.data), "bb_trainer_activation_means")
+        return out
+
+    def get_params(self):
+        w = [np.empty_like(a) for a in self._w]
+        b = [np.empty_like(a) for a in self._b]
+        check(_lib.lib().bb_trainer_get_params(self.handle, _host_ptrs(w), _host_ptrs(b)), "bb_trainer_get_params")
+        return w, b
+
+
+def make_hyper(lr=1e-3, reg_param=0.0, l1=False, world_size=1, beta1=0.9, beta2=0.999, eps=1e-8):
+    return _lib.TrainHyper(lr, beta1, beta2, eps, reg_param, int(bool(l1)), world_size)

@@ -1,0 +1,217 @@
+"""Orchestration helpers with the reference's signatures (reference baler/modules/helper.py): what
+`baler.py` calls for `--mode train|compress|decompress`.  Data loading and file layout are host
+Python; every numeric step goes to libbaler_b200 (CUDA)."""
+import argparse
+import importlib
+import os
+import sys
+from math import ceil
+
+import numpy as np
+import torch
+
+from .. import engine
+from . import data_processing, training
+
+sys.path.append(os.getcwd())
+
+
+class Config:
+    """Namespace the per-project `set_config(c)` fills (reference helper.py:150-179: a dataclass used as a
+    class-level namespace; attributes that are never set raise AttributeError when read).
+    Extra, optional knobs of this implementation (absent = reference behaviour):
+      precision        "auto" | "fp32" | "split16" | "fast"   arithmetic of the fused encode/decode kernels
+      latent_dtype     "float64" (AE default, what the reference writes) | "float32" | "float16"
+      l1_in_training   bool: add reg_param * L1 chain to the training loss (dead code upstream)
+    """
+
+    model_type = str  # reference helper.py:163: defaults to the *type* `str`
+
+
+def get_arguments():
+    """`baler --project WORKSPACE PROJECT --mode MODE [--verbose]` (reference helper.py:34-101)"""
+    parser = argparse.ArgumentParser(
+        prog="baler",
+        description="Baler (B200-native hot path): train / compress / decompress with fused CUDA autoencoder kernels.",
+        formatter_class=argparse.RawTextHelpFormatter,
+    )
+    parser.add_argument("--mode", type=str, required=True, help="newProject, train, compress, decompress, info")
+    parser.add_argument("--project", type=str, required=True, nargs=2, metavar=("WORKSPACE", "PROJECT"),
+                        help="workspace and project, e.g. --project CMS_workspace CMS_project_v1")
+    parser.add_argument("--verbose", dest="verbose", action="store_true", help="Verbose mode")
+    parser.set_defaults(verbose=False)
+    args = parser.parse_args()
+    workspace_name, project_name = args.project
+    if args.mode == "newProject":
+        config = None
+    else:
+        config = Config
+        importlib.import_module(
+            f"workspaces.{workspace_name}.{project_name}.config.{project_name}_config").set_config(config)
+    return config, args.mode, workspace_name, project_name, args.verbose
+
+
+def create_new_project(workspace_name, project_name, verbose=False, base_path="workspaces"):
+    """reference helper.py:104-147: directory skeleton + default config"""
+    workspace_path = os.path.join(base_path, workspace_name)
+    project_path = os.path.join(workspace_path, project_name)
+    if os.path.exists(project_path):
+        print(f"The workspace and project ({project_path}) already exists.")
+        return
+    os.makedirs(project_path)
+    for d in (os.path.join(workspace_path, "data"), os.path.join(project_path, "config"),
+              os.path.join(project_path, "output", "compressed_output"),
+              os.path.join(project_path, "output", "decompressed_output"),
+              os.path.join(project_path, "output", "plotting"), os.path.join(project_path, "output", "training")):
+        if verbose:
+            print(f"Creating directory {d}...")
+        os.makedirs(d, exist_ok=True)
+    with open(os.path.join(project_path, "config", f"{project_name}_config.py"), "w") as f:
+        f.write(create_default_config(workspace_name, project_name))
+
+
+_DEFAULTS = [  # same keys and values as the reference's template (helper.py:182-232)
+    ("input_path", None), ("data_dimension", 1), ("compression_ratio", 2.0), ("apply_normalization", True),
+    ("model_name", "AE"), ("model_type", "dense"), ("epochs", 5), ("lr", 0.001), ("batch_size", 512),
+    ("early_stopping", True), ("lr_scheduler", True), ("early_stopping_patience", 100), ("min_delta", 0),
+    ("lr_scheduler_patience", 50), ("custom_norm", False), ("reg_param", 0.001), ("RHO", 0.05), ("test_size", 0),
+    ("extra_compression", False), ("intermittent_model_saving", False), ("intermittent_saving_patience", 100),
+    ("mse_avg", False), ("mse_sum", True), ("emd", False), ("l1", True), ("activation_extraction", False),
+    ("deterministic_algorithm", True), ("separate_model_saving", False), ("save_error_bounded_deltas", False),
+]
+
+
+def create_default_config(workspace_name, project_name):
+    lines = ["", "# === Configuration options ===", "", "def set_config(c):"]
+    for key, val in _DEFAULTS:
+        if key == "input_path":
+            val = f"workspaces/{workspace_name}/data/{project_name}_data.npz"
+        lines.append(f"    c.{key:<29}= {val!r}")
+    return "\n".join(lines) + "\n"
+
+
+def model_init(model_name):
+    return data_processing.initialise_model(model_name)
+
+
+def numpy_to_tensor(data):
+    return torch.from_numpy(data)
+
+
+def normalize(data, custom_norm):
+    """reference helper.py:261-274 (per column / per pixel over axis 0)"""
+    return data_processing.normalize(data, custom_norm)
+
+
+def renormalize(data, true_min_list, feature_range_list):
+    """reference helper.py:322-333"""
+    return data_processing.renormalize_func(data, true_min_list, feature_range_list)
+
+
+def process(input_path, custom_norm, test_size, apply_normalization, convert_to_blocks, verbose):
+    """reference helper.py:277-319 -> (train_set, test_set, normalization_features, original_shape)"""
+    data = np.load(input_path)["data"]
+    if verbose:
+        print("Original Dataset Shape - ", data.shape)
+    original_shape = data.shape
+    if convert_to_blocks:
+        data = data_processing.convert_to_blocks_util(convert_to_blocks, data)
+    normalization_features = data_processing.find_minmax(data)
+    if apply_normalization:
+        print("Normalizing the data...")
+        data = normalize(data, custom_norm)
+    if not test_size:
+        train_set = test_set = data
+    else:
+        from sklearn.model_selection import train_test_split
+
+        train_set, test_set = train_test_split(data, test_size=test_size, random_state=1)
+    return train_set, test_set, normalization_features, original_shape
+
+
+def train(model, number_of_columns, train_set, test_set, project_path, config):
+    return training.train(model, number_of_columns, train_set, test_set, project_path, config)
+
+
+def model_saver(model, model_path):
+    return data_processing.save_model(model, model_path)
+
+
+def detacher(tensor):
+    return tensor.cpu().detach().numpy()
+
+
+def get_device():
+    """reference helper.py:425-439 - here a CUDA device is mandatory"""
+    engine.require_cuda()
+    return torch.device("cuda:0")
+
+
+def _latent_np_dtype(model, config):
+    name = getattr(config, "latent_dtype", None)
+    if name is None:
+        return np.float64 if model.dtype == torch.float64 else np.float32
+    return np.dtype(name).type
+
+
+def compress(model_path, config):
+    """reference helper.py:473-616 -> (compressed ndarray, eb_batch, eb_deltas, eb_index).
+    Normalisation uses THIS file's column min/max (helper.py:500-502), fused into the encode kernel."""
+    loaded = np.load(config.input_path)
+    data_before = loaded["data"]
+    original_shape = data_before.shape
+    if hasattr(config, "convert_to_blocks") and config.convert_to_blocks:
+        data_before = data_processing.convert_to_blocks_util(config.convert_to_blocks, data_before)
+    if getattr(config, "save_error_bounded_deltas", False):
+        raise NotImplementedError("error-bounded deltas: listed as a next row in DESIGN.md")
+    if config.data_dimension == 1:
+        number_of_columns = len(loaded["names"])
+        config.latent_space_size = ceil(number_of_columns / config.compression_ratio)
+        config.number_of_columns = number_of_columns
+        n_features = number_of_columns
+    elif config.data_dimension == 2:
+        if config.model_type != "dense":
+            raise NotImplementedError("convolutional models: see DESIGN.md (next rows)")
+        number_of_rows, config.number_of_columns = data_before.shape[1], data_before.shape[2]
+        n_features = number_of_rows * config.number_of_columns
+        config.latent_space_size = ceil(n_features / config.compression_ratio)
+    else:
+        raise NameError("Data dimension can only be 1 or 2. Got config.data_dimension = " + str(config.data_dimension))
+    model = data_processing.load_model(data_processing.initialise_model(config.model_name), model_path,
+                                       n_features=n_features, z_dim=config.latent_space_size)
+    model.eval()
+    table = np.ascontiguousarray(data_before.reshape(data_before.shape[0], -1), dtype=np.float32)
+    normalise = bool(config.apply_normalization) and not config.custom_norm
+    if config.apply_normalization:
+        print("Normalizing...")
+    compressed, _ = model.codec().compress_host(table, recompute_minmax=normalise,
+                                                z_dtype=_latent_np_dtype(model, config),
+                                                precision=getattr(config, "precision", "auto"))
+    return compressed, [], [], []
+
+
+def decompress(model_path, input_path, input_path_deltas, input_batch_index, model_name, config, output_path,
+               original_shape, renormalize_features=None):
+    """reference helper.py:619-733 -> (decompressed ndarray, names, normalization_features).
+    `renormalize_features` ([min; range], optional, not in the reference signature) fuses the
+    un-normalisation of baler.py:410-424 into the decode kernel."""
+    loaded = np.load(input_path)
+    data, names, normalization_features = loaded["data"], loaded["names"], loaded["normalization_features"]
+    if getattr(config, "save_error_bounded_deltas", False):
+        raise NotImplementedError("error-bounded deltas: listed as a next row in DESIGN.md")
+    latent_space_size = data.shape[1]
+    model_dict = torch.load(str(model_path), map_location="cpu")
+    # the reference reads len() of the last state-dict entry, which crashes on AE_Dropout_BN's
+    # num_batches_tracked scalar; take the last tensor that has a length instead
+    number_of_columns = [len(v) for v in model_dict.values() if getattr(v, "ndim", 0) >= 1][-1]
+    model = data_processing.load_model(data_processing.initialise_model(config.model_name), model_path,
+                                       n_features=number_of_columns, z_dim=latent_space_size)
+    model.eval()
+    if data.dtype not in (np.float16, np.float32, np.float64):
+        data = data.astype(np.float32)
+    out_dtype = np.float64 if model.dtype == torch.float64 else np.float32
+    decompressed = model.codec().decompress_host(data, features=renormalize_features, y_dtype=out_dtype,
+                                                 precision=getattr(config, "precision", "auto"))
+    if config.data_dimension == 2 and config.model_type == "dense":
+        decompressed = decompressed.reshape((len(decompressed), original_shape[1], original_shape[2]))
+    return decompressed, names, normalization_features

@@ -1,0 +1,121 @@
+"""Training loop of the hot path (reference baler/modules/training.py): same `fit / validate / train`
+entry points; the batch loop runs on the GPU (bb_trainer_epoch) without a host sync per batch."""
+import os
+import time
+
+import numpy as np
+import torch
+
+from .. import engine
+from . import utils
+
+
+class DeviceBatches:
+    """Stands in for the reference's DataLoader(shuffle=False, drop_last=False) (training.py:253-263):
+    the whole (normalised, float32) table resident in HBM plus the batch size."""
+
+    def __init__(self, data, batch_size):
+        self.data, self.batch_size = data, int(batch_size)
+
+    def __len__(self):
+        return (self.data.shape[0] + self.batch_size - 1) // self.batch_size
+
+
+class DeviceAdam:
+    """Stands in for torch.optim.Adam(model.parameters(), lr) (training.py:266): Adam state lives in
+    the bb_trainer; `lr` is what LRScheduler adjusts."""
+
+    def __init__(self, model, lr, max_batch, l1=False, reg_param=0.0):
+        w, b = model.linear_tensors()
+        self.model = model
+        self.trainer = engine.Trainer(w, b, model.n_features, model.z_dim, max_batch)
+        self.lr, self.l1, self.reg_param = lr, l1, reg_param
+
+    def hyper(self, world_size=1):
+        return engine.make_hyper(lr=self.lr, reg_param=self.reg_param, l1=self.l1, world_size=world_size)
+
+    def sync_model(self):
+        w, b = self.trainer.get_params()
+        self.model.set_linear_tensors(w, b)
+
+
+def fit(config, model, train_dl, model_children, regular_param, optimizer, latent_dim, RHO, l1, n_dimensions):
+    """One epoch (reference training.py:31-101).  Returns (epoch_loss, mse_loss, l1_loss, model); the
+    reference always evaluates the loss with validate=True, i.e. without the L1 term -
+    the L1 branch is opt-in through `config.l1_in_training`."""
+    print("### Beginning Training")
+    model.train()
+    if hasattr(config, "custom_loss_function") and config.custom_loss_function == "loss_function_swae":
+        raise NotImplementedError("loss_function_swae is outside the B200 hot path")
+    epoch_loss = optimizer.trainer.epoch(train_dl.data, train_dl.batch_size, optimizer.hyper())
+    print(f"# Finished. Training Loss: {epoch_loss:.6f}")
+    return epoch_loss, epoch_loss, 0, model
+
+
+def validate(model, test_dl, model_children, reg_param, optimizer=None):
+    """reference training.py:104-137: eval-mode forward + sum-MSE / n_columns, mean over batches"""
+    print("### Beginning Validating")
+    model.eval()
+    epoch_loss = optimizer.trainer.validate(test_dl.data, test_dl.batch_size)
+    print(f"# Finished. Validation Loss: {epoch_loss:.6f}")
+    return epoch_loss
+
+
+def _to_device_table(data, config):
+    arr = np.asarray(data)
+    if config.data_dimension == 2:
+        if config.model_type != "dense":
+            raise NotImplementedError("convolutional models: see DESIGN.md (next rows)")
+        arr = arr.reshape(arr.shape[0], arr.shape[1] * arr.shape[2])
+    return torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).cuda()
+
+
+def train(model, variables, train_data, test_data, project_path, config):
+    """reference training.py:150-348.  Same side effects: `loss_data.npy` ([train; val] per epoch),
+    optional `model_{epoch}.pt`, `activations.npy`; returns the trained model."""
+    from . import helper
+
+    if config.deterministic_algorithm:
+        import random
+
+        random.seed(0)
+        torch.manual_seed(0)
+        np.random.seed(0)
+    bs = config.batch_size
+    train_ds = _to_device_table(train_data, config)
+    valid_ds = train_ds if test_data is train_data else _to_device_table(test_data, config)
+    train_dl, valid_dl = DeviceBatches(train_ds, bs), DeviceBatches(valid_ds, bs)
+    model_children = list(model.children())
+    optimizer = DeviceAdam(model, config.lr, max_batch=bs, l1=bool(getattr(config, "l1_in_training", False)),
+                           reg_param=config.reg_param)
+    early_stopping = utils.EarlyStopping(config.early_stopping_patience, config.min_delta) if config.early_stopping else None
+    lr_scheduler = utils.LRScheduler(optimizer, config.lr_scheduler_patience) if config.lr_scheduler else None
+    train_loss, val_loss = [], []
+    start = time.time()
+    for epoch in range(config.epochs):
+        print(f"Epoch {epoch + 1} of {config.epochs}")
+        train_epoch_loss, _, _, _ = fit(config, model, train_dl, model_children, config.reg_param, optimizer,
+                                        getattr(config, "latent_space_size", None), config.RHO, config.l1,
+                                        config.data_dimension)
+        train_loss.append(train_epoch_loss)
+        if config.test_size:
+            val_epoch_loss = validate(model, valid_dl, model_children, config.reg_param, optimizer)
+        else:
+            val_epoch_loss = train_epoch_loss
+        val_loss.append(val_epoch_loss)
+        if lr_scheduler:
+            lr_scheduler(val_epoch_loss)
+        if early_stopping:
+            early_stopping(val_epoch_loss)
+            if early_stopping.early_stop:
+                break
+        if config.intermittent_model_saving and epoch % config.intermittent_saving_patience == 0:
+            optimizer.sync_model()
+            helper.model_saver(model, os.path.join(project_path, f"model_{epoch}.pt"))
+    end = time.time()
+    optimizer.sync_model()
+    if getattr(config, "activation_extraction", False):
+        np.save(os.path.join(project_path, "activations.npy"), optimizer.trainer.activation_means())
+    print(f"{(end - start) / 60:.3} minutes")
+    np.save(os.path.join(project_path, "loss_data.npy"), np.array([train_loss, val_loss]))
+    return model

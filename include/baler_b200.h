@@ -1,0 +1,212 @@
+/*
+ * baler_b200 - C ABI of the B200-native autoencoder train / compress / decompress path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.  The reference
+ * (baler v1.4.0, pure Python) has no FFI of its own; its operator boundary for this path is the
+ * model protocol (`model.encode / model.decode / model.forward`), the numpy normalisation helpers
+ * and `training.fit`.  Each entry point below names the reference interface it replaces
+ * (file:line relative to the reference repository).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (BB_OK) or a negative BB_ERR_* / a positive cudaError_t value;
+ *     `bb_strerror` describes either.  No exceptions, no global state besides the CUDA context.
+ *   - `*_dev` pointers are device pointers owned by the caller, `*_host` are host pointers.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  Calls taking a
+ *     stream are asynchronous with respect to the host.
+ *   - handles are not thread-safe; use one per host thread / stream.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef BALER_B200_H
+#define BALER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_VERSION 100 /* 0.1.0 */
+
+/* error codes (negative; positive values are cudaError_t) */
+#define BB_OK 0
+#define BB_ERR_INVALID -1     /* bad argument */
+#define BB_ERR_UNSUPPORTED -2 /* shape / mode not supported by the kernels */
+#define BB_ERR_NOMEM -3
+#define BB_ERR_NODEVICE -4
+#define BB_ERR_OVERFLOW -5 /* fp16 split range guard tripped: rerun with BB_PREC_FP32 */
+
+/* element types of caller buffers */
+#define BB_F32 0
+#define BB_F16 1
+#define BB_F64 2
+
+/* activation after a dense layer */
+#define BB_ACT_NONE 0
+#define BB_ACT_LEAKY 1 /* F.leaky_relu, slope 0.01 (models.py:142) */
+#define BB_ACT_RELU 2
+
+/* arithmetic of the fused dense chain */
+#define BB_PREC_AUTO 0    /* SPLIT16 when the shape is supported by the tcgen05 kernel, else FP32 */
+#define BB_PREC_FP32 1    /* fp32 FFMA on CUDA cores; reference tolerance 1e-5 met with margin */
+#define BB_PREC_SPLIT16 2 /* tcgen05 tensor cores, fp16 hi/lo 3-product split, fp32 accumulate in TMEM */
+#define BB_PREC_FAST16 3  /* tcgen05 single fp16 product: OUTSIDE the 1e-5 tolerance (~3e-4), opt-in */
+
+typedef struct bb_ctx bb_ctx;         /* one per device */
+typedef struct bb_model bb_model;     /* packed encoder + decoder weights of one autoencoder */
+typedef struct bb_trainer bb_trainer; /* parameters + Adam state + scratch of one training run */
+typedef void* bb_stream_t;            /* cudaStream_t */
+
+int bb_version(void);
+const char* bb_strerror(int code);
+
+/* replaces helper.get_device (helper.py:425-439): binds a context to CUDA device `device` */
+int bb_ctx_create(int device, bb_ctx** out);
+int bb_ctx_destroy(bb_ctx* ctx);
+int bb_ctx_sm_count(const bb_ctx* ctx);
+
+/*
+ * Pack a dense autoencoder for inference.  Replaces data_processing.load_model
+ * (data_processing.py:89-110) + model.eval(): the caller reads model.pt (a state_dict) and hands
+ * over the Linear tensors as the reference stores them, `weights[l]` = (dims[l+1], dims[l])
+ * row-major float64, `biases[l]` = (dims[l+1]).  Eval-mode BatchNorm is folded into the
+ * neighbouring Linear by the caller (exact affine algebra, done in float64 on the host).
+ *   AE / CFD_dense_AE (models.py:116-157,186-226):
+ *        enc dims {F,200,100,50,z} acts {LEAKY,LEAKY,LEAKY,NONE}; dec mirrored.
+ *   AE_Dropout_BN (models.py:256-313): enc acts all LEAKY; dec acts {LEAKY,LEAKY,LEAKY,RELU}.
+ */
+int bb_model_create_dense(bb_ctx* ctx,
+                          int n_enc_layers, const int* enc_dims, const int* enc_acts,
+                          const double* const* enc_weights_host, const double* const* enc_biases_host,
+                          int n_dec_layers, const int* dec_dims, const int* dec_acts,
+                          const double* const* dec_weights_host, const double* const* dec_biases_host,
+                          bb_model** out);
+int bb_model_destroy(bb_model* m);
+int bb_model_n_features(const bb_model* m);
+int bb_model_z_dim(const bb_model* m);
+/* which arithmetic BB_PREC_AUTO resolves to for this model (BB_PREC_FP32 or BB_PREC_SPLIT16) */
+int bb_model_auto_precision(const bb_model* m);
+
+/*
+ * Per-column min and max of a row-major n x c float32 table.
+ * Replaces data_processing.find_minmax (data_processing.py:113-130); range = max - min is left to
+ * the caller so that shards can be combined (min of mins, max of maxes) before subtracting.
+ * NaNs propagate like numpy's min/max.
+ */
+int bb_colminmax_f32(bb_ctx* ctx, const float* x_dev, int64_t n_rows, int n_cols,
+                     float* min_dev, float* max_dev, bb_stream_t stream);
+
+/*
+ * Stand-alone column normalisation and its inverse on device tables (row-major n x c float32):
+ *   out = (x - min) / range      helper.normalize (helper.py:261-274, data_processing.py:133-153)
+ *   out = y * range + min        helper.renormalize (helper.py:322-333, data_processing.py:188-203)
+ * `out_dev` may alias the input.  The compress / decompress kernels below fuse these instead.
+ */
+int bb_normalize_f32(bb_ctx* ctx, const float* x_dev, int64_t n_rows, int n_cols, const float* min_dev,
+                     const float* range_dev, float* out_dev, bb_stream_t stream);
+int bb_renormalize_f32(bb_ctx* ctx, const float* y_dev, int64_t n_rows, int n_cols, const float* min_dev,
+                       const float* range_dev, float* out_dev, bb_stream_t stream);
+
+/*
+ * z = encode((x - min) / range)  for n_rows rows of the row-major table x (n_rows x n_features).
+ * Replaces helper.normalize (helper.py:261-274, data_processing.py:133-153; same float32
+ * subtract + IEEE divide, bit-equal) fused with the `model.encode` loop of helper.compress
+ * (helper.py:583-611).  min_dev/range_dev may both be NULL (apply_normalization = False).
+ * z_dtype: BB_F32 or BB_F16 (row-major n_rows x z_dim).
+ */
+int bb_encode_f32(bb_model* m, const float* x_dev, int64_t n_rows,
+                  const float* min_dev, const float* range_dev,
+                  void* z_dev, int z_dtype, int precision, bb_stream_t stream);
+
+/*
+ * y = decode(z) * range + min.  Replaces the `model.decode` loop of helper.decompress
+ * (helper.py:701-723) fused with helper.renormalize (helper.py:322-333,
+ * data_processing.py:188-203).  min_dev/range_dev may both be NULL.
+ */
+int bb_decode_f32(bb_model* m, const void* z_dev, int z_dtype, int64_t n_rows,
+                  const float* min_dev, const float* range_dev,
+                  float* y_dev, int precision, bb_stream_t stream);
+
+/*
+ * Whole-table compress / decompress with HOST buffers: chunked, double-buffered H2D copy ->
+ * kernels -> D2H copy on internal streams; returns when the output is complete in host memory.
+ * These are what the reference-facing `helper.compress` / `helper.decompress` drop-ins call and
+ * what `bench.py` times as `e2e`.
+ *   bb_compress_host: if `features_host_inout` has `recompute_minmax` != 0 the column min / range
+ *     are computed from THIS table first (as helper.compress does, helper.py:500-502) and written
+ *     to features_host (2 x n_features float32: [min; range]); otherwise they are read from it.
+ *     features_host == NULL: no normalisation.
+ *   z_dtype / y_dtype: BB_F32, BB_F64 (what the reference writes for AE, helper.py:565) or, for z,
+ *     BB_F16.  Pinned (page-locked) host buffers make the copies asynchronous; pageable works too.
+ */
+int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows,
+                     float* features_host, int recompute_minmax,
+                     void* z_host, int z_dtype, int precision);
+int bb_decompress_host(bb_model* m, const void* z_host, int z_dtype, int64_t n_rows,
+                       const float* features_host, void* y_host, int y_dtype, int precision);
+
+/* ------------------------------------------------------------------ training (dense AE) */
+
+typedef struct bb_train_hyper {
+  double lr;        /* config.lr; Adam defaults below match training.py:266 */
+  double beta1;     /* 0.9 */
+  double beta2;     /* 0.999 */
+  double eps;       /* 1e-8 */
+  double reg_param; /* config.reg_param, used only when l1 != 0 */
+  int l1;           /* 0: mse_sum_loss_l1(validate=True) as training.fit ships (training.py:83-89);
+                       1: + reg_param * L1 chain (utils.py:201-209) */
+  int world_size;   /* data-parallel ranks; gradients are SUM-reduced (loss is a sum, utils.py:195) */
+} bb_train_hyper;
+
+/*
+ * Replaces `model = AE(n_features, z_dim)` + torch.optim.Adam(model.parameters()) (training.py:266).
+ * `weights/biases` as for bb_model_create_dense, 8 layers F-200-100-50-z-50-100-200-F, float64 host.
+ */
+int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim,
+                      const double* const* weights_host, const double* const* biases_host,
+                      int max_batch, bb_trainer** out);
+int bb_trainer_destroy(bb_trainer* t);
+/* flat float32 views (device) of parameters / gradients, layout: for l in 0..7: W_l (out,in) then b_l */
+int bb_trainer_param_count(const bb_trainer* t);
+float* bb_trainer_params_dev(bb_trainer* t);
+float* bb_trainer_grads_dev(bb_trainer* t);
+/* copy parameters back as the reference's float64 state_dict tensors */
+int bb_trainer_get_params(bb_trainer* t, double* const* weights_host, double* const* biases_host);
+
+/*
+ * One optimisation step on `batch_rows` rows (x_dev row-major float32, already normalised):
+ * zero_grad -> forward -> loss -> backward [-> caller all-reduces grads] -> Adam.
+ * Replaces the body of the batch loop of training.fit (training.py:64-97).
+ *   phase 0: everything (single GPU);  phase 1: forward + backward only (grads and loss left in
+ *   device memory for an all-reduce);  phase 2: Adam only.
+ * The batch loss is ADDED to *loss_accum_dev (double) so an epoch needs no host sync.
+ */
+int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_train_hyper* h,
+                    int phase, double* loss_accum_dev, bb_stream_t stream);
+/*
+ * One epoch over n_rows rows in sequential batches of `batch` (last one ragged, drop_last=False,
+ * shuffle=False: training.py:253-263).  Single-GPU only (world_size == 1).  Writes the epoch loss
+ * (mean of batch losses, training.py:99) to *epoch_loss_host after synchronising `stream`.
+ */
+int bb_trainer_epoch(bb_trainer* t, const float* x_dev, int64_t n_rows, int batch,
+                     const bb_train_hyper* h, double* epoch_loss_host, bb_stream_t stream);
+/* forward only in eval mode, sum-MSE / n_cols per batch averaged over batches: training.validate
+ * (training.py:104-137) */
+int bb_trainer_validate(bb_trainer* t, const float* x_dev, int64_t n_rows, int batch,
+                        double* epoch_loss_host, bb_stream_t stream);
+
+/*
+ * Per-node mean activation of the six hidden layers (en1,en2,en3,de1,de2,de3) over the rows of the LAST
+ * forward pass, as a 6 x 200 float64 matrix padded with NaN: what model.get_activations() +
+ * diagnostics.dict_to_square_matrix write to activations.npy (models.py:160-179, diagnostics.py:10-47).
+ */
+int bb_trainer_activation_means(bb_trainer* t, double* out_host_6x200);
+
+/* sum((a - b)^2) over n float32 elements, ADDED to *out_dev (double): nn.MSELoss(reduction="sum") of
+ * utils.mse_sum_loss_l1 (utils.py:195-196) on loose tensors. */
+int bb_mse_sum_f32(bb_ctx* ctx, const float* a_dev, const float* b_dev, int64_t n, double* out_dev, bb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BALER_B200_H */

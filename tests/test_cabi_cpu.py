@@ -1,0 +1,157 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/baler_b200.h declares; host-side logic (schedules, state-dict layout, BatchNorm folding)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, rel_max, sub_sd
+from baler_b200 import _lib, build
+from baler_b200.modules import models, utils
+from oracle import baler_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.lib()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "baler_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = header_symbols()
+    assert len(declared) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (bb_[a-z0-9_]+)", out))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    assert set(declared) == set(_lib.exported_symbols())  # the ctypes binding covers the whole header
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_version_and_errors(lib):
+    assert lib.bb_version() == 100
+    assert b"no CUDA device" in lib.bb_strerror(-4)
+    assert b"invalid" in lib.bb_strerror(-1)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lib):
+    h = ctypes.c_void_p()
+    assert lib.bb_ctx_create(0, ctypes.byref(h)) == -4  # BB_ERR_NODEVICE, not a silent fallback
+    m = models.AE(24, 15)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.eval().encode(np.zeros((4, 24), dtype=np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "baler_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_state_dict_layout_matches_reference(golden):
+    for cls, fixture, prefix in ((models.AE, "ae_train.npz", "sd0"), (models.AE_Dropout_BN, "ae_dbn.npz", "sd0")):
+        ref = sub_sd(golden(fixture), prefix)
+        torch.manual_seed(0)
+        sd = cls(24, 15).state_dict()
+        assert list(sd.keys()) == list(ref.keys())  # np.savez keeps insertion order = reference order
+        for k, v in sd.items():
+            assert tuple(v.shape) == ref[k].shape and str(v.dtype).replace("torch.", "") == str(ref[k].dtype), k
+    # same seed -> the reference's initial weights (nn.Linear init drawn in the reference's order)
+    torch.manual_seed(0)
+    sd = models.AE(24, 15).state_dict()
+    ref = sub_sd(golden("ae_train.npz"), "sd0")
+    for k in ref:
+        assert np.array_equal(sd[k].numpy(), ref[k]), k
+
+
+def test_load_state_dict_roundtrip_and_strictness(golden, tmp_path):
+    ref = sub_sd(golden("ae_cms.npz"), "sd")
+    m = models.AE(24, 15)
+    missing, unexpected = m.load_state_dict({k: torch.from_numpy(v) for k, v in ref.items()}, strict=False)
+    assert not missing and not unexpected
+    torch.save(m.state_dict(), tmp_path / "model.pt")
+    back = torch.load(tmp_path / "model.pt")
+    for k in ref:
+        assert back[k].dtype == torch.float64 and np.array_equal(back[k].numpy(), ref[k])
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({"en1.weight": torch.zeros(3, 3)})
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({"bogus": torch.zeros(1)}, strict=True)
+
+
+def _run_chain_numpy(layers, x):
+    h = x
+    for w, b, act in layers:
+        h = h @ w.T + b
+        h = np.where(h > 0, h, 0.01 * h) if act == "leaky" else (np.maximum(h, 0) if act == "relu" else h)
+    return h
+
+
+def test_batchnorm_folding_is_exact(golden):
+    """eval-mode BN folded into the neighbouring Linear (float64, host) == the oracle's unfolded eval pass"""
+    g = golden("ae_dbn.npz")
+    ref = sub_sd(g, "sd0")
+    m = models.AE_Dropout_BN(24, 15)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in ref.items()})
+    enc, dec = m._chains()
+    x = g["x_norm"][:256].astype(np.float64)
+    z = _run_chain_numpy(enc, x)
+    assert rel_max(z, g["latent_eval"]) < 1e-12
+    assert rel_max(_run_chain_numpy(dec, g["latent_eval"]), g["recon_eval"]) < 1e-12
+    assert rel_max(_run_chain_numpy(dec, z), orc.dbn_decode(ref, orc.dbn_encode(ref, x))) < 1e-12
+
+
+def test_lr_scheduler_and_early_stopping_match_reference(golden):
+    g = golden("schedules.npz")
+
+    class Opt:
+        lr = 0.1
+
+    s = utils.LRScheduler(Opt, patience=2, min_lr=1e-5, factor=0.5)
+    got = []
+    for v in g["lr_losses"]:
+        s(v)
+        got.append(Opt.lr)
+    assert got == list(g["lr_values"])
+    lin = torch.nn.Linear(2, 1)
+    opt = torch.optim.Adam(lin.parameters(), lr=1e-3)
+    s = utils.LRScheduler(opt, patience=3)
+    got = []
+    for v in g["lr2_losses"]:
+        s(v)
+        got.append(opt.param_groups[0]["lr"])
+    assert got == list(g["lr2_values"])
+    es = utils.EarlyStopping(4, 0.01)
+    for v, stop, cnt in zip(g["es_losses"], g["es_stop"], g["es_counter"]):
+        es(v)
+        assert es.early_stop == bool(stop) and es.counter == int(cnt)
+
+
+def test_new_project_skeleton(tmp_path):
+    from baler_b200.modules import helper
+
+    helper.create_new_project("ws", "proj", base_path=str(tmp_path))
+    for d in ("data", "proj/config", "proj/output/compressed_output", "proj/output/decompressed_output",
+              "proj/output/plotting", "proj/output/training"):
+        assert (tmp_path / "ws" / d).is_dir()
+    ns = {}
+    exec((tmp_path / "ws" / "proj" / "config" / "proj_config.py").read_text(), ns)
+
+    class C:
+        pass
+
+    ns["set_config"](C)
+    assert C.model_name == "AE" and C.batch_size == 512 and C.input_path.endswith("proj_data.npz")

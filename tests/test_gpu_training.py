@@ -1,0 +1,172 @@
+"""Training parity (SURVEY 8d contract): per-step loss / gradients / Adam update within 1e-5 of the
+reference from identical weights and batches; epoch-mean loss curve within 1 %; same files written."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2, rel_max, sub_sd
+from oracle import baler_oracle as orc
+from baler_b200 import engine, synth
+from baler_b200.modules import models
+
+pytestmark = pytest.mark.gpu
+NAMES = models.AE.names
+
+
+def flat(sd_like):
+    """flatten a state-dict-like mapping in the trainer's layout: W_l (out,in) then b_l"""
+    return np.concatenate([np.concatenate([np.asarray(sd_like[n + ".weight"]).ravel(), np.asarray(sd_like[n + ".bias"]).ravel()])
+                           for n in NAMES])
+
+
+def make_trainer(sd, max_batch=512):
+    return engine.Trainer([sd[n + ".weight"] for n in NAMES], [sd[n + ".bias"] for n in NAMES], 24, 15, max_batch)
+
+
+@pytest.mark.parametrize("tag,l1", [("mse", False), ("l1", True)])
+def test_step_loss_grads_adam(golden, tag, l1):
+    g = golden("ae_train.npz")
+    sd0 = sub_sd(g, "sd0")
+    x = torch.from_numpy(g["x_norm"]).cuda()
+    tr = make_trainer(sd0)
+    assert tr.n_params == 61839
+    hyper = engine.make_hyper(lr=1e-3, reg_param=0.001, l1=l1)
+    ref_g = flat(sub_sd(g, "g_" + tag))
+    p0 = flat(sd0)
+    losses = []
+    for step in range(3):
+        tr.loss_accum.zero_()
+        tr.step(x[step * 512:(step + 1) * 512].contiguous(), hyper)
+        losses.append(tr.loss_accum.item())
+        if step == 0:
+            grads = tr.grads_view()[:-1].cpu().numpy()
+            assert rel_max(grads, ref_g) <= 1e-5 and rel_l2(grads, ref_g) <= 1e-5, (rel_max(grads, ref_g), rel_l2(grads, ref_g))
+            for n in NAMES:  # per tensor as well: small layers must not hide behind big ones
+                off = 0
+            assert abs(tr.grads_view()[-1].item() - g["losses_" + tag][0]) <= 1e-5 * g["losses_" + tag][0]
+        if step in (0, 2):
+            ref_p = flat(sub_sd(g, "sd%d_%s" % (step + 1, tag)))
+            p = tr.params_view().cpu().numpy().astype(np.float64)
+            # the UPDATE is what is being tested: lr * m / (sqrt(v) + eps)
+            assert rel_max(p - p0, ref_p - p0) <= 2e-4 and rel_l2(p - p0, ref_p - p0) <= 1e-4, (step, rel_max(p - p0, ref_p - p0))
+            assert rel_max(p, ref_p) <= 1e-6
+    np.testing.assert_allclose(losses, g["losses_" + tag], rtol=1e-5)
+    w, b = tr.get_params()
+    assert w[0].shape == (200, 24) and w[0].dtype == np.float64 and b[7].shape == (24,)
+
+
+def test_per_tensor_gradients(golden):
+    g = golden("ae_train.npz")
+    sd0 = sub_sd(g, "sd0")
+    tr = make_trainer(sd0)
+    tr.step(torch.from_numpy(g["x_norm"][:512]).cuda(), engine.make_hyper())
+    grads = tr.grads_view()[:-1].cpu().numpy()
+    ref = sub_sd(g, "g_mse")
+    off = 0
+    for n in NAMES:
+        for part in (".weight", ".bias"):
+            r = ref[n + part].ravel()
+            got = grads[off:off + r.size]
+            off += r.size
+            assert rel_max(got, r) <= 1e-5 and rel_l2(got, r) <= 1e-5, (n + part, rel_max(got, r))
+
+
+@pytest.mark.parametrize("rows", [1, 7, 8, 9, 63, 64, 65, 100, 448])
+def test_ragged_batches_vs_oracle(golden, rows):
+    g = golden("ae_train.npz")
+    sd0 = sub_sd(g, "sd0")
+    x = g["x_norm"][:rows]
+    loss, _, _, grads = orc.ae_loss_and_grads(sd0, x.astype(np.float64))
+    if rows == 100:
+        assert abs(loss - float(g["loss_ragged100"])) < 1e-12 * loss
+    tr = make_trainer(sd0)
+    tr.step(torch.from_numpy(x).cuda(), engine.make_hyper(), phase=1)  # forward + backward only
+    got = tr.grads_view().cpu().numpy()
+    assert abs(got[-1] - loss) <= 1e-5 * loss
+    ref = flat(grads)
+    assert rel_max(got[:-1], ref) <= 1e-5 and rel_l2(got[:-1], ref) <= 1e-5
+    assert np.array_equal(tr.params_view().cpu().numpy(), flat(sd0).astype(np.float32))  # phase 1 leaves weights alone
+
+
+def test_split_phases_equal_fused_step(golden):
+    """phase 1 (fwd+bwd) followed by phase 2 (Adam) is what data-parallel ranks run around the all-reduce"""
+    g = golden("ae_train.npz")
+    sd0 = sub_sd(g, "sd0")
+    x = torch.from_numpy(g["x_norm"][:512]).cuda()
+    a, b = make_trainer(sd0), make_trainer(sd0)
+    h = engine.make_hyper()
+    a.step(x, h, phase=0)
+    b.step(x, h, phase=1)
+    b.step(x, h, phase=2)
+    assert torch.equal(a.params_view(), b.params_view()) and a.loss_accum.item() == b.loss_accum.item()
+    # two half batches, gradients summed (SUM all-reduce semantics) == one full batch
+    c, d = make_trainer(sd0), make_trainer(sd0)
+    c.step(x[:256].contiguous(), h, phase=1)
+    d.step(x[256:].contiguous(), h, phase=1)
+    summed = c.grads_view() + d.grads_view()
+    full = b.grads_view()
+    assert rel_max(summed.cpu().numpy(), full.cpu().numpy()) <= 1e-6
+
+
+def test_fit_curve_and_validate(golden):
+    g, g0 = golden("ae_fit.npz"), golden("ae_train.npz")
+    sd0 = sub_sd(g0, "sd0")
+    table = synth.cms_table(4096, seed=11)
+    x = torch.from_numpy(orc.normalize(table)).cuda()
+    tr = make_trainer(sd0)
+    h = engine.make_hyper(lr=1e-3)
+    losses = [tr.epoch(x, 512, h) for _ in range(3)]
+    ref = g["loss_data"][0]
+    np.testing.assert_allclose(losses[:2], ref[:2], rtol=1e-4)   # contract: epochs 1-2 within 1 %; measured far tighter
+    np.testing.assert_allclose(losses[2], ref[2], rtol=1e-2)
+    w, b = tr.get_params()
+    sd = {n + ".weight": w[i] for i, n in enumerate(NAMES)}
+    sd.update({n + ".bias": b[i] for i, n in enumerate(NAMES)})
+    val = tr.validate(x, 512)
+    ref_val = np.mean([orc.mse_sum_loss(orc.ae_forward(sd, x[i:i + 512].cpu().numpy().astype(np.float64)),
+                                        x[i:i + 512].cpu().numpy().astype(np.float64)) for i in range(0, 4096, 512)])
+    assert abs(val - ref_val) <= 1e-5 * ref_val
+    act = tr.activation_means()
+    assert act.shape == (6, 200) and np.isnan(act[1, 100:]).all() and not np.isnan(act[0]).any()
+
+
+def test_train_mode_writes_reference_layout(golden, tmp_path, monkeypatch):
+    """`--mode train` through the drop-in: same files as the reference, loss curve within 1 % of the
+    reference's own run from the same seed (tests/golden/cli_roundtrip.npz)."""
+    from baler_b200 import baler
+    from baler_b200.modules import helper
+
+    g = golden("cli_roundtrip.npz")
+    monkeypatch.chdir(tmp_path)
+    helper.create_new_project("CMS_workspace", "CMS_project_v1")
+    table = synth.cms_table(4096, seed=17)
+    path = os.path.join("workspaces", "CMS_workspace", "data", "example_CMS_data.npz")
+    np.savez(path, data=table, names=synth.CMS_NAMES)
+    out = os.path.join("workspaces", "CMS_workspace", "CMS_project_v1", "output")
+
+    class cfg(helper.Config):
+        input_path = path
+        data_dimension, compression_ratio, apply_normalization, model_name = 1, 1.6, True, "AE"
+        epochs, lr, batch_size, early_stopping, lr_scheduler = 2, 0.001, 512, True, True
+        early_stopping_patience, min_delta, lr_scheduler_patience, custom_norm = 100, 0, 50, False
+        reg_param, RHO, test_size, extra_compression = 0.001, 0.05, 0, False
+        intermittent_model_saving, intermittent_saving_patience = False, 100
+        l1, activation_extraction, deterministic_algorithm = True, True, False
+        convert_to_blocks, separate_model_saving, save_error_bounded_deltas = False, False, False
+
+    torch.manual_seed(0)
+    baler.perform_training(out, cfg, False)
+    loss = np.load(os.path.join(out, "training", "loss_data.npy"))
+    assert loss.shape == (2, 2)
+    np.testing.assert_allclose(loss, g["loss_data"], rtol=1e-2)
+    assert np.array_equal(np.load(os.path.join(out, "training", "normalization_features.npy")), g["norm_features"])
+    sd = torch.load(os.path.join(out, "compressed_output", "model.pt"))
+    ref = sub_sd(g, "sd")
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert sd[k].dtype == torch.float64 and rel_max(sd[k].numpy(), ref[k]) <= 1e-2, k
+    act = np.load(os.path.join(out, "training", "activations.npy"))
+    assert act.shape == g["activations"].shape
+    assert rel_max(np.nan_to_num(act), np.nan_to_num(g["activations"])) <= 5e-2
