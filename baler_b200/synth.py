@@ -53,3 +53,20 @@ def cfd_snapshots(n_snap, h=50, w=50, seed=CFD_SEED):
         out += amp * np.sin(2 * np.pi * (kx * xx + ky * yy)[None] + ph + 2 * np.pi * om * tt)
     out += 0.01 * rng.normal(size=out.shape)
     return out.astype(np.float32)
+
+
+def cms_table_device(n_rows, seed=CMS_SEED, device="cuda", chunk=10_000_000):
+    """Same marginals as cms_table, generated directly in HBM with torch's CUDA Philox generator
+    (the 100M / 1B-row tables of BASELINE.json never exist on the host)."""
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    t = torch.empty((n_rows, CMS_COLUMNS), dtype=torch.float32, device=device)
+    for lo in range(0, n_rows, chunk):
+        hi = min(n_rows, lo + chunk)
+        m = hi - lo
+        t[lo:hi, 0:12] = torch.randn((m, 12), device=device, generator=g).exp_()
+        t[lo:hi, 12:19] = torch.poisson(torch.full((m, 7), 8.0, device=device), generator=g)
+        t[lo:hi, 19:22] = torch.randn((m, 3), device=device, generator=g)
+        t[lo:hi, 22:24] = torch.randint(0, 30, (m, 2), device=device, generator=g).float()
+    return t

@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Headline benchmark: CMS AE (24 -> 15) compress + decompress of a synthetic 100M-row x 24-col float32
+table per GPU (BASELINE.json configs[1]), plus one training epoch as a secondary line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R]
+
+One step = one pass of the hot path over the table: column min/max -> normalise+encode -> latent, then
+decode+un-normalise -> reconstruction.  `value` = rows / step time with the table resident in HBM.
+`e2e` = the same pass through the C-ABI host entry points (bb_compress_host / bb_decompress_host) with
+pinned HOST buffers, H2D / D2H copies inside the timed region.  N > 1: one process per GPU (torchrun), the
+table is row-sharded (100M rows per GPU, weak scaling), the only exchange is the 2 x 24 column min / max.
+`--impl reference` times the reference path restated on its own engine (torch CPU float64, all threads:
+oracle/torch_port.py) on a bounded sample of the same workload; the reference package itself cannot travel.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_ROW = 61100          # 2 * (24*200 + 200*100 + 100*50 + 50*15) per direction
+BYTES_PER_ROW = 156           # 96 in + 60 out (fp32 latent) per direction
+METRIC = "compress+decompress rows/s (CMS AE 24->15, table resident in HBM)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback"}
+
+
+def golden_state_dict():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ae_cms.npz"))
+    return {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_pass(sd_t, table):
+    """compress + decompress of `table` as the reference computes it, on the reference's own engine (torch CPU,
+    float64) in its best case: oracle/torch_port.py (vectorised normalisation, 8192-row blocks, all threads)"""
+    from oracle import torch_port
+    z, feats = torch_port.compress(sd_t, table)
+    return z, torch_port.decompress(sd_t, z, feats)
+
+
+def cpu_baseline(sd, sample_rows, repeats=2):
+    import torch
+    from oracle import baler_oracle as orc
+    from oracle import torch_port
+    from baler_b200 import synth
+    sd_t = torch_port.to_torch(sd)
+    table = synth.cms_table(sample_rows)
+    cpu_reference_pass(sd_t, table[:50000])  # warm up the thread pool
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_reference_pass(sd_t, table)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    shipped_rows = min(sample_rows, 100_000)
+    t0 = time.perf_counter()
+    orc.compress(sd, table[:shipped_rows], batch_size=512, as_shipped=True)
+    shipped = shipped_rows / (time.perf_counter() - t0)
+    return {"value": sample_rows / best, "unit": "rows/s", "cores": int(torch.get_num_threads()), "kind": "port",
+            "sample": "%d rows of the synthetic CMS table; reference path restated on torch CPU float64 (oracle/torch_port.py): "
+                      "compress (min/max + normalise + encode) + decompress (decode + un-normalise), best case "
+                      "(8192-row blocks, preallocated output, all torch threads)" % sample_rows,
+            "as_shipped_compress_loop_rows_per_s": shipped, "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import torch_port
+    from baler_b200 import synth
+    sd = golden_state_dict()
+    sd_t = torch_port.to_torch(sd)
+    rows = args.ref_rows
+    table = synth.cms_table(rows)
+    for _ in range(args.warmup):
+        cpu_reference_pass(sd_t, table[: max(rows // 10, 1000)])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_pass(sd_t, table)
+    dt = time.perf_counter() - t0
+    value = rows * args.steps / dt
+    base = {"value": value, "unit": "rows/s", "cores": int(torch.get_num_threads()), "kind": "port",
+            "sample": "%d rows per step; reference path restated on torch CPU float64 (oracle/torch_port.py), best case" % rows,
+            "host_cpus": os.cpu_count()}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "CMS AE 24->15 compress+decompress, %d-row bounded sample per step on host CPU cores" % rows},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from baler_b200 import engine, sharded, synth
+    from baler_b200.modules import models
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    sd = golden_state_dict()
+    model = models.AE(24, 15)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    codec = model.eval().codec()
+    precision = args.precision
+    n = args.rows  # rows PER GPU (weak scaling)
+    x = synth.cms_table_device(n, seed=synth.CMS_SEED + rank, device=dev)
+    z = torch.empty((n, 15), dtype=torch.float32, device=dev)
+    y = torch.empty((n, 24), dtype=torch.float32, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    launches = {"n": 0}
+
+    def step(timed_kernels=None):
+        # compress: features of THIS table (helper.py:500-502), sharded -> one 2x24 float exchange
+        mn, mx = engine.colminmax(x)
+        if world > 1:
+            sharded.combine_minmax_(mn, mx)
+        rg = mx - mn  # torch elementwise on 24 floats: plumbing, not the hot path
+        if timed_kernels:
+            ev[0].record()
+        codec.encode(x, mn, rg, precision=precision, out=z)
+        if timed_kernels:
+            ev[1].record(); ev[2].record()
+        codec.decode(z, mn, rg, precision=precision, out=y)
+        if timed_kernels:
+            ev[3].record()
+        launches["n"] += 3
+        return mn, rg
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    enc_ms, dec_ms = [], []
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_start.record()
+    for _ in range(args.steps):
+        step(timed_kernels=True)
+    t_end.record()
+    sync_all()
+    total_ms = t_start.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel durations of the last step (events on the launching stream)
+    enc_ms, dec_ms = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    ms_per_step = total_ms / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+    gpu_launches = launches["n"]
+
+    # ---- e2e: host buffers through the C-ABI pipelines
+    e2e = None
+    if not args.no_e2e:
+        ne = min(n, args.e2e_rows)
+        xh = torch.empty((ne, 24), dtype=torch.float32, pin_memory=True)
+        zh = torch.empty((ne, 15), dtype=torch.float32, pin_memory=True)
+        yh = torch.empty((ne, 24), dtype=torch.float32, pin_memory=True)
+        xh.copy_(x[:ne])
+        torch.cuda.synchronize()
+        xn, zn, yn = xh.numpy(), zh.numpy(), yh.numpy()
+
+        def e2e_step():
+            if world > 1:
+                # sharded: local min/max -> exchange -> compress with the global features
+                mn, mx = engine.colminmax(x[:ne])
+                sharded.combine_minmax_(mn, mx)
+                feats = torch.stack([mn, mx - mn]).cpu().numpy()
+                codec.compress_host(xn, features=feats, z_dtype=np.float32, precision=precision, out=zn)
+            else:
+                _, feats = codec.compress_host(xn, recompute_minmax=True, z_dtype=np.float32, precision=precision, out=zn)
+            codec.decompress_host(zn, features=feats, y_dtype=np.float32, precision=precision, out=yn)
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        sync_all()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": ne * world * args.e2e_steps / dt.item(), "unit": "rows/s",
+               "h2d_bytes_per_step": int(ne * (96 + 60)), "d2h_bytes_per_step": int(ne * (60 + 96)),
+               "rows_per_gpu": ne, "steps": args.e2e_steps,
+               "note": "bb_compress_host + bb_decompress_host, pinned host buffers, fp32 latent; timed on the host clock "
+                       "around blocking calls (the copies are part of the call)"}
+        del xh, zh, yh
+
+    # ---- training line (secondary): one epoch of AE on a 600k-row normalised table, bs 512 per GPU
+    train = None
+    if not args.no_train:
+        tn = 600_000
+        mn, mx = engine.colminmax(x[:tn])
+        xt = engine.normalize_table(x[:tn].contiguous(), mn, mx - mn)
+        torch.manual_seed(0)
+        tm = models.AE(24, 15)
+        w, b = tm.linear_tensors()
+        tr = engine.Trainer(w, b, 24, 15, 512)
+        hyper = engine.make_hyper(lr=1e-3, world_size=world)
+        if world == 1:
+            tr.epoch(xt[:51200], 512, hyper)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            loss = tr.epoch(xt, 512, hyper)
+            dt = time.perf_counter() - t0
+            steps = (tn + 511) // 512
+        else:
+            dp = sharded.DataParallelTrainer(tr)
+            batches = [xt[i:i + 512] for i in range(0, tn, 512)]  # each rank: its 512-row slice of a 512*world batch
+            dp.epoch(batches[:100], hyper)
+            sync_all()
+            t0 = time.perf_counter()
+            loss = dp.epoch(batches, hyper)
+            sync_all()
+            dt = time.perf_counter() - t0
+            steps = len(batches)
+        train = {"samples_per_s": tn * world / dt, "us_per_step": 1e6 * dt / steps, "steps": steps,
+                 "global_batch": 512 * world, "epoch_loss": loss, "model": "AE 24-200-100-50-15-50-100-200-24",
+                 "flop_per_sample": 357000, "tflops": tn * world * 357000 / dt / 1e12}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    enc_tflops = n * FLOP_PER_ROW / (enc_ms * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(prof):
+        per_row = json.load(open(prof)).get("encode_dram_bytes_per_row")
+        traffic = per_row * n if per_row else None
+    out = {
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CMS AE 24->15 compress+decompress of a %d-row x 24-col float32 table per GPU" % n,
+                   "rows_per_gpu": n, "precision": codec.auto_precision if precision == "auto" else precision,
+                   "l2": "inputs larger than L2 (%.1f GB table per GPU)" % (n * 96 / 1e9),
+                   "weights": "reference AE(24,15) trained 2 epochs (tests/golden/ae_cms.npz)"},
+        "gpu_launches": gpu_launches, "clocks": clocks,
+        "compress_rows_per_s": n / (enc_ms * 1e-3), "decompress_rows_per_s": n / (dec_ms * 1e-3),
+        "roofline": {"bound": "tensor", "achieved": enc_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": enc_tflops / peaks["tflops"], "traffic": traffic, "kernel": "fused encode chain",
+                     "peak_source": peaks["src"] + " (bf16 dense, sustained)", "launch_ms": enc_ms,
+                     "algorithmic_flop_per_row": FLOP_PER_ROW,
+                     "hbm": {"achieved_gbs": n * BYTES_PER_ROW / (enc_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                             "frac": n * BYTES_PER_ROW / (enc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "algorithmic_bytes_per_row": BYTES_PER_ROW}},
+        "e2e": e2e, "train": train,
+    }
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(sd, args.cpu_rows)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
+    ap.add_argument("--precision", default="auto")
+    ap.add_argument("--e2e-rows", type=int, default=100_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-rows", type=int, default=2_000_000)
+    ap.add_argument("--ref-rows", type=int, default=2_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
