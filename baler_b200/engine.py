@@ -202,7 +202,7 @@ class Trainer:
         except Exception:
             pass
 
-    def _flat(self, ptr):
+    def _flat(self, ptr, n=None):
         # zero-copy torch view of library-owned device memory
         from torch.utils import dlpack  # noqa: F401  (documented route; below uses __cuda_array_interface__)
 
@@ -210,14 +210,15 @@ class Trainer:
             pass
 
         a = _Arr()
-        a.__cuda_array_interface__ = {"shape": (self.n_params,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        a.__cuda_array_interface__ = {"shape": (n or self.n_params,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
         return torch.as_tensor(a, device=self.ctx.device)
 
     def params_view(self):
         return self._flat(_lib.lib().bb_trainer_params_dev(self.handle))
 
     def grads_view(self):
-        return self._flat(_lib.lib().bb_trainer_grads_dev(self.handle))
+        """n_params gradient entries followed by the batch loss (one flat buffer = one all-reduce)"""
+        return self._flat(_lib.lib().bb_trainer_grads_dev(self.handle), self.n_params + 1)
 
     def step(self, x, hyper, phase=0):
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()

@@ -15,7 +15,8 @@ def pytest_configure(config):
 
 
 def load_golden(name):
-    return dict(np.load(os.path.join(GOLDEN, name), allow_pickle=False))
+    # some fixtures were saved Fortran-ordered (np.apply_along_axis output): hand out C-contiguous arrays
+    return {k: np.asarray(v, order="C") for k, v in np.load(os.path.join(GOLDEN, name), allow_pickle=False).items()}
 
 
 def sub_sd(d, prefix):
