@@ -77,6 +77,7 @@ int fill_chain(Chain* c, int n_layers, const int* dims, const int* acts, const d
 void free_chain(Chain* c) {
   if (c->blob_dev) cudaFree(c->blob_dev);
   if (c->tc_blob_dev) cudaFree(c->tc_blob_dev);
+  bb_tc_release(c);
 }
 
 int resolve_precision(const bb_model* m, const Chain* c, int precision) {
@@ -176,6 +177,8 @@ __global__ void range_kernel(const float* mn, const float* mx, float* rg, int c)
 
 extern "C" {
 
+int bb_model_range_flag(bb_model* m, int reset, int* out);
+
 int bb_model_create_dense(bb_ctx* ctx, int n_enc_layers, const int* enc_dims, const int* enc_acts,
                           const double* const* enc_w, const double* const* enc_b, int n_dec_layers,
                           const int* dec_dims, const int* dec_acts, const double* const* dec_w,
@@ -225,6 +228,23 @@ int bb_model_destroy(bb_model* m) {
   if (m->s_compute) cudaStreamDestroy(m->s_compute);
   if (m->s_copy_out) cudaStreamDestroy(m->s_copy_out);
   delete m;
+  return BB_OK;
+}
+
+// Test hook (not part of the public header): run one direction on the tcgen05 path and dump the scaled
+// accumulator of program step `dbg_step` (before activation) to dbg_out_dev [n_rows x step width].
+int bb_debug_tc_chain(bb_model* m, int decode, const void* in_dev, int64_t n_rows, void* out_dev, int fast,
+                      int dbg_step, float* dbg_out_dev, int force_groups, bb_stream_t stream) {
+  if (!m) return BB_ERR_INVALID;
+  const Chain* c = decode ? &m->dec : &m->enc;
+  return bb_tc_launch_dbg(m->ctx, c, in_dev, BB_F32, n_rows, nullptr, nullptr, nullptr, nullptr, out_dev, BB_F32, fast,
+                          m->flag_dev, dbg_step, dbg_out_dev, force_groups, (cudaStream_t)stream);
+}
+
+int bb_model_range_flag(bb_model* m, int reset, int* out) {
+  if (!m || !out) return BB_ERR_INVALID;
+  BB_CUDA(cudaMemcpy(out, m->flag_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (reset && *out) BB_CUDA(cudaMemset(m->flag_dev, 0, sizeof(int)));
   return BB_OK;
 }
 
@@ -354,6 +374,11 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
   for (int s = 0; s < 2; ++s)
     if (pinned_out[s]) cudaFreeHost(pinned_out[s]);
   if (resident) cudaFree(resident);
+  if (rc == BB_OK && precision == BB_PREC_AUTO && m->enc.tc_ok) {
+    int tripped = 0;  // fp16 range guard of the split path: redo on the fp32 kernel (features are already known)
+    rc = bb_model_range_flag(m, 1, &tripped);
+    if (rc == BB_OK && tripped) return bb_compress_host(m, x_host, n_rows, features_host, 0, z_host, z_dtype, BB_PREC_FP32);
+  }
   return rc;
 }
 
@@ -432,6 +457,11 @@ int bb_decompress_host(bb_model* m, const void* z_host, int z_dtype, int64_t n_r
   cudaStreamSynchronize(m->s_compute);
   cudaStreamSynchronize(m->s_copy_out);
   cleanup();
+  if (rc == BB_OK && precision == BB_PREC_AUTO && m->dec.tc_ok) {
+    int tripped = 0;
+    rc = bb_model_range_flag(m, 1, &tripped);
+    if (rc == BB_OK && tripped) return bb_decompress_host(m, z_host, z_dtype, n_rows, features_host, y_host, y_dtype, BB_PREC_FP32);
+  }
   return rc;
 }
 

@@ -1,12 +1,543 @@
-// tcgen05 / TMEM fused dense chain (fp16 hi/lo split, fp32 accumulate) - see DESIGN.md.
+// Fused 4-layer dense chain on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same contract as bb_chain_f32.cu ([normalise ->] 4 dense layers [-> un-normalise], one HBM read and one
+// HBM write per row) but the matrix products run as tcgen05.mma kind::f16 with fp32 accumulation in TMEM.
+//
+// Precision.  The reference computes in float64 and the parity bar is 1e-5 (max-norm and l2, per tensor).
+// A single fp16 product misses that by ~30x, so every operand is split x = hi + lo with hi = fp16(x) and
+// lo = fp16(x - hi) (22 significant bits) and each product is three MMAs accumulated into the same
+// TMEM accumulator: hi*hi + hi*lo + lo*hi (lo*lo ~ 2^-22 is dropped).  Weights are split on the host
+// from the float64 state dict after a per-layer power-of-two scaling that keeps their lo parts out of the
+// fp16 subnormal range (undone exactly in the epilogue); activations are split in the epilogue.
+// BB_PREC_FAST16 issues only the hi*hi product (opt-in, outside the tolerance).
+//
+// Data flow per 128-row tile (rows are the MMA M dimension, one row per TMEM lane / per thread):
+//   global -> smem stage (cp.async, prefetched one tile ahead) -> registers (normalise, split)
+//   -> tcgen05.st A1 (fp16 hi|lo packed two per column) -> MMA -> D1 (fp32, TMEM) -> tcgen05.ld
+//   -> scale, activation, split -> tcgen05.st A2 IN PLACE over D1 -> MMA -> ... -> D4 -> registers
+//   -> smem stage -> coalesced global store.
+// The A operand of every MMA is read from TMEM (the ".ts" form), the B operand (weights, hi and lo
+// images of all four layers, 149 KiB) stays resident in shared memory for the whole kernel in the
+// canonical no-swizzle K-major core-matrix layout (8 rows x 16 bytes per core matrix), loaded once per
+// CTA with cp.async.bulk.  Biases ride along as one extra K column: every padded A operand has a spare
+// K slot that holds 1.0 (produced by an extra weight row of the previous layer), and the matching weight
+// column holds the bias, so the epilogue has no bias add.
+//
+// TMEM budget.  fp32 accumulator columns and packed hi|lo A columns have the same footprint, so the
+// conversion is in place.  The 200-wide layer is processed in two N halves (112 + 96) that reuse one
+// region, which keeps a tile pipeline at 256 columns (X 112 | Y 112 | Z 32): two independent pipelines
+// (warp groups of 128 threads, tiles interleaved) share the SM, one runs its epilogue on the CUDA cores
+// while the other's MMAs occupy the tensor pipe.
+#include <cmath>
+#include <cstring>
+
 #include "bb_common.cuh"
 
-int bb_tc_prepare(bb_ctx*, Chain* c) {
-  c->tc_ok = false;
-  return BB_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int TILE = 128;      // rows per tile = MMA M
+constexpr int GROUP_T = 128;   // threads per pipeline
+constexpr int MAX_STEPS = 6;
+constexpr int REG_X = 0, REG_Y = 112, REG_Z = 224, PIPE_COLS = 256;
+
+struct TcMma {
+  int a_col, a_w;          // A operand region (TMEM columns == K elements: hi|lo packed per 32/16-column chunk)
+  int ks0, ks_n;           // B k-step offset, number of k-steps (K = 16 per step)
+  uint32_t b_hi, b_lo;     // smem byte offsets of the hi / lo weight images (already offset for N splits)
+  uint32_t lbo;            // byte distance between the two 8-element K chunks of one k-step = Npad * 16
+  int n, d_col, acc;       // MMA N, accumulator region, accumulate onto existing D
+};
+struct TcEpi {
+  int col, w;              // accumulator region to drain
+  float scale;             // 2^-sw: undoes the weight scaling
+  int act, final;
+};
+struct TcStep { int n_mma; TcMma mma[2]; TcEpi epi; };
+struct TcProgram {
+  int n_steps, in_dim, out_dim;
+  int a1_col, a1_w;        // where the loader puts the first A operand (a1_w = padded K of layer 0)
+  int out_stride;          // floats per row in the output stage (odd -> conflict-free)
+  uint32_t w_bytes;        // size of the resident weight image
+  TcStep step[MAX_STEPS];
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends the thread for a bounded time in hardware; a protocol bug must not hang the GPU, so
+  // give up (trap -> launch error) after ~2 s of SM clock
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GROUP_T) : "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, M = 128, K = 16, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
 
-int bb_tc_launch(bb_ctx*, const Chain*, const void*, int, int64_t, const float*, const float*, const float*,
-                 const float*, void*, int, int, int*, cudaStream_t) {
-  return BB_ERR_UNSUPPORTED;
+#define TC_REGS16(v, o) "=r"(v[o+0]), "=r"(v[o+1]), "=r"(v[o+2]), "=r"(v[o+3]), "=r"(v[o+4]), "=r"(v[o+5]), "=r"(v[o+6]), "=r"(v[o+7]), \
+                        "=r"(v[o+8]), "=r"(v[o+9]), "=r"(v[o+10]), "=r"(v[o+11]), "=r"(v[o+12]), "=r"(v[o+13]), "=r"(v[o+14]), "=r"(v[o+15])
+#define TC_IN8(v, o) "r"(v[o+0]), "r"(v[o+1]), "r"(v[o+2]), "r"(v[o+3]), "r"(v[o+4]), "r"(v[o+5]), "r"(v[o+6]), "r"(v[o+7])
+
+// each thread receives 32 / 16 consecutive fp32 columns of its own lane (row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : TC_REGS16(v, 0), TC_REGS16(v, 16) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : TC_REGS16(v, 0) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[32], const int o) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+               TC_IN8(v, o), TC_IN8(v, o + 8) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[32], const int o) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), TC_IN8(v, o) : "memory");
+}
+
+// smem matrix descriptor: no swizzle, K-major; core matrix = 8 rows x 16 B, rows 16 B apart;
+// SBO = 128 B between 8-row groups, LBO = distance between the two K chunks of a k-step
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) |
+         (1ull << 46);
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  // c_format F32 (1) @4, a/b format F16 (0) @7/@10, a/b K-major, N>>3 @17, M>>4 @24
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+}
+
+// split two fp32 values into packed fp16 hi and lo words: hi = top 11 significant bits (truncated, so
+// that x - hi is exact in fp32), lo = fp16_rn(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  const __half2 h = __floats2half2_rn(ah, bh);
+  const __half2 l = __floats2half2_rn(a - ah, b - bh);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ float act_apply(float s, int act) {
+  if (act == BB_ACT_LEAKY) return fmaxf(s, BB_LEAKY * s);
+  if (act == BB_ACT_RELU) return fmaxf(s, 0.f);
+  return s;
+}
+
+// TMEM column of the hi part of k-step s of an A region (width w columns, chunked 32 | 16); lo = hi + half chunk
+__device__ __forceinline__ void a_cols(int col, int w, int s, uint32_t& hi, uint32_t& lo) {
+  const int base = col + ((s >> 1) << 5);
+  const bool full = ((s >> 1) << 5) + 32 <= w;
+  hi = base + (full ? ((s & 1) << 3) : 0);
+  lo = hi + (full ? 16 : 8);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int NGROUPS>
+__global__ void __launch_bounds__(NGROUPS * GROUP_T, 1)
+chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restrict__ wimg, const void* __restrict__ in,
+                const int in_dtype, const int in_aligned, const int64_t n_rows, const float* __restrict__ pre_min,
+                const float* __restrict__ pre_range, const float* __restrict__ post_min,
+                const float* __restrict__ post_range, void* __restrict__ out, const int out_dtype, const int fast,
+                int* __restrict__ flag, const int dbg_step, float* __restrict__ dbg_out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[1 + NGROUPS];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int g = tid / GROUP_T;            // pipeline index
+  const int tg = tid - g * GROUP_T;       // thread within the pipeline == tile row == TMEM lane
+  const int in_dim = prog.in_dim, out_dim = prog.out_dim;
+  const int in_esz = in_dtype == BB_F16 ? 2 : 4;
+  const uint32_t in_stage_bytes = (uint32_t)((TILE * in_dim * in_esz + 127) & ~127);
+  const uint32_t out_stage_bytes = (uint32_t)((TILE * prog.out_stride * 4 + 127) & ~127);
+  uint8_t* w_s = smem;
+  uint8_t* in_s = smem + prog.w_bytes + g * (in_stage_bytes + out_stage_bytes);
+  float* out_s = reinterpret_cast<float*>(in_s + in_stage_bytes);
+  const uint32_t bar_w = smem_u32(&bars[0]);
+  const uint32_t bar_m = smem_u32(&bars[1 + g]);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    for (int i = 0; i < NGROUPS; ++i) mbar_init(smem_u32(&bars[1 + i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {  // warp 0 owns the TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {  // resident weight image: global -> smem through the async proxy (what the MMA reads through)
+    mbar_expect_tx(bar_w, prog.w_bytes);
+    for (uint32_t off = 0; off < prog.w_bytes; off += 32768) {
+      const uint32_t n = prog.w_bytes - off < 32768 ? prog.w_bytes - off : 32768;
+      bulk_g2s(smem_u32(w_s + off), wimg + off, n, bar_w);
+    }
+  }
+
+  const int64_t n_tiles = (n_rows + TILE - 1) / TILE;
+  const int64_t tile_stride = (int64_t)gridDim.x * NGROUPS;
+  const uint32_t lane_addr = (uint32_t)((tg & ~31) << 16);  // TMEM lane base of this warp (32 lanes per warp)
+  const uint32_t tcol0 = tmem_base + g * PIPE_COLS;
+
+  // cooperative copy of one input tile into the stage (16-byte cp.async when aligned and full)
+  auto fetch = [&](int64_t tile) {
+    const int rows = (int)min((int64_t)TILE, n_rows - tile * TILE);
+    const size_t base = (size_t)tile * TILE * in_dim * in_esz;
+    const int bytes = rows * in_dim * in_esz;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + base;
+    if (in_aligned && rows == TILE) {
+      for (int c = tg * 16; c < bytes; c += GROUP_T * 16) cp_async16(smem_u32(in_s + c), src + c);
+    } else if (in_esz == 4) {
+      for (int e = tg; e < bytes / 4; e += GROUP_T) reinterpret_cast<float*>(in_s)[e] = reinterpret_cast<const float*>(src)[e];
+    } else {
+      for (int e = tg; e < bytes / 2; e += GROUP_T) reinterpret_cast<__half*>(in_s)[e] = reinterpret_cast<const __half*>(src)[e];
+    }
+    cp_async_commit();
+  };
+
+  int64_t tile = (int64_t)blockIdx.x * NGROUPS + g;
+  if (tile < n_tiles) fetch(tile);
+  mbar_wait(bar_w, 0);  // weights resident
+  uint32_t parity = 0;
+
+  for (; tile < n_tiles; tile += tile_stride) {
+    const int rows = (int)min((int64_t)TILE, n_rows - tile * TILE);
+    cp_async_wait_all();
+    group_bar(1 + g);
+    // ---- A1: this thread's row -> normalise -> 1.0 in the bias slot -> split -> TMEM
+    {
+      const int kpad = prog.a1_w;  // 16, 32, 48 or 64 ... (multiple of 16)
+      for (int c0 = 0; c0 < kpad; c0 += 32) {
+        const int cw = kpad - c0 >= 32 ? 32 : 16;
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = c0 + 2 * j + h;
+            float x = 0.f;
+            if (2 * j + h < cw) {
+              if (k < in_dim && tg < rows) {
+                x = in_esz == 4 ? reinterpret_cast<const float*>(in_s)[tg * in_dim + k]
+                                : __half2float(reinterpret_cast<const __half*>(in_s)[tg * in_dim + k]);
+                if (pre_min != nullptr) x = __fdiv_rn(__fsub_rn(x, __ldg(pre_min + k)), __ldg(pre_range + k));
+              } else if (k == in_dim) {
+                x = 1.f;
+              }
+            }
+            v[h] = x;
+          }
+          // chunk layout: hi words first, lo words after (cw/2 words each)
+          if (cw == 32) split2(v[0], v[1], pk[j], pk[16 + j]);
+          else if (j < 8) split2(v[0], v[1], pk[j], pk[8 + j]);
+        }
+        const uint32_t taddr = tcol0 + lane_addr + prog.a1_col + c0;
+        if (cw == 32) { tmem_st16(taddr, pk, 0); tmem_st16(taddr + 16, pk, 16); }
+        else { tmem_st8(taddr, pk, 0); tmem_st8(taddr + 8, pk, 8); }
+      }
+    }
+    tc_wait_st();
+    tc_fence_before();
+    group_bar(1 + g);
+    {  // the stage is free again: prefetch this pipeline's next tile while the layers run
+      const int64_t nxt = tile + tile_stride;
+      if (nxt < n_tiles) fetch(nxt);
+    }
+
+    for (int s = 0; s < prog.n_steps; ++s) {
+      const TcStep& st = prog.step[s];
+      if (tg == 0) {  // one thread issues the MMAs of this step for its pipeline
+        tc_fence_after();
+        for (int m = 0; m < st.n_mma; ++m) {
+          const TcMma& mm = st.mma[m];
+          const uint32_t idesc = make_idesc(mm.n);
+          const uint32_t d = tcol0 + mm.d_col;
+          for (int k = 0; k < mm.ks_n; ++k) {
+            uint32_t a_hi, a_lo;
+            a_cols(mm.a_col, mm.a_w, k, a_hi, a_lo);
+            const uint32_t koff = (uint32_t)(mm.ks0 + k) * 2u * mm.lbo;  // two 8-wide K chunks per k-step
+            const uint64_t bh = make_b_desc(smem_u32(w_s) + mm.b_hi + koff, mm.lbo);
+            tc_mma_ts(d, tcol0 + a_hi, bh, idesc, (k > 0 || mm.acc) ? 1u : 0u);
+            if (!fast) {
+              const uint64_t bl = make_b_desc(smem_u32(w_s) + mm.b_lo + koff, mm.lbo);
+              tc_mma_ts(d, tcol0 + a_hi, bl, idesc, 1u);
+              tc_mma_ts(d, tcol0 + a_lo, bh, idesc, 1u);
+            }
+          }
+        }
+        tc_commit(bar_m);
+      }
+      mbar_wait(bar_m, parity);
+      parity ^= 1u;
+      tc_fence_after();
+
+      // ---- epilogue: drain the accumulator region; either re-split in place or emit the output row
+      const TcEpi& ep = st.epi;
+      for (int c0 = 0; c0 < ep.w; c0 += 32) {
+        const int cw = ep.w - c0 >= 32 ? 32 : 16;
+        const uint32_t taddr = tcol0 + lane_addr + ep.col + c0;
+        uint32_t v[32];
+        if (cw == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        tc_wait_ld();
+        if (dbg_out != nullptr && dbg_step == s && tg < rows) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < cw) dbg_out[((size_t)tile * TILE + tg) * ep.w + c0 + j] = __uint_as_float(v[j]) * ep.scale;
+        }
+        if (!ep.final) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = act_apply(__uint_as_float(v[2 * j]) * ep.scale, ep.act);
+            const float b = act_apply(__uint_as_float(v[2 * j + 1]) * ep.scale, ep.act);
+            if (cw == 32) split2(a, b, pk[j], pk[16 + j]);
+            else if (j < 8) split2(a, b, pk[j], pk[8 + j]);
+          }
+          if (cw == 32) { tmem_st16(taddr, pk, 0); tmem_st16(taddr + 16, pk, 16); }
+          else { tmem_st8(taddr, pk, 0); tmem_st8(taddr + 8, pk, 8); }
+        } else {
+          bool bad = false;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            if (j < cw && c < out_dim) {
+              float y = act_apply(__uint_as_float(v[j]) * ep.scale, ep.act);
+              bad |= !(fabsf(y) <= 3.0e38f);  // inf / NaN: an fp16 operand overflowed somewhere upstream
+              if (post_min != nullptr) y = fmaf(y, __ldg(post_range + c), __ldg(post_min + c));
+              out_s[tg * prog.out_stride + c] = y;
+            }
+          }
+          if (bad && tg < rows) atomicOr(flag, 1);
+        }
+      }
+      if (!ep.final) tc_wait_st();
+      tc_fence_before();
+      group_bar(1 + g);
+    }
+    // ---- coalesced store of the output tile
+    {
+      const size_t base = (size_t)tile * TILE * out_dim;
+      const int n_el = rows * out_dim;
+      for (int e = tg; e < n_el; e += GROUP_T) {
+        const int r = e / out_dim, c = e - r * out_dim;
+        const float y = out_s[r * prog.out_stride + c];
+        if (out_dtype == BB_F16) reinterpret_cast<__half*>(out)[base + e] = __float2half_rn(y);
+        else reinterpret_cast<float*>(out)[base + e] = y;
+      }
+    }
+  }
+  cp_async_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct TcHost {
+  TcProgram prog;
+  int n_groups;
+  size_t smem_bytes;
+};
+
+inline int rup16(int x) { return (x + 15) & ~15; }
+
+uint16_t f2h(float f) {  // float -> fp16 bits, round to nearest even (host)
+  __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+float h2f(uint16_t u) {
+  __half h;
+  memcpy(&h, &u, 2);
+  return __half2float(h);
+}
+
+}  // namespace
+
+// Builds the weight image + step program for a 4-layer chain whose only wide layer is 113..208 padded
+// columns (the hidden 200) and whose other padded widths fit 112; anything else stays on the fp32 kernel.
+int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
+  c->tc_ok = false;
+  const ChainDesc& d = c->desc;
+  if (d.n_layers != 4) return BB_ERR_UNSUPPORTED;
+  int K[4], N[4], Kp[4], Np[4];
+  for (int l = 0; l < 4; ++l) { K[l] = d.layer[l].K; N[l] = d.layer[l].N; Kp[l] = rup16(K[l] + 1); }
+  for (int l = 0; l < 4; ++l) Np[l] = l < 3 ? Kp[l + 1] : rup16(N[l]);
+  // region plan (see header comment): exactly one wide layer, at position 0 (encoder) or 2 (decoder)
+  int wide = -1;
+  for (int l = 0; l < 4; ++l)
+    if (Np[l] > 112) { if (wide >= 0 || Np[l] > 208) return BB_ERR_UNSUPPORTED; wide = l; }
+  if (wide != 0 && wide != 2) return BB_ERR_UNSUPPORTED;
+  if (Kp[0] > 32 || Np[3] > 32) return BB_ERR_UNSUPPORTED;            // first A operand / last accumulator live in Z (32 columns)
+  if (wide == 0 && (Np[2] > 112 || Np[1] > 112)) return BB_ERR_UNSUPPORTED;
+  if (wide == 2 && (Np[0] > 112 || Np[1] > 112)) return BB_ERR_UNSUPPORTED;
+
+  TcHost* h = new TcHost();
+  TcProgram& p = h->prog;
+  memset(&p, 0, sizeof(p));
+  p.in_dim = d.in_dim; p.out_dim = d.out_dim;
+  p.out_stride = d.out_dim | 1;
+  // ---- weight image: per layer hi then lo, canonical K-major core matrices: ((k/8) * Np + n) * 16 B + (k%8) * 2 B
+  uint32_t off = 0, b_hi[4], b_lo[4];
+  float scale[4];
+  std::vector<uint8_t> img;
+  for (int l = 0; l < 4; ++l) {
+    const size_t mat = (size_t)Np[l] * Kp[l] * 2;
+    b_hi[l] = off; b_lo[l] = off + (uint32_t)mat; off += 2 * (uint32_t)mat;
+    img.resize(off, 0);
+    std::vector<double> w((size_t)Np[l] * Kp[l], 0.0);
+    double mx = 1.0;
+    for (int n = 0; n < N[l]; ++n) {
+      for (int k = 0; k < K[l]; ++k) w[(size_t)n * Kp[l] + k] = c->w_host[l][(size_t)n * K[l] + k];
+      w[(size_t)n * Kp[l] + K[l]] = c->b_host[l][n];   // bias rides on the constant-one K slot
+    }
+    if (l < 3) w[(size_t)N[l] * Kp[l] + K[l]] = 1.0;    // produces the constant one of the next layer's bias slot
+    for (double v : w) mx = std::fabs(v) > mx ? std::fabs(v) : mx;
+    const int sw = (int)std::floor(std::log2(2047.0 / mx));
+    scale[l] = (float)std::ldexp(1.0, -sw);
+    uint16_t* hi = reinterpret_cast<uint16_t*>(img.data() + b_hi[l]);
+    uint16_t* lo = reinterpret_cast<uint16_t*>(img.data() + b_lo[l]);
+    for (int n = 0; n < Np[l]; ++n)
+      for (int k = 0; k < Kp[l]; ++k) {
+        const double v = std::ldexp(w[(size_t)n * Kp[l] + k], sw);
+        const uint16_t hb = f2h((float)v);
+        const uint16_t lb = f2h((float)(v - (double)h2f(hb)));
+        const size_t idx = ((size_t)(k / 8) * Np[l] + n) * 8 + (k % 8);
+        hi[idx] = hb; lo[idx] = lb;
+      }
+  }
+  p.w_bytes = off;
+  // ---- step program
+  auto mma = [&](int l, int a_col, int a_w, int ks0, int ks_n, int n0, int n, int d_col, int acc) {
+    TcMma m;
+    m.a_col = a_col; m.a_w = a_w; m.ks0 = ks0; m.ks_n = ks_n;
+    m.b_hi = b_hi[l] + (uint32_t)n0 * 16; m.b_lo = b_lo[l] + (uint32_t)n0 * 16;
+    m.lbo = (uint32_t)Np[l] * 16; m.n = n; m.d_col = d_col; m.acc = acc;
+    return m;
+  };
+  auto epi = [&](int l, int col, int w, int fin) {
+    TcEpi e;
+    e.col = col; e.w = w; e.scale = scale[l]; e.act = d.layer[l].act; e.final = fin;
+    return e;
+  };
+  p.a1_col = REG_Z; p.a1_w = Kp[0];
+  int s = 0;
+  if (wide == 0) {  // encoder: K0 -> 208 -> Np1 -> Np2 -> Np3
+    const int na = 112, nb = Np[0] - 112;
+    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(0, REG_Z, Kp[0], 0, Kp[0] / 16, 0, na, REG_X, 0); p.step[s].epi = epi(0, REG_X, na, 0); ++s;
+    p.step[s].n_mma = 2; p.step[s].mma[0] = mma(1, REG_X, na, 0, na / 16, 0, Np[1], REG_Y, 0);
+    p.step[s].mma[1] = mma(0, REG_Z, Kp[0], 0, Kp[0] / 16, na, nb, REG_X, 0); p.step[s].epi = epi(0, REG_X, nb, 0); ++s;
+    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(1, REG_X, nb, na / 16, nb / 16, 0, Np[1], REG_Y, 1); p.step[s].epi = epi(1, REG_Y, Np[1], 0); ++s;
+    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(2, REG_Y, Np[1], 0, Np[1] / 16, 0, Np[2], REG_X, 0); p.step[s].epi = epi(2, REG_X, Np[2], 0); ++s;
+    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(3, REG_X, Np[2], 0, Np[2] / 16, 0, Np[3], REG_Y, 0); p.step[s].epi = epi(3, REG_Y, Np[3], 1); ++s;
+  } else {          // decoder: K0 -> Np0 -> Np1 -> 208 -> Np3
+    const int na = 112, nb = Np[2] - 112;
+    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(0, REG_Z, Kp[0], 0, Kp[0] / 16, 0, Np[0], REG_X, 0); p.step[s].epi = epi(0, REG_X, Np[0], 0); ++s;
+    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(1, REG_X, Np[0], 0, Np[0] / 16, 0, Np[1], REG_Y, 0); p.step[s].epi = epi(1, REG_Y, Np[1], 0); ++s;
+    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(2, REG_Y, Np[1], 0, Np[1] / 16, 0, na, REG_X, 0); p.step[s].epi = epi(2, REG_X, na, 0); ++s;
+    p.step[s].n_mma = 2; p.step[s].mma[0] = mma(3, REG_X, na, 0, na / 16, 0, Np[3], REG_Z, 0);
+    p.step[s].mma[1] = mma(2, REG_Y, Np[1], 0, Np[1] / 16, na, nb, REG_X, 0); p.step[s].epi = epi(2, REG_X, nb, 0); ++s;
+    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(3, REG_X, nb, na / 16, nb / 16, 0, Np[3], REG_Z, 1); p.step[s].epi = epi(3, REG_Z, Np[3], 1); ++s;
+  }
+  p.n_steps = s;
+  // ---- shared memory: weight image + per pipeline (input stage + output stage); prefer two pipelines
+  auto smem_need = [&](int groups, int in_esz) {
+    const size_t in_b = ((size_t)TILE * d.in_dim * in_esz + 127) & ~(size_t)127;
+    const size_t out_b = ((size_t)TILE * p.out_stride * 4 + 127) & ~(size_t)127;
+    return (size_t)p.w_bytes + groups * (in_b + out_b);
+  };
+  h->n_groups = smem_need(2, 4) + 1024 <= ctx->smem_optin ? 2 : (smem_need(1, 4) + 1024 <= ctx->smem_optin ? 1 : 0);
+  if (h->n_groups == 0 || (p.w_bytes & 15)) { delete h; return BB_ERR_UNSUPPORTED; }
+  h->smem_bytes = smem_need(h->n_groups, 4);
+  if (c->tc_blob_dev) cudaFree(c->tc_blob_dev);
+  BB_CUDA(cudaMalloc(&c->tc_blob_dev, img.size()));
+  BB_CUDA(cudaMemcpy(c->tc_blob_dev, img.data(), img.size(), cudaMemcpyHostToDevice));
+  c->tc_blob_bytes = img.size();
+  if (h->n_groups == 2)
+    BB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  else
+    BB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  delete reinterpret_cast<TcHost*>(c->tc_host);
+  c->tc_host = h;
+  c->tc_ok = true;
+  return BB_OK;
+}
+
+void bb_tc_release(Chain* c) {
+  delete reinterpret_cast<TcHost*>(c->tc_host);
+  c->tc_host = nullptr;
+}
+
+int bb_tc_launch_dbg(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows, const float* pre_min,
+                     const float* pre_range, const float* post_min, const float* post_range, void* out, int out_dtype,
+                     int fast, int* flag_dev, int dbg_step, float* dbg_out, int force_groups, cudaStream_t stream) {
+  if (!c->tc_ok) return BB_ERR_UNSUPPORTED;
+  if (n_rows == 0) return BB_OK;
+  const TcHost* h = reinterpret_cast<const TcHost*>(c->tc_host);
+  const int groups = force_groups > 0 && force_groups < h->n_groups ? force_groups : h->n_groups;
+  const int64_t n_tiles = (n_rows + TILE - 1) / TILE;
+  const int64_t want = (n_tiles + groups - 1) / groups;
+  const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
+  const int aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+  if (groups == 2)
+    chain_tc_kernel<2><<<grid, 2 * GROUP_T, h->smem_bytes, stream>>>(h->prog, (const uint8_t*)c->tc_blob_dev, in, in_dtype, aligned,
+                                                                     n_rows, pre_min, pre_range, post_min, post_range, out,
+                                                                     out_dtype, fast, flag_dev, dbg_step, dbg_out);
+  else
+    chain_tc_kernel<1><<<grid, GROUP_T, h->smem_bytes, stream>>>(h->prog, (const uint8_t*)c->tc_blob_dev, in, in_dtype, aligned,
+                                                                 n_rows, pre_min, pre_range, post_min, post_range, out,
+                                                                 out_dtype, fast, flag_dev, dbg_step, dbg_out);
+  return (int)cudaGetLastError();
+}
+
+int bb_tc_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows, const float* pre_min,
+                 const float* pre_range, const float* post_min, const float* post_range, void* out, int out_dtype,
+                 int fast, int* flag_dev, cudaStream_t stream) {
+  return bb_tc_launch_dbg(ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range, out, out_dtype, fast,
+                          flag_dev, -1, nullptr, 0, stream);
 }

@@ -52,6 +52,7 @@ struct Chain {
   bool tc_ok = false;
   void* tc_blob_dev = nullptr;
   size_t tc_blob_bytes = 0;
+  void* tc_host = nullptr;     // TcHost: step program + launch geometry of the tcgen05 kernel
   std::vector<double> w_host[BB_MAX_LAYERS];  // kept for re-packing
   std::vector<double> b_host[BB_MAX_LAYERS];
 };
@@ -76,6 +77,10 @@ int bb_chain_f32_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtyp
 int bb_colminmax_launch(bb_ctx* ctx, const float* x, int64_t n_rows, int n_cols, float* min_dev,
                         float* max_dev, int reset, cudaStream_t stream);
 int bb_tc_prepare(bb_ctx* ctx, Chain* c);
+void bb_tc_release(Chain* c);
+int bb_tc_launch_dbg(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows, const float* pre_min,
+                     const float* pre_range, const float* post_min, const float* post_range, void* out, int out_dtype,
+                     int fast, int* flag_dev, int dbg_step, float* dbg_out, int force_groups, cudaStream_t stream);
 int bb_tc_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
                  const float* pre_min, const float* pre_range, const float* post_min,
                  const float* post_range, void* out, int out_dtype, int fast, int* flag_dev,

@@ -136,21 +136,36 @@ class DenseCodec:
         return {v: k for k, v in PRECISIONS.items() if k in ("fp32", "split16")}[
             _lib.lib().bb_model_auto_precision(self.handle)]
 
+    def range_flag(self, reset=True):
+        """sticky fp16-range flag of the split16 path (synchronises the device)"""
+        flag = C.c_int(0)
+        check(_lib.lib().bb_model_range_flag(self.handle, int(reset), C.byref(flag)), "bb_model_range_flag")
+        return bool(flag.value)
+
+    def _guarded(self, launch, precision, check_range):
+        """run `launch(precision)`; with precision "auto" on the tensor-core path, re-run on the fp32 kernel if a
+        value left the fp16 range (costs one 4-byte device->host read; pass check_range=False to stay async)"""
+        launch(_prec(precision))
+        if check_range and _prec(precision) == _lib.BB_PREC_AUTO and self.auto_precision == "split16" and self.range_flag():
+            launch(_lib.BB_PREC_FP32)
+
     # ---- device-resident tensors
-    def encode(self, x, fmin=None, frange=None, out_dtype=torch.float32, precision="auto", out=None):
+    def encode(self, x, fmin=None, frange=None, out_dtype=torch.float32, precision="auto", out=None, check_range=True):
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == self.n_features
         n = x.numel() // self.n_features
         z = out if out is not None else torch.empty((n, self.z_dim), dtype=out_dtype, device=x.device)
-        check(_lib.lib().bb_encode_f32(self.handle, _ptr(x), n, _ptr(fmin), _ptr(frange), _ptr(z), _T2BB[z.dtype],
-                                       _prec(precision), _stream(self.ctx)), "bb_encode_f32")
+        self._guarded(lambda p: check(_lib.lib().bb_encode_f32(
+            self.handle, _ptr(x), n, _ptr(fmin), _ptr(frange), _ptr(z), _T2BB[z.dtype], p, _stream(self.ctx)),
+            "bb_encode_f32"), precision, check_range)
         return z
 
-    def decode(self, z, fmin=None, frange=None, precision="auto", out=None):
+    def decode(self, z, fmin=None, frange=None, precision="auto", out=None, check_range=True):
         assert z.is_cuda and z.dtype in _T2BB and z.is_contiguous() and z.shape[-1] == self.z_dim
         n = z.numel() // self.z_dim
         y = out if out is not None else torch.empty((n, self.n_features), dtype=torch.float32, device=z.device)
-        check(_lib.lib().bb_decode_f32(self.handle, _ptr(z), _T2BB[z.dtype], n, _ptr(fmin), _ptr(frange), _ptr(y),
-                                       _prec(precision), _stream(self.ctx)), "bb_decode_f32")
+        self._guarded(lambda p: check(_lib.lib().bb_decode_f32(
+            self.handle, _ptr(z), _T2BB[z.dtype], n, _ptr(fmin), _ptr(frange), _ptr(y), p, _stream(self.ctx)),
+            "bb_decode_f32"), precision, check_range)
         return y
 
     # ---- host buffers (numpy), chunked copy/compute pipeline inside the library

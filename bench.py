@@ -190,10 +190,10 @@ def run_ours(args):
         rg = mx - mn  # torch elementwise on 24 floats: plumbing, not the hot path
         if timed_kernels:
             ev[0].record()
-        codec.encode(x, mn, rg, precision=precision, out=z)
+        codec.encode(x, mn, rg, precision=precision, out=z, check_range=False)
         if timed_kernels:
             ev[1].record(); ev[2].record()
-        codec.decode(z, mn, rg, precision=precision, out=y)
+        codec.decode(z, mn, rg, precision=precision, out=y, check_range=False)
         if timed_kernels:
             ev[3].record()
         launches["n"] += 3
@@ -220,6 +220,8 @@ def run_ours(args):
     t_end.record()
     sync_all()
     total_ms = t_start.elapsed_time(t_end)
+    if codec.auto_precision == "split16" and codec.range_flag():
+        raise RuntimeError("fp16 range guard tripped on the synthetic table: timed steps are invalid")
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel durations of the last step (events on the launching stream)
     enc_ms, dec_ms = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])

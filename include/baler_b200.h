@@ -86,6 +86,14 @@ int bb_model_n_features(const bb_model* m);
 int bb_model_z_dim(const bb_model* m);
 /* which arithmetic BB_PREC_AUTO resolves to for this model (BB_PREC_FP32 or BB_PREC_SPLIT16) */
 int bb_model_auto_precision(const bb_model* m);
+/*
+ * Range guard of BB_PREC_SPLIT16 / FAST16: activations are carried as fp16 hi + lo, so a value beyond
+ * +-65504 anywhere in the chain poisons that row (inf/NaN).  The kernels raise a sticky device flag when
+ * an output is not finite.  This call synchronises the device, returns the flag in *out (0 / 1) and
+ * clears it when `reset` != 0; on 1 the caller re-runs the rows with BB_PREC_FP32.  The host pipelines
+ * (bb_compress_host / bb_decompress_host) do this check and fall back internally.
+ */
+int bb_model_range_flag(bb_model* m, int reset, int* out);
 
 /*
  * Per-column min and max of a row-major n x c float32 table.
