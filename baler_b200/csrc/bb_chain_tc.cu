@@ -500,8 +500,7 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
   c->tc_blob_bytes = img.size();
   if (h->n_groups == 2)
     BB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  else
-    BB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  BB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   delete reinterpret_cast<TcHost*>(c->tc_host);
   c->tc_host = h;
   c->tc_ok = true;
