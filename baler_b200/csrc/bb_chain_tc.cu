@@ -36,7 +36,8 @@
 namespace {
 
 constexpr int TILE = 128;      // rows per tile = MMA M
-constexpr int GROUP_T = 128;   // threads per pipeline
+constexpr int GROUP_T = 256;   // threads per pipeline: 2 warps per TMEM lane quarter, splitting the columns
+constexpr int MAX_KITER = 40;  // k-steps of all MMAs of one program (28 for the CMS AE)
 constexpr int MAX_STEPS = 6;
 constexpr int REG_X = 0, REG_Y = 112, REG_Z = 224, PIPE_COLS = 256;
 
@@ -137,10 +138,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[32]
 
 // smem matrix descriptor: no swizzle, K-major; core matrix = 8 rows x 16 B, rows 16 B apart;
 // SBO = 128 B between 8-row groups, LBO = distance between the two K chunks of a k-step
-__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr, uint32_t lbo) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) |
-         (1ull << 46);
-}
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   // c_format F32 (1) @4, a/b format F16 (0) @7/@10, a/b K-major, N>>3 @17, M>>4 @24
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
@@ -172,6 +169,39 @@ __device__ __forceinline__ void a_cols(int col, int w, int s, uint32_t& hi, uint
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
+// One k-step of the issue table: TMEM columns (relative to the pipeline) and the low descriptor words.
+struct __align__(16) KIter { uint32_t a_hi, a_lo, b_hi, b_lo, d_acc, idesc, pad0, pad1; };
+constexpr uint32_t B_DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1 (bit 46)
+
+// drain CW accumulator columns: scale, activation, split into fp16 hi|lo, write back in place
+template <int CW, int ACT>
+__device__ __forceinline__ void epi_chunk_inplace(const uint32_t taddr, const float scale) {
+  uint32_t v[32], pk[32];
+  if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+  tc_wait_ld();
+  const float s2 = ACT == BB_ACT_LEAKY ? scale * BB_LEAKY : 0.f;
+#pragma unroll
+  for (int j = 0; j < CW / 2; ++j) {
+    float a = __uint_as_float(v[2 * j]) * scale, b = __uint_as_float(v[2 * j + 1]) * scale;
+    if constexpr (ACT == BB_ACT_LEAKY) {
+      a = fmaxf(a, __uint_as_float(v[2 * j]) * s2);
+      b = fmaxf(b, __uint_as_float(v[2 * j + 1]) * s2);
+    } else if constexpr (ACT == BB_ACT_RELU) {
+      a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
+    }
+    split2(a, b, pk[j], pk[CW / 2 + j]);
+  }
+  if constexpr (CW == 32) { tmem_st16(taddr, pk, 0); tmem_st16(taddr + 16, pk, 16); }
+  else { tmem_st8(taddr, pk, 0); tmem_st8(taddr + 8, pk, 8); }
+}
+
+template <int CW>
+__device__ __forceinline__ void epi_chunk_dispatch(const uint32_t taddr, const float scale, const int act) {
+  if (act == BB_ACT_LEAKY) epi_chunk_inplace<CW, BB_ACT_LEAKY>(taddr, scale);
+  else if (act == BB_ACT_RELU) epi_chunk_inplace<CW, BB_ACT_RELU>(taddr, scale);
+  else epi_chunk_inplace<CW, BB_ACT_NONE>(taddr, scale);
+}
+
 template <int NGROUPS>
 __global__ void __launch_bounds__(NGROUPS * GROUP_T, 1)
 chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restrict__ wimg, const void* __restrict__ in,
@@ -182,10 +212,15 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[1 + NGROUPS];
   __shared__ uint32_t tmem_base_s;
+  __shared__ KIter kit[MAX_KITER];
+  __shared__ int kit_begin[MAX_STEPS + 1];
+  __shared__ float norm_s[4][32];  // pre_min, pre_range, post_min, post_range (first 32 features)
 
   const int tid = threadIdx.x;
   const int g = tid / GROUP_T;            // pipeline index
-  const int tg = tid - g * GROUP_T;       // thread within the pipeline == tile row == TMEM lane
+  const int tg = tid - g * GROUP_T;       // thread within the pipeline
+  const int row = tg & (TILE - 1);        // tile row == TMEM lane
+  const int half = tg >> 7;               // which half of the column chunks this warp drains
   const int in_dim = prog.in_dim, out_dim = prog.out_dim;
   const int in_esz = in_dtype == BB_F16 ? 2 : 4;
   const uint32_t in_stage_bytes = (uint32_t)((TILE * in_dim * in_esz + 127) & ~127);
@@ -200,6 +235,33 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
     mbar_init(bar_w, 1);
     for (int i = 0; i < NGROUPS; ++i) mbar_init(smem_u32(&bars[1 + i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // issue table: every k-step of every MMA of the program, in issue order
+    int n = 0;
+    for (int s = 0; s < prog.n_steps; ++s) {
+      kit_begin[s] = n;
+      for (int m = 0; m < prog.step[s].n_mma; ++m) {
+        const TcMma& mm = prog.step[s].mma[m];
+        for (int k = 0; k < mm.ks_n; ++k, ++n) {
+          KIter e;
+          a_cols(mm.a_col, mm.a_w, k, e.a_hi, e.a_lo);
+          const uint32_t koff = (uint32_t)(mm.ks0 + k) * 2u * mm.lbo;  // two 8-wide K chunks per k-step
+          const uint32_t lbo_f = ((mm.lbo >> 4) & 0x3FFF) << 16;
+          e.b_hi = (((smem_u32(w_s) + mm.b_hi + koff) >> 4) & 0x3FFF) | lbo_f;
+          e.b_lo = (((smem_u32(w_s) + mm.b_lo + koff) >> 4) & 0x3FFF) | lbo_f;
+          e.d_acc = (uint32_t)mm.d_col | ((k > 0 || mm.acc) ? 0x80000000u : 0u);
+          e.idesc = make_idesc(mm.n);
+          e.pad0 = e.pad1 = 0;
+          kit[n] = e;
+        }
+      }
+    }
+    kit_begin[prog.n_steps] = n;
+  }
+  if (tid < 128) {  // column (de)normalisation vectors, read by every thread for every row
+    const int which = tid >> 5, k = tid & 31;
+    const float* src = which == 0 ? pre_min : which == 1 ? pre_range : which == 2 ? post_min : post_range;
+    const int dim = which < 2 ? in_dim : out_dim;
+    norm_s[which][k] = (src != nullptr && k < dim) ? src[k] : (which & 1 ? 1.f : 0.f);
   }
   if (tid < 32) {  // warp 0 owns the TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
@@ -219,8 +281,9 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
 
   const int64_t n_tiles = (n_rows + TILE - 1) / TILE;
   const int64_t tile_stride = (int64_t)gridDim.x * NGROUPS;
-  const uint32_t lane_addr = (uint32_t)((tg & ~31) << 16);  // TMEM lane base of this warp (32 lanes per warp)
+  const uint32_t lane_addr = (uint32_t)((row & ~31) << 16);  // TMEM lane base of this warp (32 lanes per warp)
   const uint32_t tcol0 = tmem_base + g * PIPE_COLS;
+  const bool has_pre = pre_min != nullptr, has_post = post_min != nullptr;
 
   // cooperative copy of one input tile into the stage (16-byte cp.async when aligned and full)
   auto fetch = [&](int64_t tile) {
@@ -247,40 +310,36 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
     const int rows = (int)min((int64_t)TILE, n_rows - tile * TILE);
     cp_async_wait_all();
     group_bar(1 + g);
-    // ---- A1: this thread's row -> normalise -> 1.0 in the bias slot -> split -> TMEM
-    {
-      const int kpad = prog.a1_w;  // 16, 32, 48 or 64 ... (multiple of 16)
-      for (int c0 = 0; c0 < kpad; c0 += 32) {
-        const int cw = kpad - c0 >= 32 ? 32 : 16;
-        uint32_t pk[32];
+    // ---- A1: this thread's row, k-step `half` (16 features) -> normalise -> 1.0 in the bias slot -> split -> TMEM
+    if (half * 16 < prog.a1_w) {
+      uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v[2];
+      for (int j = 0; j < 8; ++j) {
+        float v[2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int k = c0 + 2 * j + h;
-            float x = 0.f;
-            if (2 * j + h < cw) {
-              if (k < in_dim && tg < rows) {
-                x = in_esz == 4 ? reinterpret_cast<const float*>(in_s)[tg * in_dim + k]
-                                : __half2float(reinterpret_cast<const __half*>(in_s)[tg * in_dim + k]);
-                if (pre_min != nullptr) x = __fdiv_rn(__fsub_rn(x, __ldg(pre_min + k)), __ldg(pre_range + k));
-              } else if (k == in_dim) {
-                x = 1.f;
-              }
+        for (int h = 0; h < 2; ++h) {
+          const int k = half * 16 + 2 * j + h;
+          float x = 0.f;
+          if (k < in_dim) {
+            if (row < rows) {
+              x = in_esz == 4 ? reinterpret_cast<const float*>(in_s)[row * in_dim + k]
+                              : __half2float(reinterpret_cast<const __half*>(in_s)[row * in_dim + k]);
+              // numpy float32: (x - min) / range with IEEE division (data_processing.py:151)
+              if (has_pre) x = __fdiv_rn(__fsub_rn(x, norm_s[0][k]), norm_s[1][k]);
             }
-            v[h] = x;
+          } else if (k == in_dim) {
+            x = 1.f;
           }
-          // chunk layout: hi words first, lo words after (cw/2 words each)
-          if (cw == 32) split2(v[0], v[1], pk[j], pk[16 + j]);
-          else if (j < 8) split2(v[0], v[1], pk[j], pk[8 + j]);
+          v[h] = x;
         }
-        const uint32_t taddr = tcol0 + lane_addr + prog.a1_col + c0;
-        if (cw == 32) { tmem_st16(taddr, pk, 0); tmem_st16(taddr + 16, pk, 16); }
-        else { tmem_st8(taddr, pk, 0); tmem_st8(taddr + 8, pk, 8); }
+        split2(v[0], v[1], pk[j], pk[8 + j]);
       }
+      // k-step s of a 32-wide chunk: hi words at +8s, lo words at +16+8s; a 16-wide chunk: hi +0, lo +8
+      const uint32_t taddr = tcol0 + lane_addr + prog.a1_col + (prog.a1_w >= 32 ? half * 8 : 0);
+      tmem_st8(taddr, pk, 0);
+      tmem_st8(taddr + (prog.a1_w >= 32 ? 16 : 8), pk, 8);
+      tc_wait_st();
     }
-    tc_wait_st();
     tc_fence_before();
     group_bar(1 + g);
     {  // the stage is free again: prefetch this pipeline's next tile while the layers run
@@ -289,24 +348,19 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
     }
 
     for (int s = 0; s < prog.n_steps; ++s) {
-      const TcStep& st = prog.step[s];
       if (tg == 0) {  // one thread issues the MMAs of this step for its pipeline
         tc_fence_after();
-        for (int m = 0; m < st.n_mma; ++m) {
-          const TcMma& mm = st.mma[m];
-          const uint32_t idesc = make_idesc(mm.n);
-          const uint32_t d = tcol0 + mm.d_col;
-          for (int k = 0; k < mm.ks_n; ++k) {
-            uint32_t a_hi, a_lo;
-            a_cols(mm.a_col, mm.a_w, k, a_hi, a_lo);
-            const uint32_t koff = (uint32_t)(mm.ks0 + k) * 2u * mm.lbo;  // two 8-wide K chunks per k-step
-            const uint64_t bh = make_b_desc(smem_u32(w_s) + mm.b_hi + koff, mm.lbo);
-            tc_mma_ts(d, tcol0 + a_hi, bh, idesc, (k > 0 || mm.acc) ? 1u : 0u);
-            if (!fast) {
-              const uint64_t bl = make_b_desc(smem_u32(w_s) + mm.b_lo + koff, mm.lbo);
-              tc_mma_ts(d, tcol0 + a_hi, bl, idesc, 1u);
-              tc_mma_ts(d, tcol0 + a_lo, bh, idesc, 1u);
-            }
+        const int e1 = kit_begin[s + 1];
+        for (int e = kit_begin[s]; e < e1; ++e) {
+          const uint4 p0 = *reinterpret_cast<const uint4*>(&kit[e]);
+          const uint2 p1 = *reinterpret_cast<const uint2*>(&kit[e].d_acc);
+          const uint64_t bh = ((uint64_t)B_DESC_HI << 32) | p0.z;
+          const uint32_t d = tcol0 + (p1.x & 0xFFFF);
+          tc_mma_ts(d, tcol0 + p0.x, bh, p1.y, p1.x >> 31);
+          if (!fast) {
+            const uint64_t bl = ((uint64_t)B_DESC_HI << 32) | p0.w;
+            tc_mma_ts(d, tcol0 + p0.x, bl, p1.y, 1u);
+            tc_mma_ts(d, tcol0 + p0.y, bh, p1.y, 1u);
           }
         }
         tc_commit(bar_m);
@@ -316,45 +370,45 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
       tc_fence_after();
 
       // ---- epilogue: drain the accumulator region; either re-split in place or emit the output row
-      const TcEpi& ep = st.epi;
-      for (int c0 = 0; c0 < ep.w; c0 += 32) {
-        const int cw = ep.w - c0 >= 32 ? 32 : 16;
-        const uint32_t taddr = tcol0 + lane_addr + ep.col + c0;
-        uint32_t v[32];
-        if (cw == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-        tc_wait_ld();
-        if (dbg_out != nullptr && dbg_step == s && tg < rows) {
+      const TcEpi& ep = prog.step[s].epi;
+      const int ep_w = ep.w, ep_col = ep.col, ep_act = ep.act;
+      const float ep_scale = ep.scale;
+      if (dbg_out != nullptr && dbg_step == s && half == 0) {  // test hook: scaled accumulator
+        for (int c0 = 0; c0 < ep_w; c0 += 16) {
+          uint32_t v[32];
+          tmem_ld16(tcol0 + lane_addr + ep_col + c0, v);  // .sync.aligned: the whole warp, also rows past the tail
+          tc_wait_ld();
+          if (row < rows) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < cw) dbg_out[((size_t)tile * TILE + tg) * ep.w + c0 + j] = __uint_as_float(v[j]) * ep.scale;
-        }
-        if (!ep.final) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = act_apply(__uint_as_float(v[2 * j]) * ep.scale, ep.act);
-            const float b = act_apply(__uint_as_float(v[2 * j + 1]) * ep.scale, ep.act);
-            if (cw == 32) split2(a, b, pk[j], pk[16 + j]);
-            else if (j < 8) split2(a, b, pk[j], pk[8 + j]);
+            for (int j = 0; j < 16; ++j) dbg_out[((size_t)tile * TILE + row) * ep_w + c0 + j] = __uint_as_float(v[j]) * ep_scale;
           }
-          if (cw == 32) { tmem_st16(taddr, pk, 0); tmem_st16(taddr + 16, pk, 16); }
-          else { tmem_st8(taddr, pk, 0); tmem_st8(taddr + 8, pk, 8); }
-        } else {
-          bool bad = false;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            if (j < cw && c < out_dim) {
-              float y = act_apply(__uint_as_float(v[j]) * ep.scale, ep.act);
-              bad |= !(fabsf(y) <= 3.0e38f);  // inf / NaN: an fp16 operand overflowed somewhere upstream
-              if (post_min != nullptr) y = fmaf(y, __ldg(post_range + c), __ldg(post_min + c));
-              out_s[tg * prog.out_stride + c] = y;
-            }
-          }
-          if (bad && tg < rows) atomicOr(flag, 1);
         }
       }
-      if (!ep.final) tc_wait_st();
+      if (dbg_out != nullptr) group_bar(1 + g);  // the dump must read before the in-place rewrite of the other half
+      if (!ep.final) {
+        for (int c0 = half * 32; c0 < ep_w; c0 += 64) {
+          const uint32_t taddr = tcol0 + lane_addr + ep_col + c0;
+          if (ep_w - c0 >= 32) epi_chunk_dispatch<32>(taddr, ep_scale, ep_act);
+          else epi_chunk_dispatch<16>(taddr, ep_scale, ep_act);
+        }
+        tc_wait_st();
+      } else if (half == 0) {
+        uint32_t v[32];
+        const uint32_t taddr = tcol0 + lane_addr + ep_col;
+        if (ep_w > 16) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        tc_wait_ld();
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < out_dim && j < ep_w) {
+            float y = act_apply(__uint_as_float(v[j]) * ep_scale, ep_act);
+            bad |= !(fabsf(y) <= 3.0e38f);  // inf / NaN: an fp16 operand overflowed somewhere upstream
+            if (has_post) y = fmaf(y, norm_s[3][j], norm_s[2][j]);  // y * range + min (data_processing.py:203)
+            out_s[row * prog.out_stride + j] = y;
+          }
+        }
+        if (bad && row < rows) atomicOr(flag, 1);
+      }
       tc_fence_before();
       group_bar(1 + g);
     }
@@ -413,7 +467,7 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
   for (int l = 0; l < 4; ++l)
     if (Np[l] > 112) { if (wide >= 0 || Np[l] > 208) return BB_ERR_UNSUPPORTED; wide = l; }
   if (wide != 0 && wide != 2) return BB_ERR_UNSUPPORTED;
-  if (Kp[0] > 32 || Np[3] > 32) return BB_ERR_UNSUPPORTED;            // first A operand / last accumulator live in Z (32 columns)
+  if (Kp[0] > 32 || Np[3] > 32 || d.in_dim > 31 || d.out_dim > 32) return BB_ERR_UNSUPPORTED;  // first A operand / last accumulator live in Z (32 columns)
   if (wide == 0 && (Np[2] > 112 || Np[1] > 112)) return BB_ERR_UNSUPPORTED;
   if (wide == 2 && (Np[0] > 112 || Np[1] > 112)) return BB_ERR_UNSUPPORTED;
 
