@@ -72,18 +72,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // try_wait suspends the thread for a bounded time in hardware; a protocol bug must not hang the GPU, so
-  // give up (trap -> launch error) after ~2 s of SM clock
-  const long long t0 = clock64();
-  for (;;) {
+  // try_wait with a suspend-time hint parks the warp in hardware until the phase completes (or ~20 us pass), so
+  // waiting warps do not burn issue slots the other pipeline's epilogue needs.  A protocol bug must not hang
+  // the GPU: give up (trap -> launch error) after ~2 s.
+  for (uint32_t spins = 0;; ++spins) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if (spins > 100000u) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
