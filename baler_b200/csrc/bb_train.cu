@@ -24,8 +24,9 @@
 namespace {
 
 constexpr int NL = 8;       // dense layers F-200-100-50-z-50-100-200-F
-constexpr int RT = 8;       // rows per CTA in the forward/backward kernel
-constexpr int NT = 256;
+constexpr int RT = 4;       // rows per CTA in the forward/backward kernel (128 CTAs for a 512-row batch)
+constexpr int NT = 256;      // dW and Adam kernels
+constexpr int NT_FB = 512;   // forward/backward kernel: more warps to hide shared-memory latency, wider reduction splits
 constexpr int DW_T = 64;    // dW tile edge and rows per split
 constexpr int DW_LD = DW_T + 4;
 
@@ -39,9 +40,59 @@ struct TrainDims {
   int z_off[NL];         // offset of dZ_l in the per-row dZ scratch
   int n_params;
   int max_dim;
+  int max_mat;           // floats of one staged weight matrix buffer (largest layer + alignment slack)
 };
 
 struct DwTile { int l, n0, k0; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// Weight staging.  A chain is a fixed sequence of passes (8 forward layers on W^T, then 7 backward layers
+// 7..1 on W); the matrix of pass p+1 is copied L2 -> shared memory with cp.async while pass p computes, so the
+// per-thread weight reads of the inner loops are shared-memory loads instead of exposed L2 latency.
+struct WStage {
+  float* buf[2];
+  int gp, total, per_chain;  // global pass counter, number of passes of this launch, passes per chain (15 or 8)
+};
+
+__device__ __forceinline__ void pass_src(const TrainDims& d, const float* params, const float* wt, const int p,
+                                         const float*& src, int& n) {
+  if (p < NL) { src = wt + d.wt_off[p]; n = d.dims[p] * d.dims[p + 1]; }
+  else { const int l = 2 * NL - 1 - p; src = params + d.w_off[l]; n = d.dims[l] * d.dims[l + 1]; }
+}
+
+__device__ __forceinline__ void prefetch_pass(const TrainDims& d, const float* params, const float* wt, const int p, float* buf) {
+  const float* src; int n;
+  pass_src(d, params, wt, p, src, n);
+  const float* a = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15);
+  const int n_chunk = ((int)(src - a) + n + 3) >> 2;  // 16-byte chunks from the aligned address below the matrix
+  // every CTA copies the same matrix at the same time: start each CTA at a different offset so the requests
+  // spread over the L2 slices instead of all SMs hammering one line after the other in lock-step
+  const int rot = (int)(((long long)blockIdx.x * n_chunk) / gridDim.x);
+  for (int i = threadIdx.x; i < n_chunk; i += NT_FB) {
+    int c = i + rot;
+    c = (c >= n_chunk ? c - n_chunk : c) << 2;
+    cp_async16(smem_u32(buf + c), a + c);
+  }
+}
+
+// start the copy of the next pass, wait for the current one; returns the shared-memory address of its matrix
+__device__ __forceinline__ const float* acquire_pass(const TrainDims& d, const float* params, const float* wt, WStage& ws) {
+  const int cur = ws.gp;
+  if (cur + 1 < ws.total) prefetch_pass(d, params, wt, (cur + 1) % ws.per_chain, ws.buf[(cur + 1) & 1]);
+  cp_async_commit();
+  cp_async_wait_1();
+  __syncthreads();
+  const float* src; int n;
+  pass_src(d, params, wt, cur % ws.per_chain, src, n);
+  ws.gp = cur + 1;
+  return ws.buf[cur & 1] + ((reinterpret_cast<uintptr_t>(src) & 15) >> 2);
+}
 
 __device__ __forceinline__ float act_fwd(float v, int act) {
   if (act == BB_ACT_LEAKY) return v > 0.f ? v : BB_LEAKY * v;
@@ -58,13 +109,13 @@ __device__ __forceinline__ void gemv8_slice(const float* __restrict__ in_s, cons
   const float* a = in_s + i0 * RT;
 #pragma unroll 4
   for (int i = i0; i < i1; ++i) {
-    const float wv = __ldg(w);
-    const float4 a0 = *reinterpret_cast<const float4*>(a);
-    const float4 a1 = *reinterpret_cast<const float4*>(a + 4);
-    acc[0] = fmaf(a0.x, wv, acc[0]); acc[1] = fmaf(a0.y, wv, acc[1]);
-    acc[2] = fmaf(a0.z, wv, acc[2]); acc[3] = fmaf(a0.w, wv, acc[3]);
-    acc[4] = fmaf(a1.x, wv, acc[4]); acc[5] = fmaf(a1.y, wv, acc[5]);
-    acc[6] = fmaf(a1.z, wv, acc[6]); acc[7] = fmaf(a1.w, wv, acc[7]);
+    const float wv = *w;
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) {
+      const float4 a4 = *reinterpret_cast<const float4*>(a + 4 * q);
+      acc[4 * q + 0] = fmaf(a4.x, wv, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(a4.y, wv, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(a4.z, wv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a4.w, wv, acc[4 * q + 3]);
+    }
     w += Dout;
     a += RT;
   }
@@ -74,11 +125,11 @@ __device__ __forceinline__ void gemv8_slice(const float* __restrict__ in_s, cons
 // reduction over KP thread groups (combined later in fixed order by red_sum).  Ends with __syncthreads.
 __device__ __forceinline__ int gemv8(const float* __restrict__ in_s, const float* __restrict__ Wm, const int Din,
                                      const int Dout, float* __restrict__ red_s) {
-  int KP = NT / Dout;
+  int KP = NT_FB / Dout;
   KP = KP < 1 ? 1 : (KP > 16 ? 16 : KP);
   float acc[RT];
   if (KP == 1) {
-    for (int j = threadIdx.x; j < Dout; j += NT) {
+    for (int j = threadIdx.x; j < Dout; j += NT_FB) {
       gemv8_slice(in_s, Wm, Dout, j, 0, Din, acc);
 #pragma unroll
       for (int r = 0; r < RT; ++r) red_s[r * Dout + j] = acc[r];
@@ -108,16 +159,16 @@ template <int CHAIN>
 __device__ void run_chain(const TrainDims& d, const float* __restrict__ params, const float* __restrict__ wt,
                           float* __restrict__ act_g, float* __restrict__ dz_g, const int row0, const int rows,
                           const bool backward, const float reg, const float inv_rows, float* act_s, float* dz_s0,
-                          float* dz_s1, float* red_s, float& loss_local) {
+                          float* dz_s1, float* red_s, float& loss_local, WStage& ws) {
   // ---- forward: act_s[a_off[l]*RT + j*RT + r]
   for (int l = 0; l < NL; ++l) {
     const int K = d.dims[l], N = d.dims[l + 1];
     const float* in_s = act_s + d.a_off[l] * RT;
     float* out_s = act_s + d.a_off[l + 1] * RT;
-    const int KP = gemv8(in_s, wt + d.wt_off[l], K, N, red_s);
+    const int KP = gemv8(in_s, acquire_pass(d, params, wt, ws), K, N, red_s);
     const float* bias = params + d.b_off[l];
     const int act = CHAIN == 0 ? d.act[l] : BB_ACT_RELU;
-    for (int o = threadIdx.x; o < RT * N; o += NT) {
+    for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
       const int r = o / N, j = o - r * N;
       const float v = act_fwd(red_sum(red_s, KP, N, r, j) + __ldg(bias + j), act);
       out_s[j * RT + r] = v;
@@ -133,7 +184,7 @@ __device__ void run_chain(const TrainDims& d, const float* __restrict__ params, 
   {
     const float* out_s = act_s + d.a_off[NL] * RT;
     const float* x_s = act_s;  // a_off[0] == 0
-    for (int o = threadIdx.x; o < RT * F; o += NT) {
+    for (int o = threadIdx.x; o < RT * F; o += NT_FB) {
       const int r = o / F, j = o - r * F;
       float g = 0.f;
       if (r < rows) {
@@ -154,11 +205,11 @@ __device__ void run_chain(const TrainDims& d, const float* __restrict__ params, 
   // ---- backward: dZ_{l-1} = (dZ_l W_l [+ l1 seed]) * act'(A_l)
   for (int l = NL - 1; l >= 1; --l) {
     const int K = d.dims[l], N = d.dims[l + 1];
-    const int KP = gemv8(dz_cur, params + d.w_off[l], N, K, red_s);
+    const int KP = gemv8(dz_cur, acquire_pass(d, params, wt, ws), N, K, red_s);
     const float* a_s = act_s + d.a_off[l] * RT;  // output of layer l-1 (post-activation)
     const int act = CHAIN == 0 ? d.act[l - 1] : BB_ACT_RELU;
     const float seed = CHAIN == 1 ? reg * inv_rows / K : 0.f;
-    for (int o = threadIdx.x; o < RT * K; o += NT) {
+    for (int o = threadIdx.x; o < RT * K; o += NT_FB) {
       const int r = o / K, j = o - r * K;
       float g = red_sum(red_s, KP, K, r, j) + seed;
       const float a = a_s[j * RT + r];
@@ -174,7 +225,7 @@ __device__ void run_chain(const TrainDims& d, const float* __restrict__ params, 
 }
 
 // scratch layout per chain c: act_g + c * B_max * a_stride ; dz_g + c * B_max * z_stride
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT_FB)
 train_fwd_bwd_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ params,
                      const float* __restrict__ wt, const float* __restrict__ x, const int batch_rows,
                      float* __restrict__ act_g, float* __restrict__ dz_g, const size_t chain_act_stride,
@@ -184,13 +235,21 @@ train_fwd_bwd_kernel(const __grid_constant__ TrainDims d, const float* __restric
   float* act_s = smem;                           // a_stride * RT
   float* dz_s0 = act_s + d.a_stride * RT;        // max_dim * RT
   float* dz_s1 = dz_s0 + d.max_dim * RT;
-  float* red_s = dz_s1 + d.max_dim * RT;         // max(max_dim, NT) * RT
-  __shared__ float warp_loss[NT / 32];
+  float* red_s = dz_s1 + d.max_dim * RT;         // max(max_dim, NT_FB) * RT
+  __shared__ float warp_loss[NT_FB / 32];
+  WStage ws;
+  ws.buf[0] = red_s + (d.max_dim > NT_FB ? d.max_dim : NT_FB) * RT;
+  ws.buf[1] = ws.buf[0] + d.max_mat;
+  ws.per_chain = backward ? 2 * NL - 1 : NL;
+  ws.total = ws.per_chain * (l1 ? 2 : 1);
+  ws.gp = 0;
+  prefetch_pass(d, params, wt, 0, ws.buf[0]);
+  cp_async_commit();
 
   const int row0 = blockIdx.x * RT;
   const int rows = min(RT, batch_rows - row0);
   const int F = d.dims[0];
-  for (int o = threadIdx.x; o < RT * F; o += NT) {
+  for (int o = threadIdx.x; o < RT * F; o += NT_FB) {
     const int r = o / F, j = o - r * F;
     const float v = r < rows ? __ldg(x + (size_t)(row0 + r) * F + j) : 0.f;
     act_s[j * RT + r] = v;
@@ -198,15 +257,15 @@ train_fwd_bwd_kernel(const __grid_constant__ TrainDims d, const float* __restric
   }
   __syncthreads();
   float loss_local = 0.f;
-  run_chain<0>(d, params, wt, act_g, dz_g, row0, rows, backward != 0, 0.f, 0.f, act_s, dz_s0, dz_s1, red_s, loss_local);
+  run_chain<0>(d, params, wt, act_g, dz_g, row0, rows, backward != 0, 0.f, 0.f, act_s, dz_s0, dz_s1, red_s, loss_local, ws);
   if (l1) {
     __syncthreads();
-    for (int o = threadIdx.x; o < RT * F; o += NT) {  // A_0 of the second chain is x as well
+    for (int o = threadIdx.x; o < RT * F; o += NT_FB) {  // A_0 of the second chain is x as well
       const int r = o / F, j = o - r * F;
       if (r < rows) act_g[chain_act_stride + (size_t)(row0 + r) * d.a_stride + j] = act_s[j * RT + r];
     }
     run_chain<1>(d, params, wt, act_g + chain_act_stride, dz_g + chain_dz_stride, row0, rows, backward != 0, reg,
-                 inv_global_rows, act_s, dz_s0, dz_s1, red_s, loss_local);
+                 inv_global_rows, act_s, dz_s0, dz_s1, red_s, loss_local, ws);
   }
   // block-reduce the loss partial in a fixed order
 #pragma unroll
@@ -215,7 +274,7 @@ train_fwd_bwd_kernel(const __grid_constant__ TrainDims d, const float* __restric
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int w = 0; w < NT / 32; ++w) s += warp_loss[w];
+    for (int w = 0; w < NT_FB / 32; ++w) s += warp_loss[w];
     loss_part[blockIdx.x] = s;
   }
 }
@@ -339,7 +398,7 @@ int launch_fwd_bwd(bb_trainer* t, const float* x, int rows, int backward, const 
   t->last_rows = rows;
   const int world = h && h->world_size > 0 ? h->world_size : 1;
   const float inv_rows = 1.f / ((float)rows * world);
-  train_fwd_bwd_kernel<<<grid, NT, t->smem_bytes, s>>>(
+  train_fwd_bwd_kernel<<<grid, NT_FB, t->smem_bytes, s>>>(
       t->d, t->params, t->wt, x, rows, t->act_g, t->dz_g, (size_t)t->max_batch * t->d.a_stride,
       (size_t)t->max_batch * t->d.z_stride, backward, h ? h->l1 : 0, h ? (float)h->reg_param : 0.f, inv_rows, t->loss_part);
   return (int)cudaGetLastError();
@@ -375,8 +434,11 @@ int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim, const double* cons
     d.z_off[l] = z; z += dims[l + 1];
   }
   d.a_stride = a; d.z_stride = z; d.n_params = p; d.max_dim = mx;
+  int mm = 0;
+  for (int l = 0; l < NL; ++l) mm = dims[l] * dims[l + 1] > mm ? dims[l] * dims[l + 1] : mm;
+  d.max_mat = (mm + 8 + 3) & ~3;
   t->wt_floats = wtp;
-  t->smem_bytes = (size_t)(d.a_stride + 2 * mx + (mx > NT ? mx : NT)) * RT * sizeof(float);
+  t->smem_bytes = ((size_t)(d.a_stride + 2 * mx + (mx > NT_FB ? mx : NT_FB)) * RT + 2 * (size_t)d.max_mat) * sizeof(float);
   if (t->smem_bytes > ctx->smem_optin) { delete t; return BB_ERR_UNSUPPORTED; }
 
   std::vector<float> hp(p), hwt(wtp);
@@ -402,8 +464,8 @@ int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim, const double* cons
   const int max_ctas = (max_batch + RT - 1) / RT;
   int rc = BB_OK;
   auto alloc = [&](void** ptr, size_t bytes) { if (rc == BB_OK) rc = (int)cudaMalloc(ptr, bytes); };
-  alloc((void**)&t->params, sizeof(float) * p);
-  alloc((void**)&t->wt, sizeof(float) * wtp);
+  alloc((void**)&t->params, sizeof(float) * (p + 8));
+  alloc((void**)&t->wt, sizeof(float) * (wtp + 8));
   alloc((void**)&t->grads, sizeof(float) * (p + 1));
   alloc((void**)&t->m, sizeof(float) * p);
   alloc((void**)&t->v, sizeof(float) * p);

@@ -300,7 +300,16 @@ def run_ours(args):
             sync_all()
             dt = time.perf_counter() - t0
             steps = len(batches)
-        train = {"samples_per_s": tn * world / dt, "us_per_step": 1e6 * dt / steps, "steps": steps,
+        cpu_train = None
+        if world == 1 and not args.no_cpu:
+            from oracle import torch_port
+            sd0 = {k: v.numpy() for k, v in tm.state_dict().items()}
+            xs = xt[:512 * 64].cpu().numpy()
+            torch_port.fit_steps(sd0, xs, 512, 10)
+            _, sec = torch_port.fit_steps(sd0, xs, 512, 300)
+            cpu_train = {"samples_per_s": 300 * 512 / sec, "cores": int(torch.get_num_threads()), "kind": "port",
+                         "sample": "300 steps of bs 512, reference loop body restated on torch CPU float64 (oracle/torch_port.py)"}
+        train = {"cpu_baseline": cpu_train, "samples_per_s": tn * world / dt, "us_per_step": 1e6 * dt / steps, "steps": steps,
                  "global_batch": 512 * world, "epoch_loss": loss, "model": "AE 24-200-100-50-15-50-100-200-24",
                  "flop_per_sample": 357000, "tflops": tn * world * 357000 / dt / 1e12}
 

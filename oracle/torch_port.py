@@ -48,3 +48,24 @@ def decompress(sd, z, feats, block=BLOCK):
     for i in range(0, zt.shape[0], block):
         out[i:i + block] = _chain(sd, DEC, zt[i:i + block]) * rg + mn
     return out.numpy()
+
+
+def fit_steps(sd, x_norm, batch, n_steps, lr=1e-3):
+    """Timing port of the reference's training loop body (training.py:64-97) on torch CPU float64:
+    zero_grad -> forward -> sum-MSE / n_cols -> backward -> Adam.step -> loss.item() per batch.
+    Returns (mean loss, seconds)."""
+    import time
+
+    params = {k: v.clone().requires_grad_(True) for k, v in to_torch(sd).items()}
+    opt = torch.optim.Adam(list(params.values()), lr=lr)
+    x = torch.from_numpy(np.ascontiguousarray(x_norm)).to(torch.float64)
+    total = 0.0
+    t0 = time.perf_counter()
+    for s in range(n_steps):
+        xb = x[(s * batch) % max(len(x) - batch, 1):][:batch]
+        opt.zero_grad()
+        loss = ((_chain(params, DEC, _chain(params, ENC, xb)) - xb) ** 2).sum() / xb.shape[1]
+        loss.backward()
+        opt.step()
+        total += loss.item()
+    return total / n_steps, time.perf_counter() - t0

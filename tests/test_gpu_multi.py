@@ -1,0 +1,85 @@
+"""2-GPU checks (skipped on a 1-GPU box): the data-parallel step (SUM all-reduce over NCCL between backward and
+Adam) equals the single-GPU step at the same global batch; sharded compress equals the single-GPU result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    from baler_b200 import engine, sharded, synth
+    from baler_b200.modules import models
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g = np.load(os.path.join(GOLDEN, "ae_train.npz"))
+        sd0 = {k[4:]: np.asarray(g[k], order="C") for k in g.files if k.startswith("sd0/")}
+        names = models.AE.names
+        x = torch.from_numpy(np.ascontiguousarray(g["x_norm"])).cuda()
+        tr = engine.Trainer([sd0[n + ".weight"] for n in names], [sd0[n + ".bias"] for n in names], 24, 15, 1024)
+        dp = sharded.DataParallelTrainer(tr)
+        hyper = engine.make_hyper(lr=1e-3, world_size=world)
+        slices = sharded.dp_batch_slices(2048, 1024, rank, world)  # two global batches of 1024 rows
+        loss = dp.epoch([x[lo:hi].contiguous() for lo, hi in slices], hyper)
+        np.save(os.path.join(out_dir, "dp_params_%d.npy" % rank), tr.params_view().cpu().numpy())
+        np.save(os.path.join(out_dir, "dp_loss_%d.npy" % rank), np.array([loss]))
+        # sharded compress: local min/max -> exchange -> encode of the local rows with the global features
+        table = synth.cms_table(40_001, seed=8)
+        lo, hi = sharded.row_range(len(table), rank, world)
+        xs = torch.from_numpy(table[lo:hi]).cuda()
+        mn, mx = engine.colminmax(xs)
+        sharded.combine_minmax_(mn, mx)
+        m = models.AE(24, 15)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd0.items()})
+        z = m.eval().codec().encode(xs, mn, mx - mn)
+        np.save(os.path.join(out_dir, "z_%d.npy" % rank), z.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_equals_single_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    from baler_b200 import engine, synth
+    from baler_b200.modules import models
+
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = np.load(tmp_path / "dp_params_0.npy"), np.load(tmp_path / "dp_params_1.npy")
+    assert np.array_equal(p0, p1)  # replicated Adam state stays bit-identical
+    g = np.load(os.path.join(GOLDEN, "ae_train.npz"))
+    sd0 = {k[4:]: np.asarray(g[k], order="C") for k in g.files if k.startswith("sd0/")}
+    names = models.AE.names
+    x = torch.from_numpy(np.ascontiguousarray(g["x_norm"])).cuda()
+    tr = engine.Trainer([sd0[n + ".weight"] for n in names], [sd0[n + ".bias"] for n in names], 24, 15, 1024)
+    loss = tr.epoch(x, 1024, engine.make_hyper(lr=1e-3))
+    single = tr.params_view().cpu().numpy()
+    start = np.concatenate([np.concatenate([sd0[n + ".weight"].ravel(), sd0[n + ".bias"].ravel()]) for n in names])
+    upd, ref = p0 - start, single - start
+    assert np.abs(upd - ref).max() <= 0.02 * np.abs(ref).max()  # fp32 summation order differs between 1 and 2 ranks
+    assert abs(float(np.load(tmp_path / "dp_loss_0.npy")[0]) - loss) <= 1e-5 * loss
+    # sharded compress == one-GPU compress, bit for bit (rows are independent, features are global)
+    table = synth.cms_table(40_001, seed=8)
+    m = models.AE(24, 15)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd0.items()})
+    xs = torch.from_numpy(table).cuda()
+    mn, mx = engine.colminmax(xs)
+    z = m.eval().codec().encode(xs, mn, mx - mn).cpu().numpy()
+    zs = np.concatenate([np.load(tmp_path / "z_0.npy"), np.load(tmp_path / "z_1.npy")])
+    assert np.array_equal(z, zs)
