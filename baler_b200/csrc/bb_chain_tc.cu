@@ -26,8 +26,14 @@
 // TMEM budget.  fp32 accumulator columns and packed hi|lo A columns have the same footprint, so the
 // conversion is in place.  The 200-wide layer is processed in two N halves (112 + 96) that reuse one
 // region, which keeps a tile pipeline at 256 columns (X 112 | Y 112 | Z 32): two independent pipelines
-// (warp groups of 128 threads, tiles interleaved) share the SM, one runs its epilogue on the CUDA cores
-// while the other's MMAs occupy the tensor pipe.
+// (tiles interleaved) share the SM.
+//
+// Warp roles (576 threads): per pipeline 8 epilogue warps (two per TMEM lane quarter, splitting the 32-column
+// chunks of an accumulator region) and one MMA-issuer warp.  Synchronisation is mbarrier-only on the hot
+// path: the issuer commits a step's MMAs to `full_d`; epilogue warps drain chunk by chunk and arrive on
+// `chunk_ready[c]` as soon as chunk c has been rewritten as the next A operand, so the issuer starts the next
+// layer's k-steps on chunk c while later chunks are still being converted (the MMA latency hides behind the
+// epilogue instead of adding to it).
 #include <cmath>
 #include <cstring>
 
@@ -36,7 +42,7 @@
 namespace {
 
 constexpr int TILE = 128;      // rows per tile = MMA M
-constexpr int GROUP_T = 256;   // threads per pipeline: 2 warps per TMEM lane quarter, splitting the columns
+constexpr int GROUP_T = 256;   // epilogue threads per pipeline: 2 warps per TMEM lane quarter, splitting the columns
 constexpr int MAX_KITER = 40;  // k-steps of all MMAs of one program (28 for the CMS AE)
 constexpr int MAX_STEPS = 6;
 constexpr int REG_X = 0, REG_Y = 112, REG_Z = 224, PIPE_COLS = 256;
@@ -47,6 +53,7 @@ struct TcMma {
   uint32_t b_hi, b_lo;     // smem byte offsets of the hi / lo weight images (already offset for N splits)
   uint32_t lbo;            // byte distance between the two 8-element K chunks of one k-step = Npad * 16
   int n, d_col, acc;       // MMA N, accumulator region, accumulate onto existing D
+  int dep;                 // A operand is produced chunk by chunk by the previous step's epilogue
 };
 struct TcEpi {
   int col, w;              // accumulator region to drain
@@ -94,7 +101,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GROUP_T) : "memory"); }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -170,8 +176,31 @@ __device__ __forceinline__ void a_cols(int col, int w, int s, uint32_t& hi, uint
 
 // ------------------------------------------------------------------------------------------------ kernel
 // One k-step of the issue table: TMEM columns (relative to the pipeline) and the low descriptor words.
-struct __align__(16) KIter { uint32_t a_hi, a_lo, b_hi, b_lo, d_acc, idesc, pad0, pad1; };
+struct __align__(16) KIter { uint32_t a_hi, a_lo, b_hi, b_lo, d_acc, idesc, wait, pad; };
 constexpr uint32_t B_DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1 (bit 46)
+constexpr int MAX_CHUNKS = 4;                             // 32-column chunks of the widest accumulator region (112)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): two elements per instruction
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo32(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi32(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
 // drain CW accumulator columns: scale, activation, split into fp16 hi|lo, write back in place
 template <int CW, int ACT>
@@ -179,17 +208,26 @@ __device__ __forceinline__ void epi_chunk_inplace(const uint32_t taddr, const fl
   uint32_t v[32], pk[32];
   if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
   tc_wait_ld();
-  const float s2 = ACT == BB_ACT_LEAKY ? scale * BB_LEAKY : 0.f;
+  const uint64_t c1 = pack2(scale, scale), c2 = pack2(scale * BB_LEAKY, scale * BB_LEAKY);
 #pragma unroll
   for (int j = 0; j < CW / 2; ++j) {
-    float a = __uint_as_float(v[2 * j]) * scale, b = __uint_as_float(v[2 * j + 1]) * scale;
+    const uint64_t vv = pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+    const uint64_t sv = mul2(vv, c1);
+    float a = lo32(sv), b = hi32(sv);
     if constexpr (ACT == BB_ACT_LEAKY) {
-      a = fmaxf(a, __uint_as_float(v[2 * j]) * s2);
-      b = fmaxf(b, __uint_as_float(v[2 * j + 1]) * s2);
+      const uint64_t lv = mul2(vv, c2);
+      a = fmaxf(a, lo32(lv)); b = fmaxf(b, hi32(lv));
     } else if constexpr (ACT == BB_ACT_RELU) {
       a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
     }
-    split2(a, b, pk[j], pk[CW / 2 + j]);
+    // hi = top 11 significant bits (truncated so that x - hi is exact in fp32), lo = fp16_rn(x - hi)
+    const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+    const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+    const uint64_t dl = sub2(pack2(a, b), pack2(ah, bh));
+    const __half2 h = __floats2half2_rn(ah, bh);
+    const __half2 l = __floats2half2_rn(lo32(dl), hi32(dl));
+    pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+    pk[CW / 2 + j] = *reinterpret_cast<const uint32_t*>(&l);
   }
   if constexpr (CW == 32) { tmem_st16(taddr, pk, 0); tmem_st16(taddr + 16, pk, 16); }
   else { tmem_st8(taddr, pk, 0); tmem_st8(taddr + 8, pk, 8); }
@@ -203,37 +241,47 @@ __device__ __forceinline__ void epi_chunk_dispatch(const uint32_t taddr, const f
 }
 
 template <int NGROUPS>
-__global__ void __launch_bounds__(NGROUPS * GROUP_T, 1)
+__global__ void __launch_bounds__(NGROUPS * (GROUP_T + 32), 1)
 chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restrict__ wimg, const void* __restrict__ in,
                 const int in_dtype, const int in_aligned, const int64_t n_rows, const float* __restrict__ pre_min,
                 const float* __restrict__ pre_range, const float* __restrict__ post_min,
                 const float* __restrict__ post_range, void* __restrict__ out, const int out_dtype, const int fast,
                 int* __restrict__ flag, const int dbg_step, float* __restrict__ dbg_out) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[1 + NGROUPS];
+  // per pipeline: [0] full_d (MMA -> epilogue), [1] a1_ready (loader -> MMA), [2..5] chunk_ready (epilogue -> MMA)
+  __shared__ __align__(8) uint64_t bars[1 + NGROUPS * (2 + MAX_CHUNKS)];
   __shared__ uint32_t tmem_base_s;
   __shared__ KIter kit[MAX_KITER];
   __shared__ int kit_begin[MAX_STEPS + 1];
   __shared__ float norm_s[4][32];  // pre_min, pre_range, post_min, post_range (first 32 features)
 
   const int tid = threadIdx.x;
-  const int g = tid / GROUP_T;            // pipeline index
-  const int tg = tid - g * GROUP_T;       // thread within the pipeline
+  const int warp = tid >> 5;
+  const bool is_mma = warp >= NGROUPS * (GROUP_T / 32);
+  const int g = is_mma ? warp - NGROUPS * (GROUP_T / 32) : warp / (GROUP_T / 32);  // pipeline index
+  const int tg = tid - g * GROUP_T;       // epilogue thread within the pipeline
   const int row = tg & (TILE - 1);        // tile row == TMEM lane
-  const int half = tg >> 7;               // which half of the column chunks this warp drains
+  const int half = (tg >> 7) & 1;         // which half of the column chunks this warp drains
   const int in_dim = prog.in_dim, out_dim = prog.out_dim;
   const int in_esz = in_dtype == BB_F16 ? 2 : 4;
   const uint32_t in_stage_bytes = (uint32_t)((TILE * in_dim * in_esz + 127) & ~127);
   const uint32_t out_stage_bytes = (uint32_t)((TILE * prog.out_stride * 4 + 127) & ~127);
   uint8_t* w_s = smem;
-  uint8_t* in_s = smem + prog.w_bytes + g * (in_stage_bytes + out_stage_bytes);
-  float* out_s = reinterpret_cast<float*>(in_s + in_stage_bytes);
+  uint8_t* in_s0 = smem + prog.w_bytes + g * (2 * in_stage_bytes + out_stage_bytes);  // two input stages
+  float* out_s = reinterpret_cast<float*>(in_s0 + 2 * in_stage_bytes);
   const uint32_t bar_w = smem_u32(&bars[0]);
-  const uint32_t bar_m = smem_u32(&bars[1 + g]);
+  const uint32_t bar_full = smem_u32(&bars[1 + g * (2 + MAX_CHUNKS)]);
+  const uint32_t bar_a1 = bar_full + 8;
+  const uint32_t bar_chunk0 = bar_full + 16;
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    for (int i = 0; i < NGROUPS; ++i) mbar_init(smem_u32(&bars[1 + i]), 1);
+    for (int i = 0; i < NGROUPS; ++i) {
+      const uint32_t b0 = smem_u32(&bars[1 + i * (2 + MAX_CHUNKS)]);
+      mbar_init(b0, 1);                      // full_d: one tcgen05.commit
+      mbar_init(b0 + 8, GROUP_T / 32);       // a1_ready: every epilogue warp
+      for (int c = 0; c < MAX_CHUNKS; ++c) mbar_init(b0 + 16 + 8 * c, 4);  // chunk_ready: the 4 warps of one half
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // issue table: every k-step of every MMA of the program, in issue order
     int n = 0;
@@ -250,7 +298,8 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
           e.b_lo = (((smem_u32(w_s) + mm.b_lo + koff) >> 4) & 0x3FFF) | lbo_f;
           e.d_acc = (uint32_t)mm.d_col | ((k > 0 || mm.acc) ? 0x80000000u : 0u);
           e.idesc = make_idesc(mm.n);
-          e.pad0 = e.pad1 = 0;
+          e.wait = (mm.dep && (k & 1) == 0) ? (uint32_t)(k >> 1) + 1u : 0u;  // first k-step of a 32-column chunk
+          e.pad = 0;
           kit[n] = e;
         }
       }
@@ -281,150 +330,177 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
 
   const int64_t n_tiles = (n_rows + TILE - 1) / TILE;
   const int64_t tile_stride = (int64_t)gridDim.x * NGROUPS;
-  const uint32_t lane_addr = (uint32_t)((row & ~31) << 16);  // TMEM lane base of this warp (32 lanes per warp)
+  const int64_t tile0 = (int64_t)blockIdx.x * NGROUPS + g;
   const uint32_t tcol0 = tmem_base + g * PIPE_COLS;
-  const bool has_pre = pre_min != nullptr, has_post = post_min != nullptr;
 
-  // cooperative copy of one input tile into the stage (16-byte cp.async when aligned and full)
-  auto fetch = [&](int64_t tile) {
-    const int rows = (int)min((int64_t)TILE, n_rows - tile * TILE);
-    const size_t base = (size_t)tile * TILE * in_dim * in_esz;
-    const int bytes = rows * in_dim * in_esz;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + base;
-    if (in_aligned && rows == TILE) {
-      for (int c = tg * 16; c < bytes; c += GROUP_T * 16) cp_async16(smem_u32(in_s + c), src + c);
-    } else if (in_esz == 4) {
-      for (int e = tg; e < bytes / 4; e += GROUP_T) reinterpret_cast<float*>(in_s)[e] = reinterpret_cast<const float*>(src)[e];
-    } else {
-      for (int e = tg; e < bytes / 2; e += GROUP_T) reinterpret_cast<__half*>(in_s)[e] = reinterpret_cast<const __half*>(src)[e];
-    }
-    cp_async_commit();
-  };
-
-  int64_t tile = (int64_t)blockIdx.x * NGROUPS + g;
-  if (tile < n_tiles) fetch(tile);
-  mbar_wait(bar_w, 0);  // weights resident
-  uint32_t parity = 0;
-
-  for (; tile < n_tiles; tile += tile_stride) {
-    const int rows = (int)min((int64_t)TILE, n_rows - tile * TILE);
-    cp_async_wait_all();
-    group_bar(1 + g);
-    // ---- A1: this thread's row, k-step `half` (16 features) -> normalise -> 1.0 in the bias slot -> split -> TMEM
-    if (half * 16 < prog.a1_w) {
-      uint32_t pk[32];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k = half * 16 + 2 * j + h;
-          float x = 0.f;
-          if (k < in_dim) {
-            if (row < rows) {
-              x = in_esz == 4 ? reinterpret_cast<const float*>(in_s)[row * in_dim + k]
-                              : __half2float(reinterpret_cast<const __half*>(in_s)[row * in_dim + k]);
-              // numpy float32: (x - min) / range with IEEE division (data_processing.py:151)
-              if (has_pre) x = __fdiv_rn(__fsub_rn(x, norm_s[0][k]), norm_s[1][k]);
-            }
-          } else if (k == in_dim) {
-            x = 1.f;
-          }
-          v[h] = x;
-        }
-        split2(v[0], v[1], pk[j], pk[8 + j]);
-      }
-      // k-step s of a 32-wide chunk: hi words at +8s, lo words at +16+8s; a 16-wide chunk: hi +0, lo +8
-      const uint32_t taddr = tcol0 + lane_addr + prog.a1_col + (prog.a1_w >= 32 ? half * 8 : 0);
-      tmem_st8(taddr, pk, 0);
-      tmem_st8(taddr + (prog.a1_w >= 32 ? 16 : 8), pk, 8);
-      tc_wait_st();
-    }
-    tc_fence_before();
-    group_bar(1 + g);
-    {  // the stage is free again: prefetch this pipeline's next tile while the layers run
-      const int64_t nxt = tile + tile_stride;
-      if (nxt < n_tiles) fetch(nxt);
-    }
-
-    for (int s = 0; s < prog.n_steps; ++s) {
-      if (tg == 0) {  // one thread issues the MMAs of this step for its pipeline
+  if (is_mma) {
+    // ================================================================== MMA issuer (one lane per pipeline)
+    if ((tid & 31) == 0) {
+      mbar_wait(bar_w, 0);  // weights resident
+      uint32_t par_a1 = 0, par_chunk = 0;
+      for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+        mbar_wait(bar_a1, par_a1);
+        par_a1 ^= 1u;
         tc_fence_after();
-        const int e1 = kit_begin[s + 1];
-        for (int e = kit_begin[s]; e < e1; ++e) {
-          const uint4 p0 = *reinterpret_cast<const uint4*>(&kit[e]);
-          const uint2 p1 = *reinterpret_cast<const uint2*>(&kit[e].d_acc);
-          const uint64_t bh = ((uint64_t)B_DESC_HI << 32) | p0.z;
-          const uint32_t d = tcol0 + (p1.x & 0xFFFF);
-          tc_mma_ts(d, tcol0 + p0.x, bh, p1.y, p1.x >> 31);
-          if (!fast) {
-            const uint64_t bl = ((uint64_t)B_DESC_HI << 32) | p0.w;
-            tc_mma_ts(d, tcol0 + p0.x, bl, p1.y, 1u);
-            tc_mma_ts(d, tcol0 + p0.y, bh, p1.y, 1u);
+        for (int s = 0; s < prog.n_steps; ++s) {
+          const int e1 = kit_begin[s + 1];
+          for (int e = kit_begin[s]; e < e1; ++e) {
+            const uint4 p0 = *reinterpret_cast<const uint4*>(&kit[e]);
+            const uint4 p1 = *reinterpret_cast<const uint4*>(&kit[e].d_acc);
+            if (p1.z) {  // this k-step opens a chunk the previous step's epilogue is still producing
+              const uint32_t c = p1.z - 1u;
+              mbar_wait(bar_chunk0 + 8u * c, (par_chunk >> c) & 1u);
+              par_chunk ^= 1u << c;
+              tc_fence_after();
+            }
+            const uint64_t bh = ((uint64_t)B_DESC_HI << 32) | p0.z;
+            const uint32_t d = tcol0 + (p1.x & 0xFFFF);
+            tc_mma_ts(d, tcol0 + p0.x, bh, p1.y, p1.x >> 31);
+            if (!fast) {
+              const uint64_t bl = ((uint64_t)B_DESC_HI << 32) | p0.w;
+              tc_mma_ts(d, tcol0 + p0.x, bl, p1.y, 1u);
+              tc_mma_ts(d, tcol0 + p0.y, bh, p1.y, 1u);
+            }
           }
+          tc_commit(bar_full);
         }
-        tc_commit(bar_m);
       }
-      mbar_wait(bar_m, parity);
-      parity ^= 1u;
-      tc_fence_after();
+    }
+    __syncwarp();
+  } else {
+    // ================================================================== loader + epilogue warps
+    const uint32_t lane_addr = (uint32_t)((row & ~31) << 16);  // TMEM lane base of this warp (32 lanes per warp)
+    const bool has_pre = pre_min != nullptr, has_post = post_min != nullptr;
+    const int bar_id = 1 + g;
 
-      // ---- epilogue: drain the accumulator region; either re-split in place or emit the output row
-      const TcEpi& ep = prog.step[s].epi;
-      const int ep_w = ep.w, ep_col = ep.col, ep_act = ep.act;
-      const float ep_scale = ep.scale;
-      if (dbg_out != nullptr && dbg_step == s && half == 0) {  // test hook: scaled accumulator
-        for (int c0 = 0; c0 < ep_w; c0 += 16) {
-          uint32_t v[32];
-          tmem_ld16(tcol0 + lane_addr + ep_col + c0, v);  // .sync.aligned: the whole warp, also rows past the tail
-          tc_wait_ld();
-          if (row < rows) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) dbg_out[((size_t)tile * TILE + row) * ep_w + c0 + j] = __uint_as_float(v[j]) * ep_scale;
-          }
-        }
+    // cooperative copy of one input tile into a stage (16-byte cp.async when aligned and full)
+    auto fetch = [&](int64_t tile, uint8_t* dst) {
+      const int rows = (int)min((int64_t)TILE, n_rows - tile * TILE);
+      const size_t base = (size_t)tile * TILE * in_dim * in_esz;
+      const int bytes = rows * in_dim * in_esz;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + base;
+      if (in_aligned && rows == TILE) {
+        for (int c = tg * 16; c < bytes; c += GROUP_T * 16) cp_async16(smem_u32(dst + c), src + c);
+      } else if (in_esz == 4) {
+        for (int e = tg; e < bytes / 4; e += GROUP_T) reinterpret_cast<float*>(dst)[e] = reinterpret_cast<const float*>(src)[e];
+      } else {
+        for (int e = tg; e < bytes / 2; e += GROUP_T) reinterpret_cast<__half*>(dst)[e] = reinterpret_cast<const __half*>(src)[e];
       }
-      if (dbg_out != nullptr) group_bar(1 + g);  // the dump must read before the in-place rewrite of the other half
-      if (!ep.final) {
-        for (int c0 = half * 32; c0 < ep_w; c0 += 64) {
-          const uint32_t taddr = tcol0 + lane_addr + ep_col + c0;
-          if (ep_w - c0 >= 32) epi_chunk_dispatch<32>(taddr, ep_scale, ep_act);
-          else epi_chunk_dispatch<16>(taddr, ep_scale, ep_act);
-        }
-        tc_wait_st();
-      } else if (half == 0) {
-        uint32_t v[32];
-        const uint32_t taddr = tcol0 + lane_addr + ep_col;
-        if (ep_w > 16) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-        tc_wait_ld();
-        bool bad = false;
+    };
+
+    if (tile0 < n_tiles) fetch(tile0, in_s0);
+    cp_async_commit();
+    uint32_t parity = 0, stage = 0;
+
+    for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, stage ^= 1u) {
+      const int rows = (int)min((int64_t)TILE, n_rows - tile * TILE);
+      const uint8_t* in_s = in_s0 + stage * in_stage_bytes;
+      {  // prefetch this pipeline's next tile into the other stage, then wait for the current one
+        const int64_t nxt = tile + tile_stride;
+        if (nxt < n_tiles) fetch(nxt, in_s0 + (stage ^ 1u) * in_stage_bytes);
+        cp_async_commit();
+        cp_async_wait_1();
+      }
+      group_bar(bar_id);
+      // ---- A1: this thread's row, k-step `half` (16 features) -> normalise -> 1.0 in the bias slot -> split -> TMEM
+      if (half * 16 < prog.a1_w) {
+        uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < out_dim && j < ep_w) {
-            float y = act_apply(__uint_as_float(v[j]) * ep_scale, ep_act);
-            bad |= !(fabsf(y) <= 3.0e38f);  // inf / NaN: an fp16 operand overflowed somewhere upstream
-            if (has_post) y = fmaf(y, norm_s[3][j], norm_s[2][j]);  // y * range + min (data_processing.py:203)
-            out_s[row * prog.out_stride + j] = y;
+        for (int j = 0; j < 8; ++j) {
+          float v[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = half * 16 + 2 * j + h;
+            float x = 0.f;
+            if (k < in_dim) {
+              if (row < rows) {
+                x = in_esz == 4 ? reinterpret_cast<const float*>(in_s)[row * in_dim + k]
+                                : __half2float(reinterpret_cast<const __half*>(in_s)[row * in_dim + k]);
+                // numpy float32: (x - min) / range with IEEE division (data_processing.py:151)
+                if (has_pre) x = __fdiv_rn(__fsub_rn(x, norm_s[0][k]), norm_s[1][k]);
+              }
+            } else if (k == in_dim) {
+              x = 1.f;
+            }
+            v[h] = x;
           }
+          split2(v[0], v[1], pk[j], pk[8 + j]);
         }
-        if (bad && row < rows) atomicOr(flag, 1);
+        // k-step s of a 32-wide chunk: hi words at +8s, lo words at +16+8s; a 16-wide chunk: hi +0, lo +8
+        const uint32_t taddr = tcol0 + lane_addr + prog.a1_col + (prog.a1_w >= 32 ? half * 8 : 0);
+        tmem_st8(taddr, pk, 0);
+        tmem_st8(taddr + (prog.a1_w >= 32 ? 16 : 8), pk, 8);
+        tc_wait_st();
       }
       tc_fence_before();
-      group_bar(1 + g);
-    }
-    // ---- coalesced store of the output tile
-    {
-      const size_t base = (size_t)tile * TILE * out_dim;
-      const int n_el = rows * out_dim;
-      for (int e = tg; e < n_el; e += GROUP_T) {
-        const int r = e / out_dim, c = e - r * out_dim;
-        const float y = out_s[r * prog.out_stride + c];
-        if (out_dtype == BB_F16) reinterpret_cast<__half*>(out)[base + e] = __float2half_rn(y);
-        else reinterpret_cast<float*>(out)[base + e] = y;
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(bar_a1);
+
+      for (int s = 0; s < prog.n_steps; ++s) {
+        mbar_wait(bar_full, parity);  // the accumulator of step s is complete
+        parity ^= 1u;
+        tc_fence_after();
+        const TcEpi& ep = prog.step[s].epi;
+        const int ep_w = ep.w, ep_col = ep.col, ep_act = ep.act;
+        const float ep_scale = ep.scale;
+        if (dbg_out != nullptr) {  // test hook: dump the scaled accumulator before it is rewritten in place
+          if (dbg_step == s && half == 0) {
+            for (int c0 = 0; c0 < ep_w; c0 += 16) {
+              uint32_t v[32];
+              tmem_ld16(tcol0 + lane_addr + ep_col + c0, v);  // .sync.aligned: the whole warp, also rows past the tail
+              tc_wait_ld();
+              if (row < rows) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dbg_out[((size_t)tile * TILE + row) * ep_w + c0 + j] = __uint_as_float(v[j]) * ep_scale;
+              }
+            }
+          }
+          group_bar(bar_id);
+        }
+        if (!ep.final) {
+          for (int c0 = half * 32; c0 < ep_w; c0 += 64) {
+            const uint32_t taddr = tcol0 + lane_addr + ep_col + c0;
+            if (ep_w - c0 >= 32) epi_chunk_dispatch<32>(taddr, ep_scale, ep_act);
+            else epi_chunk_dispatch<16>(taddr, ep_scale, ep_act);
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_chunk0 + 8u * (uint32_t)(c0 >> 5));  // chunk c0/32 is a valid A operand now
+          }
+        } else if (half == 0) {
+          uint32_t v[32];
+          const uint32_t taddr = tcol0 + lane_addr + ep_col;
+          if (ep_w > 16) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+          tc_wait_ld();
+          bool bad = false;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < out_dim && j < ep_w) {
+              float y = act_apply(__uint_as_float(v[j]) * ep_scale, ep_act);
+              bad |= !(fabsf(y) <= 3.0e38f);  // inf / NaN: an fp16 operand overflowed somewhere upstream
+              if (has_post) y = fmaf(y, norm_s[3][j], norm_s[2][j]);  // y * range + min (data_processing.py:203)
+              out_s[row * prog.out_stride + j] = y;
+            }
+          }
+          if (bad && row < rows) atomicOr(flag, 1);
+        }
+      }
+      tc_fence_before();
+      group_bar(bar_id);
+      // ---- coalesced store of the output tile
+      {
+        const size_t base = (size_t)tile * TILE * out_dim;
+        const int n_el = rows * out_dim;
+        for (int e = tg; e < n_el; e += GROUP_T) {
+          const int r = e / out_dim, c = e - r * out_dim;
+          const float y = out_s[r * prog.out_stride + c];
+          if (out_dtype == BB_F16) reinterpret_cast<__half*>(out)[base + e] = __float2half_rn(y);
+          else reinterpret_cast<float*>(out)[base + e] = y;
+        }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
-  cp_async_wait_all();
   tc_fence_before();
   __syncthreads();
   if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -511,7 +587,7 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
     TcMma m;
     m.a_col = a_col; m.a_w = a_w; m.ks0 = ks0; m.ks_n = ks_n;
     m.b_hi = b_hi[l] + (uint32_t)n0 * 16; m.b_lo = b_lo[l] + (uint32_t)n0 * 16;
-    m.lbo = (uint32_t)Np[l] * 16; m.n = n; m.d_col = d_col; m.acc = acc;
+    m.lbo = (uint32_t)Np[l] * 16; m.n = n; m.d_col = d_col; m.acc = acc; m.dep = 0;
     return m;
   };
   auto epi = [&](int l, int col, int w, int fin) {
@@ -539,11 +615,15 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
     p.step[s].n_mma = 1; p.step[s].mma[0] = mma(3, REG_X, nb, na / 16, nb / 16, 0, Np[3], REG_Z, 1); p.step[s].epi = epi(3, REG_Z, Np[3], 1); ++s;
   }
   p.n_steps = s;
+  // an MMA whose A region is the accumulator the previous step's epilogue rewrites in place can start chunk by chunk
+  for (int i = 1; i < s; ++i)
+    for (int m = 0; m < p.step[i].n_mma; ++m)
+      p.step[i].mma[m].dep = (!p.step[i - 1].epi.final && p.step[i].mma[m].a_col == p.step[i - 1].epi.col) ? 1 : 0;
   // ---- shared memory: weight image + per pipeline (input stage + output stage); prefer two pipelines
   auto smem_need = [&](int groups, int in_esz) {
     const size_t in_b = ((size_t)TILE * d.in_dim * in_esz + 127) & ~(size_t)127;
     const size_t out_b = ((size_t)TILE * p.out_stride * 4 + 127) & ~(size_t)127;
-    return (size_t)p.w_bytes + groups * (in_b + out_b);
+    return (size_t)p.w_bytes + groups * (2 * in_b + out_b);
   };
   h->n_groups = smem_need(2, 4) + 1024 <= ctx->smem_optin ? 2 : (smem_need(1, 4) + 1024 <= ctx->smem_optin ? 1 : 0);
   if (h->n_groups == 0 || (p.w_bytes & 15)) { delete h; return BB_ERR_UNSUPPORTED; }
@@ -578,11 +658,11 @@ int bb_tc_launch_dbg(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, 
   const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
   const int aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
   if (groups == 2)
-    chain_tc_kernel<2><<<grid, 2 * GROUP_T, h->smem_bytes, stream>>>(h->prog, (const uint8_t*)c->tc_blob_dev, in, in_dtype, aligned,
+    chain_tc_kernel<2><<<grid, 2 * (GROUP_T + 32), h->smem_bytes, stream>>>(h->prog, (const uint8_t*)c->tc_blob_dev, in, in_dtype, aligned,
                                                                      n_rows, pre_min, pre_range, post_min, post_range, out,
                                                                      out_dtype, fast, flag_dev, dbg_step, dbg_out);
   else
-    chain_tc_kernel<1><<<grid, GROUP_T, h->smem_bytes, stream>>>(h->prog, (const uint8_t*)c->tc_blob_dev, in, in_dtype, aligned,
+    chain_tc_kernel<1><<<grid, GROUP_T + 32, h->smem_bytes, stream>>>(h->prog, (const uint8_t*)c->tc_blob_dev, in, in_dtype, aligned,
                                                                  n_rows, pre_min, pre_range, post_min, post_range, out,
                                                                  out_dtype, fast, flag_dev, dbg_step, dbg_out);
   return (int)cudaGetLastError();
