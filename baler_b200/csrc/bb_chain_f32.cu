@@ -220,11 +220,11 @@ int bb_chain_f32_prepare(bb_ctx* ctx, Chain* c) {
   if (c->blob_dev) cudaFree(c->blob_dev);
   BB_CUDA(cudaMalloc(&c->blob_dev, blob.size() * sizeof(float)));
   BB_CUDA(cudaMemcpy(c->blob_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
-  switch (chosen) {
-    case 80: BB_CUDA(cudaFuncSetAttribute(chain_f32_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes)); break;
-    case 64: BB_CUDA(cudaFuncSetAttribute(chain_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes)); break;
-    default: BB_CUDA(cudaFuncSetAttribute(chain_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes)); break;
-  }
+  // the attribute belongs to the kernel, not to this chain (encoder and decoder share it): allow the device maximum
+  const int max_dyn = (int)ctx->smem_optin;
+  BB_CUDA(cudaFuncSetAttribute(chain_f32_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  BB_CUDA(cudaFuncSetAttribute(chain_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  BB_CUDA(cudaFuncSetAttribute(chain_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   return BB_OK;
 }
 

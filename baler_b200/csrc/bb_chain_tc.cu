@@ -35,6 +35,7 @@
 // layer's k-steps on chunk c while later chunks are still being converted (the MMA latency hides behind the
 // epilogue instead of adding to it).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "bb_common.cuh"
@@ -64,6 +65,7 @@ struct TcStep { int n_mma; TcMma mma[2]; TcEpi epi; };
 struct TcProgram {
   int n_steps, in_dim, out_dim;
   int a1_col, a1_w;        // where the loader puts the first A operand (a1_w = padded K of layer 0)
+  int a1_after_step;       // that region is free for the NEXT tile once full_d of this step has been observed
   int out_stride;          // floats per row in the output stage (odd -> conflict-free)
   uint32_t w_bytes;        // size of the resident weight image
   TcStep step[MAX_STEPS];
@@ -107,18 +109,6 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T, M = 128, K = 16, fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-
 #define TC_REGS16(v, o) "=r"(v[o+0]), "=r"(v[o+1]), "=r"(v[o+2]), "=r"(v[o+3]), "=r"(v[o+4]), "=r"(v[o+5]), "=r"(v[o+6]), "=r"(v[o+7]), \
                         "=r"(v[o+8]), "=r"(v[o+9]), "=r"(v[o+10]), "=r"(v[o+11]), "=r"(v[o+12]), "=r"(v[o+13]), "=r"(v[o+14]), "=r"(v[o+15])
 #define TC_IN8(v, o) "r"(v[o+0]), "r"(v[o+1]), "r"(v[o+2]), "r"(v[o+3]), "r"(v[o+4]), "r"(v[o+5]), "r"(v[o+6]), "r"(v[o+7])
@@ -248,10 +238,11 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
                 const float* __restrict__ post_range, void* __restrict__ out, const int out_dtype, const int fast,
                 int* __restrict__ flag, const int dbg_step, float* __restrict__ dbg_out) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // per pipeline: [0] full_d (MMA -> epilogue), [1] a1_ready (loader -> MMA), [2..5] chunk_ready (epilogue -> MMA)
-  __shared__ __align__(8) uint64_t bars[1 + NGROUPS * (2 + MAX_CHUNKS)];
+  // per pipeline: [0,1] full_d of even / odd tiles (MMA -> epilogue; two so that the issuer may run one tile
+  // ahead without phase aliasing), [2] a1_ready (loader -> MMA), [3..6] chunk_ready (epilogue -> MMA)
+  __shared__ __align__(8) uint64_t bars[1 + NGROUPS * (3 + MAX_CHUNKS)];
   __shared__ uint32_t tmem_base_s;
-  __shared__ KIter kit[MAX_KITER];
+  __shared__ KIter kit[MAX_KITER + 1];  // + one spare slot: the issuer prefetches entry e + 1
   __shared__ int kit_begin[MAX_STEPS + 1];
   __shared__ float norm_s[4][32];  // pre_min, pre_range, post_min, post_range (first 32 features)
 
@@ -270,17 +261,18 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
   uint8_t* in_s0 = smem + prog.w_bytes + g * (2 * in_stage_bytes + out_stage_bytes);  // two input stages
   float* out_s = reinterpret_cast<float*>(in_s0 + 2 * in_stage_bytes);
   const uint32_t bar_w = smem_u32(&bars[0]);
-  const uint32_t bar_full = smem_u32(&bars[1 + g * (2 + MAX_CHUNKS)]);
-  const uint32_t bar_a1 = bar_full + 8;
-  const uint32_t bar_chunk0 = bar_full + 16;
+  const uint32_t bar_full = smem_u32(&bars[1 + g * (3 + MAX_CHUNKS)]);  // + 8 * (tile parity)
+  const uint32_t bar_a1 = bar_full + 16;
+  const uint32_t bar_chunk0 = bar_full + 24;
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
     for (int i = 0; i < NGROUPS; ++i) {
-      const uint32_t b0 = smem_u32(&bars[1 + i * (2 + MAX_CHUNKS)]);
-      mbar_init(b0, 1);                      // full_d: one tcgen05.commit
-      mbar_init(b0 + 8, GROUP_T / 32);       // a1_ready: every epilogue warp
-      for (int c = 0; c < MAX_CHUNKS; ++c) mbar_init(b0 + 16 + 8 * c, 4);  // chunk_ready: the 4 warps of one half
+      const uint32_t b0 = smem_u32(&bars[1 + i * (3 + MAX_CHUNKS)]);
+      mbar_init(b0, 1);                      // full_d (even tiles): one tcgen05.commit
+      mbar_init(b0 + 8, 1);                  // full_d (odd tiles)
+      mbar_init(b0 + 16, GROUP_T / 32);      // a1_ready: every epilogue warp
+      for (int c = 0; c < MAX_CHUNKS; ++c) mbar_init(b0 + 24 + 8 * c, 4);  // chunk_ready: the 4 warps of one half
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // issue table: every k-step of every MMA of the program, in issue order
@@ -310,7 +302,9 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
     const int which = tid >> 5, k = tid & 31;
     const float* src = which == 0 ? pre_min : which == 1 ? pre_range : which == 2 ? post_min : post_range;
     const int dim = which < 2 ? in_dim : out_dim;
-    norm_s[which][k] = (src != nullptr && k < dim) ? src[k] : (which & 1 ? 1.f : 0.f);
+    float v = (src != nullptr && k < dim) ? src[k] : (which & 1 ? 1.f : 0.f);
+    if (which == 1) v = __frcp_rn(v);  // the loader multiplies by 1 / range
+    norm_s[which][k] = v;
   }
   if (tid < 32) {  // warp 0 owns the TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
@@ -332,37 +326,72 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
   const int64_t tile_stride = (int64_t)gridDim.x * NGROUPS;
   const int64_t tile0 = (int64_t)blockIdx.x * NGROUPS + g;
   const uint32_t tcol0 = tmem_base + g * PIPE_COLS;
+  // test hook, dbg_step == -2: SM-clock timestamps of the pipeline events of CTA 0 / pipeline 0, 64 slots per
+  // tile (0..31 epilogue warp 0, 32..63 MMA issuer), first 16 tiles
+  const bool tracing = dbg_out != nullptr && dbg_step == -2 && blockIdx.x == 0 && g == 0;
+  auto trace = [&](int64_t local_tile, int slot) {
+    if (tracing && local_tile < 16) reinterpret_cast<uint32_t*>(dbg_out)[local_tile * 64 + slot] = (uint32_t)clock64();
+  };
 
   if (is_mma) {
     // ================================================================== MMA issuer (one lane per pipeline)
-    if ((tid & 31) == 0) {
+    // The whole warp runs this loop converged (all values are warp-uniform); only the tcgen05 instructions are
+    // predicated on one elected lane.  A lane-0-only loop makes the compiler wrap every UTCHMMA in an
+    // ELECT / R2UR / BRA.U.ANY serialisation sequence (~130 cycles per MMA).
+    {
       mbar_wait(bar_w, 0);  // weights resident
       uint32_t par_a1 = 0, par_chunk = 0;
-      for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+      int64_t lt = 0;
+      const int n_steps = prog.n_steps;
+      const bool lane0 = (tid & 31) == 0;
+      for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, ++lt) {
+        if (lane0) trace(lt, 32);
         mbar_wait(bar_a1, par_a1);
         par_a1 ^= 1u;
         tc_fence_after();
-        for (int s = 0; s < prog.n_steps; ++s) {
+        if (lane0) trace(lt, 33);
+        int e = 0;
+        for (int s = 0; s < n_steps; ++s) {
           const int e1 = kit_begin[s + 1];
-          for (int e = kit_begin[s]; e < e1; ++e) {
-            const uint4 p0 = *reinterpret_cast<const uint4*>(&kit[e]);
-            const uint4 p1 = *reinterpret_cast<const uint4*>(&kit[e].d_acc);
-            if (p1.z) {  // this k-step opens a chunk the previous step's epilogue is still producing
-              const uint32_t c = p1.z - 1u;
+          for (; e < e1; ++e) {
+            const uint4 q0 = *reinterpret_cast<const uint4*>(&kit[e]);
+            const uint4 q1 = *reinterpret_cast<const uint4*>(&kit[e].d_acc);
+            if (q1.z) {  // this k-step opens a chunk the previous step's epilogue is still producing
+              const uint32_t c = q1.z - 1u;
               mbar_wait(bar_chunk0 + 8u * c, (par_chunk >> c) & 1u);
               par_chunk ^= 1u << c;
               tc_fence_after();
+              if (lane0) trace(lt, 34 + 5 * s + (int)c);
             }
-            const uint64_t bh = ((uint64_t)B_DESC_HI << 32) | p0.z;
-            const uint32_t d = tcol0 + (p1.x & 0xFFFF);
-            tc_mma_ts(d, tcol0 + p0.x, bh, p1.y, p1.x >> 31);
+            // hi*hi (accumulate flag from the table), then hi*lo and lo*hi (always accumulate)
             if (!fast) {
-              const uint64_t bl = ((uint64_t)B_DESC_HI << 32) | p0.w;
-              tc_mma_ts(d, tcol0 + p0.x, bl, p1.y, 1u);
-              tc_mma_ts(d, tcol0 + p0.y, bh, p1.y, 1u);
+              asm volatile(
+                  "{\n\t.reg .pred e, p, t;\n\t.reg .b64 bh, bl;\n\t"
+                  "elect.sync _|e, 0xffffffff;\n\t"
+                  "setp.ne.b32 p, %6, 0;\n\t"
+                  "setp.eq.b32 t, %6, %6;\n\t"
+                  "mov.b64 bh, {%2, %7};\n\t"
+                  "mov.b64 bl, {%3, %7};\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%4], [%0], bh, %5, p;\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%4], [%0], bl, %5, t;\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%4], [%1], bh, %5, t;\n\t}"
+                  ::"r"(tcol0 + q0.x), "r"(tcol0 + q0.y), "r"(q0.z), "r"(q0.w), "r"(tcol0 + (q1.x & 0xFFFF)), "r"(q1.y),
+                    "r"(q1.x >> 31), "r"(B_DESC_HI) : "memory");
+            } else {
+              asm volatile(
+                  "{\n\t.reg .pred e, p;\n\t.reg .b64 bh;\n\t"
+                  "elect.sync _|e, 0xffffffff;\n\t"
+                  "setp.ne.b32 p, %4, 0;\n\t"
+                  "mov.b64 bh, {%1, %5};\n\t"
+                  "@e tcgen05.mma.cta_group::1.kind::f16 [%2], [%0], bh, %3, p;\n\t}"
+                  ::"r"(tcol0 + q0.x), "r"(q0.z), "r"(tcol0 + (q1.x & 0xFFFF)), "r"(q1.y), "r"(q1.x >> 31), "r"(B_DESC_HI) : "memory");
             }
           }
-          tc_commit(bar_full);
+          asm volatile(
+              "{\n\t.reg .pred e;\n\t"
+              "elect.sync _|e, 0xffffffff;\n\t"
+              "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_full + 8u * (uint32_t)(lt & 1)) : "memory");
+          if (lane0) trace(lt, 34 + 5 * s + 4);
         }
       }
     }
@@ -388,44 +417,42 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
       }
     };
 
-    if (tile0 < n_tiles) fetch(tile0, in_s0);
-    cp_async_commit();
-    uint32_t parity = 0, stage = 0;
-
-    for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, stage ^= 1u) {
+    // first A operand of a tile: this thread's row, k-step `half` (16 features) -> normalise -> 1.0 in the bias
+    // slot -> split -> TMEM, then tell the issuer.
+    auto convert_a1 = [&](int64_t tile, const uint8_t* in_s) {
       const int rows = (int)min((int64_t)TILE, n_rows - tile * TILE);
-      const uint8_t* in_s = in_s0 + stage * in_stage_bytes;
-      {  // prefetch this pipeline's next tile into the other stage, then wait for the current one
-        const int64_t nxt = tile + tile_stride;
-        if (nxt < n_tiles) fetch(nxt, in_s0 + (stage ^ 1u) * in_stage_bytes);
-        cp_async_commit();
-        cp_async_wait_1();
-      }
-      group_bar(bar_id);
-      // ---- A1: this thread's row, k-step `half` (16 features) -> normalise -> 1.0 in the bias slot -> split -> TMEM
       if (half * 16 < prog.a1_w) {
         uint32_t pk[32];
+        float xv[16];
+        const int k0 = half * 16;
+        if (in_esz == 4 && (in_dim & 3) == 0) {  // 128-bit loads of this row's 16 features
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int k = half * 16 + 2 * j + h;
-            float x = 0.f;
-            if (k < in_dim) {
-              if (row < rows) {
-                x = in_esz == 4 ? reinterpret_cast<const float*>(in_s)[row * in_dim + k]
-                                : __half2float(reinterpret_cast<const __half*>(in_s)[row * in_dim + k]);
-                // numpy float32: (x - min) / range with IEEE division (data_processing.py:151)
-                if (has_pre) x = __fdiv_rn(__fsub_rn(x, norm_s[0][k]), norm_s[1][k]);
-              }
-            } else if (k == in_dim) {
-              x = 1.f;
-            }
-            v[h] = x;
+          for (int q = 0; q < 4; ++q) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + 4 * q < in_dim && row < rows) t = reinterpret_cast<const float4*>(in_s)[(row * in_dim + k0) / 4 + q];
+            xv[4 * q] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
           }
-          split2(v[0], v[1], pk[j], pk[8 + j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = k0 + j;
+            float x = 0.f;
+            if (k < in_dim && row < rows)
+              x = in_esz == 4 ? reinterpret_cast<const float*>(in_s)[row * in_dim + k]
+                              : __half2float(reinterpret_cast<const __half*>(in_s)[row * in_dim + k]);
+            xv[j] = x;
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = k0 + j;
+          // numpy float32 (x - min) / range (data_processing.py:151); here the quotient is x * rcp_rn(range):
+          // within 1 ulp of the IEEE quotient, far inside the 1e-5 budget of the latent
+          if (k < in_dim) { if (has_pre && row < rows) xv[j] = __fsub_rn(xv[j], norm_s[0][k]) * norm_s[1][k]; }
+          else xv[j] = k == in_dim ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split2(xv[2 * j], xv[2 * j + 1], pk[j], pk[8 + j]);
         // k-step s of a 32-wide chunk: hi words at +8s, lo words at +16+8s; a 16-wide chunk: hi +0, lo +8
         const uint32_t taddr = tcol0 + lane_addr + prog.a1_col + (prog.a1_w >= 32 ? half * 8 : 0);
         tmem_st8(taddr, pk, 0);
@@ -435,11 +462,38 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
       tc_fence_before();
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(bar_a1);
+    };
+
+    if (tile0 < n_tiles) fetch(tile0, in_s0);
+    cp_async_commit();
+    uint32_t parity2 = 0;  // bit p: phase parity of full_d[p]
+    int64_t lt = 0;
+    const bool tr0 = tg == 0;
+    // Variant tried and dropped: converting the NEXT tile's first operand mid-tile (as soon as its TMEM region is
+    // free) so the issuer runs a tile ahead.  TMEM loads queue in order behind every MMA already issued on the SM,
+    // so the run-ahead MMAs delayed the remaining epilogues by more than the loader latency they hid
+    // (2.81 vs 3.15 G rows/s, profiles/r01_tc_trace.md).
+
+    for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, ++lt) {
+      const int rows = (int)min((int64_t)TILE, n_rows - tile * TILE);
+      const uint32_t tp = (uint32_t)(lt & 1);
+      if (tr0) trace(lt, 0);
+      {  // prefetch this pipeline's next tile into the other stage, then wait for the current one
+        const int64_t nxt = tile + tile_stride;
+        if (nxt < n_tiles) fetch(nxt, in_s0 + (uint32_t)((lt + 1) & 1) * in_stage_bytes);
+        cp_async_commit();
+        cp_async_wait_1();
+      }
+      group_bar(bar_id);
+      if (tr0) trace(lt, 1);
+      convert_a1(tile, in_s0 + (uint32_t)(lt & 1) * in_stage_bytes);
+      if (tr0) trace(lt, 2);
 
       for (int s = 0; s < prog.n_steps; ++s) {
-        mbar_wait(bar_full, parity);  // the accumulator of step s is complete
-        parity ^= 1u;
+        mbar_wait(bar_full + 8u * tp, (parity2 >> tp) & 1u);  // the accumulator of step s is complete
+        parity2 ^= 1u << tp;
         tc_fence_after();
+        if (tr0) trace(lt, 3 + 4 * s);
         const TcEpi& ep = prog.step[s].epi;
         const int ep_w = ep.w, ep_col = ep.col, ep_act = ep.act;
         const float ep_scale = ep.scale;
@@ -466,6 +520,7 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
             tc_fence_before();
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar_chunk0 + 8u * (uint32_t)(c0 >> 5));  // chunk c0/32 is a valid A operand now
+            if (tr0) trace(lt, 4 + 4 * s + (c0 >> 6));
           }
         } else if (half == 0) {
           uint32_t v[32];
@@ -485,17 +540,23 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
           if (bad && row < rows) atomicOr(flag, 1);
         }
       }
+      if (tr0) trace(lt, 24);
       tc_fence_before();
       group_bar(bar_id);
-      // ---- coalesced store of the output tile
+      if (tr0) trace(lt, 25);
+      // ---- coalesced store of the output tile (the stage is dense row-major, so this is a flat copy)
       {
         const size_t base = (size_t)tile * TILE * out_dim;
         const int n_el = rows * out_dim;
-        for (int e = tg; e < n_el; e += GROUP_T) {
-          const int r = e / out_dim, c = e - r * out_dim;
-          const float y = out_s[r * prog.out_stride + c];
-          if (out_dtype == BB_F16) reinterpret_cast<__half*>(out)[base + e] = __float2half_rn(y);
-          else reinterpret_cast<float*>(out)[base + e] = y;
+        if (out_dtype == BB_F32 && rows == TILE && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + base);
+          for (int e = tg; e < n_el / 4; e += GROUP_T) dst[e] = reinterpret_cast<const float4*>(out_s)[e];
+        } else {
+          for (int e = tg; e < n_el; e += GROUP_T) {
+            const float y = out_s[e];
+            if (out_dtype == BB_F16) reinterpret_cast<__half*>(out)[base + e] = __float2half_rn(y);
+            else reinterpret_cast<float*>(out)[base + e] = y;
+          }
         }
       }
     }
@@ -551,7 +612,7 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
   TcProgram& p = h->prog;
   memset(&p, 0, sizeof(p));
   p.in_dim = d.in_dim; p.out_dim = d.out_dim;
-  p.out_stride = d.out_dim | 1;
+  p.out_stride = d.out_dim;  // dense rows: the tile leaves the stage as one flat copy
   // ---- weight image: per layer hi then lo, canonical K-major core matrices: ((k/8) * Np + n) * 16 B + (k%8) * 2 B
   uint32_t off = 0, b_hi[4], b_lo[4];
   float scale[4];
@@ -595,7 +656,11 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
     e.col = col; e.w = w; e.scale = scale[l]; e.act = d.layer[l].act; e.final = fin;
     return e;
   };
-  p.a1_col = REG_Z; p.a1_w = Kp[0];
+  // the first A operand lives where nothing else is live at the start of a tile AND becomes free early, so the next
+  // tile's operand can be written while this tile is still running: encoder Z (read by steps 0 and 1), decoder Y
+  // (A1 is read by step 0; Y then holds D2/A3 until step 3 has consumed it, and is idle during the last step)
+  p.a1_col = wide == 0 ? REG_Z : REG_Y; p.a1_w = Kp[0];
+  p.a1_after_step = wide == 0 ? 1 : 3;  // informational: first step after which the A1 region is idle
   int s = 0;
   if (wide == 0) {  // encoder: K0 -> 208 -> Np1 -> Np2 -> Np3
     const int na = 112, nb = Np[0] - 112;
@@ -607,7 +672,7 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
     p.step[s].n_mma = 1; p.step[s].mma[0] = mma(3, REG_X, Np[2], 0, Np[2] / 16, 0, Np[3], REG_Y, 0); p.step[s].epi = epi(3, REG_Y, Np[3], 1); ++s;
   } else {          // decoder: K0 -> Np0 -> Np1 -> 208 -> Np3
     const int na = 112, nb = Np[2] - 112;
-    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(0, REG_Z, Kp[0], 0, Kp[0] / 16, 0, Np[0], REG_X, 0); p.step[s].epi = epi(0, REG_X, Np[0], 0); ++s;
+    p.step[s].n_mma = 1; p.step[s].mma[0] = mma(0, REG_Y, Kp[0], 0, Kp[0] / 16, 0, Np[0], REG_X, 0); p.step[s].epi = epi(0, REG_X, Np[0], 0); ++s;
     p.step[s].n_mma = 1; p.step[s].mma[0] = mma(1, REG_X, Np[0], 0, Np[0] / 16, 0, Np[1], REG_Y, 0); p.step[s].epi = epi(1, REG_Y, Np[1], 0); ++s;
     p.step[s].n_mma = 1; p.step[s].mma[0] = mma(2, REG_Y, Np[1], 0, Np[1] / 16, 0, na, REG_X, 0); p.step[s].epi = epi(2, REG_X, na, 0); ++s;
     p.step[s].n_mma = 2; p.step[s].mma[0] = mma(3, REG_X, na, 0, na / 16, 0, Np[3], REG_Z, 0);
@@ -625,16 +690,20 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
     const size_t out_b = ((size_t)TILE * p.out_stride * 4 + 127) & ~(size_t)127;
     return (size_t)p.w_bytes + groups * (2 * in_b + out_b);
   };
-  h->n_groups = smem_need(2, 4) + 1024 <= ctx->smem_optin ? 2 : (smem_need(1, 4) + 1024 <= ctx->smem_optin ? 1 : 0);
+  h->n_groups = smem_need(2, 4) + 4096 <= ctx->smem_optin ? 2 : (smem_need(1, 4) + 4096 <= ctx->smem_optin ? 1 : 0);
   if (h->n_groups == 0 || (p.w_bytes & 15)) { delete h; return BB_ERR_UNSUPPORTED; }
   h->smem_bytes = smem_need(h->n_groups, 4);
   if (c->tc_blob_dev) cudaFree(c->tc_blob_dev);
   BB_CUDA(cudaMalloc(&c->tc_blob_dev, img.size()));
   BB_CUDA(cudaMemcpy(c->tc_blob_dev, img.data(), img.size(), cudaMemcpyHostToDevice));
   c->tc_blob_bytes = img.size();
-  if (h->n_groups == 2)
-    BB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  BB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  // the attribute belongs to the kernel, not to this chain (encoder and decoder share the kernels): always
+  // allow the device maximum
+  cudaFuncAttributes fa;
+  BB_CUDA(cudaFuncGetAttributes(&fa, chain_tc_kernel<2>));
+  BB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - fa.sharedSizeBytes)));
+  BB_CUDA(cudaFuncGetAttributes(&fa, chain_tc_kernel<1>));
+  BB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - fa.sharedSizeBytes)));
   delete reinterpret_cast<TcHost*>(c->tc_host);
   c->tc_host = h;
   c->tc_ok = true;
