@@ -49,6 +49,9 @@ _SIGNATURES = {
     "bb_compress_host": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P, C.c_int, C.c_int]),
     "bb_decompress_host": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, C.c_int, C.c_int]),
     "bb_trainer_create": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _PP]),
+    "bb_trainer_create_dbn": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int, _PP]),
+    "bb_trainer_set_dropout": (C.c_int, [_P, C.c_uint64, _P]),
+    "bb_trainer_get_bn": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "bb_trainer_destroy": (C.c_int, [_P]),
     "bb_trainer_param_count": (C.c_int, [_P]),
     "bb_trainer_params_dev": (_P, [_P]),

@@ -19,6 +19,9 @@
 #include <cmath>
 #include <new>
 
+#include <cooperative_groups.h>
+#include <curand_philox4x32_x.h>
+
 #include "bb_common.cuh"
 
 namespace {
@@ -41,6 +44,11 @@ struct TrainDims {
   int n_params;
   int max_dim;
   int max_mat;           // floats of one staged weight matrix buffer (largest layer + alignment slack)
+  // AE_Dropout_BN only: BatchNorm affine parameters follow the 8 Linear layers in the flat parameter vector
+  int n_linear;          // number of Linear parameters (= n_params for the plain AE)
+  int bn_g_off[4], bn_b_off[4];  // gamma / beta of the 4 decoder BatchNorms
+  int bn_f_off[4];       // offset of BN layer i in per-feature BN arrays (running stats, xhat cache)
+  int bn_f_total;        // sum of the 4 decoder widths
 };
 
 struct DwTile { int l, n0, k0; };
@@ -279,6 +287,251 @@ train_fwd_bwd_kernel(const __grid_constant__ TrainDims d, const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------ AE_Dropout_BN
+// reference baler/modules/models.py:256-313 in train mode:
+//   encoder 4 x (Linear -> Dropout(p = .5,.4,.3,.2) -> LeakyReLU)   [activation also on the latent]
+//   decoder 3 x (Linear -> LeakyReLU -> BatchNorm1d) + Linear -> BatchNorm1d -> ReLU
+// BatchNorm in train mode uses the statistics of the WHOLE batch (biased variance, eps 1e-5) and updates the
+// running statistics with momentum 0.1 and the unbiased variance.  The batch is spread over CTAs (4 rows each), so
+// the kernel is launched cooperatively and meets at a grid-wide barrier at each of the 4 BatchNorms in the forward
+// and in the backward pass; per-CTA partial sums are combined in a fixed order (reproducible).
+struct DbnArgs {
+  const float* x;
+  int batch_rows;
+  int mode;                   // 0: train forward + backward, 1: eval forward (no dropout, running statistics), loss only
+  float* act_g;
+  float* dz_g;
+  float* loss_part;
+  float* bn_part;             // [8 barriers][gridDim.x][2 * max_dim] partial sums
+  float* rm;                  // running mean / var, bn_f_total floats each
+  float* rv;
+  long long* nbt;             // num_batches_tracked[4]
+  float* bn_grad;             // split 0 of the gradient partial buffer (BN gamma / beta gradients land there)
+  const unsigned char* mask[4];  // injected dropout keep-masks [batch][N_l] (parity tests) or nullptr (Philox)
+  unsigned long long seed, step;
+};
+
+__device__ __forceinline__ bool dropout_keep(const DbnArgs& a, const int l, const int grow, const int j, const int N) {
+  if (a.mask[l] != nullptr) return a.mask[l][(size_t)grow * N + j] != 0;
+  // Philox4x32-10 keyed by (seed, step), counter (column / 4, row, layer): stateless, any launch geometry
+  const uint4 r = curand_Philox4x32_10(make_uint4((unsigned)(j >> 2), (unsigned)grow, (unsigned)l, (unsigned)a.step),
+                                       make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32) ^ (unsigned)(a.step >> 32)));
+  const unsigned v = (j & 3) == 0 ? r.x : (j & 3) == 1 ? r.y : (j & 3) == 2 ? r.z : r.w;
+  const float keep_p[4] = {0.5f, 0.6f, 0.7f, 0.8f};  // 1 - p of models.py:263-275
+  return v < (unsigned)(keep_p[l] * 4294967296.0);
+}
+
+__global__ void __launch_bounds__(NT_FB)
+train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ params, const float* __restrict__ wt,
+                 const __grid_constant__ DbnArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) float smem[];
+  float* act_s = smem;                             // a_stride * RT : layer inputs A_0..A_7 and the reconstruction
+  float* dz_s0 = act_s + d.a_stride * RT;
+  float* dz_s1 = dz_s0 + d.max_dim * RT;
+  float* red_s = dz_s1 + d.max_dim * RT;
+  float* xhat_s = red_s + (d.max_dim > NT_FB ? d.max_dim : NT_FB) * RT;  // bn_f_total * RT : normalised BN inputs
+  float* u_s = xhat_s + d.bn_f_total * RT;                               // bn_f_total * RT : BN inputs (sign for LeakyReLU')
+  float* inv_s = u_s + d.bn_f_total * RT;                                // bn_f_total : 1 / sqrt(var + eps)
+  float* tot_s = inv_s + d.bn_f_total;                                   // 2 * max_dim : batch sums
+  __shared__ float warp_loss[NT_FB / 32];
+  WStage ws;
+  ws.buf[0] = tot_s + 2 * d.max_dim;
+  ws.buf[1] = ws.buf[0] + d.max_mat;
+  const bool train = a.mode == 0;
+  ws.per_chain = train ? 2 * NL - 1 : NL;
+  ws.total = ws.per_chain;
+  ws.gp = 0;
+  prefetch_pass(d, params, wt, 0, ws.buf[0]);
+  cp_async_commit();
+
+  const int B = a.batch_rows;
+  const int row0 = blockIdx.x * RT;
+  const int rows = max(0, min(RT, B - row0));
+  const int F = d.dims[0];
+  const float keep_scale[4] = {1.f / 0.5f, 1.f / 0.6f, 1.f / 0.7f, 1.f / 0.8f};
+  for (int o = threadIdx.x; o < RT * F; o += NT_FB) {
+    const int r = o / F, j = o - r * F;
+    const float v = r < rows ? __ldg(a.x + (size_t)(row0 + r) * F + j) : 0.f;
+    act_s[j * RT + r] = v;
+    if (r < rows) a.act_g[(size_t)(row0 + r) * d.a_stride + j] = v;
+  }
+  __syncthreads();
+
+  // ---------------- forward: encoder
+  for (int l = 0; l < 4; ++l) {
+    const int K = d.dims[l], N = d.dims[l + 1];
+    const int KP = gemv8(act_s + d.a_off[l] * RT, acquire_pass(d, params, wt, ws), K, N, red_s);
+    const float* bias = params + d.b_off[l];
+    float* out_s = act_s + d.a_off[l + 1] * RT;
+    for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
+      const int r = o / N, j = o - r * N;
+      float v = red_sum(red_s, KP, N, r, j) + __ldg(bias + j);
+      if (train && r < rows) v = dropout_keep(a, l, row0 + r, j, N) ? v * keep_scale[l] : 0.f;
+      v = act_fwd(v, BB_ACT_LEAKY);
+      out_s[j * RT + r] = v;
+      if (r < rows) a.act_g[(size_t)(row0 + r) * d.a_stride + d.a_off[l + 1] + j] = v;
+    }
+    __syncthreads();
+  }
+  // ---------------- forward: decoder with BatchNorm
+  const int n_cta = gridDim.x;
+  for (int i = 0; i < 4; ++i) {
+    const int l = 4 + i, K = d.dims[l], N = d.dims[l + 1], fo = d.bn_f_off[i];
+    const int KP = gemv8(act_s + d.a_off[l] * RT, acquire_pass(d, params, wt, ws), K, N, red_s);
+    const float* bias = params + d.b_off[l];
+    for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
+      const int r = o / N, j = o - r * N;
+      float v = red_sum(red_s, KP, N, r, j) + __ldg(bias + j);
+      if (i < 3) v = act_fwd(v, BB_ACT_LEAKY);
+      u_s[(fo + j) * RT + r] = r < rows ? v : 0.f;
+    }
+    __syncthreads();
+    const float* gam = params + d.bn_g_off[i];
+    const float* bet = params + d.bn_b_off[i];
+    if (train) {
+      float* part = a.bn_part + ((size_t)i * n_cta + blockIdx.x) * 2 * d.max_dim;
+      for (int j = threadIdx.x; j < N; j += NT_FB) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) { const float u = u_s[(fo + j) * RT + r]; s1 += u; s2 = fmaf(u, u, s2); }
+        part[j] = s1; part[N + j] = s2;
+      }
+      __threadfence();
+      grid.sync();
+      const float* all = a.bn_part + (size_t)i * n_cta * 2 * d.max_dim;
+      for (int j = threadIdx.x; j < N; j += NT_FB) {
+        double S1 = 0.0, S2 = 0.0;
+        for (int c = 0; c < n_cta; ++c) { S1 += (double)__ldcg(all + (size_t)c * 2 * d.max_dim + j); S2 += (double)__ldcg(all + (size_t)c * 2 * d.max_dim + N + j); }
+        const double mean = S1 / B;
+        double var = S2 / B - mean * mean;  // biased batch variance
+        var = var > 0.0 ? var : 0.0;
+        tot_s[j] = (float)mean;
+        inv_s[fo + j] = (float)(1.0 / sqrt(var + 1e-5));
+        if (blockIdx.x == 0) {  // running statistics: momentum 0.1, unbiased variance
+          a.rm[fo + j] = 0.9f * a.rm[fo + j] + 0.1f * (float)mean;
+          a.rv[fo + j] = 0.9f * a.rv[fo + j] + 0.1f * (float)(var * B / (B > 1 ? B - 1 : 1));
+          if (j == 0) a.nbt[i] += 1;
+        }
+      }
+    } else {
+      for (int j = threadIdx.x; j < N; j += NT_FB) {
+        tot_s[j] = a.rm[fo + j];
+        inv_s[fo + j] = rsqrtf(a.rv[fo + j] + 1e-5f);
+      }
+    }
+    __syncthreads();
+    float* out_s = act_s + d.a_off[l + 1] * RT;
+    for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
+      const int r = o / N, j = o - r * N;
+      const float xh = (u_s[(fo + j) * RT + r] - tot_s[j]) * inv_s[fo + j];
+      float h = fmaf(xh, __ldg(gam + j), __ldg(bet + j));
+      if (i == 3) h = fmaxf(h, 0.f);
+      xhat_s[(fo + j) * RT + r] = xh;
+      out_s[j * RT + r] = h;
+      if (r < rows && l + 1 < NL) a.act_g[(size_t)(row0 + r) * d.a_stride + d.a_off[l + 1] + j] = h;
+    }
+    __syncthreads();
+  }
+  // ---------------- loss and the seed gradient
+  float loss_local = 0.f;
+  float* dz_cur = dz_s0;
+  float* dz_nxt = dz_s1;
+  {
+    const float* out_s = act_s + d.a_off[NL] * RT;
+    for (int o = threadIdx.x; o < RT * F; o += NT_FB) {
+      const int r = o / F, j = o - r * F;
+      float g = 0.f;
+      if (r < rows) {
+        const float rec = out_s[j * RT + r];
+        const float diff = rec - act_s[j * RT + r];
+        loss_local += diff * diff / F;
+        g = rec > 0.f ? 2.f * diff / F : 0.f;  // through the final ReLU
+      }
+      dz_cur[j * RT + r] = g;
+    }
+    __syncthreads();
+  }
+  if (train) {
+    // ---------------- backward: decoder
+    for (int i = 3; i >= 0; --i) {
+      const int l = 4 + i, K = d.dims[l], N = d.dims[l + 1], fo = d.bn_f_off[i];
+      float* part = a.bn_part + ((size_t)(4 + 3 - i) * n_cta + blockIdx.x) * 2 * d.max_dim;
+      for (int j = threadIdx.x; j < N; j += NT_FB) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) { const float g = dz_cur[j * RT + r]; t1 += g; t2 = fmaf(g, xhat_s[(fo + j) * RT + r], t2); }
+        part[j] = t1; part[N + j] = t2;
+      }
+      __threadfence();
+      grid.sync();
+      const float* all = a.bn_part + (size_t)(4 + 3 - i) * n_cta * 2 * d.max_dim;
+      for (int j = threadIdx.x; j < N; j += NT_FB) {
+        double T1 = 0.0, T2 = 0.0;
+        for (int c = 0; c < n_cta; ++c) { T1 += (double)__ldcg(all + (size_t)c * 2 * d.max_dim + j); T2 += (double)__ldcg(all + (size_t)c * 2 * d.max_dim + N + j); }
+        tot_s[j] = (float)T1; tot_s[d.max_dim + j] = (float)T2;
+        if (blockIdx.x == 0) { a.bn_grad[d.bn_b_off[i] + j] = (float)T1; a.bn_grad[d.bn_g_off[i] + j] = (float)T2; }
+      }
+      __syncthreads();
+      const float* gam = params + d.bn_g_off[i];
+      const float invB = 1.f / B;
+      for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
+        const int r = o / N, j = o - r * N;
+        const float g = __ldg(gam + j);
+        // dx = inv / B * (B dxh - sum(dxh) - xhat sum(dxh xhat)), dxh = dy * gamma
+        float dx = inv_s[fo + j] * g * (dz_cur[j * RT + r] - invB * tot_s[j] - xhat_s[(fo + j) * RT + r] * invB * tot_s[d.max_dim + j]);
+        if (i < 3) dx *= u_s[(fo + j) * RT + r] > 0.f ? 1.f : BB_LEAKY;
+        if (r >= rows) dx = 0.f;
+        dz_nxt[j * RT + r] = dx;
+        if (r < rows) a.dz_g[(size_t)(row0 + r) * d.z_stride + d.z_off[l] + j] = dx;
+      }
+      __syncthreads();
+      {  // dX = dZ W_l  (gradient w.r.t. the input of Linear l = output of the previous block)
+        const int KP = gemv8(dz_nxt, acquire_pass(d, params, wt, ws), N, K, red_s);
+        for (int o = threadIdx.x; o < RT * K; o += NT_FB) {
+          const int r = o / K, j = o - r * K;
+          dz_cur[j * RT + r] = red_sum(red_s, KP, K, r, j);
+        }
+        __syncthreads();
+      }
+    }
+    // ---------------- backward: encoder (dz_cur = gradient w.r.t. the output of encoder layer l)
+    for (int l = 3; l >= 0; --l) {
+      const int K = d.dims[l], N = d.dims[l + 1];
+      const float* a_out = act_s + d.a_off[l + 1] * RT;
+      for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
+        const int r = o / N, j = o - r * N;
+        float g = 0.f;
+        if (r < rows) {
+          g = dz_cur[j * RT + r] * (a_out[j * RT + r] > 0.f ? 1.f : BB_LEAKY);
+          g = dropout_keep(a, l, row0 + r, j, N) ? g * keep_scale[l] : 0.f;
+          a.dz_g[(size_t)(row0 + r) * d.z_stride + d.z_off[l] + j] = g;
+        }
+        dz_nxt[j * RT + r] = g;
+      }
+      __syncthreads();
+      if (l >= 1) {
+        const int KP = gemv8(dz_nxt, acquire_pass(d, params, wt, ws), N, K, red_s);
+        for (int o = threadIdx.x; o < RT * K; o += NT_FB) {
+          const int r = o / K, j = o - r * K;
+          dz_cur[j * RT + r] = red_sum(red_s, KP, K, r, j);
+        }
+        __syncthreads();
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, off);
+  if ((threadIdx.x & 31) == 0) warp_loss[threadIdx.x >> 5] = loss_local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < NT_FB / 32; ++w) s += warp_loss[w];
+    a.loss_part[blockIdx.x] = s;
+  }
+}
+
 // partial[split][w_off[l] + n*K + k] = sum_{r in split} dZ_l[r][n] * A_l[r][k]   (+ second chain)
 __global__ void __launch_bounds__(NT)
 train_dw_kernel(const __grid_constant__ TrainDims d, const DwTile* __restrict__ tiles, const float* __restrict__ act_g,
@@ -389,6 +642,14 @@ struct bb_trainer {
   DwTile* tiles = nullptr;
   double* loss_accum = nullptr;  // internal accumulator used by bb_trainer_epoch / validate
   size_t smem_bytes = 0;
+  // AE_Dropout_BN
+  int kind = 0;                  // 0: AE / CFD_dense_AE, 1: AE_Dropout_BN
+  float *bn_part = nullptr, *rm = nullptr, *rv = nullptr;
+  long long* nbt = nullptr;
+  const unsigned char* mask_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long long seed = 0;
+  size_t dbn_smem = 0;
+  int dbn_max_ctas = 0;
 };
 
 namespace {
@@ -404,12 +665,78 @@ int launch_fwd_bwd(bb_trainer* t, const float* x, int rows, int backward, const 
   return (int)cudaGetLastError();
 }
 
+int launch_dbn(bb_trainer* t, const float* x, int rows, int mode, cudaStream_t s) {
+  const int grid = (rows + RT - 1) / RT;
+  if (grid > t->dbn_max_ctas) return BB_ERR_UNSUPPORTED;  // cooperative launch: every CTA must be resident
+  t->last_rows = rows;
+  DbnArgs a;
+  a.x = x; a.batch_rows = rows; a.mode = mode;
+  a.act_g = t->act_g; a.dz_g = t->dz_g; a.loss_part = t->loss_part; a.bn_part = t->bn_part;
+  a.rm = t->rm; a.rv = t->rv; a.nbt = t->nbt; a.bn_grad = t->partial;
+  for (int i = 0; i < 4; ++i) a.mask[i] = t->mask_dev[i];
+  a.seed = t->seed; a.step = (unsigned long long)t->step;
+  void* args[] = {(void*)&t->d, (void*)&t->params, (void*)&t->wt, (void*)&a};
+  return (int)cudaLaunchCooperativeKernel((const void*)train_dbn_kernel, dim3(grid), dim3(NT_FB), args, t->dbn_smem, s);
+}
+
+int create_common(bb_ctx* ctx, int n_features, int z_dim, const double* const* weights_host, const double* const* biases_host,
+                  int max_batch, int kind, const double* const* bn_gamma, const double* const* bn_beta,
+                  const double* const* bn_mean, const double* const* bn_var, const long long* bn_nbt, bb_trainer** out);
+
 }  // namespace
 
 extern "C" {
 
 int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim, const double* const* weights_host,
                       const double* const* biases_host, int max_batch, bb_trainer** out) {
+  return create_common(ctx, n_features, z_dim, weights_host, biases_host, max_batch, 0, nullptr, nullptr, nullptr, nullptr,
+                       nullptr, out);
+}
+
+int bb_trainer_create_dbn(bb_ctx* ctx, int n_features, int z_dim, const double* const* weights_host,
+                          const double* const* biases_host, const double* const* bn_weight_host,
+                          const double* const* bn_bias_host, const double* const* bn_mean_host,
+                          const double* const* bn_var_host, const long long* bn_batches_tracked, int max_batch,
+                          bb_trainer** out) {
+  if (!bn_weight_host || !bn_bias_host || !bn_mean_host || !bn_var_host) return BB_ERR_INVALID;
+  return create_common(ctx, n_features, z_dim, weights_host, biases_host, max_batch, 1, bn_weight_host, bn_bias_host,
+                       bn_mean_host, bn_var_host, bn_batches_tracked, out);
+}
+
+int bb_trainer_set_dropout(bb_trainer* t, unsigned long long seed, const unsigned char* const* masks_dev) {
+  if (!t || t->kind != 1) return BB_ERR_INVALID;
+  t->seed = seed;
+  for (int i = 0; i < 4; ++i) t->mask_dev[i] = masks_dev ? masks_dev[i] : nullptr;
+  return BB_OK;
+}
+
+int bb_trainer_get_bn(bb_trainer* t, double* const* bn_weight_host, double* const* bn_bias_host,
+                      double* const* bn_mean_host, double* const* bn_var_host, long long* bn_batches_tracked) {
+  if (!t || t->kind != 1 || !bn_weight_host || !bn_bias_host || !bn_mean_host || !bn_var_host || !bn_batches_tracked)
+    return BB_ERR_INVALID;
+  std::vector<float> hp(t->d.n_params), hm(t->d.bn_f_total), hv(t->d.bn_f_total);
+  BB_CUDA(cudaMemcpy(hp.data(), t->params, sizeof(float) * hp.size(), cudaMemcpyDeviceToHost));
+  BB_CUDA(cudaMemcpy(hm.data(), t->rm, sizeof(float) * hm.size(), cudaMemcpyDeviceToHost));
+  BB_CUDA(cudaMemcpy(hv.data(), t->rv, sizeof(float) * hv.size(), cudaMemcpyDeviceToHost));
+  BB_CUDA(cudaMemcpy(bn_batches_tracked, t->nbt, sizeof(long long) * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) {
+    const int n = t->d.dims[5 + i];
+    for (int j = 0; j < n; ++j) {
+      bn_weight_host[i][j] = (double)hp[t->d.bn_g_off[i] + j];
+      bn_bias_host[i][j] = (double)hp[t->d.bn_b_off[i] + j];
+      bn_mean_host[i][j] = (double)hm[t->d.bn_f_off[i] + j];
+      bn_var_host[i][j] = (double)hv[t->d.bn_f_off[i] + j];
+    }
+  }
+  return BB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+int create_common(bb_ctx* ctx, int n_features, int z_dim, const double* const* weights_host, const double* const* biases_host,
+                  int max_batch, int kind, const double* const* bn_gamma, const double* const* bn_beta,
+                  const double* const* bn_mean, const double* const* bn_var, const long long* bn_nbt, bb_trainer** out) {
   if (!ctx || !out || n_features < 1 || z_dim < 1 || max_batch < 1 || !weights_host || !biases_host) return BB_ERR_INVALID;
   BB_CUDA(cudaSetDevice(ctx->device));
   bb_trainer* t = new (std::nothrow) bb_trainer();
@@ -419,6 +746,7 @@ int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim, const double* cons
   TrainDims& d = t->d;
   const int dims[NL + 1] = {n_features, 200, 100, 50, z_dim, 50, 100, 200, n_features};
   const int acts[NL] = {BB_ACT_LEAKY, BB_ACT_LEAKY, BB_ACT_LEAKY, BB_ACT_NONE, BB_ACT_LEAKY, BB_ACT_LEAKY, BB_ACT_LEAKY, BB_ACT_NONE};
+  t->kind = kind;
   int p = 0, wtp = 0, a = 0, z = 0, mx = 0;
   for (int l = 0; l <= NL; ++l) {
     d.dims[l] = dims[l];
@@ -433,6 +761,17 @@ int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim, const double* cons
     d.wt_off[l] = wtp; wtp += dims[l] * dims[l + 1];
     d.z_off[l] = z; z += dims[l + 1];
   }
+  d.n_linear = p;
+  d.bn_f_total = 0;
+  for (int i = 0; i < 4; ++i) {
+    d.bn_f_off[i] = d.bn_f_total;
+    d.bn_g_off[i] = d.bn_b_off[i] = 0;
+    if (kind == 1) {
+      d.bn_g_off[i] = p; p += dims[5 + i];
+      d.bn_b_off[i] = p; p += dims[5 + i];
+    }
+    d.bn_f_total += dims[5 + i];
+  }
   d.a_stride = a; d.z_stride = z; d.n_params = p; d.max_dim = mx;
   int mm = 0;
   for (int l = 0; l < NL; ++l) mm = dims[l] * dims[l + 1] > mm ? dims[l] * dims[l + 1] : mm;
@@ -441,7 +780,7 @@ int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim, const double* cons
   t->smem_bytes = ((size_t)(d.a_stride + 2 * mx + (mx > NT_FB ? mx : NT_FB)) * RT + 2 * (size_t)d.max_mat) * sizeof(float);
   if (t->smem_bytes > ctx->smem_optin) { delete t; return BB_ERR_UNSUPPORTED; }
 
-  std::vector<float> hp(p), hwt(wtp);
+  std::vector<float> hp(p, 0.f), hwt(wtp);
   std::vector<int> hidx(p, -1);
   std::vector<DwTile> tiles;
   for (int l = 0; l < NL; ++l) {
@@ -458,6 +797,20 @@ int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim, const double* cons
     }
     for (int n0 = 0; n0 < N; n0 += DW_T)
       for (int k0 = 0; k0 < K; k0 += DW_T) tiles.push_back({l, n0, k0});
+  }
+  std::vector<float> hrm(d.bn_f_total, 0.f), hrv(d.bn_f_total, 1.f);
+  long long hnbt[4] = {0, 0, 0, 0};
+  if (kind == 1) {
+    for (int i = 0; i < 4; ++i) {
+      if (!bn_gamma[i] || !bn_beta[i] || !bn_mean[i] || !bn_var[i]) { delete t; return BB_ERR_INVALID; }
+      for (int j = 0; j < dims[5 + i]; ++j) {
+        hp[d.bn_g_off[i] + j] = (float)bn_gamma[i][j];
+        hp[d.bn_b_off[i] + j] = (float)bn_beta[i][j];
+        hrm[d.bn_f_off[i] + j] = (float)bn_mean[i][j];
+        hrv[d.bn_f_off[i] + j] = (float)bn_var[i][j];
+      }
+      hnbt[i] = bn_nbt ? bn_nbt[i] : 0;
+    }
   }
   t->n_tiles = (int)tiles.size();
   const int max_splits = (max_batch + DW_T - 1) / DW_T;
@@ -476,6 +829,12 @@ int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim, const double* cons
   alloc((void**)&t->wt_index, sizeof(int) * p);
   alloc((void**)&t->tiles, sizeof(DwTile) * tiles.size());
   alloc((void**)&t->loss_accum, sizeof(double));
+  if (kind == 1) {
+    alloc((void**)&t->bn_part, sizeof(float) * 8 * (size_t)max_ctas * 2 * mx);
+    alloc((void**)&t->rm, sizeof(float) * d.bn_f_total);
+    alloc((void**)&t->rv, sizeof(float) * d.bn_f_total);
+    alloc((void**)&t->nbt, sizeof(long long) * 4);
+  }
   if (rc == BB_OK) rc = (int)cudaMemcpy(t->params, hp.data(), sizeof(float) * p, cudaMemcpyHostToDevice);
   if (rc == BB_OK) rc = (int)cudaMemcpy(t->wt, hwt.data(), sizeof(float) * wtp, cudaMemcpyHostToDevice);
   if (rc == BB_OK) rc = (int)cudaMemcpy(t->wt_index, hidx.data(), sizeof(int) * p, cudaMemcpyHostToDevice);
@@ -484,15 +843,31 @@ int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim, const double* cons
   if (rc == BB_OK) rc = (int)cudaMemset(t->v, 0, sizeof(float) * p);
   if (rc == BB_OK) rc = (int)cudaMemset(t->grads, 0, sizeof(float) * (p + 1));
   if (rc == BB_OK) rc = (int)cudaMemset(t->loss_accum, 0, sizeof(double));
+  if (rc == BB_OK) rc = (int)cudaMemset(t->partial, 0, sizeof(float) * (size_t)max_splits * p);  // BN slots of splits > 0 stay zero
+  if (rc == BB_OK && kind == 1) {
+    rc = (int)cudaMemcpy(t->rm, hrm.data(), sizeof(float) * hrm.size(), cudaMemcpyHostToDevice);
+    if (rc == BB_OK) rc = (int)cudaMemcpy(t->rv, hrv.data(), sizeof(float) * hrv.size(), cudaMemcpyHostToDevice);
+    if (rc == BB_OK) rc = (int)cudaMemcpy(t->nbt, hnbt, sizeof(hnbt), cudaMemcpyHostToDevice);
+    t->dbn_smem = t->smem_bytes + ((size_t)2 * d.bn_f_total * RT + d.bn_f_total + 2 * mx) * sizeof(float);
+    if (t->dbn_smem > ctx->smem_optin) rc = BB_ERR_UNSUPPORTED;
+    if (rc == BB_OK) rc = (int)cudaFuncSetAttribute(train_dbn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->dbn_smem);
+    int per_sm = 0;
+    if (rc == BB_OK) rc = (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_dbn_kernel, NT_FB, t->dbn_smem);
+    t->dbn_max_ctas = per_sm * ctx->sm_count;
+  }
   if (rc == BB_OK) rc = (int)cudaFuncSetAttribute(train_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem_bytes);
   if (rc != BB_OK) { bb_trainer_destroy(t); return rc; }
   *out = t;
   return BB_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int bb_trainer_destroy(bb_trainer* t) {
   if (!t) return BB_OK;
-  void* ptrs[] = {t->params, t->wt, t->grads, t->m, t->v, t->act_g, t->dz_g, t->partial, t->loss_part, t->wt_index, t->tiles, t->loss_accum};
+  void* ptrs[] = {t->params, t->wt, t->grads, t->m, t->v, t->act_g, t->dz_g, t->partial, t->loss_part, t->wt_index, t->tiles, t->loss_accum,
+                  t->bn_part, t->rm, t->rv, t->nbt};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete t;
@@ -523,7 +898,8 @@ int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_
   const int n_splits = (batch_rows + DW_T - 1) / DW_T;
   const int n_ctas = (batch_rows + RT - 1) / RT;
   if (phase != 2) {
-    int rc = launch_fwd_bwd(t, x_dev, batch_rows, 1, h, s);
+    if (t->kind == 1 && (h->l1 || h->world_size > 1)) return BB_ERR_UNSUPPORTED;  // MSE only, single GPU (whole-batch BN statistics)
+    int rc = t->kind == 1 ? launch_dbn(t, x_dev, batch_rows, 0, s) : launch_fwd_bwd(t, x_dev, batch_rows, 1, h, s);
     if (rc != BB_OK) return rc;
     train_dw_kernel<<<dim3(t->n_tiles, n_splits), NT, 0, s>>>(t->d, t->tiles, t->act_g, t->dz_g,
                                                             (size_t)t->max_batch * t->d.a_stride,
@@ -572,7 +948,8 @@ int bb_trainer_validate(bb_trainer* t, const float* x_dev, int64_t n_rows, int b
   int64_t n_batches = 0;
   for (int64_t r0 = 0; r0 < n_rows; r0 += batch, ++n_batches) {
     const int rows = (int)(n_rows - r0 < batch ? n_rows - r0 : batch);
-    int rc = launch_fwd_bwd(t, x_dev + (size_t)r0 * t->d.dims[0], rows, 0, nullptr, s);
+    int rc = t->kind == 1 ? launch_dbn(t, x_dev + (size_t)r0 * t->d.dims[0], rows, 1, s)
+                          : launch_fwd_bwd(t, x_dev + (size_t)r0 * t->d.dims[0], rows, 0, nullptr, s);
     if (rc != BB_OK) return rc;
     // mode 1 with zero splits: only folds the loss partials into the gradient's loss slot ...
     train_adam_kernel<<<1, NT, 0, s>>>(0, 1, t->partial, 0, t->grads + t->d.n_params, nullptr, nullptr, nullptr, nullptr,

@@ -198,14 +198,27 @@ class DenseCodec:
 class Trainer:
     """bb_trainer: parameters, Adam state and scratch of one dense-AE training run on one GPU."""
 
-    def __init__(self, weights, biases, n_features, z_dim, max_batch, device=None):
+    def __init__(self, weights, biases, n_features, z_dim, max_batch, device=None, bn=None):
+        """bn: None for AE / CFD_dense_AE; for AE_Dropout_BN a dict with lists of 4 arrays `weight`, `bias`,
+        `running_mean`, `running_var` and `num_batches_tracked` (4 ints)"""
         self.ctx = get_context(device)
         self.handle = C.c_void_p()
         self._w = [np.ascontiguousarray(w, dtype=np.float64) for w in weights]
         self._b = [np.ascontiguousarray(b, dtype=np.float64) for b in biases]
+        self._bn = None
+        self._masks = None
         with torch.cuda.device(self.ctx.device):
-            check(_lib.lib().bb_trainer_create(self.ctx.handle, n_features, z_dim, _host_ptrs(self._w),
-                                               _host_ptrs(self._b), max_batch, C.byref(self.handle)), "bb_trainer_create")
+            if bn is None:
+                check(_lib.lib().bb_trainer_create(self.ctx.handle, n_features, z_dim, _host_ptrs(self._w),
+                                                   _host_ptrs(self._b), max_batch, C.byref(self.handle)), "bb_trainer_create")
+            else:
+                self._bn = {k: [np.ascontiguousarray(a, dtype=np.float64) for a in bn[k]]
+                            for k in ("weight", "bias", "running_mean", "running_var")}
+                nbt = (C.c_longlong * 4)(*[int(v) for v in bn["num_batches_tracked"]])
+                check(_lib.lib().bb_trainer_create_dbn(
+                    self.ctx.handle, n_features, z_dim, _host_ptrs(self._w), _host_ptrs(self._b),
+                    _host_ptrs(self._bn["weight"]), _host_ptrs(self._bn["bias"]), _host_ptrs(self._bn["running_mean"]),
+                    _host_ptrs(self._bn["running_var"]), nbt, max_batch, C.byref(self.handle)), "bb_trainer_create_dbn")
         self.n_params = _lib.lib().bb_trainer_param_count(self.handle)
         self.loss_accum = torch.zeros(1, dtype=torch.float64, device=self.ctx.device)
 
@@ -251,6 +264,23 @@ class Trainer:
         check(_lib.lib().bb_trainer_validate(self.handle, _ptr(x), x.shape[0], batch, C.byref(out), _stream(self.ctx)),
               "bb_trainer_validate")
         return out.value
+
+    def set_dropout(self, seed=0, masks=None):
+        """AE_Dropout_BN: Philox seed, or 4 CUDA uint8 keep-masks [batch, width] injected for parity tests"""
+        self._masks = None if masks is None else [m.contiguous() for m in masks]
+        ptrs = None
+        if self._masks is not None:
+            ptrs = (C.c_void_p * 4)(*[m.data_ptr() for m in self._masks])
+        check(_lib.lib().bb_trainer_set_dropout(self.handle, int(seed), ptrs), "bb_trainer_set_dropout")
+
+    def get_bn(self):
+        out = {k: [np.empty_like(a) for a in self._bn[k]] for k in ("weight", "bias", "running_mean", "running_var")}
+        nbt = (C.c_longlong * 4)()
+        check(_lib.lib().bb_trainer_get_bn(self.handle, _host_ptrs(out["weight"]), _host_ptrs(out["bias"]),
+                                           _host_ptrs(out["running_mean"]), _host_ptrs(out["running_var"]), nbt),
+              "bb_trainer_get_bn")
+        out["num_batches_tracked"] = [int(v) for v in nbt]
+        return out
 
     def activation_means(self):
         out = np.empty((6, 200), dtype=np.float64)

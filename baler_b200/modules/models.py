@@ -226,6 +226,29 @@ class AE_Dropout_BN(_DenseBase):
             dec.append((w, b, "relu" if i == 3 else "leaky"))
         return enc, dec
 
+    # what bb_trainer_create_dbn takes / returns
+    def linear_tensors(self):
+        names = self.enc_names + self.dec_names
+        return [self._np(n + ".weight") for n in names], [self._np(n + ".bias") for n in names]
+
+    def bn_tensors(self):
+        out = {k: [self._np(bn + "." + k) for bn in self.bn_names] for k in ("weight", "bias", "running_mean", "running_var")}
+        out["num_batches_tracked"] = [int(self._sd[bn + ".num_batches_tracked"]) for bn in self.bn_names]
+        return out
+
+    def set_linear_tensors(self, weights, biases):
+        for n, w, b in zip(self.enc_names + self.dec_names, weights, biases):
+            self._sd[n + ".weight"] = torch.from_numpy(np.asarray(w)).to(self.dtype).clone()
+            self._sd[n + ".bias"] = torch.from_numpy(np.asarray(b)).to(self.dtype).clone()
+        self._codec = None
+
+    def set_bn_tensors(self, bn):
+        for i, name in enumerate(self.bn_names):
+            for k in ("weight", "bias", "running_mean", "running_var"):
+                self._sd[name + "." + k] = torch.from_numpy(np.asarray(bn[k][i])).to(self.dtype).clone()
+            self._sd[name + ".num_batches_tracked"] = torch.tensor(int(bn["num_batches_tracked"][i]), dtype=torch.long)
+        self._codec = None
+
     def forward(self, x):
         if self.training:
             raise NotImplementedError("train-mode forward of AE_Dropout_BN runs inside training.train")

@@ -25,10 +25,14 @@ class DeviceAdam:
     """Stands in for torch.optim.Adam(model.parameters(), lr) (training.py:266): Adam state lives in
     the bb_trainer; `lr` is what LRScheduler adjusts."""
 
-    def __init__(self, model, lr, max_batch, l1=False, reg_param=0.0):
+    def __init__(self, model, lr, max_batch, l1=False, reg_param=0.0, dropout_seed=0):
         w, b = model.linear_tensors()
         self.model = model
-        self.trainer = engine.Trainer(w, b, model.n_features, model.z_dim, max_batch)
+        self.has_bn = hasattr(model, "bn_tensors")
+        self.trainer = engine.Trainer(w, b, model.n_features, model.z_dim, max_batch,
+                                      bn=model.bn_tensors() if self.has_bn else None)
+        if self.has_bn:
+            self.trainer.set_dropout(seed=dropout_seed)
         self.lr, self.l1, self.reg_param = lr, l1, reg_param
 
     def hyper(self, world_size=1):
@@ -37,6 +41,8 @@ class DeviceAdam:
     def sync_model(self):
         w, b = self.trainer.get_params()
         self.model.set_linear_tensors(w, b)
+        if self.has_bn:
+            self.model.set_bn_tensors(self.trainer.get_bn())
 
 
 def fit(config, model, train_dl, model_children, regular_param, optimizer, latent_dim, RHO, l1, n_dimensions):
@@ -87,7 +93,7 @@ def train(model, variables, train_data, test_data, project_path, config):
     train_dl, valid_dl = DeviceBatches(train_ds, bs), DeviceBatches(valid_ds, bs)
     model_children = list(model.children())
     optimizer = DeviceAdam(model, config.lr, max_batch=bs, l1=bool(getattr(config, "l1_in_training", False)),
-                           reg_param=config.reg_param)
+                           reg_param=config.reg_param, dropout_seed=int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF)
     early_stopping = utils.EarlyStopping(config.early_stopping_patience, config.min_delta) if config.early_stopping else None
     lr_scheduler = utils.LRScheduler(optimizer, config.lr_scheduler_patience) if config.lr_scheduler else None
     train_loss, val_loss = [], []

@@ -173,6 +173,23 @@ typedef struct bb_train_hyper {
 int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim,
                       const double* const* weights_host, const double* const* biases_host,
                       int max_batch, bb_trainer** out);
+/*
+ * AE_Dropout_BN (models.py:256-313) in train mode: the 8 Linear tensors as above plus, for the 4 decoder
+ * BatchNorm1d layers (dec_nn.2, .5, .8, .10), weight / bias / running_mean / running_var (float64 host) and
+ * num_batches_tracked.  Dropout p = .5/.4/.3/.2 after the encoder Linears, BatchNorm with whole-batch statistics
+ * (biased variance, eps 1e-5, momentum 0.1).  Restrictions: MSE loss only (what training.fit evaluates), single
+ * GPU (the batch statistics are not exchanged), batch <= 4 rows x resident CTAs (592 on B200).
+ */
+int bb_trainer_create_dbn(bb_ctx* ctx, int n_features, int z_dim,
+                          const double* const* weights_host, const double* const* biases_host,
+                          const double* const* bn_weight_host, const double* const* bn_bias_host,
+                          const double* const* bn_mean_host, const double* const* bn_var_host,
+                          const long long* bn_batches_tracked, int max_batch, bb_trainer** out);
+/* dropout: in-kernel Philox4x32-10 keyed by (seed, step, layer, row, column); `masks_dev` (4 device pointers to
+ * [batch x width] uint8 keep-masks, or NULL) injects torch-generated masks for parity tests */
+int bb_trainer_set_dropout(bb_trainer* t, unsigned long long seed, const unsigned char* const* masks_dev);
+int bb_trainer_get_bn(bb_trainer* t, double* const* bn_weight_host, double* const* bn_bias_host,
+                      double* const* bn_mean_host, double* const* bn_var_host, long long* bn_batches_tracked);
 int bb_trainer_destroy(bb_trainer* t);
 /* flat float32 views (device) of parameters / gradients, layout: for l in 0..7: W_l (out,in) then b_l */
 int bb_trainer_param_count(const bb_trainer* t);
