@@ -334,7 +334,7 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
   float* xhat_s = red_s + (d.max_dim > NT_FB ? d.max_dim : NT_FB) * RT;  // bn_f_total * RT : normalised BN inputs
   float* u_s = xhat_s + d.bn_f_total * RT;                               // bn_f_total * RT : BN inputs (sign for LeakyReLU')
   float* inv_s = u_s + d.bn_f_total * RT;                                // bn_f_total : 1 / sqrt(var + eps)
-  float* tot_s = inv_s + d.bn_f_total;                                   // 2 * max_dim : batch sums
+  float* tot_s = inv_s + ((d.bn_f_total + 3) & ~3);                      // 2 * max_dim : batch sums (16-byte aligned)
   __shared__ float warp_loss[NT_FB / 32];
   WStage ws;
   ws.buf[0] = tot_s + 2 * d.max_dim;
@@ -848,7 +848,7 @@ int create_common(bb_ctx* ctx, int n_features, int z_dim, const double* const* w
     rc = (int)cudaMemcpy(t->rm, hrm.data(), sizeof(float) * hrm.size(), cudaMemcpyHostToDevice);
     if (rc == BB_OK) rc = (int)cudaMemcpy(t->rv, hrv.data(), sizeof(float) * hrv.size(), cudaMemcpyHostToDevice);
     if (rc == BB_OK) rc = (int)cudaMemcpy(t->nbt, hnbt, sizeof(hnbt), cudaMemcpyHostToDevice);
-    t->dbn_smem = t->smem_bytes + ((size_t)2 * d.bn_f_total * RT + d.bn_f_total + 2 * mx) * sizeof(float);
+    t->dbn_smem = t->smem_bytes + ((size_t)2 * d.bn_f_total * RT + d.bn_f_total + 4 + 2 * mx) * sizeof(float);
     if (t->dbn_smem > ctx->smem_optin) rc = BB_ERR_UNSUPPORTED;
     if (rc == BB_OK) rc = (int)cudaFuncSetAttribute(train_dbn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->dbn_smem);
     int per_sm = 0;

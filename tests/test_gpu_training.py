@@ -218,7 +218,12 @@ def test_dropout_bn_train_step_with_injected_masks(golden):
     p0, p1 = dbn_flat(sd0), dbn_flat(sd1)
     big = np.abs(ref) > 1e-3 * gscale  # Adam's first step amplifies rounding where |g| ~ eps (see the AE test)
     assert rel_max((p - p0)[big], (p1 - p0)[big]) <= 1e-3
-    assert np.abs(p - p1).max() <= 0.05 * 1e-3
+    # Linear biases that feed a BatchNorm have a mathematically zero gradient (the BN removes the shift): the
+    # reference's own value there is 1e-16 rounding noise and Adam turns any noise into a +-lr step, so those
+    # parameters (which do not influence the model output) are only required to move by at most lr
+    live = np.abs(ref) > 1e-6 * gscale
+    assert np.abs(p - p1)[live].max() <= 0.05 * 1e-3
+    assert np.abs(p - p1).max() <= 1.001e-3
 
 
 def test_dropout_bn_philox_keep_rates_and_training(golden):
