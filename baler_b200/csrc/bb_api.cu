@@ -44,6 +44,7 @@ int bb_ctx_create(int device, bb_ctx** out) {
 int bb_ctx_destroy(bb_ctx* ctx) {
   if (!ctx) return BB_OK;
   if (ctx->minmax_scratch) cudaFree(ctx->minmax_scratch);
+  if (ctx->lay_scratch) cudaFree(ctx->lay_scratch);
   delete ctx;
   return BB_OK;
 }
@@ -77,6 +78,7 @@ int fill_chain(Chain* c, int n_layers, const int* dims, const int* acts, const d
 void free_chain(Chain* c) {
   if (c->blob_dev) cudaFree(c->blob_dev);
   if (c->tc_blob_dev) cudaFree(c->tc_blob_dev);
+  if (c->lay_blob_dev) cudaFree(c->lay_blob_dev);
   bb_tc_release(c);
 }
 
@@ -93,9 +95,13 @@ int run_chain(bb_model* m, const Chain* c, const void* in, int in_dtype, int64_t
     return BB_ERR_INVALID;
   if ((in_dtype != BB_F32 && in_dtype != BB_F16) || (out_dtype != BB_F32 && out_dtype != BB_F16)) return BB_ERR_INVALID;
   const int p = resolve_precision(m, c, precision);
-  if (p == BB_PREC_FP32)
+  if (p == BB_PREC_FP32) {
+    if (!c->f32_ok)  // weights do not fit shared memory: one GEMM launch per layer
+      return bb_chain_layered_launch(m->ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range, out,
+                                     out_dtype, stream);
     return bb_chain_f32_launch(m->ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range,
                                out, out_dtype, stream);
+  }
   if (p == BB_PREC_SPLIT16 || p == BB_PREC_FAST16) {
     if (!c->tc_ok) return BB_ERR_UNSUPPORTED;
     return bb_tc_launch(m->ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range, out,
@@ -191,8 +197,12 @@ int bb_model_create_dense(bb_ctx* ctx, int n_enc_layers, const int* enc_dims, co
   int rc = fill_chain(&m->enc, n_enc_layers, enc_dims, enc_acts, enc_w, enc_b);
   if (rc == BB_OK) rc = fill_chain(&m->dec, n_dec_layers, dec_dims, dec_acts, dec_w, dec_b);
   if (rc == BB_OK && m->enc.desc.out_dim != m->dec.desc.in_dim) rc = BB_ERR_INVALID;
-  if (rc == BB_OK) rc = bb_chain_f32_prepare(ctx, &m->enc);
-  if (rc == BB_OK) rc = bb_chain_f32_prepare(ctx, &m->dec);
+  for (Chain* c : {&m->enc, &m->dec}) {
+    if (rc != BB_OK) break;
+    rc = bb_chain_f32_prepare(ctx, c);
+    c->f32_ok = rc == BB_OK;
+    if (rc == BB_ERR_UNSUPPORTED) rc = bb_chain_layered_prepare(ctx, c);  // too big for the fused kernels
+  }
   if (rc == BB_OK) rc = (int)cudaMalloc(&m->flag_dev, sizeof(int));
   if (rc == BB_OK) rc = (int)cudaMemset(m->flag_dev, 0, sizeof(int));
   if (rc == BB_OK) {

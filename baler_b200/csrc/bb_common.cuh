@@ -23,6 +23,8 @@ struct bb_ctx {
   float* minmax_scratch = nullptr;  // [2][blocks][cols] partials of the column min/max pass
   size_t minmax_scratch_bytes = 0;
   unsigned int* minmax_counter = nullptr;
+  float* lay_scratch = nullptr;     // ping-pong activation scratch of the layered GEMM path
+  size_t lay_scratch_bytes = 0;
 };
 
 // One dense layer of a fused chain as the fp32 kernel sees it.
@@ -53,6 +55,12 @@ struct Chain {
   void* tc_blob_dev = nullptr;
   size_t tc_blob_bytes = 0;
   void* tc_host = nullptr;     // TcHost: step program + launch geometry of the tcgen05 kernel
+  // layered GEMM path (any shape)
+  bool f32_ok = false;         // the fused fp32 kernel fits shared memory
+  bool lay_ok = false;
+  float* lay_blob_dev = nullptr;
+  size_t lay_w_off[BB_MAX_LAYERS] = {0}, lay_b_off[BB_MAX_LAYERS] = {0};
+  int lay_max_ld = 0;
   std::vector<double> w_host[BB_MAX_LAYERS];  // kept for re-packing
   std::vector<double> b_host[BB_MAX_LAYERS];
 };
@@ -74,6 +82,10 @@ int bb_chain_f32_prepare(bb_ctx* ctx, Chain* c);
 int bb_chain_f32_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
                         const float* pre_min, const float* pre_range, const float* post_min,
                         const float* post_range, void* out, int out_dtype, cudaStream_t stream);
+int bb_chain_layered_prepare(bb_ctx* ctx, Chain* c);
+int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
+                            const float* pre_min, const float* pre_range, const float* post_min,
+                            const float* post_range, void* out, int out_dtype, cudaStream_t stream);
 int bb_colminmax_launch(bb_ctx* ctx, const float* x, int64_t n_rows, int n_cols, float* min_dev,
                         float* max_dev, int reset, cudaStream_t stream);
 int bb_tc_prepare(bb_ctx* ctx, Chain* c);

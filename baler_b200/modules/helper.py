@@ -164,17 +164,21 @@ def compress(model_path, config):
         data_before = data_processing.convert_to_blocks_util(config.convert_to_blocks, data_before)
     if getattr(config, "save_error_bounded_deltas", False):
         raise NotImplementedError("error-bounded deltas: listed as a next row in DESIGN.md")
+    conv = False
     if config.data_dimension == 1:
         number_of_columns = len(loaded["names"])
         config.latent_space_size = ceil(number_of_columns / config.compression_ratio)
         config.number_of_columns = number_of_columns
         n_features = number_of_columns
     elif config.data_dimension == 2:
-        if config.model_type != "dense":
-            raise NotImplementedError("convolutional models: see DESIGN.md (next rows)")
-        number_of_rows, config.number_of_columns = data_before.shape[1], data_before.shape[2]
-        n_features = number_of_rows * config.number_of_columns
-        config.latent_space_size = ceil(n_features / config.compression_ratio)
+        if config.model_type == "dense":
+            number_of_rows, config.number_of_columns = data_before.shape[1], data_before.shape[2]
+            n_features = number_of_rows * config.number_of_columns
+        else:  # convolutional (reference helper.py:521-524): sizes come from the ORIGINAL snapshot shape
+            conv = True
+            number_of_rows, config.number_of_columns = original_shape[1], original_shape[2]
+            n_features = config.number_of_columns
+        config.latent_space_size = ceil((number_of_rows * config.number_of_columns) / config.compression_ratio)
     else:
         raise NameError("Data dimension can only be 1 or 2. Got config.data_dimension = " + str(config.data_dimension))
     model = data_processing.load_model(data_processing.initialise_model(config.model_name), model_path,
@@ -184,9 +188,10 @@ def compress(model_path, config):
     normalise = bool(config.apply_normalization) and not config.custom_norm
     if config.apply_normalization:
         print("Normalizing...")
-    compressed, _ = model.codec().compress_host(table, recompute_minmax=normalise,
-                                                z_dtype=_latent_np_dtype(model, config),
-                                                precision=getattr(config, "precision", "auto"))
+    codec = model.codec(data_before.shape[1], data_before.shape[2]) if conv else model.codec()
+    compressed, _ = codec.compress_host(table, recompute_minmax=normalise,
+                                        z_dtype=_latent_np_dtype(model, config),
+                                        precision=getattr(config, "precision", "auto"))
     return compressed, [], [], []
 
 
@@ -210,8 +215,17 @@ def decompress(model_path, input_path, input_path_deltas, input_batch_index, mod
     if data.dtype not in (np.float16, np.float32, np.float64):
         data = data.astype(np.float32)
     out_dtype = np.float64 if model.dtype == torch.float64 else np.float32
-    decompressed = model.codec().decompress_host(data, features=renormalize_features, y_dtype=out_dtype,
-                                                 precision=getattr(config, "precision", "auto"))
+    conv = config.data_dimension == 2 and config.model_type == "convolutional"
+    if conv:  # block shape: convert_to_blocks = [1, h, w], else the whole snapshot
+        blocks = getattr(config, "convert_to_blocks", None)
+        h, w = (int(blocks[1]), int(blocks[2])) if blocks else (original_shape[1], original_shape[2])
+        codec = model.codec(h, w)
+    else:
+        codec = model.codec()
+    decompressed = codec.decompress_host(data, features=renormalize_features, y_dtype=out_dtype,
+                                         precision=getattr(config, "precision", "auto"))
+    if conv:
+        decompressed = decompressed.reshape(len(decompressed), 1, h, w)
     if config.data_dimension == 2 and config.model_type == "dense":
         decompressed = decompressed.reshape((len(decompressed), original_shape[1], original_shape[2]))
     return decompressed, names, normalization_features

@@ -263,3 +263,144 @@ class AE_Dropout_BN(_DenseBase):
         if self.training:
             raise NotImplementedError("train-mode forward of AE_Dropout_BN runs inside training.train")
         return super().decode(z, precision)
+
+
+class Conv_AE:
+    """reference models.py:316-407 (float32).  Only inputs whose conv stack flattens to 128 values are valid
+    upstream (5x5, 3x6, 2x8 blocks: the Linear(128, 2000) is hard-coded); `convert_to_blocks=[1,5,5]`
+    is the working configuration.
+
+    Inference here: on a fixed block shape every (transposed) convolution is a linear map of the flattened tensor,
+    so the whole network is a dense chain
+        encode  HW -> 8x(H+1)x(W-2) -> 16x.. (BN2d folded) -> 128 -> 2000 -> z        (ReLU after every layer)
+        decode  z -> 2000 -> 128 -> 16x.. (BN folded) -> 8x.. (BN folded) -> HW      (ReLU except the output)
+    whose matrices are built once on the host (float64, by pushing an identity basis through torch's own conv on
+    the CPU - weight preprocessing, not the data path) and run by the CUDA GEMM chain (96 % of the FLOPs are the
+    two 2000-wide Linears either way).  Training of Conv_AE is not part of this round."""
+
+    dtype = torch.float32
+
+    def __init__(self, n_features, z_dim, *args, **kwargs):
+        nn = torch.nn
+        self.n_features, self.z_dim = n_features, z_dim
+        self.q_z_mid_dim, self.q_z_output_dim = 2000, 128
+        self.conv_op_shape = None
+        self.training = True
+        # same construction order as the reference so that the RNG stream (initial weights) is identical
+        mods = OrderedDict()
+        mods["q_z_conv.0"] = nn.Conv2d(1, 8, kernel_size=(2, 5), stride=1, padding=1)
+        mods["q_z_conv.2"] = nn.Conv2d(8, 16, kernel_size=3, stride=1, padding=1)
+        mods["q_z_conv.3"] = nn.BatchNorm2d(16)
+        mods["q_z_conv.5"] = nn.Conv2d(16, 32, kernel_size=3, stride=1, padding=0)
+        mods["q_z_lin.0"] = nn.Linear(self.q_z_output_dim, self.q_z_mid_dim)
+        mods["q_z_lin.2"] = nn.Linear(self.q_z_mid_dim, z_dim)
+        mods["p_x_lin.0"] = nn.Linear(z_dim, self.q_z_mid_dim)
+        mods["p_x_lin.2"] = nn.Linear(self.q_z_mid_dim, self.q_z_output_dim)
+        mods["p_x_conv.0"] = nn.ConvTranspose2d(32, 16, kernel_size=3, stride=1, padding=0)
+        mods["p_x_conv.1"] = nn.BatchNorm2d(16)
+        mods["p_x_conv.3"] = nn.ConvTranspose2d(16, 8, kernel_size=3, stride=1, padding=1)
+        mods["p_x_conv.4"] = nn.BatchNorm2d(8)
+        mods["p_x_conv.6"] = nn.ConvTranspose2d(8, 1, kernel_size=(2, 5), stride=1, padding=1)
+        self._sd = OrderedDict()
+        for name, m in mods.items():
+            for k, v in m.state_dict().items():
+                self._sd[name + "." + k] = v.detach().clone()
+        self._codec, self._codec_hw = None, None
+
+    # -- nn.Module-like protocol (same as the dense models)
+    state_dict = _DenseBase.state_dict
+    load_state_dict = _DenseBase.load_state_dict
+    train = _DenseBase.train
+    eval = _DenseBase.eval
+    to = _DenseBase.to
+    __call__ = _DenseBase.__call__
+
+    def parameters(self):
+        return [v for k, v in self._sd.items() if k.endswith((".weight", ".bias"))]
+
+    def children(self):
+        return ["q_z_conv", "flatten", "q_z_lin", "p_x_lin", "p_x_conv"]
+
+    def get_final_layer_dims(self):
+        return self.conv_op_shape
+
+    def set_final_layer_dims(self, conv_op_shape):
+        self.conv_op_shape = conv_op_shape
+
+    # -- dense-equivalent chains for a block shape (h, w)
+    def _t(self, key):
+        return self._sd[key].detach().to(torch.float64)
+
+    def _bn(self, name):
+        s = self._t(name + ".weight") / torch.sqrt(self._t(name + ".running_var") + BN_EPS)
+        return s, self._t(name + ".bias") - s * self._t(name + ".running_mean")
+
+    @staticmethod
+    def _as_matrix(fn, in_shape):
+        """dense (out, in) matrix and bias of the affine map `fn` on tensors of shape in_shape"""
+        n_in = int(np.prod(in_shape))
+        with torch.no_grad():
+            b = fn(torch.zeros((1,) + in_shape, dtype=torch.float64))
+            out_shape = tuple(b.shape[1:])
+            m = fn(torch.eye(n_in, dtype=torch.float64).reshape((n_in,) + in_shape)) - b
+        return m.reshape(n_in, -1).T.contiguous().numpy(), b.reshape(-1).numpy(), out_shape
+
+    def _chains(self, h, w):
+        F = torch.nn.functional
+
+        def chan_affine(mat, bias, shape, s, t):  # per-channel y * s + t on a flattened (C, H, W) output
+            rep = shape[1] * shape[2]
+            sv, tv = s.repeat_interleave(rep).numpy(), t.repeat_interleave(rep).numpy()
+            return mat * sv[:, None], bias * sv + tv
+
+        enc, shape = [], (1, h, w)
+        m, b, shape = self._as_matrix(lambda x: F.conv2d(x, self._t("q_z_conv.0.weight"), self._t("q_z_conv.0.bias"), padding=1), shape)
+        enc.append((m, b, "relu"))
+        m, b, shape = self._as_matrix(lambda x: F.conv2d(x, self._t("q_z_conv.2.weight"), self._t("q_z_conv.2.bias"), padding=1), shape)
+        m, b = chan_affine(m, b, shape, *self._bn("q_z_conv.3"))
+        enc.append((m, b, "relu"))
+        m, b, shape = self._as_matrix(lambda x: F.conv2d(x, self._t("q_z_conv.5.weight"), self._t("q_z_conv.5.bias"), padding=0), shape)
+        enc.append((m, b, "relu"))
+        conv_out = shape
+        if int(np.prod(shape)) != self.q_z_output_dim:
+            raise RuntimeError("Conv_AE: a %dx%d block flattens to %d values, the model's Linear expects %d "
+                               "(reference models.py:320-343)" % (h, w, int(np.prod(shape)), self.q_z_output_dim))
+        enc.append((self._t("q_z_lin.0.weight").numpy(), self._t("q_z_lin.0.bias").numpy(), "relu"))
+        enc.append((self._t("q_z_lin.2.weight").numpy(), self._t("q_z_lin.2.bias").numpy(), "relu"))
+        dec = [(self._t("p_x_lin.0.weight").numpy(), self._t("p_x_lin.0.bias").numpy(), "relu"),
+               (self._t("p_x_lin.2.weight").numpy(), self._t("p_x_lin.2.bias").numpy(), "relu")]
+        shape = conv_out
+        m, b, shape = self._as_matrix(lambda x: F.conv_transpose2d(x, self._t("p_x_conv.0.weight"), self._t("p_x_conv.0.bias"), padding=0), shape)
+        m, b = chan_affine(m, b, shape, *self._bn("p_x_conv.1"))
+        dec.append((m, b, "relu"))
+        m, b, shape = self._as_matrix(lambda x: F.conv_transpose2d(x, self._t("p_x_conv.3.weight"), self._t("p_x_conv.3.bias"), padding=1), shape)
+        m, b = chan_affine(m, b, shape, *self._bn("p_x_conv.4"))
+        dec.append((m, b, "relu"))
+        m, b, shape = self._as_matrix(lambda x: F.conv_transpose2d(x, self._t("p_x_conv.6.weight"), self._t("p_x_conv.6.bias"), padding=1), shape)
+        dec.append((m, b, "none"))
+        return enc, dec, conv_out
+
+    def codec(self, h=5, w=5):
+        if self._codec is None or self._codec_hw != (h, w):
+            enc, dec, conv_out = self._chains(h, w)
+            self._codec, self._codec_hw, self._conv_out = engine.DenseCodec(enc, dec), (h, w), conv_out
+        return self._codec
+
+    def encode(self, x, precision="auto"):
+        if self.training:
+            raise NotImplementedError("Conv_AE training (batch-statistics BatchNorm2d) is not part of this round")
+        x = _as_cuda_f32(x)
+        h, w = x.shape[-2], x.shape[-1]
+        z = self.codec(h, w).encode(x.reshape(-1, h * w), precision=precision)
+        self.conv_op_shape = torch.Size((z.shape[0],) + self._conv_out)
+        return z
+
+    def decode(self, z, precision="auto"):
+        if self.training:
+            raise NotImplementedError("Conv_AE training (batch-statistics BatchNorm2d) is not part of this round")
+        h, w = self._codec_hw if self._codec_hw else (5, 5)
+        y = self.codec(h, w).decode(_as_cuda_f32(z).reshape(-1, self.z_dim), precision=precision)
+        return y.reshape(-1, 1, h, w)  # any batch size: the reference's view() to the LAST TRAINING batch (F7c) is not reproduced
+
+    def forward(self, x):
+        return self.decode(self.encode(x))

@@ -18,7 +18,8 @@ Fixtures (all float64 unless noted; state-dict tensors stored under "<prefix>/<k
   ae_dbn.npz        AE_Dropout_BN(24,15): eval encode/decode; one train step with captured masks
   cli_roundtrip.npz perform_training/compression/decompression in a temp workspace (4096 rows)
   schedules.npz     LRScheduler / EarlyStopping decision sequences
-  conv_ae.npz       Conv_AE(5, 250) on 5x5 blocks: eval encode/decode, one train step
+  conv_ae.npz       Conv_AE(5, 250) on 5x5 blocks: eval encode / decode (weights by seed + checksums)
+  cfd_dense.npz     CFD_dense_AE(2500, 25) on 50x50 snapshots: encode / decode (weights by seed + checksums)
 """
 import os
 import sys
@@ -312,13 +313,13 @@ def gen_schedules():
     print("schedules", lrs[-1], lrs2[-1], stops)
 
 
-def gen_conv_ae():
-    snaps = synth.cfd_snapshots(6)  # 6 x 50 x 50 -> 600 blocks of 1x5x5
-    blocks = ref_helper.data_processing.convert_to_blocks_util([1, 5, 5], snaps)
-    xs = torch.tensor(blocks, dtype=torch.float32).view(blocks.shape[0], 1, 5, 5)
-    torch.manual_seed(0)
-    model = ref_models.Conv_AE(5, 250)
-    g = torch.Generator().manual_seed(2)
+def _checksums(model):
+    return {f"chk/{k}": np.array(float(v.double().abs().sum())) for k, v in model.state_dict().items()}
+
+
+def randomise_bn2d(model, seed=2):
+    """non-trivial BatchNorm2d buffers / affine so that folding is actually tested; the test applies the same"""
+    g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for m in model.modules():
             if isinstance(m, torch.nn.BatchNorm2d):
@@ -326,21 +327,49 @@ def gen_conv_ae():
                 m.bias.copy_(0.2 * torch.randn(m.bias.shape, generator=g))
                 m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
                 m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
-    d = dict(blocks=blocks[:64].astype(np.float32))
-    sd0 = {f"sd0/{k}": v.detach().numpy().copy().astype(np.float16 if False else np.float32)
-           for k, v in model.state_dict().items()}
-    d.update(sd0)
+
+
+def gen_conv_ae():
+    """Conv_AE(5, 250) on 5x5 blocks (the only block shapes the reference model accepts).  The 6 MB of
+    weights are not stored: they are torch.manual_seed(0) initial weights (reproduced by the drop-in class, checked
+    through per-tensor checksums) plus the BatchNorm2d statistics written here."""
+    snaps = synth.cfd_snapshots(6)  # 6 x 50 x 50 -> 600 blocks of 1x5x5
+    blocks = ref_helper.data_processing.convert_to_blocks_util([1, 5, 5], snaps)
+    xs = torch.tensor(blocks, dtype=torch.float32).view(blocks.shape[0], 1, 5, 5)
+    torch.manual_seed(0)
+    model = ref_models.Conv_AE(5, 250)
+    randomise_bn2d(model)
+    d = dict(blocks=blocks.astype(np.float32))
+    d.update(_checksums(model))
+    d.update({f"bn/{k}": v.numpy().copy() for k, v in model.state_dict().items()
+              if ".3." in k and k.startswith("q_z_conv") or k.startswith(("p_x_conv.1.", "p_x_conv.4."))})
     model.eval()
     with torch.no_grad():
-        z = model.encode(xs[:64])
+        z = model.encode(xs)
         y = model.decode(z)
     d.update(latent_eval=z.numpy(), recon_eval=y.numpy())
     np.savez_compressed(os.path.join(OUT, "conv_ae.npz"), **d)
     print("conv_ae", z.shape, y.shape, os.path.getsize(os.path.join(OUT, "conv_ae.npz")) / 1e6, "MB")
 
 
+def gen_cfd_dense():
+    """CFD_dense_AE(2500, 25) (float32) on 50x50 snapshots, as CFD_project_animation configures it."""
+    snaps = synth.cfd_snapshots(60)
+    xs = torch.tensor(snaps, dtype=torch.float32).view(60, 2500)
+    torch.manual_seed(0)
+    model = ref_models.CFD_dense_AE(2500, 25)
+    d = dict(_checksums(model))
+    model.eval()
+    with torch.no_grad():
+        z = model.encode(xs)
+        y = model.decode(z)
+    d.update(latent=z.numpy(), recon=y.numpy())
+    np.savez_compressed(os.path.join(OUT, "cfd_dense.npz"), **d)
+    print("cfd_dense", z.shape, y.shape, os.path.getsize(os.path.join(OUT, "cfd_dense.npz")) / 1e6, "MB")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules"]
+    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules", "conv_ae", "cfd_dense"]
     for name in which:
         globals()["gen_" + name]()
