@@ -236,7 +236,7 @@ def run_ours(args):
     # ---- e2e: host buffers through the C-ABI pipelines
     e2e = None
     if not args.no_e2e:
-        ne = min(n, args.e2e_rows)
+        ne = min(n, max(args.e2e_rows // world, 1_000_000))  # total pinned host memory stays ~25 GB whatever N
         xh = torch.empty((ne, 24), dtype=torch.float32, pin_memory=True)
         zh = torch.empty((ne, 15), dtype=torch.float32, pin_memory=True)
         yh = torch.empty((ne, 24), dtype=torch.float32, pin_memory=True)
