@@ -5,11 +5,12 @@
 // with utils.mse_sum_loss_l1 (utils.py:176-211) and torch.optim.Adam defaults (training.py:266).
 //
 // A step is three launches on one stream, no host synchronisation:
-//   1. train_fwd_bwd_kernel  one CTA per 8 rows of the batch.  The CTA walks the 8 layers forward and the
-//      8 layers backward with every activation of its rows in shared memory; weights stream from L2
-//      (W^T [K][N] forward, W [N][K] backward, both unit-stride across threads).  Narrow layers split the
-//      reduction over threads (KP partial sums, combined in a fixed order).  It leaves the layer inputs A_l
-//      and the pre-activation gradients dZ_l (row-major [B][dim]) in global scratch and one loss partial per CTA.
+//   1. train_fwd_bwd_kernel  one CTA (512 threads) per 4 rows of the batch.  The CTA walks the 8 layers forward and
+//      the 8 layers backward with every activation of its rows in shared memory; the weight matrix of the next
+//      pass (W^T [K][N] forward, W [N][K] backward) is staged L2 -> shared memory with cp.async while the current
+//      pass computes.  Narrow layers split the reduction over threads (KP partial sums, combined in a fixed
+//      order).  It leaves the layer inputs A_l and the pre-activation gradients dZ_l (row-major [B][dim]) in
+//      global scratch and one loss partial per CTA.
 //   2. train_dw_kernel       dW_l = dZ_l^T A_l as 64x64 output tiles x 64-row splits, 4x4 register tiles,
 //      written as per-split partial sums (no atomics: the sum order is fixed, results are reproducible).
 //   3. train_adam_kernel     sums the split partials into the flat gradient, applies Adam and refreshes the
@@ -108,7 +109,7 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
   return v;
 }
 
-// acc[r] = sum_{i in [i0, i1)} in_s[i][r] * Wm[i * Dout + j]   (8 rows r)
+// acc[r] = sum_{i in [i0, i1)} in_s[i][r] * Wm[i * Dout + j]   (RT rows r)
 __device__ __forceinline__ void gemv8_slice(const float* __restrict__ in_s, const float* __restrict__ Wm, const int Dout,
                                             const int j, const int i0, const int i1, float (&acc)[RT]) {
 #pragma unroll
@@ -160,7 +161,7 @@ __device__ __forceinline__ float red_sum(const float* red_s, int KP, int Dout, i
   return s;
 }
 
-// One chain (model chain: activations from d.act; L1 chain: ReLU everywhere) forward + backward for 8 rows.
+// One chain (model chain: activations from d.act; L1 chain: ReLU everywhere) forward + backward for RT rows.
 //   chain 0: loss term sum((recon - x)^2) / C, seed gradient 2 (recon - x) / C
 //   chain 1: loss term reg * sum_l mean|v_l|,  gradient reg / (B * N_l) injected at every layer output
 template <int CHAIN>
