@@ -99,8 +99,15 @@ def cpu_reference_pass(sd_t, table):
     return z, torch_port.decompress(sd_t, z, feats)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host thread it can"""
+    import torch
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+
+
 def cpu_baseline(sd, sample_rows, repeats=2):
     import torch
+    use_all_host_threads()
     from oracle import baler_oracle as orc
     from oracle import torch_port
     from baler_b200 import synth
@@ -131,6 +138,7 @@ def run_reference(args):
     import torch
     from oracle import torch_port
     from baler_b200 import synth
+    use_all_host_threads()
     sd = golden_state_dict()
     sd_t = torch_port.to_torch(sd)
     rows = args.ref_rows
@@ -168,6 +176,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     sd = golden_state_dict()
@@ -303,6 +312,7 @@ def run_ours(args):
         cpu_train = None
         if world == 1 and not args.no_cpu:
             from oracle import torch_port
+            use_all_host_threads()
             sd0 = {k: v.numpy() for k, v in tm.state_dict().items()}
             xs = xt[:512 * 64].cpu().numpy()
             torch_port.fit_steps(sd0, xs, 512, 10)
