@@ -109,24 +109,46 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
   return v;
 }
 
-// acc[r] = sum_{i in [i0, i1)} in_s[i][r] * Wm[i * Dout + j]   (RT rows r)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// o -> (o / n, o % n) without a division per element: q = mulhi(o, ceil(2^32 / n)), exact for o * n < 2^32
+struct FastDiv {
+  unsigned n, magic;
+  __device__ explicit FastDiv(int n_) : n((unsigned)n_), magic(n_ > 1 ? 0xFFFFFFFFu / (unsigned)n_ + 1u : 0u) {}
+  __device__ __forceinline__ void divmod(int o, int& q, int& r) const {
+    q = n > 1 ? (int)__umulhi((unsigned)o, magic) : o;
+    r = o - q * (int)n;
+  }
+};
+
+// acc[r] = sum_{i in [i0, i1)} in_s[i][r] * Wm[i * Dout + j]   (RT rows r); both operands in shared memory, addressed
+// with 32-bit shared-window addresses (generic pointers cost 64-bit address arithmetic on every load)
 __device__ __forceinline__ void gemv8_slice(const float* __restrict__ in_s, const float* __restrict__ Wm, const int Dout,
                                             const int j, const int i0, const int i1, float (&acc)[RT]) {
 #pragma unroll
   for (int r = 0; r < RT; ++r) acc[r] = 0.f;
-  const float* w = Wm + (size_t)i0 * Dout + j;
-  const float* a = in_s + i0 * RT;
+  uint32_t w = smem_u32(Wm) + (uint32_t)(i0 * Dout + j) * 4u;
+  uint32_t a = smem_u32(in_s) + (uint32_t)(i0 * RT) * 4u;
+  const uint32_t wstep = (uint32_t)Dout * 4u;
 #pragma unroll 4
   for (int i = i0; i < i1; ++i) {
-    const float wv = *w;
+    const float wv = lds_f32(w);
 #pragma unroll
     for (int q = 0; q < RT / 4; ++q) {
-      const float4 a4 = *reinterpret_cast<const float4*>(a + 4 * q);
+      const float4 a4 = lds_v4(a + 16u * q);
       acc[4 * q + 0] = fmaf(a4.x, wv, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(a4.y, wv, acc[4 * q + 1]);
       acc[4 * q + 2] = fmaf(a4.z, wv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a4.w, wv, acc[4 * q + 3]);
     }
-    w += Dout;
-    a += RT;
+    w += wstep;
+    a += RT * 4u;
   }
 }
 
@@ -145,7 +167,8 @@ __device__ __forceinline__ int gemv8(const float* __restrict__ in_s, const float
     }
   } else if (threadIdx.x < KP * Dout) {
     const int per = (Din + KP - 1) / KP;
-    const int kp = threadIdx.x / Dout, j = threadIdx.x - kp * Dout;
+    int kp, j;
+    FastDiv(Dout).divmod((int)threadIdx.x, kp, j);
     const int i0 = min(Din, kp * per), i1 = min(Din, i0 + per);
     gemv8_slice(in_s, Wm, Dout, j, i0, i1, acc);
 #pragma unroll
@@ -178,7 +201,8 @@ __device__ void run_chain(const TrainDims& d, const float* __restrict__ params, 
     const float* bias = params + d.b_off[l];
     const int act = CHAIN == 0 ? d.act[l] : BB_ACT_RELU;
     for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
-      const int r = o / N, j = o - r * N;
+      int r, j;
+      FastDiv(N).divmod(o, r, j);
       const float v = act_fwd(red_sum(red_s, KP, N, r, j) + __ldg(bias + j), act);
       out_s[j * RT + r] = v;
       if (r < rows && l + 1 < NL) act_g[(size_t)(row0 + r) * d.a_stride + d.a_off[l + 1] + j] = v;
@@ -194,7 +218,8 @@ __device__ void run_chain(const TrainDims& d, const float* __restrict__ params, 
     const float* out_s = act_s + d.a_off[NL] * RT;
     const float* x_s = act_s;  // a_off[0] == 0
     for (int o = threadIdx.x; o < RT * F; o += NT_FB) {
-      const int r = o / F, j = o - r * F;
+      int r, j;
+      FastDiv(F).divmod(o, r, j);
       float g = 0.f;
       if (r < rows) {
         if (CHAIN == 0) {
@@ -219,7 +244,8 @@ __device__ void run_chain(const TrainDims& d, const float* __restrict__ params, 
     const int act = CHAIN == 0 ? d.act[l - 1] : BB_ACT_RELU;
     const float seed = CHAIN == 1 ? reg * inv_rows / K : 0.f;
     for (int o = threadIdx.x; o < RT * K; o += NT_FB) {
-      const int r = o / K, j = o - r * K;
+      int r, j;
+      FastDiv(K).divmod(o, r, j);
       float g = red_sum(red_s, KP, K, r, j) + seed;
       const float a = a_s[j * RT + r];
       if (act == BB_ACT_LEAKY) g *= (a > 0.f ? 1.f : BB_LEAKY);
@@ -259,7 +285,8 @@ train_fwd_bwd_kernel(const __grid_constant__ TrainDims d, const float* __restric
   const int rows = min(RT, batch_rows - row0);
   const int F = d.dims[0];
   for (int o = threadIdx.x; o < RT * F; o += NT_FB) {
-    const int r = o / F, j = o - r * F;
+    int r, j;
+    FastDiv(F).divmod(o, r, j);
     const float v = r < rows ? __ldg(x + (size_t)(row0 + r) * F + j) : 0.f;
     act_s[j * RT + r] = v;
     if (r < rows) act_g[(size_t)(row0 + r) * d.a_stride + j] = v;  // A_0 copy keeps the dW kernel uniform
@@ -353,7 +380,8 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
   const int F = d.dims[0];
   const float keep_scale[4] = {1.f / 0.5f, 1.f / 0.6f, 1.f / 0.7f, 1.f / 0.8f};
   for (int o = threadIdx.x; o < RT * F; o += NT_FB) {
-    const int r = o / F, j = o - r * F;
+    int r, j;
+    FastDiv(F).divmod(o, r, j);
     const float v = r < rows ? __ldg(a.x + (size_t)(row0 + r) * F + j) : 0.f;
     act_s[j * RT + r] = v;
     if (r < rows) a.act_g[(size_t)(row0 + r) * d.a_stride + j] = v;
@@ -367,7 +395,8 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
     const float* bias = params + d.b_off[l];
     float* out_s = act_s + d.a_off[l + 1] * RT;
     for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
-      const int r = o / N, j = o - r * N;
+      int r, j;
+      FastDiv(N).divmod(o, r, j);
       float v = red_sum(red_s, KP, N, r, j) + __ldg(bias + j);
       if (train && r < rows) v = dropout_keep(a, l, row0 + r, j, N) ? v * keep_scale[l] : 0.f;
       v = act_fwd(v, BB_ACT_LEAKY);
@@ -383,7 +412,8 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
     const int KP = gemv8(act_s + d.a_off[l] * RT, acquire_pass(d, params, wt, ws), K, N, red_s);
     const float* bias = params + d.b_off[l];
     for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
-      const int r = o / N, j = o - r * N;
+      int r, j;
+      FastDiv(N).divmod(o, r, j);
       float v = red_sum(red_s, KP, N, r, j) + __ldg(bias + j);
       if (i < 3) v = act_fwd(v, BB_ACT_LEAKY);
       u_s[(fo + j) * RT + r] = r < rows ? v : 0.f;
@@ -425,7 +455,8 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
     __syncthreads();
     float* out_s = act_s + d.a_off[l + 1] * RT;
     for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
-      const int r = o / N, j = o - r * N;
+      int r, j;
+      FastDiv(N).divmod(o, r, j);
       const float xh = (u_s[(fo + j) * RT + r] - tot_s[j]) * inv_s[fo + j];
       float h = fmaf(xh, __ldg(gam + j), __ldg(bet + j));
       if (i == 3) h = fmaxf(h, 0.f);
@@ -442,7 +473,8 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
   {
     const float* out_s = act_s + d.a_off[NL] * RT;
     for (int o = threadIdx.x; o < RT * F; o += NT_FB) {
-      const int r = o / F, j = o - r * F;
+      int r, j;
+      FastDiv(F).divmod(o, r, j);
       float g = 0.f;
       if (r < rows) {
         const float rec = out_s[j * RT + r];
@@ -478,7 +510,8 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
       const float* gam = params + d.bn_g_off[i];
       const float invB = 1.f / B;
       for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
-        const int r = o / N, j = o - r * N;
+        int r, j;
+        FastDiv(N).divmod(o, r, j);
         const float g = __ldg(gam + j);
         // dx = inv / B * (B dxh - sum(dxh) - xhat sum(dxh xhat)), dxh = dy * gamma
         float dx = inv_s[fo + j] * g * (dz_cur[j * RT + r] - invB * tot_s[j] - xhat_s[(fo + j) * RT + r] * invB * tot_s[d.max_dim + j]);
@@ -491,7 +524,8 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
       {  // dX = dZ W_l  (gradient w.r.t. the input of Linear l = output of the previous block)
         const int KP = gemv8(dz_nxt, acquire_pass(d, params, wt, ws), N, K, red_s);
         for (int o = threadIdx.x; o < RT * K; o += NT_FB) {
-          const int r = o / K, j = o - r * K;
+          int r, j;
+          FastDiv(K).divmod(o, r, j);
           dz_cur[j * RT + r] = red_sum(red_s, KP, K, r, j);
         }
         __syncthreads();
@@ -502,7 +536,8 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
       const int K = d.dims[l], N = d.dims[l + 1];
       const float* a_out = act_s + d.a_off[l + 1] * RT;
       for (int o = threadIdx.x; o < RT * N; o += NT_FB) {
-        const int r = o / N, j = o - r * N;
+        int r, j;
+        FastDiv(N).divmod(o, r, j);
         float g = 0.f;
         if (r < rows) {
           g = dz_cur[j * RT + r] * (a_out[j * RT + r] > 0.f ? 1.f : BB_LEAKY);
@@ -515,7 +550,8 @@ train_dbn_kernel(const __grid_constant__ TrainDims d, const float* __restrict__ 
       if (l >= 1) {
         const int KP = gemv8(dz_nxt, acquire_pass(d, params, wt, ws), N, K, red_s);
         for (int o = threadIdx.x; o < RT * K; o += NT_FB) {
-          const int r = o / K, j = o - r * K;
+          int r, j;
+          FastDiv(K).divmod(o, r, j);
           dz_cur[j * RT + r] = red_sum(red_s, KP, K, r, j);
         }
         __syncthreads();
