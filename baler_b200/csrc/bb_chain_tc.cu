@@ -342,56 +342,83 @@ chain_tc_kernel(const __grid_constant__ TcProgram prog, const uint8_t* __restric
       mbar_wait(bar_w, 0);  // weights resident
       uint32_t par_a1 = 0, par_chunk = 0;
       int64_t lt = 0;
-      const int n_steps = prog.n_steps;
       const bool lane0 = (tid & 31) == 0;
+      // Everything the tcgen05 instructions consume is warp-uniform and is derived here from kernel parameters
+      // (constant bank) and two shuffled values, so the compiler keeps descriptors and TMEM addresses in uniform
+      // registers: a k-step costs a handful of uniform adds, not a shared-memory table read plus a dozen R2UR.
+      const uint32_t tcol_u = __shfl_sync(0xffffffffu, tcol0, 0);
+      const uint32_t w_addr = __shfl_sync(0xffffffffu, smem_u32(w_s), 0);
+      const uint32_t bar_full_u = __shfl_sync(0xffffffffu, bar_full, 0);
+      const uint32_t bar_chunk_u = bar_full_u + 24u, bar_a1_u = bar_full_u + 16u;
       for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, ++lt) {
         if (lane0) trace(lt, 32);
-        mbar_wait(bar_a1, par_a1);
+        mbar_wait(bar_a1_u, par_a1);
         par_a1 ^= 1u;
         tc_fence_after();
         if (lane0) trace(lt, 33);
-        int e = 0;
-        for (int s = 0; s < n_steps; ++s) {
-          const int e1 = kit_begin[s + 1];
-          for (; e < e1; ++e) {
-            const uint4 q0 = *reinterpret_cast<const uint4*>(&kit[e]);
-            const uint4 q1 = *reinterpret_cast<const uint4*>(&kit[e].d_acc);
-            if (q1.z) {  // this k-step opens a chunk the previous step's epilogue is still producing
-              const uint32_t c = q1.z - 1u;
-              mbar_wait(bar_chunk0 + 8u * c, (par_chunk >> c) & 1u);
-              par_chunk ^= 1u << c;
-              tc_fence_after();
-              if (lane0) trace(lt, 34 + 5 * s + (int)c);
+#pragma unroll
+        for (int s = 0; s < MAX_STEPS; ++s) {
+          if (s < prog.n_steps) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              if (m < prog.step[s].n_mma) {
+                const TcMma& mm = prog.step[s].mma[m];
+                const uint32_t idesc = make_idesc(mm.n);
+                const uint32_t lbo_f = ((mm.lbo >> 4) & 0x3FFFu) << 16;
+                const uint32_t k_off = (uint32_t)mm.ks0 * 2u * mm.lbo;
+                uint32_t bh = (((w_addr + mm.b_hi + k_off) >> 4) & 0x3FFFu) | lbo_f;
+                uint32_t bl = (((w_addr + mm.b_lo + k_off) >> 4) & 0x3FFFu) | lbo_f;
+                const uint32_t b_step = (2u * mm.lbo) >> 4;  // two 8-wide K chunks per k-step
+                const uint32_t d_addr = tcol_u + (uint32_t)mm.d_col;
+                const int ks_n = mm.ks_n, a_w = mm.a_w, dep = mm.dep;
+                const uint32_t a_base = tcol_u + (uint32_t)mm.a_col;
+                for (int k = 0; k < ks_n; ++k) {
+                  if (dep && (k & 1) == 0) {  // this k-step opens a chunk the previous step's epilogue is still producing
+                    const uint32_t c = (uint32_t)k >> 1;
+                    mbar_wait(bar_chunk_u + 8u * c, (par_chunk >> c) & 1u);
+                    par_chunk ^= 1u << c;
+                    tc_fence_after();
+                    if (lane0) trace(lt, 34 + 5 * s + (int)c);
+                  }
+                  // A columns of k-step k: 32-column chunks hold hi k-steps at +0 / +8 and lo at +16 / +24; a trailing
+                  // 16-column chunk holds hi at +0 and lo at +8
+                  const uint32_t cb = ((uint32_t)k >> 1) << 5;
+                  const bool full = (int)cb + 32 <= a_w;
+                  const uint32_t a_hi = a_base + cb + (full ? ((uint32_t)k & 1u) << 3 : 0u);
+                  const uint32_t a_lo = a_hi + (full ? 16u : 8u);
+                  const uint32_t acc = (k > 0 || mm.acc) ? 1u : 0u;
+                  // hi*hi (accumulate flag), then hi*lo and lo*hi (always accumulate)
+                  if (!fast) {
+                    asm volatile(
+                        "{\n\t.reg .pred e, p, t;\n\t.reg .b64 bh, bl;\n\t"
+                        "elect.sync _|e, 0xffffffff;\n\t"
+                        "setp.ne.b32 p, %6, 0;\n\t"
+                        "setp.eq.b32 t, %6, %6;\n\t"
+                        "mov.b64 bh, {%2, %7};\n\t"
+                        "mov.b64 bl, {%3, %7};\n\t"
+                        "@e tcgen05.mma.cta_group::1.kind::f16 [%4], [%0], bh, %5, p;\n\t"
+                        "@e tcgen05.mma.cta_group::1.kind::f16 [%4], [%0], bl, %5, t;\n\t"
+                        "@e tcgen05.mma.cta_group::1.kind::f16 [%4], [%1], bh, %5, t;\n\t}"
+                        ::"r"(a_hi), "r"(a_lo), "r"(bh), "r"(bl), "r"(d_addr), "r"(idesc), "r"(acc), "r"(B_DESC_HI) : "memory");
+                  } else {
+                    asm volatile(
+                        "{\n\t.reg .pred e, p;\n\t.reg .b64 bh;\n\t"
+                        "elect.sync _|e, 0xffffffff;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "mov.b64 bh, {%1, %5};\n\t"
+                        "@e tcgen05.mma.cta_group::1.kind::f16 [%2], [%0], bh, %3, p;\n\t}"
+                        ::"r"(a_hi), "r"(bh), "r"(d_addr), "r"(idesc), "r"(acc), "r"(B_DESC_HI) : "memory");
+                  }
+                  bh += b_step; bl += b_step;
+                }
+              }
             }
-            // hi*hi (accumulate flag from the table), then hi*lo and lo*hi (always accumulate)
-            if (!fast) {
-              asm volatile(
-                  "{\n\t.reg .pred e, p, t;\n\t.reg .b64 bh, bl;\n\t"
-                  "elect.sync _|e, 0xffffffff;\n\t"
-                  "setp.ne.b32 p, %6, 0;\n\t"
-                  "setp.eq.b32 t, %6, %6;\n\t"
-                  "mov.b64 bh, {%2, %7};\n\t"
-                  "mov.b64 bl, {%3, %7};\n\t"
-                  "@e tcgen05.mma.cta_group::1.kind::f16 [%4], [%0], bh, %5, p;\n\t"
-                  "@e tcgen05.mma.cta_group::1.kind::f16 [%4], [%0], bl, %5, t;\n\t"
-                  "@e tcgen05.mma.cta_group::1.kind::f16 [%4], [%1], bh, %5, t;\n\t}"
-                  ::"r"(tcol0 + q0.x), "r"(tcol0 + q0.y), "r"(q0.z), "r"(q0.w), "r"(tcol0 + (q1.x & 0xFFFF)), "r"(q1.y),
-                    "r"(q1.x >> 31), "r"(B_DESC_HI) : "memory");
-            } else {
-              asm volatile(
-                  "{\n\t.reg .pred e, p;\n\t.reg .b64 bh;\n\t"
-                  "elect.sync _|e, 0xffffffff;\n\t"
-                  "setp.ne.b32 p, %4, 0;\n\t"
-                  "mov.b64 bh, {%1, %5};\n\t"
-                  "@e tcgen05.mma.cta_group::1.kind::f16 [%2], [%0], bh, %3, p;\n\t}"
-                  ::"r"(tcol0 + q0.x), "r"(q0.z), "r"(tcol0 + (q1.x & 0xFFFF)), "r"(q1.y), "r"(q1.x >> 31), "r"(B_DESC_HI) : "memory");
-            }
+            asm volatile(
+                "{\n\t.reg .pred e;\n\t"
+                "elect.sync _|e, 0xffffffff;\n\t"
+                "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_full_u + 8u * (uint32_t)(lt & 1)) : "memory");
+            if (lane0) trace(lt, 34 + 5 * s + 4);
           }
-          asm volatile(
-              "{\n\t.reg .pred e;\n\t"
-              "elect.sync _|e, 0xffffffff;\n\t"
-              "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_full + 8u * (uint32_t)(lt & 1)) : "memory");
-          if (lane0) trace(lt, 34 + 5 * s + 4);
         }
       }
     }
@@ -707,6 +734,20 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
   delete reinterpret_cast<TcHost*>(c->tc_host);
   c->tc_host = h;
   c->tc_ok = true;
+  // the reference AE family (hidden 200 / 100 / 50) also runs on the statically shaped kernel (bb_chain_tc4.cu),
+  // which reads the same weight image
+  Tc4Plan& t4 = c->tc4;
+  t4 = Tc4Plan();
+  const bool enc_family = wide == 0 && Np[0] == 208 && Np[1] == 112 && Np[2] == 64;
+  const bool dec_family = wide == 2 && Np[0] == 64 && Np[1] == 112 && Np[2] == 208;
+  if ((enc_family || dec_family) && getenv("BALER_B200_TC_V3") == nullptr) {
+    t4.ok = true; t4.enc = enc_family ? 1 : 0; t4.ka = Kp[0]; t4.nl = Np[3];
+    for (int l = 0; l < 4; ++l) {
+      const int act = d.layer[l].act;
+      t4.c1[l] = scale[l];
+      t4.c2[l] = act == BB_ACT_LEAKY ? scale[l] * BB_LEAKY : act == BB_ACT_RELU ? 0.f : scale[l];
+    }
+  }
   return BB_OK;
 }
 
@@ -720,6 +761,11 @@ int bb_tc_launch_dbg(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, 
                      int fast, int* flag_dev, int dbg_step, float* dbg_out, int force_groups, cudaStream_t stream) {
   if (!c->tc_ok) return BB_ERR_UNSUPPORTED;
   if (n_rows == 0) return BB_OK;
+  if (c->tc4.ok && in_dtype == BB_F32 && out_dtype == BB_F32 && force_groups == 0 && (dbg_step == -1 || dbg_step == -2)) {
+    const int rc = bb_tc4_launch(ctx, c, in, n_rows, pre_min, pre_range, post_min, post_range, out, fast, flag_dev,
+                                 dbg_step == -2 ? reinterpret_cast<uint32_t*>(dbg_out) : nullptr, stream);
+    if (rc != BB_ERR_UNSUPPORTED) return rc;
+  }
   const TcHost* h = reinterpret_cast<const TcHost*>(c->tc_host);
   const int groups = force_groups > 0 && force_groups < h->n_groups ? force_groups : h->n_groups;
   const int64_t n_tiles = (n_rows + TILE - 1) / TILE;

@@ -44,6 +44,13 @@ struct ChainDesc {
   ChainLayer layer[BB_MAX_LAYERS];
 };
 
+// Launch plan of the statically shaped tcgen05 kernel (bb_chain_tc4.cu); filled by bb_tc_prepare.
+struct Tc4Plan {
+  bool ok = false;
+  int enc = 0, ka = 0, nl = 0;  // direction, padded K of the first layer, padded N of the last layer
+  float c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};  // y = max(c1 * acc, c2 * acc) per layer
+};
+
 // Host + device state of one direction (encoder or decoder).
 struct Chain {
   ChainDesc desc;
@@ -55,6 +62,7 @@ struct Chain {
   void* tc_blob_dev = nullptr;
   size_t tc_blob_bytes = 0;
   void* tc_host = nullptr;     // TcHost: step program + launch geometry of the tcgen05 kernel
+  Tc4Plan tc4;                 // statically shaped kernel, when the chain is the reference AE family
   // layered GEMM path (any shape)
   bool f32_ok = false;         // the fused fp32 kernel fits shared memory
   bool lay_ok = false;
@@ -93,6 +101,9 @@ void bb_tc_release(Chain* c);
 int bb_tc_launch_dbg(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows, const float* pre_min,
                      const float* pre_range, const float* post_min, const float* post_range, void* out, int out_dtype,
                      int fast, int* flag_dev, int dbg_step, float* dbg_out, int force_groups, cudaStream_t stream);
+int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int64_t n_rows, const float* pre_min, const float* pre_range,
+                  const float* post_min, const float* post_range, void* out, int fast, int* flag_dev, uint32_t* trace,
+                  cudaStream_t stream);
 int bb_tc_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
                  const float* pre_min, const float* pre_range, const float* post_min,
                  const float* post_range, void* out, int out_dtype, int fast, int* flag_dev,

@@ -1,6 +1,8 @@
+"""SM-clock trace of one tile pipeline of the tcgen05 chain kernel (CTA 0, pipeline 0).
+usage: python tools/trace_tc.py [groups]   (groups > 0 forces the table-driven kernel with that many pipelines)"""
 import ctypes as C, sys, numpy as np, torch
 sys.path.insert(0, '.')
-from baler_b200 import _lib, synth
+from baler_b200 import _lib
 from baler_b200.modules import models
 g = np.load('tests/golden/ae_cms.npz')
 m = models.AE(24, 15); m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('sd/')})
@@ -20,13 +22,13 @@ for decode, dim_in, dim_out in ((0, 24, 15), (1, 15, 24)):
         assert rc == 0
         torch.cuda.synchronize()
     t = dbg.cpu().numpy().astype(np.int64).reshape(16, 64) & 0xffffffff
-    base = t[4, 0]
     print('decode' if decode else 'encode', 'tile period (cycles):', np.diff(t[2:12, 0]))
     for lt in (5, 6):
-        e = (t[lt, :32] - t[lt, 0]) & 0xffffffff
-        mm = (t[lt, 32:] - t[lt, 0]) & 0xffffffff
-        print(' tile', lt, 'EPI: start 0 | in ready', e[1], '| a1 arrive', e[2])
+        rel = lambda v: int((v - t[lt, 0]) & 0xffffffff) if v else -1
+        e = [rel(v) for v in t[lt, :32]]
+        mm = [rel(v) for v in t[lt, 32:]]
+        print(' tile', lt, 'EPI: start 0 | next-tile a1 conversion (h=1 warps) from', e[1], 'to', e[2])
         for s in range(5):
-            print('   step', s, 'full_d seen', e[3 + 4 * s], 'chunkA done', e[4 + 4 * s], 'chunkB done', e[5 + 4 * s],
-                  '| MMA waits', [int(mm[2 + 5 * s + c]) for c in range(4)], 'commit', mm[2 + 5 * s + 4])
-        print('   final done', e[24], 'after bar', e[25], '| MMA tile start', mm[0], 'a1 seen', mm[1])
+            print('   step', s, 'full_d seen', e[3 + 4 * s], 'sub0 done', e[4 + 4 * s], 'sub1 done', e[5 + 4 * s],
+                  '| MMA waits', [mm[2 + 5 * s + c] for c in range(4)], 'commit', mm[2 + 5 * s + 4])
+        print('   final: ld done', e[25], 'stage written', e[26], 'store issued', e[27], 'tile done', e[24], '| MMA tile start', mm[0], 'a1 seen', mm[1])
