@@ -744,8 +744,9 @@ int bb_tc_prepare(bb_ctx* ctx, Chain* c) {
     t4.ok = true; t4.enc = enc_family ? 1 : 0; t4.ka = Kp[0]; t4.nl = Np[3];
     for (int l = 0; l < 4; ++l) {
       const int act = d.layer[l].act;
-      t4.c1[l] = scale[l];
-      t4.c2[l] = act == BB_ACT_LEAKY ? scale[l] * BB_LEAKY : act == BB_ACT_RELU ? 0.f : scale[l];
+      // activation as y = c1 * v + c2 * |v| (see convert16 in bb_chain_tc4.cu)
+      t4.c1[l] = act == BB_ACT_LEAKY ? scale[l] * (0.5f + 0.5f * BB_LEAKY) : act == BB_ACT_RELU ? scale[l] * 0.5f : scale[l];
+      t4.c2[l] = act == BB_ACT_LEAKY ? scale[l] * (0.5f - 0.5f * BB_LEAKY) : act == BB_ACT_RELU ? scale[l] * 0.5f : 0.f;
     }
   }
   return BB_OK;

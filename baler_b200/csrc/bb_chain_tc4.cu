@@ -38,11 +38,14 @@ struct Tc4Params {
   float* out;
   int64_t n_rows;
   const float *pre_min, *pre_range, *post_min, *post_range;
-  float c1[4], c2[4];   // per layer: y = max(c1 * acc, c2 * acc)  (c1 = 2^-sw, c2 = c1 * {0.01 leaky, 0 relu, 1 none})
+  float c1[4], c2[4];   // per layer: y = c1 * acc + c2 * |acc|  (s = 2^-sw; leaky: 0.505 s, 0.495 s; relu: 0.5 s, 0.5 s; none: s, 0)
+  int epi_col[4], epi_nsub[4];      // steps 0..3: accumulator region (pipeline-relative column) and its 16-column sub-chunks
+  float epi_c1[4], epi_c2[4];       // the multipliers of the layer that step drains
   int in_dim, out_dim;
   int fast;
   int* flag;
-  uint32_t* trace;      // optional: SM-clock timestamps of CTA 0 / pipeline 0 (64 slots per tile, first 16 tiles)
+  uint32_t* trace;      // optional: SM-clock timestamps of CTA 0 / pipeline trace_pipe (64 slots per tile, first 16 tiles)
+  int trace_pipe;
 };
 
 // ------------------------------------------------------------------------------------------------ static program
@@ -104,10 +107,22 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done != 0;
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   // a protocol bug must not hang the GPU: trap (-> launch error) after ~1 s of polling
-  for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
-    if (spins > (1u << 24)) __trap();
+  // back off between polls: hot polling by the ~12 warps that wait at any time took 40 % of the SM's issue slots
+  for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins) {
+    __nanosleep(32);
+    if (spins > (1u << 22)) __trap();
+  }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   // try_wait blocks for a bounded, hardware-chosen time; the first poll usually succeeds on the hot path.  (The
@@ -175,13 +190,16 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// 16 accumulator columns -> scale + activation -> the next layer's k-step operand: 8 words hi | 8 words lo
-__device__ __forceinline__ void convert16(const uint32_t (&v)[16], const uint64_t c1, const uint64_t c2, uint32_t (&pk)[16]) {
+// 16 accumulator columns -> scale + activation -> the next layer's k-step operand: 8 words hi | 8 words lo.
+// The activation is y = c * v + d * |v| (leaky: c = 0.505 s, d = 0.495 s; relu: c = d = 0.5 s; none: c = s, d = 0;
+// s = 2^-sw undoes the weight scaling): FMUL + FFMA on the FMA pipe instead of two multiplies and an FMNMX, because
+// the ALU pipe (FMNMX, LOP3, F2FP: 2 cycles per warp instruction each, tools/alu_bench.cu) is what bounds this loop.
+__device__ __forceinline__ void convert16(const uint32_t (&v)[16], const uint64_t c2x, const float d, uint32_t (&pk)[16]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint64_t vv = pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-    const uint64_t sv = mul2(vv, c1), lv = mul2(vv, c2);
-    split2(fmaxf(lo32(sv), lo32(lv)), fmaxf(hi32(sv), hi32(lv)), pk[j], pk[8 + j]);
+    const float v0 = __uint_as_float(v[2 * j]), v1 = __uint_as_float(v[2 * j + 1]);
+    const uint64_t t = mul2(pack2(v0, v1), c2x);
+    split2(fmaf(fabsf(v0), d, lo32(t)), fmaf(fabsf(v1), d, hi32(t)), pk[j], pk[8 + j]);
   }
 }
 
@@ -221,45 +239,62 @@ constexpr int BAR_FULL = 0, BAR_A1 = 2, BAR_IN = 3, BAR_SUB = 5, BARS_PER_PIPE =
 
 // ------------------------------------------------------------------------------------------------ MMA issuer
 // All k-steps of MMA M of step S: every address and descriptor is a compile-time constant plus sb4 (a uniform value).
-template <class P, int G, int S, int M>
-__device__ __forceinline__ void issue_mma(const uint32_t bar_p, const uint32_t sb4, uint32_t& par_sub, const int fast) {
+constexpr int kstep_index(const SStep* st, int S, int M) {  // running k-step number of (step S, mma M, k = 0) within a tile
+  int n = 0;
+  for (int s = 0; s <= S; ++s)
+    for (int m = 0; m < st[s].n_mma; ++m) {
+      if (s == S && m == M) return n;
+      n += st[s].mma[m].ks_n;
+    }
+  return n;
+}
+template <class P, int S, int M, bool TRACE>
+__device__ __forceinline__ void issue_mma(const uint32_t tcol, const uint32_t bar_p, const uint32_t sb4, uint32_t& par_sub, const int fast,
+                                          uint32_t* tr) {
   constexpr SMma mm = P::step(S).mma[M];
-  constexpr uint32_t tcol = (uint32_t)G * PIPE_COLS;
+  constexpr SStep all[5] = {P::step(0), P::step(1), P::step(2), P::step(3), P::step(4)};
+  constexpr int k_index0 = kstep_index(all, S, M);
   constexpr uint32_t np16 = (uint32_t)P::Np(mm.layer) * 16u;  // bytes between the two 8-wide K chunks of a k-step
   constexpr uint32_t idesc = make_idesc(mm.n);
   constexpr uint32_t lbo_f = ((np16 >> 4) & 0x3FFFu) << 16;
   constexpr uint32_t mat = 2u * (uint32_t)P::Np(mm.layer) * (uint32_t)P::Kp(mm.layer);  // bytes of one image (hi or lo)
   constexpr uint32_t b_base = P::w_off(mm.layer) + (uint32_t)mm.ks0 * 2u * np16 + (uint32_t)mm.n0 * 16u;
+  bool ready = false;  // sub-chunk k was already seen complete by the probe issued before the previous k-step's MMAs
 #pragma unroll
   for (int k = 0; k < mm.ks_n; ++k) {
     if (mm.dep) {  // this k-step's operand is sub-chunk k of the accumulator the previous epilogue rewrites
-      mbar_wait(bar_p + 8u * (BAR_SUB + (uint32_t)k), (par_sub >> k) & 1u);
+      if (!ready) mbar_wait(bar_p + 8u * (BAR_SUB + (uint32_t)k), (par_sub >> k) & 1u);
       par_sub ^= 1u << k;
       tc_fence_after();
+      // probe the next sub-chunk now: the probe's latency (~80 cycles) hides behind this k-step's MMAs
+      if (k + 1 < mm.ks_n) ready = mbar_test(bar_p + 8u * (BAR_SUB + (uint32_t)(k + 1)), (par_sub >> (k + 1)) & 1u);
     }
+    if constexpr (TRACE) { if (tr) tr[2 * (k_index0 + k)] = (uint32_t)clock64(); }
     const uint32_t b_off = b_base + (uint32_t)k * 2u * np16;
     // smem_base is 128-byte aligned and the whole window is < 256 KiB, so the 14-bit address field cannot carry
     const uint32_t b_hi = sb4 + ((b_off >> 4) | lbo_f);
     const uint32_t b_lo = sb4 + (((b_off + mat) >> 4) | lbo_f);
     const uint32_t a_hi = tcol + (uint32_t)mm.a_col + 16u * (uint32_t)k;
     issue_kstep(tcol + (uint32_t)mm.d_col, a_hi, a_hi + 8u, b_hi, b_lo, idesc, (k > 0 || mm.acc) ? 1u : 0u, fast);
+    if constexpr (TRACE) { if (tr) tr[2 * (k_index0 + k) + 1] = (uint32_t)clock64(); }
   }
 }
-template <class P, int G, int S>
-__device__ __forceinline__ void issue_step(const uint32_t bar_p, const uint32_t bar_full, const uint32_t sb4, uint32_t& par_sub,
-                                           const int fast) {
-  issue_mma<P, G, S, 0>(bar_p, sb4, par_sub, fast);
-  if constexpr (P::step(S).n_mma > 1) issue_mma<P, G, S, 1>(bar_p, sb4, par_sub, fast);
+template <class P, int S, bool TRACE>
+__device__ __forceinline__ void issue_step(const uint32_t tcol, const uint32_t bar_p, const uint32_t bar_full, const uint32_t sb4,
+                                           uint32_t& par_sub, const int fast, uint32_t* tr) {
+  issue_mma<P, S, 0, TRACE>(tcol, bar_p, sb4, par_sub, fast, tr);
+  if constexpr (P::step(S).n_mma > 1) issue_mma<P, S, 1, TRACE>(tcol, bar_p, sb4, par_sub, fast, tr);
   issue_commit(bar_full);
 }
 
-template <bool ENC, int KA, int NL, bool TRACE, int G>
-__device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t smem_base, const uint32_t bars_base,
+template <bool ENC, int KA, int NL, bool TRACE>
+__device__ __forceinline__ void run_issuer(const Tc4Params& p, const int G, const uint32_t smem_base, const uint32_t bars_base,
                                            const uint32_t in_stage_bytes, const uint32_t in0_off) {
   using P = Prog<ENC, KA, NL>;
-  // Everything below is warp-uniform and derived from constants and kernel parameters.  TMEM: this CTA owns all 512
-  // columns of the SM (one CTA per SM), so the allocation base is column 0 / lane 0 (checked by the caller).
-  constexpr uint32_t tcol = (uint32_t)G * PIPE_COLS;
+  // Everything below is warp-uniform.  TMEM: this CTA owns all 512 columns of the SM (one CTA per SM), so the
+  // allocation base is column 0 / lane 0 (checked by the caller).  One copy of this code serves both pipelines
+  // (the unrolled step program is ~1.5k instructions; two copies pushed the kernel past the instruction cache).
+  const uint32_t tcol = (uint32_t)G * PIPE_COLS;
   const uint32_t bar_w = bars_base;
   const uint32_t bar_p = bars_base + 8u * (1 + G * BARS_PER_PIPE);
   const uint32_t sb4 = smem_base >> 4;
@@ -271,7 +306,7 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t sm
   const uint32_t row_bytes = (uint32_t)p.in_dim * 4u;
   auto trace = [&](int64_t lt, int slot) {
     if constexpr (TRACE) {
-      if (blockIdx.x == 0 && G == 0 && lane0 && lt < 16) p.trace[lt * 64 + slot] = (uint32_t)clock64();
+      if (blockIdx.x == 0 && G == p.trace_pipe && lane0 && lt < 16) p.trace[lt * 64 + slot] = (uint32_t)clock64();
     }
   };
   // input tile -> stage (lt & 1) by cp.async.bulk; a ragged tail (bytes not a multiple of 16) is finished by hand
@@ -307,15 +342,17 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t sm
     tc_fence_after();
     trace(lt, 33);
     const uint32_t bar_full = bar_p + 8u * (BAR_FULL + (uint32_t)(lt & 1));
+    uint32_t* tr = nullptr;  // second half of the trace buffer: per k-step (wait passed, issued) clocks of the issuer
+    if constexpr (TRACE) { if (blockIdx.x == 0 && G == p.trace_pipe && lane0 && lt < 16) tr = p.trace + 1024 + lt * 64; }
     auto after_commit = [&](int s_done) {
       trace(lt, 34 + 5 * s_done + 4);
       if (s_done == 0) load_tile(tile + 2 * tile_stride, lt);  // this tile's stage was consumed before a1_ready; off the s0 critical path
     };
-    issue_step<P, G, 0>(bar_p, bar_full, sb4, par_sub, fast); after_commit(0);
-    issue_step<P, G, 1>(bar_p, bar_full, sb4, par_sub, fast); after_commit(1);
-    issue_step<P, G, 2>(bar_p, bar_full, sb4, par_sub, fast); after_commit(2);
-    issue_step<P, G, 3>(bar_p, bar_full, sb4, par_sub, fast); after_commit(3);
-    issue_step<P, G, 4>(bar_p, bar_full, sb4, par_sub, fast); after_commit(4);
+    issue_step<P, 0, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(0);
+    issue_step<P, 1, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(1);
+    issue_step<P, 2, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(2);
+    issue_step<P, 3, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(3);
+    issue_step<P, 4, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(4);
   }
 }
 
@@ -340,7 +377,7 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
   const bool has_pre = p.pre_min != nullptr, has_post = p.post_min != nullptr;
   auto trace = [&](int64_t lt, int slot) {
     if constexpr (TRACE) {
-      if (blockIdx.x == 0 && g == 0 && wq == 0 && lane == 0 && lt < 16 && (h == 0) != (slot == 1 || slot == 2)) p.trace[lt * 64 + slot] = (uint32_t)clock64();
+      if (blockIdx.x == 0 && g == p.trace_pipe && wq == 0 && lane == 0 && lt < 16 && (h == 0) != (slot == 1 || slot == 2 || (slot >= 29 && slot <= 31))) p.trace[lt * 64 + slot] = (uint32_t)clock64();
     }
   };
 
@@ -350,6 +387,7 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
     const int rows = (int)min((int64_t)TILE, p.n_rows - tile * TILE);
     mbar_wait(bar_p + 8u * (BAR_IN + (uint32_t)(lt & 1)), (uint32_t)(lt >> 1) & 1u);
     const float* xr = reinterpret_cast<const float*>(in_s + (uint32_t)(lt & 1) * in_stage_bytes) + row * in_dim;
+    trace(lt - 1, 29);
 #pragma unroll
     for (int ks = 0; ks < KA / 16; ++ks) {
       float xv[16];
@@ -376,9 +414,11 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) split2(xv[2 * j], xv[2 * j + 1], pk[j], pk[8 + j]);
+      if (ks == KA / 16 - 1) trace(lt - 1, 30);
       tmem_st16(tbase + P::A1_COL + 16u * (uint32_t)ks, pk);
     }
     tc_wait_st();
+    trace(lt - 1, 31);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p + 8u * BAR_A1);
@@ -392,96 +432,106 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
     const uint32_t bar_full = bar_p + 8u * (BAR_FULL + (uint32_t)(lt & 1));
     const uint32_t par0 = (uint32_t)(lt >> 1);  // five phases per tile on each of the two barriers: parity of step s = (par0 + s) & 1
     trace(lt, 0);
-#pragma unroll
-    for (int s = 0; s < P::N_STEPS; ++s) {
-      const SStep st = P::step(s);
-      const SEpi ep = st.epi;
-      if (ep.fin && h == 1) {
-        // the last accumulator is drained by the h == 0 warps; meanwhile the first operand of the next tile (its TMEM
-        // region has been idle since step 1 / step 3, which this warp has seen complete)
-        trace(lt, 1);
-        if (tile + tile_stride < n_tiles) convert_a1(tile + tile_stride, lt + 1);
-        trace(lt, 2);
-        continue;
-      }
+    // ---- steps 0..3: drain the accumulator into the next layer's operand, in place.  Sub-chunks h, h + 2, ... of the
+    // region are this warp's; the TMEM load of the next one is in flight while the current one is converted.  The loop
+    // over steps is rolled (region, width and multipliers come from the parameter table): code size matters here.
+#pragma unroll 1
+    for (int s = 0; s < P::N_STEPS - 1; ++s) {
+      const uint32_t col = tbase + (uint32_t)p.epi_col[s];
+      const int n_sub = p.epi_nsub[s];
+      const uint64_t c1 = pack2(p.epi_c1[s], p.epi_c1[s]);
+      const float c2 = p.epi_c2[s];
       mbar_wait(bar_full, (par0 + (uint32_t)s) & 1u);  // the accumulator of step s is complete
       tc_fence_after();
       trace(lt, 3 + 4 * s);
-      if (!ep.fin) {
-        const uint64_t c1 = pack2(p.c1[ep.layer], p.c1[ep.layer]), c2 = pack2(p.c2[ep.layer], p.c2[ep.layer]);
-        // sub-chunks h, h + 2, ... of this region; the TMEM load of the next one is in flight while this one is converted
-        const int n_sub = ep.w / 16;
-        uint32_t va[16], vb[16], pk[16];
-        if (h < n_sub) tmem_ld16(tbase + (uint32_t)ep.col + 16u * (uint32_t)h, va);
-#pragma unroll
-        for (int it = 0; it < (MAX_SUB + 1) / 2; ++it) {
-          if (2 * it < n_sub) {  // compile-time bound on the region width
-            const int i = h + 2 * it;
-            if (i < n_sub) {
-              tc_wait_ld();
-              if (i + 2 < n_sub) tmem_ld16(tbase + (uint32_t)ep.col + 16u * (uint32_t)(i + 2), (it & 1) ? va : vb);
-              convert16((it & 1) ? vb : va, c1, c2, pk);
-              tmem_st16(tbase + (uint32_t)ep.col + 16u * (uint32_t)i, pk);
-              tc_wait_st();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_p + 8u * (BAR_SUB + (uint32_t)i));  // sub-chunk i is a valid A operand now
-              if (it < 2) trace(lt, 4 + 4 * s + it);
-            }
-          }
+      uint32_t va[16], vb[16], pk[16];
+      auto finish = [&](int i) {
+        tmem_st16(col + 16u * (uint32_t)i, pk);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p + 8u * (BAR_SUB + (uint32_t)i));  // sub-chunk i is a valid A operand now
+      };
+      int i = h;
+      if (i < n_sub) tmem_ld16(col + 16u * (uint32_t)i, va);
+#pragma unroll 1
+      for (; i < n_sub; i += 4) {
+        tc_wait_ld();
+        if (i + 2 < n_sub) tmem_ld16(col + 16u * (uint32_t)(i + 2), vb);
+        convert16(va, c1, c2, pk);
+        finish(i);
+        if (i == h) trace(lt, 4 + 4 * s);
+        if (i + 2 < n_sub) {
+          tc_wait_ld();
+          if (i + 4 < n_sub) tmem_ld16(col + 16u * (uint32_t)(i + 4), va);
+          convert16(vb, c1, c2, pk);
+          finish(i + 2);
+          if (i == h) trace(lt, 5 + 4 * s);
         }
-      } else {
-        // ---- last accumulator -> scale, activation, range check, un-normalise -> this warp's slice of the out stage
-        uint32_t v[NL];
-        {
-          uint32_t t0[16];
-          tmem_ld16(tbase + (uint32_t)ep.col, t0);
-          if constexpr (NL == 32) {
-            uint32_t t1[16];
-            tmem_ld16(tbase + (uint32_t)ep.col + 16u, t1);
-            tc_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j] = t0[j]; v[16 + j] = t1[j]; }
-          } else {
-            tc_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = t0[j];
-          }
-        }
-        trace(lt, 25);
-        if (store_pending) {  // the previous tile's bulk store must have finished READING the stage
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
-        }
-        bool bad = false;
-        const float s1 = p.c1[ep.layer], s2 = p.c2[ep.layer];
-#pragma unroll
-        for (int j = 0; j < NL; ++j) {
-          if (j < out_dim) {
-            const float a = __uint_as_float(v[j]);
-            float y = fmaxf(a * s1, a * s2);
-            bad |= !(fabsf(y) <= 3.0e38f);  // inf / NaN: an fp16 operand overflowed somewhere upstream
-            if (has_post) y = fmaf(y, norm_s[3][j], norm_s[2][j]);  // y * range + min (data_processing.py:203)
-            out_s[lane * out_dim + j] = y;
-          }
-        }
-        if (bad && row < rows) atomicOr(p.flag, 1);
-        trace(lt, 26);
-        const int my_rows = min(32, max(0, rows - wq * 32));
-        const uint32_t bytes = (uint32_t)(my_rows * out_dim) * 4u;
-        float* gdst = p.out + ((size_t)tile * TILE + (size_t)wq * 32) * out_dim;
-        if ((bytes & 15u) == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0 && bytes) { bulk_s2g(gdst, out_s_addr, bytes); }
-          store_pending = true;
-        } else {  // ragged tail: plain stores
-          __syncwarp();
-          for (int e = lane; e < my_rows * out_dim; e += 32) gdst[e] = out_s[e];
-          __syncwarp();
-        }
-        trace(lt, 27);
       }
+    }
+    if (h == 1) {
+      // the last accumulator is drained by the h == 0 warps; meanwhile the first operand of the next tile (its TMEM
+      // region has been idle since step 1 / step 3, which this warp has seen complete)
+      trace(lt, 1);
+      if (tile + tile_stride < n_tiles) convert_a1(tile + tile_stride, lt + 1);
+      trace(lt, 2);
+    } else {
+      constexpr SEpi ep = P::step(P::N_STEPS - 1).epi;
+      mbar_wait(bar_full, (par0 + (uint32_t)(P::N_STEPS - 1)) & 1u);
+      tc_fence_after();
+      trace(lt, 3 + 4 * (P::N_STEPS - 1));
+      // ---- last accumulator -> scale, activation, range check, un-normalise -> this warp's slice of the out stage
+      uint32_t v[NL];
+      {
+        uint32_t t0[16];
+        tmem_ld16(tbase + (uint32_t)ep.col, t0);
+        if constexpr (NL == 32) {
+          uint32_t t1[16];
+          tmem_ld16(tbase + (uint32_t)ep.col + 16u, t1);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = t0[j]; v[16 + j] = t1[j]; }
+        } else {
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = t0[j];
+        }
+      }
+      trace(lt, 25);
+      if (store_pending) {  // the previous tile's bulk store must have finished READING the stage
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
+      trace(lt, 28);
+      bool bad = false;
+      const float s1 = p.c1[ep.layer], s2 = p.c2[ep.layer];
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        if (j < out_dim) {
+          const float a = __uint_as_float(v[j]);
+          float y = fmaf(fabsf(a), s2, a * s1);
+          bad |= !(fabsf(y) <= 3.0e38f);  // inf / NaN: an fp16 operand overflowed somewhere upstream
+          if (has_post) y = fmaf(y, norm_s[3][j], norm_s[2][j]);  // y * range + min (data_processing.py:203)
+          out_s[lane * out_dim + j] = y;
+        }
+      }
+      if (bad && row < rows) atomicOr(p.flag, 1);
+      trace(lt, 26);
+      const int my_rows = min(32, max(0, rows - wq * 32));
+      const uint32_t bytes = (uint32_t)(my_rows * out_dim) * 4u;
+      float* gdst = p.out + ((size_t)tile * TILE + (size_t)wq * 32) * out_dim;
+      if ((bytes & 15u) == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && bytes) { bulk_s2g(gdst, out_s_addr, bytes); }
+        store_pending = true;
+      } else {  // ragged tail: plain stores
+        __syncwarp();
+        for (int e = lane; e < my_rows * out_dim; e += 32) gdst[e] = out_s[e];
+        __syncwarp();
+      }
+      trace(lt, 27);
     }
     trace(lt, 24);
   }
@@ -545,8 +595,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
     }
   }
 
-  if (warp == NPIPE * EPI_WARPS) run_issuer<ENC, KA, NL, TRACE, 0>(p, smem_base, bars_base, in_stage_bytes, in0_off);
-  else if (warp == NPIPE * EPI_WARPS + 1) run_issuer<ENC, KA, NL, TRACE, 1>(p, smem_base, bars_base, in_stage_bytes, in0_off);
+  if (warp >= NPIPE * EPI_WARPS) run_issuer<ENC, KA, NL, TRACE>(p, warp - NPIPE * EPI_WARPS, smem_base, bars_base, in_stage_bytes, in0_off);
   else run_epilogue<ENC, KA, NL, TRACE>(p, warp / EPI_WARPS, warp & 3, (warp >> 2) & 1, smem_base, smem, bars_base, in_stage_bytes,
                                         in0_off, out0_off, out_stage_bytes, norm_s);
 
@@ -556,8 +605,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
 }
 
 template <bool ENC, int KA, int NL, bool TRACE = false>
-int launch_one(const bb_ctx* ctx, const Tc4Params& p, cudaStream_t stream) {
+int launch_one(const bb_ctx* ctx, Tc4Params p, cudaStream_t stream) {
   using P = Prog<ENC, KA, NL>;
+  for (int s = 0; s < P::N_STEPS - 1; ++s) {
+    const SEpi ep = P::step(s).epi;
+    p.epi_col[s] = ep.col; p.epi_nsub[s] = ep.w / 16;
+    p.epi_c1[s] = p.c1[ep.layer]; p.epi_c2[s] = p.c2[ep.layer];
+  }
   const size_t in_b = ((size_t)TILE * p.in_dim * 4 + 127) & ~(size_t)127;
   const size_t out_b = ((size_t)TILE * p.out_dim * 4 + 127) & ~(size_t)127;
   const size_t smem_bytes = ((P::W_BYTES + 127u) & ~127u) + NPIPE * (2 * in_b + out_b);
@@ -597,6 +651,7 @@ int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int64_t n_rows, c
   for (int l = 0; l < 4; ++l) { p.c1[l] = t.c1[l]; p.c2[l] = t.c2[l]; }
   p.in_dim = c->desc.in_dim; p.out_dim = c->desc.out_dim;
   p.fast = fast; p.flag = flag_dev; p.trace = trace;
+  p.trace_pipe = getenv("BALER_B200_TRACE_PIPE") ? atoi(getenv("BALER_B200_TRACE_PIPE")) : 0;
   if (trace != nullptr) {  // SM-clock trace build: the two CMS shapes only
     if (t.enc && t.ka == 32 && t.nl == 16) return launch_one<true, 32, 16, true>(ctx, p, stream);
     if (!t.enc && t.ka == 16 && t.nl == 32) return launch_one<false, 16, 32, true>(ctx, p, stream);

@@ -48,7 +48,7 @@ struct ChainDesc {
 struct Tc4Plan {
   bool ok = false;
   int enc = 0, ka = 0, nl = 0;  // direction, padded K of the first layer, padded N of the last layer
-  float c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};  // y = max(c1 * acc, c2 * acc) per layer
+  float c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};  // y = c1 * acc + c2 * |acc| per layer
 };
 
 // Host + device state of one direction (encoder or decoder).

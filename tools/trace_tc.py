@@ -16,12 +16,14 @@ x = torch.rand((n, 24), device='cuda')
 for decode, dim_in, dim_out in ((0, 24, 15), (1, 15, 24)):
     xin = x if not decode else torch.rand((n, 15), device='cuda')
     out = torch.empty((n, dim_out), device='cuda')
-    dbg = torch.zeros(16 * 64, dtype=torch.int32, device='cuda')
+    dbg = torch.zeros(2 * 16 * 64, dtype=torch.int32, device='cuda')
     for it in range(2):
         rc = fn(codec.handle, decode, xin.data_ptr(), n, out.data_ptr(), 0, -2, dbg.data_ptr(), GROUPS, None)
         assert rc == 0
         torch.cuda.synchronize()
-    t = dbg.cpu().numpy().astype(np.int64).reshape(16, 64) & 0xffffffff
+    full = dbg.cpu().numpy().astype(np.int64) & 0xffffffff
+    t = full[:1024].reshape(16, 64)
+    ks = full[1024:].reshape(16, 64)
     print('decode' if decode else 'encode', 'tile period (cycles):', np.diff(t[2:12, 0]))
     for lt in (5, 6):
         rel = lambda v: int((v - t[lt, 0]) & 0xffffffff) if v else -1
@@ -31,4 +33,7 @@ for decode, dim_in, dim_out in ((0, 24, 15), (1, 15, 24)):
         for s in range(5):
             print('   step', s, 'full_d seen', e[3 + 4 * s], 'sub0 done', e[4 + 4 * s], 'sub1 done', e[5 + 4 * s],
                   '| MMA waits', [mm[2 + 5 * s + c] for c in range(4)], 'commit', mm[2 + 5 * s + 4])
+        kk = [rel(v) for v in ks[lt, :56]]
+        print('   issuer k-steps (wait passed, issued):', ' '.join(f'{kk[2*i]}/{kk[2*i+1]}' for i in range(28)))
+        print('   a1: in_full passed', e[29], 'converted', e[30], 'st waited', e[31], '| final: read-wait done', e[28])
         print('   final: ld done', e[25], 'stage written', e[26], 'store issued', e[27], 'tile done', e[24], '| MMA tile start', mm[0], 'a1 seen', mm[1])
