@@ -46,6 +46,10 @@ struct Tc4Params {
   int* flag;
   uint32_t* trace;      // optional: SM-clock timestamps of CTA 0 / pipeline trace_pipe (64 slots per tile, first 16 tiles)
   int trace_pipe;
+  uint32_t smem_off;    // low 18 bits of the shared-window address of the dynamic shared memory (probed once per kernel, see launch_one)
+  uint32_t tmem0;       // TMEM base address (0: the CTA owns all 512 columns); a parameter so that addresses are UR adds, not R2UR moves
+  uint32_t* probe;      // probe launch: thread 0 writes that address here and the kernel returns
+  int pipes;            // tile pipelines in use (2; 1 = experiment: the second pipeline idles)
 };
 
 // ------------------------------------------------------------------------------------------------ static program
@@ -279,6 +283,11 @@ __device__ __forceinline__ void issue_mma(const uint32_t tcol, const uint32_t ba
     if constexpr (TRACE) { if (tr) tr[2 * (k_index0 + k) + 1] = (uint32_t)clock64(); }
   }
 }
+// Experiments that did not pay (profiles/r01_tc4_notes.md): serialising the two pipelines' steps on the tensor pipe, by a
+// shared-memory ticket lock or by a token passed through two mbarriers.  Left alone the pipelines fall into lock-step
+// (both convert, then both issue MMAs); the token does break that, but a step that waits for sub-chunks then holds the
+// pipe idle, and any lane-0 polling loop in the issuer warp makes ptxas treat the warp as divergent and fall back to
+// the slow tcgen05.mma issue sequence (4x slower).  Net effect: -1 % .. -75 %.
 template <class P, int S, bool TRACE>
 __device__ __forceinline__ void issue_step(const uint32_t tcol, const uint32_t bar_p, const uint32_t bar_full, const uint32_t sb4,
                                            uint32_t& par_sub, const int fast, uint32_t* tr) {
@@ -287,21 +296,23 @@ __device__ __forceinline__ void issue_step(const uint32_t tcol, const uint32_t b
   issue_commit(bar_full);
 }
 
-template <bool ENC, int KA, int NL, bool TRACE>
-__device__ __forceinline__ void run_issuer(const Tc4Params& p, const int G, const uint32_t smem_base, const uint32_t bars_base,
+template <bool ENC, int KA, int NL, bool TRACE, int G>
+__device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t smem_base, const uint32_t bars_base,
                                            const uint32_t in_stage_bytes, const uint32_t in0_off) {
   using P = Prog<ENC, KA, NL>;
   // Everything below is warp-uniform.  TMEM: this CTA owns all 512 columns of the SM (one CTA per SM), so the
   // allocation base is column 0 / lane 0 (checked by the caller).  One copy of this code serves both pipelines
   // (the unrolled step program is ~1.5k instructions; two copies pushed the kernel past the instruction cache).
-  const uint32_t tcol = (uint32_t)G * PIPE_COLS;
+  const uint32_t tcol = p.tmem0 + (uint32_t)G * PIPE_COLS;
   const uint32_t bar_w = bars_base;
   const uint32_t bar_p = bars_base + 8u * (1 + G * BARS_PER_PIPE);
-  const uint32_t sb4 = smem_base >> 4;
+  // descriptors only carry address bits [4, 18): take them from the kernel parameter (a uniform register) rather than
+  // from the cvta'd pointer, so that every tcgen05.mma operand is provably warp-uniform
+  const uint32_t sb4 = p.smem_off >> 4;
   const bool lane0 = (threadIdx.x & 31) == 0;
-  const int64_t n_tiles = (p.n_rows + TILE - 1) / TILE;
-  const int64_t tile_stride = (int64_t)gridDim.x * NPIPE;
-  const int64_t tile0 = (int64_t)blockIdx.x * NPIPE + G;
+  const int64_t n_tiles = G < p.pipes ? (p.n_rows + TILE - 1) / TILE : 0;
+  const int64_t tile_stride = (int64_t)gridDim.x * p.pipes;
+  const int64_t tile0 = (int64_t)blockIdx.x * p.pipes + G;
   const uint32_t in_s = smem_base + in0_off + (uint32_t)G * 2u * in_stage_bytes;
   const uint32_t row_bytes = (uint32_t)p.in_dim * 4u;
   auto trace = [&](int64_t lt, int slot) {
@@ -334,7 +345,7 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const int G, cons
   mbar_wait(bar_w, 0);  // weights resident
   uint32_t par_a1 = 0, par_sub = 0;
   int64_t lt = 0;
-  const int fast = p.fast;
+  constexpr int fast = 0;  // the single-product mode stays on the table-driven kernel
   for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, ++lt) {
     trace(lt, 32);
     mbar_wait(bar_p + 8u * BAR_A1, par_a1);
@@ -367,9 +378,9 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
   const int row = wq * 32 + lane;                                      // tile row == TMEM lane
   const uint32_t tbase = ((uint32_t)(wq * 32) << 16) + (uint32_t)g * PIPE_COLS;  // TMEM address of this warp's lanes, pipeline columns
   const uint32_t bar_p = bars_base + 8u * (1 + g * BARS_PER_PIPE);
-  const int64_t n_tiles = (p.n_rows + TILE - 1) / TILE;
-  const int64_t tile_stride = (int64_t)gridDim.x * NPIPE;
-  const int64_t tile0 = (int64_t)blockIdx.x * NPIPE + g;
+  const int64_t n_tiles = g < p.pipes ? (p.n_rows + TILE - 1) / TILE : 0;
+  const int64_t tile_stride = (int64_t)gridDim.x * p.pipes;
+  const int64_t tile0 = (int64_t)blockIdx.x * p.pipes + g;
   const int in_dim = p.in_dim, out_dim = p.out_dim;
   const uint8_t* in_s = smem + in0_off + (uint32_t)g * 2u * in_stage_bytes;
   float* out_s = reinterpret_cast<float*>(smem + out0_off + (uint32_t)g * out_stage_bytes) + (size_t)wq * 32 * out_dim;  // this warp's 32 rows
@@ -545,11 +556,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[1 + NPIPE * BARS_PER_PIPE];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float norm_s[4][32];  // pre_min, 1 / pre_range, post_min, post_range
+  __shared__ float norm_s[4][32];   // pre_min, 1 / pre_range, post_min, post_range
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler too (role dispatch below)
   const uint32_t smem_base = smem_u32(smem);
+  if (p.probe != nullptr) {
+    if (tid == 0) *p.probe = smem_base & 0x3FFFFu;
+    return;
+  }
+  if ((smem_base & 0x3FFFFu) != p.smem_off) __trap();
   const uint32_t bars_base = smem_u32(&bars[0]);
   const uint32_t in_stage_bytes = (uint32_t)((TILE * p.in_dim * 4 + 127) & ~127);
   const uint32_t out_stage_bytes = (uint32_t)((TILE * p.out_dim * 4 + 127) & ~127);
@@ -586,7 +602,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
   tc_fence_after();
   // all 512 columns of the SM belong to this CTA, so the base is column 0, lane 0; the issuer relies on that to keep
   // its TMEM addresses compile-time constants
-  if (tmem_base_s != 0u) __trap();
+  if (tmem_base_s != 0u || p.tmem0 != 0u) __trap();
   if (tid == 0) {  // resident weight image: global -> smem through the async proxy (what the MMA reads through)
     mbar_expect_tx(bars_base, P::W_BYTES);
     for (uint32_t off = 0; off < P::W_BYTES; off += 32768) {
@@ -595,7 +611,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
     }
   }
 
-  if (warp >= NPIPE * EPI_WARPS) run_issuer<ENC, KA, NL, TRACE>(p, warp - NPIPE * EPI_WARPS, smem_base, bars_base, in_stage_bytes, in0_off);
+  if (warp == NPIPE * EPI_WARPS) run_issuer<ENC, KA, NL, TRACE, 0>(p, smem_base, bars_base, in_stage_bytes, in0_off);
+  else if (warp == NPIPE * EPI_WARPS + 1) run_issuer<ENC, KA, NL, TRACE, 1>(p, smem_base, bars_base, in_stage_bytes, in0_off);
   else run_epilogue<ENC, KA, NL, TRACE>(p, warp / EPI_WARPS, warp & 3, (warp >> 2) & 1, smem_base, smem, bars_base, in_stage_bytes,
                                         in0_off, out0_off, out_stage_bytes, norm_s);
 
@@ -617,13 +634,26 @@ int launch_one(const bb_ctx* ctx, Tc4Params p, cudaStream_t stream) {
   const size_t smem_bytes = ((P::W_BYTES + 127u) & ~127u) + NPIPE * (2 * in_b + out_b);
   auto k = chain_tc4_kernel<ENC, KA, NL, TRACE>;
   static bool attr_set = false;  // per instantiation
+  static uint32_t smem_off = 0;
   if (!attr_set) {
     cudaFuncAttributes fa;
     BB_CUDA(cudaFuncGetAttributes(&fa, k));
     if (smem_bytes + fa.sharedSizeBytes > ctx->smem_optin) return BB_ERR_UNSUPPORTED;
     BB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - fa.sharedSizeBytes)));
+    // where the dynamic shared memory of THIS kernel starts (a link-time constant the host cannot query): one probe launch
+    uint32_t* probe_dev = nullptr;
+    BB_CUDA(cudaMalloc(&probe_dev, 4));
+    Tc4Params q = p;
+    q.probe = probe_dev;
+    k<<<1, NTHREADS, smem_bytes, stream>>>(q);
+    BB_CUDA(cudaMemcpyAsync(&smem_off, probe_dev, 4, cudaMemcpyDeviceToHost, stream));
+    BB_CUDA(cudaStreamSynchronize(stream));
+    BB_CUDA(cudaFree(probe_dev));
     attr_set = true;
   }
+  p.smem_off = smem_off;
+  p.tmem0 = 0;
+  p.probe = nullptr;
   const int64_t n_tiles = (p.n_rows + TILE - 1) / TILE;
   const int64_t want = (n_tiles + NPIPE - 1) / NPIPE;
   const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
@@ -639,7 +669,7 @@ int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int64_t n_rows, c
                   const float* post_min, const float* post_range, void* out, int fast, int* flag_dev, uint32_t* trace,
                   cudaStream_t stream) {
   const Tc4Plan& t = c->tc4;
-  if (!t.ok) return BB_ERR_UNSUPPORTED;
+  if (!t.ok || fast) return BB_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return BB_ERR_UNSUPPORTED;
   if (n_rows == 0) return BB_OK;
   Tc4Params p;
@@ -651,6 +681,7 @@ int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int64_t n_rows, c
   for (int l = 0; l < 4; ++l) { p.c1[l] = t.c1[l]; p.c2[l] = t.c2[l]; }
   p.in_dim = c->desc.in_dim; p.out_dim = c->desc.out_dim;
   p.fast = fast; p.flag = flag_dev; p.trace = trace;
+  p.pipes = getenv("BALER_B200_TC4_PIPES") ? atoi(getenv("BALER_B200_TC4_PIPES")) : NPIPE;
   p.trace_pipe = getenv("BALER_B200_TRACE_PIPE") ? atoi(getenv("BALER_B200_TRACE_PIPE")) : 0;
   if (trace != nullptr) {  // SM-clock trace build: the two CMS shapes only
     if (t.enc && t.ka == 32 && t.nl == 16) return launch_one<true, 32, 16, true>(ctx, p, stream);

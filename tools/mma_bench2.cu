@@ -17,6 +17,8 @@ struct Cfg {
   int mode;       // 0 plain, 1 collector a: fill,use,lastuse per group of 3 (same A), 2 .ws plain, 3 .ws with b0 fill/use/lastuse
   int ld_warps;   // warps 1..ld_warps loop on tcgen05.ld while the MMAs run
   int batch;      // > 0: commit + wait after every `batch` MMAs (bounded queue depth)
+  int tm_op;      // what the interfering warps do: 0 ld.x32, 1 st.x16, 2 ld.x16 + st.x16 + both waits (the epilogue pattern), 3 same + ~70 ALU ops
+  int tm_gap;     // extra clock-spin between interfering ops (cycles)
 };
 
 #define R16(v, o) "=r"(v[o+0]), "=r"(v[o+1]), "=r"(v[o+2]), "=r"(v[o+3]), "=r"(v[o+4]), "=r"(v[o+5]), "=r"(v[o+6]), "=r"(v[o+7]), \
@@ -51,7 +53,7 @@ __device__ __forceinline__ void issue3(uint32_t d, uint32_t a_t, uint64_t a_d, u
 }
 
 template <int MODE, int A_SMEM>
-__global__ void __launch_bounds__(160, 1) bench(const Cfg c, long long* out) {
+__global__ void __launch_bounds__(544, 1) bench(const Cfg c, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -115,11 +117,28 @@ __global__ void __launch_bounds__(160, 1) bench(const Cfg c, long long* out) {
     int n = 0;
     while (!stop_s && n < 100000) {
       const long long a = clock64();
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                   "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                   : R16(v, 0), R16(v, 16) : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (c.tm_op == 0) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                     "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : R16(v, 0), R16(v, 16) : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+        if (c.tm_op >= 2) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                       : R16(v, 0) : "r"(taddr) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        if (c.tm_op == 3) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]) * 1.01f, 0.5f)) & 0xffffe000u; v[j] ^= v[(j + 1) & 15] >> 3; v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.25f)); }
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                     "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
       const long long b = clock64();
+      if (c.tm_gap) { while (clock64() - b < c.tm_gap) {} }
       tot += b - a; mx = b - a > mx ? b - a : mx; ++n;
     }
     uint32_t s = 0;
@@ -137,8 +156,8 @@ static int run1(const Cfg& c) {
   auto k = bench<MODE, A_SMEM>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   for (int rep = 0; rep < 2; ++rep) {
-    for (int i = 0; i < 16; ++i) out[i] = 0;
-    k<<<1, 160, 96 * 1024>>>(c, out);
+    for (int i = 0; i < 64; ++i) out[i] = 0;
+    k<<<1, 32 * (1 + (c.ld_warps > 4 ? c.ld_warps : 4)), 96 * 1024>>>(c, out);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
   }
@@ -156,36 +175,21 @@ static int run(const Cfg& c) {
   if (rc) return rc;
   printf("M=%-3d N=%-3d nmma=%-4d nacc=%d A=%s Bswz=%d mode=%d batch=%-2d ldw=%d | issue/mma %6.1f total/mma %6.1f", c.M, c.N, c.n_mma, c.n_acc,
          c.a_src == 0 ? "tmem" : c.a_src == 1 ? "smem" : "sswz", c.b_swz, c.mode, c.batch, c.ld_warps, out[0] / (double)c.n_mma, out[1] / (double)c.n_mma);
-  if (c.ld_warps) printf(" | ld avg %6.1f max %lld (n=%lld)", out[2] / (double)(out[3] ? out[3] : 1), out[4], out[3]);
+  if (c.ld_warps) printf(" | tm_op %d gap %d: avg %6.1f max %lld (n=%lld)", c.tm_op, c.tm_gap, out[2] / (double)(out[3] ? out[3] : 1), out[4], out[3]);
   printf("\n");
   fflush(stdout);
   return 0;
 }
 
-int main() {
-  cudaMallocManaged(&out, 16 * sizeof(long long));
-  // 1. fixed latency vs per-MMA cost: N = 64, TMEM A, n_mma sweep
-  for (int n : {6, 24, 96, 384}) if (run({n, 128, 64, 2, 0, 0, 0, 0, 0})) return 1;
-  for (int N : {16, 64, 112, 208}) if (run({96, 128, N, 1, 0, 0, 0, 0, 0})) return 1;  // one accumulator (a real k-loop)
-  // 2. N sweep, M = 128 / 64, A from TMEM / SMEM / swizzled SMEM, B plain / swizzled
-  for (int M : {128, 64})
-    for (int a : {0, 1, 2})
-      for (int bs : {0, 1})
-        for (int N : {16, 32, 64, 112, 128, 160, 208, 224, 256}) {
-          if (a == 1 && bs == 1) continue;
-          if (run({96, M, N, N <= 224 ? 2 : 1, a, bs, 0, 0, 0})) return 1;
+int main(int argc, char** argv) {
+  cudaMallocManaged(&out, 64 * sizeof(long long));
+  // MMA stream (N = 112 and 64, one accumulator region) next to 0 / 4 / 8 / 16 warps doing TMEM traffic of several kinds
+  for (int N : {112, 64})
+    for (int op : {0, 1, 2, 3})
+      for (int ldw : {0, 4, 8, 16})
+        for (int gap : {0, 200}) {
+          if (ldw == 0 && (op > 0 || gap > 0)) continue;
+          if (run({768, 128, N, 2, 0, 0, 0, ldw, 0, op, gap})) return 1;
         }
-  // 3. collector hints and .ws
-  for (int mode : {1, 2, 3})
-    for (int a : {0, 2})
-      for (int N : {16, 64, 112, 128, 224, 256}) {
-        if (mode >= 2 && N != 64 && N != 128 && N != 256) continue;  // .ws shapes
-        if (run({96, 128, N, N <= 224 ? 2 : 1, a, 0, mode, 0, 0})) return 1;
-      }
-  // 4. interference: tcgen05.ld latency next to an MMA stream, unbounded and bounded queue depth
-  for (int N : {64, 112})
-    for (int batch : {0, 6, 12, 24})
-      for (int ldw : {1, 4}) if (run({384, 128, N, 2, 0, 0, 0, ldw, batch})) return 1;
-  if (run({6, 128, 16, 2, 0, 0, 0, 4, 0})) return 1;  // ld latency with an (almost) idle tensor pipe
   return 0;
 }
