@@ -37,6 +37,7 @@ _SIGNATURES = {
     "bb_ctx_sm_count": (C.c_int, [_P]),
     "bb_model_create_dense": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _PP]),
     "bb_model_destroy": (C.c_int, [_P]),
+    "bb_model_trim": (C.c_int, [_P]),
     "bb_model_n_features": (C.c_int, [_P]),
     "bb_model_z_dim": (C.c_int, [_P]),
     "bb_model_auto_precision": (C.c_int, [_P]),

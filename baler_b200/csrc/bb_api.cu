@@ -173,6 +173,43 @@ int pipe_init(bb_model* m, size_t in_bytes, size_t out_bytes) {
   return BB_OK;
 }
 
+// pinned float32 bounce buffers (two slots) of the float64 host paths, grown on demand and kept
+int pinned_init(bb_model* m, int io, size_t bytes) {
+  if (m->pinned_bytes[io] >= bytes) return BB_OK;
+  for (int s = 0; s < 2; ++s) {
+    if (m->pinned_f32[io][s]) cudaFreeHost(m->pinned_f32[io][s]);
+    m->pinned_f32[io][s] = nullptr;
+  }
+  m->pinned_bytes[io] = 0;
+  for (int s = 0; s < 2; ++s)
+    if (cudaMallocHost(&m->pinned_f32[io][s], bytes) != cudaSuccess) { cudaGetLastError(); return BB_ERR_NOMEM; }
+  m->pinned_bytes[io] = bytes;
+  return BB_OK;
+}
+
+// device copy of the whole table between the two passes of bb_compress_host, when it fits in half of the free memory
+float* resident_get(bb_model* m, size_t bytes) {
+  if (m->resident_bytes >= bytes) return m->resident_dev;
+  if (m->resident_dev) { cudaFree(m->resident_dev); m->resident_dev = nullptr; m->resident_bytes = 0; }
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes >= free_b / 2) return nullptr;
+  if (cudaMalloc(&m->resident_dev, bytes) != cudaSuccess) { cudaGetLastError(); m->resident_dev = nullptr; return nullptr; }
+  m->resident_bytes = bytes;
+  return m->resident_dev;
+}
+
+void model_trim(bb_model* m) {
+  if (m->resident_dev) cudaFree(m->resident_dev);
+  m->resident_dev = nullptr; m->resident_bytes = 0;
+  for (int io = 0; io < 2; ++io) {
+    for (int s = 0; s < 2; ++s) {
+      if (m->pinned_f32[io][s]) cudaFreeHost(m->pinned_f32[io][s]);
+      m->pinned_f32[io][s] = nullptr;
+    }
+    m->pinned_bytes[io] = 0;
+  }
+}
+
 // range = max - min on device (float32 subtraction, like numpy on a float32 table)
 __global__ void range_kernel(const float* mn, const float* mx, float* rg, int c) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,12 +257,21 @@ int bb_model_create_dense(bb_ctx* ctx, int n_enc_layers, const int* enc_dims, co
   return BB_OK;
 }
 
+int bb_model_trim(bb_model* m) {
+  if (!m) return BB_ERR_INVALID;
+  cudaSetDevice(m->ctx->device);
+  if (m->s_compute) { cudaStreamSynchronize(m->s_copy_in); cudaStreamSynchronize(m->s_compute); cudaStreamSynchronize(m->s_copy_out); }
+  model_trim(m);
+  return BB_OK;
+}
+
 int bb_model_destroy(bb_model* m) {
   if (!m) return BB_OK;
   free_chain(&m->enc);
   free_chain(&m->dec);
   if (m->flag_dev) cudaFree(m->flag_dev);
   if (m->feat_dev) cudaFree(m->feat_dev);
+  model_trim(m);
   for (int io = 0; io < 2; ++io)
     for (int s = 0; s < 2; ++s)
       if (m->stage_dev[io][s]) cudaFree(m->stage_dev[io][s]);
@@ -306,13 +352,7 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
   // the table resident when it fits, or the features handed in.
   float* resident = nullptr;
   if (norm && recompute_minmax && n_rows) {
-    size_t free_b = 0, total_b = 0;
-    BB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t table_b = (size_t)n_rows * F * sizeof(float);
-    if (table_b < free_b / 2 && cudaMalloc(&resident, table_b) != cudaSuccess) {
-      resident = nullptr;
-      cudaGetLastError();
-    }
+    resident = resident_get(m, (size_t)n_rows * F * sizeof(float));
     for (int64_t k = 0; k < n_chunks; ++k) {
       const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
       const int s = (int)(k & 1);
@@ -322,7 +362,7 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
       BB_CUDA(cudaEventRecord(m->ev_in[s], m->s_copy_in));
       BB_CUDA(cudaStreamWaitEvent(m->s_compute, m->ev_in[s], 0));
       rc = bb_colminmax_launch(m->ctx, dst, rows, F, fmin, fmax, k == 0, m->s_compute);
-      if (rc != BB_OK) { if (resident) cudaFree(resident); return rc; }
+      if (rc != BB_OK) return rc;
       BB_CUDA(cudaEventRecord(m->ev_done[s], m->s_compute));
     }
     range_kernel<<<(F + 127) / 128, 128, 0, m->s_compute>>>(fmin, fmax, frange, F);
@@ -335,11 +375,8 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
   std::vector<float> widen_tmp;
   float* pinned_out[2] = {nullptr, nullptr};
   if (z_dtype == BB_F64 && n_rows) {
-    for (int s = 0; s < 2; ++s)
-      if (cudaMallocHost(&pinned_out[s], (size_t)chunk * Z * sizeof(float)) != cudaSuccess) {
-        if (resident) cudaFree(resident);
-        return BB_ERR_NOMEM;
-      }
+    if (pinned_init(m, 1, (size_t)chunk * Z * sizeof(float)) != BB_OK) return BB_ERR_NOMEM;
+    pinned_out[0] = m->pinned_f32[1][0]; pinned_out[1] = m->pinned_f32[1][1];
   }
   auto finish_chunk = [&](int64_t k) -> int {  // host side of chunk k: wait for its D2H, widen if needed
     const int s = (int)(k & 1);
@@ -381,9 +418,6 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
   for (int64_t k = std::max<int64_t>(0, n_chunks - 2); k < n_chunks && rc == BB_OK; ++k) rc = finish_chunk(k);
   cudaStreamSynchronize(m->s_compute);
   cudaStreamSynchronize(m->s_copy_out);
-  for (int s = 0; s < 2; ++s)
-    if (pinned_out[s]) cudaFreeHost(pinned_out[s]);
-  if (resident) cudaFree(resident);
   if (rc == BB_OK && precision == BB_PREC_AUTO && m->enc.tc_ok) {
     int tripped = 0;  // fp16 range guard of the split path: redo on the fp32 kernel (features are already known)
     rc = bb_model_range_flag(m, 1, &tripped);
@@ -412,16 +446,15 @@ int bb_decompress_host(bb_model* m, const void* z_host, int z_dtype, int64_t n_r
 
   float* pin_in[2] = {nullptr, nullptr};
   float* pin_out[2] = {nullptr, nullptr};
-  auto cleanup = [&]() {
-    for (int s = 0; s < 2; ++s) {
-      if (pin_in[s]) cudaFreeHost(pin_in[s]);
-      if (pin_out[s]) cudaFreeHost(pin_out[s]);
-    }
-  };
+  auto cleanup = [&]() {};  // the bounce buffers belong to the model
   if (n_rows) {
-    for (int s = 0; s < 2; ++s) {
-      if (z_dtype == BB_F64 && cudaMallocHost(&pin_in[s], (size_t)chunk * Z * sizeof(float)) != cudaSuccess) { cleanup(); return BB_ERR_NOMEM; }
-      if (y_dtype == BB_F64 && cudaMallocHost(&pin_out[s], (size_t)chunk * F * sizeof(float)) != cudaSuccess) { cleanup(); return BB_ERR_NOMEM; }
+    if (z_dtype == BB_F64) {
+      if (pinned_init(m, 0, (size_t)chunk * Z * sizeof(float)) != BB_OK) return BB_ERR_NOMEM;
+      pin_in[0] = m->pinned_f32[0][0]; pin_in[1] = m->pinned_f32[0][1];
+    }
+    if (y_dtype == BB_F64) {
+      if (pinned_init(m, 1, (size_t)chunk * F * sizeof(float)) != BB_OK) return BB_ERR_NOMEM;
+      pin_out[0] = m->pinned_f32[1][0]; pin_out[1] = m->pinned_f32[1][1];
     }
   }
   auto finish_chunk = [&](int64_t k) -> int {

@@ -131,6 +131,10 @@ class DenseCodec:
         except Exception:
             pass
 
+    def trim(self):
+        """release the scratch the host pipelines keep between calls (resident table copy, pinned bounce buffers)"""
+        check(_lib.lib().bb_model_trim(self.handle), "bb_model_trim")
+
     @property
     def auto_precision(self):
         return {v: k for k, v in PRECISIONS.items() if k in ("fp32", "split16")}[

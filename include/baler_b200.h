@@ -82,6 +82,10 @@ int bb_model_create_dense(bb_ctx* ctx,
                           const double* const* dec_weights_host, const double* const* dec_biases_host,
                           bb_model** out);
 int bb_model_destroy(bb_model* m);
+/* The host pipelines keep their device / pinned scratch between calls (the resident copy of the table between the two
+ * passes of bb_compress_host can be as large as the table).  This releases it; the next call allocates again.  The
+ * reference has no counterpart: helper.compress (helper.py:473-616) holds the whole table in host memory instead. */
+int bb_model_trim(bb_model* m);
 int bb_model_n_features(const bb_model* m);
 int bb_model_z_dim(const bb_model* m);
 /* which arithmetic BB_PREC_AUTO resolves to for this model (BB_PREC_FP32 or BB_PREC_SPLIT16) */
