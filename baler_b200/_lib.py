@@ -53,6 +53,7 @@ _SIGNATURES = {
     "bb_trainer_create_dbn": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int, _PP]),
     "bb_trainer_set_dropout": (C.c_int, [_P, C.c_uint64, _P]),
     "bb_trainer_get_bn": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "bb_trainer_bn_running_dev": (C.c_int, [_P, _PP, _PP, C.POINTER(C.c_int)]),
     "bb_trainer_destroy": (C.c_int, [_P]),
     "bb_trainer_param_count": (C.c_int, [_P]),
     "bb_trainer_params_dev": (_P, [_P]),

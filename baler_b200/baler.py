@@ -69,6 +69,8 @@ def perform_training(output_path, config, verbose):
     model = helper.model_init(config.model_name)(n_features=n_features, z_dim=config.latent_space_size)
     training_path = os.path.join(output_path, "training")
     trained_model = helper.train(model, number_of_columns, train_set, test_set, training_path, config)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return  # data-parallel launch (torchrun): the replicas are identical, rank 0 writes the files
     if config.apply_normalization:
         np.save(os.path.join(training_path, "normalization_features.npy"), normalization_features)
     if config.separate_model_saving:

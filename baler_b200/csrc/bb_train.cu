@@ -747,6 +747,12 @@ int bb_trainer_set_dropout(bb_trainer* t, unsigned long long seed, const unsigne
   return BB_OK;
 }
 
+int bb_trainer_bn_running_dev(bb_trainer* t, float** running_mean_dev, float** running_var_dev, int* n) {
+  if (!t || t->kind != 1 || !running_mean_dev || !running_var_dev || !n) return BB_ERR_INVALID;
+  *running_mean_dev = t->rm; *running_var_dev = t->rv; *n = t->d.bn_f_total;
+  return BB_OK;
+}
+
 int bb_trainer_get_bn(bb_trainer* t, double* const* bn_weight_host, double* const* bn_bias_host,
                       double* const* bn_mean_host, double* const* bn_var_host, long long* bn_batches_tracked) {
   if (!t || t->kind != 1 || !bn_weight_host || !bn_bias_host || !bn_mean_host || !bn_var_host || !bn_batches_tracked)
@@ -935,7 +941,9 @@ int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_
   const int n_splits = (batch_rows + DW_T - 1) / DW_T;
   const int n_ctas = (batch_rows + RT - 1) / RT;
   if (phase != 2) {
-    if (t->kind == 1 && (h->l1 || h->world_size > 1)) return BB_ERR_UNSUPPORTED;  // MSE only, single GPU (whole-batch BN statistics)
+    // AE_Dropout_BN: MSE only.  world_size > 1 is data parallel with per-rank BatchNorm statistics (each rank normalises
+    // its slice of the global batch, what torch DistributedDataParallel does with this model); gradients are summed.
+    if (t->kind == 1 && h->l1) return BB_ERR_UNSUPPORTED;
     int rc = t->kind == 1 ? launch_dbn(t, x_dev, batch_rows, 0, s) : launch_fwd_bwd(t, x_dev, batch_rows, 1, h, s);
     if (rc != BB_OK) return rc;
     train_dw_kernel<<<dim3(t->n_tiles, n_splits), NT, 0, s>>>(t->d, t->tiles, t->act_g, t->dz_g,

@@ -277,6 +277,12 @@ class Trainer:
             ptrs = (C.c_void_p * 4)(*[m.data_ptr() for m in self._masks])
         check(_lib.lib().bb_trainer_set_dropout(self.handle, int(seed), ptrs), "bb_trainer_set_dropout")
 
+    def bn_running_views(self):
+        """AE_Dropout_BN: zero-copy views (running_mean, running_var) of the concatenated BatchNorm buffers"""
+        rm, rv, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        check(_lib.lib().bb_trainer_bn_running_dev(self.handle, C.byref(rm), C.byref(rv), C.byref(n)), "bb_trainer_bn_running_dev")
+        return self._flat(rm.value, n.value), self._flat(rv.value, n.value)
+
     def get_bn(self):
         out = {k: [np.empty_like(a) for a in self._bn[k]] for k in ("weight", "bias", "running_mean", "running_var")}
         nbt = (C.c_longlong * 4)()

@@ -6,8 +6,24 @@ import time
 import numpy as np
 import torch
 
-from .. import engine
+from .. import engine, sharded
 from . import utils
+
+
+def dist_env():
+    """(rank, world).  Launched under torchrun (`python -m torch.distributed.run --nproc-per-node N -m baler_b200
+    --mode train ...`) the run is data-parallel: one process per GPU, NCCL; otherwise (1 process) rank 0 of 1.
+    The reference has no distributed code; the global batch stays `config.batch_size`, cut into `world` contiguous
+    slices in the reference's batch order (sharded.dp_batch_slices), gradients are summed."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
 
 
 class DeviceBatches:
@@ -31,12 +47,22 @@ class DeviceAdam:
         self.has_bn = hasattr(model, "bn_tensors")
         self.trainer = engine.Trainer(w, b, model.n_features, model.z_dim, max_batch,
                                       bn=model.bn_tensors() if self.has_bn else None)
+        self.rank, self.world = dist_env()
         if self.has_bn:
-            self.trainer.set_dropout(seed=dropout_seed)
+            self.trainer.set_dropout(seed=dropout_seed + self.rank)  # every rank draws its own dropout stream
+        self.dp = sharded.DataParallelTrainer(self.trainer) if self.world > 1 else None
         self.lr, self.l1, self.reg_param = lr, l1, reg_param
 
-    def hyper(self, world_size=1):
-        return engine.make_hyper(lr=self.lr, reg_param=self.reg_param, l1=self.l1, world_size=world_size)
+    def hyper(self, world_size=None):
+        return engine.make_hyper(lr=self.lr, reg_param=self.reg_param, l1=self.l1,
+                                 world_size=self.world if world_size is None else world_size)
+
+    def epoch(self, data, batch_size):
+        """one pass over `data` in the reference's batch order; data-parallel when launched with several ranks"""
+        if self.dp is None:
+            return self.trainer.epoch(data, batch_size, self.hyper())
+        slices = sharded.dp_batch_slices(data.shape[0], batch_size, self.rank, self.world)
+        return self.dp.epoch([data[lo:hi] for lo, hi in slices], self.hyper())
 
     def sync_model(self):
         w, b = self.trainer.get_params()
@@ -53,7 +79,7 @@ def fit(config, model, train_dl, model_children, regular_param, optimizer, laten
     model.train()
     if hasattr(config, "custom_loss_function") and config.custom_loss_function == "loss_function_swae":
         raise NotImplementedError("loss_function_swae is outside the B200 hot path")
-    epoch_loss = optimizer.trainer.epoch(train_dl.data, train_dl.batch_size, optimizer.hyper())
+    epoch_loss = optimizer.epoch(train_dl.data, train_dl.batch_size)
     print(f"# Finished. Training Loss: {epoch_loss:.6f}")
     return epoch_loss, epoch_loss, 0, model
 
@@ -117,11 +143,13 @@ def train(model, variables, train_data, test_data, project_path, config):
                 break
         if config.intermittent_model_saving and epoch % config.intermittent_saving_patience == 0:
             optimizer.sync_model()
-            helper.model_saver(model, os.path.join(project_path, f"model_{epoch}.pt"))
+            if optimizer.rank == 0:
+                helper.model_saver(model, os.path.join(project_path, f"model_{epoch}.pt"))
     end = time.time()
     optimizer.sync_model()
-    if getattr(config, "activation_extraction", False):
-        np.save(os.path.join(project_path, "activations.npy"), optimizer.trainer.activation_means())
+    if optimizer.rank == 0:  # replicas are identical: one writer
+        if getattr(config, "activation_extraction", False):
+            np.save(os.path.join(project_path, "activations.npy"), optimizer.trainer.activation_means())
+        np.save(os.path.join(project_path, "loss_data.npy"), np.array([train_loss, val_loss]))
     print(f"{(end - start) / 60:.3} minutes")
-    np.save(os.path.join(project_path, "loss_data.npy"), np.array([train_loss, val_loss]))
     return model

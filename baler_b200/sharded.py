@@ -50,6 +50,19 @@ class DataParallelTrainer:
     def __init__(self, trainer, group=None):
         self.trainer, self.group = trainer, group
         self.grads = trainer.grads_view()  # n_params + 1 floats: gradient, then the batch loss
+        # AE_Dropout_BN: every rank normalises ITS slice of the batch (per-rank BatchNorm statistics, as torch
+        # DistributedDataParallel runs the reference model) and draws its own dropout stream; the running statistics
+        # are averaged over ranks at the end of an epoch so that the replicas save the same model.pt
+        self.bn_running = trainer.bn_running_views() if getattr(trainer, "_bn", None) is not None else None
+
+    def sync_running_stats(self):
+        if self.bn_running is None or not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(self.group)
+        if world > 1:
+            for t in self.bn_running:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                t.div_(world)
 
     def step(self, x_local, hyper):
         """x_local: this rank's contiguous slice of the global batch (may have 0 rows)"""
@@ -68,4 +81,5 @@ class DataParallelTrainer:
         self.trainer.loss_accum.zero_()
         for xb in x_local_batches:
             self.step(xb, hyper)
+        self.sync_running_stats()
         return self.trainer.loss_accum.item() / max(len(x_local_batches), 1)

@@ -176,7 +176,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")  # stdout carries exactly one JSON line
+        # stdout carries exactly one JSON line: NCCL logs (even its version banner at WARN) go to stderr, and only on request
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("BENCH_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     sd = golden_state_dict()

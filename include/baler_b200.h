@@ -192,6 +192,9 @@ int bb_trainer_create_dbn(bb_ctx* ctx, int n_features, int z_dim,
 /* dropout: in-kernel Philox4x32-10 keyed by (seed, step, layer, row, column); `masks_dev` (4 device pointers to
  * [batch x width] uint8 keep-masks, or NULL) injects torch-generated masks for parity tests */
 int bb_trainer_set_dropout(bb_trainer* t, unsigned long long seed, const unsigned char* const* masks_dev);
+/* device views of the concatenated BatchNorm running statistics (4 layers, 200 + 100 + 50 + n_features values each):
+ * data-parallel runs average them over ranks (torch DDP broadcasts rank 0's buffers instead; models.py:275-296) */
+int bb_trainer_bn_running_dev(bb_trainer* t, float** running_mean_dev, float** running_var_dev, int* n);
 int bb_trainer_get_bn(bb_trainer* t, double* const* bn_weight_host, double* const* bn_bias_host,
                       double* const* bn_mean_host, double* const* bn_var_host, long long* bn_batches_tracked);
 int bb_trainer_destroy(bb_trainer* t);

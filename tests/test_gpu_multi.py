@@ -40,6 +40,22 @@ def _worker(rank, world, port, out_dir):
         loss = dp.epoch([x[lo:hi].contiguous() for lo, hi in slices], hyper)
         np.save(os.path.join(out_dir, "dp_params_%d.npy" % rank), tr.params_view().cpu().numpy())
         np.save(os.path.join(out_dir, "dp_loss_%d.npy" % rank), np.array([loss]))
+        # AE_Dropout_BN, data parallel: per-rank BatchNorm statistics and dropout streams, SUM all-reduce, identical Adam step
+        gd = np.load(os.path.join(GOLDEN, "ae_dbn.npz"))
+        sdb = {k[4:]: np.asarray(gd[k], order="C") for k in gd.files if k.startswith("sd0/")}
+        lin = models.AE_Dropout_BN.enc_names + models.AE_Dropout_BN.dec_names
+        bnn = models.AE_Dropout_BN.bn_names
+        bn = {k: [sdb[b + "." + k] for b in bnn] for k in ("weight", "bias", "running_mean", "running_var")}
+        bn["num_batches_tracked"] = [int(sdb[b + ".num_batches_tracked"]) for b in bnn]
+        trb = engine.Trainer([sdb[n + ".weight"] for n in lin], [sdb[n + ".bias"] for n in lin], 24, 15, 512, bn=bn)
+        trb.set_dropout(seed=5 + rank)
+        dpb = sharded.DataParallelTrainer(trb)
+        xb = torch.from_numpy(np.ascontiguousarray(gd["x_norm"][:1024])).cuda()
+        sl = sharded.dp_batch_slices(1024, 512, rank, world)
+        losses = [dpb.epoch([xb[lo:hi].contiguous() for lo, hi in sl], hyper) for _ in range(3)]
+        rm, rv = trb.bn_running_views()
+        np.save(os.path.join(out_dir, "dbn_%d.npy" % rank),
+                np.concatenate([trb.params_view().cpu().numpy(), rm.cpu().numpy(), rv.cpu().numpy(), np.array(losses, dtype=np.float32)]))
         # sharded compress: local min/max -> exchange -> encode of the local rows with the global features
         table = synth.cms_table(40_001, seed=8)
         lo, hi = sharded.row_range(len(table), rank, world)
@@ -63,6 +79,9 @@ def test_data_parallel_equals_single_gpu(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     p0, p1 = np.load(tmp_path / "dp_params_0.npy"), np.load(tmp_path / "dp_params_1.npy")
     assert np.array_equal(p0, p1)  # replicated Adam state stays bit-identical
+    d0, d1 = np.load(tmp_path / "dbn_0.npy"), np.load(tmp_path / "dbn_1.npy")
+    assert np.array_equal(d0, d1) and np.isfinite(d0).all()  # AE_Dropout_BN replicas: parameters, running statistics, losses
+    assert d0[-1] < d0[-3]  # three epochs: the loss goes down
     g = np.load(os.path.join(GOLDEN, "ae_train.npz"))
     sd0 = {k[4:]: np.asarray(g[k], order="C") for k in g.files if k.startswith("sd0/")}
     names = models.AE.names

@@ -264,3 +264,37 @@ def test_dropout_bn_validate_equals_folded_codec(golden):
     rec = orc.dbn_decode(sd0, orc.dbn_encode(sd0, x.astype(np.float64)))
     ref = orc.mse_sum_loss(rec, x.astype(np.float64))
     assert abs(val - ref) <= 1e-5 * ref
+
+
+def test_dropout_bn_data_parallel_step_matches_oracle(golden):
+    """data-parallel AE_Dropout_BN: every rank runs the train-mode forward / backward on ITS slice of the global batch
+    (per-rank BatchNorm statistics), the flat gradients are SUMMED and every rank applies the same Adam step.  Two
+    trainers on one GPU play the two ranks; the reference arithmetic for each slice comes from the oracle."""
+    g = golden("ae_dbn.npz")
+    sd0 = sub_sd(g, "sd0")
+    x = g["x_norm"][:512]
+    masks = [g["mask%d" % i].astype(np.uint8) for i in range(4)]
+    h = engine.make_hyper(lr=1e-3, world_size=2)
+    ranks, ref_g, ref_loss = [], None, 0.0
+    for r, (lo, hi) in enumerate(((0, 256), (256, 512))):
+        tr = dbn_trainer(sd0)
+        tr.set_dropout(masks=[torch.from_numpy(np.ascontiguousarray(m[lo:hi])).cuda() for m in masks])
+        tr.step(torch.from_numpy(np.ascontiguousarray(x[lo:hi])).cuda(), h, phase=1)
+        ranks.append(tr)
+        loss, _, grads, _ = orc.dbn_train_step({k: np.asarray(v, dtype=np.float64) for k, v in sd0.items()},
+                                               x[lo:hi].astype(np.float64), [m[lo:hi].astype(np.float64) for m in masks])
+        flat = dbn_flat(grads)
+        ref_g = flat if ref_g is None else ref_g + flat
+        ref_loss += loss
+    total = ranks[0].grads_view() + ranks[1].grads_view()  # what the SUM all-reduce leaves on every rank
+    for tr in ranks:
+        tr.grads_view().copy_(total)
+    got = total[:-1].cpu().numpy()
+    gscale = np.abs(ref_g).max()
+    assert np.abs(got - ref_g).max() <= 2e-5 * gscale and rel_l2(got, ref_g) <= 2e-5
+    assert abs(float(total[-1]) - ref_loss) <= 1e-5 * ref_loss
+    for tr, (lo, hi) in zip(ranks, ((0, 256), (256, 512))):
+        tr.step(torch.from_numpy(np.ascontiguousarray(x[lo:hi])).cuda(), h, phase=2)
+    assert torch.equal(ranks[0].params_view(), ranks[1].params_view())  # replicas stay bit-identical
+    rm, rv = ranks[0].bn_running_views()
+    assert rm.numel() == 200 + 100 + 50 + 24 and torch.isfinite(rm).all() and torch.isfinite(rv).all()
