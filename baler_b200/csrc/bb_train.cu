@@ -26,6 +26,26 @@
 #include "bb_common.cuh"
 
 namespace {
+// Programmatic dependent launch: the three kernels of a training step are launched back to back with
+// cudaLaunchAttributeProgrammaticStreamSerialization, every kernel lets its successor's CTAs be scheduled at once
+// (launch_dependents) and waits for its predecessor's results (wait) before touching global memory, so launch latency
+// and CTA scheduling of kernel n + 1 overlap the execution of kernel n.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+}  // namespace
+
+namespace {
 
 constexpr int NL = 8;       // dense layers F-200-100-50-z-50-100-200-F
 constexpr int RT = 4;       // rows per CTA in the forward/backward kernel (128 CTAs for a 512-row batch)
@@ -267,6 +287,8 @@ train_fwd_bwd_kernel(const __grid_constant__ TrainDims d, const float* __restric
                      const size_t chain_dz_stride, const int backward, const int l1, const float reg,
                      const float inv_global_rows, float* __restrict__ loss_part) {
   extern __shared__ __align__(16) float smem[];
+  pdl_launch_dependents();
+  pdl_wait();  // parameters come from the previous step's Adam kernel
   float* act_s = smem;                           // a_stride * RT
   float* dz_s0 = act_s + d.a_stride * RT;        // max_dim * RT
   float* dz_s1 = dz_s0 + d.max_dim * RT;
@@ -576,6 +598,8 @@ train_dw_kernel(const __grid_constant__ TrainDims d, const DwTile* __restrict__ 
                 const int n_chains, const int batch_rows, float* __restrict__ partial) {
   __shared__ __align__(16) float dz_s[DW_T][DW_LD];
   __shared__ __align__(16) float a_s[DW_T][DW_LD];
+  pdl_launch_dependents();
+  pdl_wait();  // activations and dZ come from the forward / backward kernel
   const DwTile tile = tiles[blockIdx.x];
   const int l = tile.l, N = d.dims[l + 1], K = d.dims[l];
   const int r0 = blockIdx.y * DW_T;
@@ -633,6 +657,8 @@ train_adam_kernel(const int n_params, const int mode, const float* __restrict__ 
                   const int* __restrict__ wt_index, float* __restrict__ m, float* __restrict__ v, const float lr_bc1,
                   const float inv_sqrt_bc2, const float beta1, const float beta2, const float eps,
                   const float* __restrict__ loss_part, const int n_loss_parts, double* __restrict__ loss_accum) {
+  pdl_launch_dependents();
+  pdl_wait();  // gradient partials come from the dW kernel
   const int p = blockIdx.x * NT + threadIdx.x;
   if (p < n_params) {
     float g;
@@ -696,10 +722,9 @@ int launch_fwd_bwd(bb_trainer* t, const float* x, int rows, int backward, const 
   t->last_rows = rows;
   const int world = h && h->world_size > 0 ? h->world_size : 1;
   const float inv_rows = 1.f / ((float)rows * world);
-  train_fwd_bwd_kernel<<<grid, NT_FB, t->smem_bytes, s>>>(
-      t->d, t->params, t->wt, x, rows, t->act_g, t->dz_g, (size_t)t->max_batch * t->d.a_stride,
-      (size_t)t->max_batch * t->d.z_stride, backward, h ? h->l1 : 0, h ? (float)h->reg_param : 0.f, inv_rows, t->loss_part);
-  return (int)cudaGetLastError();
+  return (int)pdl_launch(train_fwd_bwd_kernel, dim3(grid), dim3(NT_FB), t->smem_bytes, s, t->d, t->params, t->wt, x, rows, t->act_g,
+                         t->dz_g, (size_t)t->max_batch * t->d.a_stride, (size_t)t->max_batch * t->d.z_stride, backward,
+                         h ? h->l1 : 0, h ? (float)h->reg_param : 0.f, inv_rows, t->loss_part);
 }
 
 int launch_dbn(bb_trainer* t, const float* x, int rows, int mode, cudaStream_t s) {
@@ -946,11 +971,9 @@ int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_
     if (t->kind == 1 && h->l1) return BB_ERR_UNSUPPORTED;
     int rc = t->kind == 1 ? launch_dbn(t, x_dev, batch_rows, 0, s) : launch_fwd_bwd(t, x_dev, batch_rows, 1, h, s);
     if (rc != BB_OK) return rc;
-    train_dw_kernel<<<dim3(t->n_tiles, n_splits), NT, 0, s>>>(t->d, t->tiles, t->act_g, t->dz_g,
-                                                            (size_t)t->max_batch * t->d.a_stride,
-                                                            (size_t)t->max_batch * t->d.z_stride, h->l1 ? 2 : 1,
-                                                            batch_rows, t->partial);
-    BB_CUDA(cudaGetLastError());
+    BB_CUDA(pdl_launch(train_dw_kernel, dim3(t->n_tiles, n_splits), dim3(NT), 0, s, t->d, t->tiles, t->act_g, t->dz_g,
+                       (size_t)t->max_batch * t->d.a_stride, (size_t)t->max_batch * t->d.z_stride, h->l1 ? 2 : 1, batch_rows,
+                       t->partial));
   }
   float lr_bc1 = 0.f, inv_sqrt_bc2 = 0.f;
   if (phase != 1) {
@@ -960,10 +983,9 @@ int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_
     lr_bc1 = (float)(h->lr / bc1);
     inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
   }
-  train_adam_kernel<<<(p + NT - 1) / NT, NT, 0, s>>>(p, phase, t->partial, n_splits, t->grads, t->params, t->wt,
-                                                    t->wt_index, t->m, t->v, lr_bc1, inv_sqrt_bc2, (float)h->beta1,
-                                                    (float)h->beta2, (float)h->eps, t->loss_part, n_ctas, loss_accum_dev);
-  return (int)cudaGetLastError();
+  return (int)pdl_launch(train_adam_kernel, dim3((p + NT - 1) / NT), dim3(NT), 0, s, p, phase, t->partial, n_splits, t->grads,
+                         t->params, t->wt, t->wt_index, t->m, t->v, lr_bc1, inv_sqrt_bc2, (float)h->beta1, (float)h->beta2,
+                         (float)h->eps, t->loss_part, n_ctas, loss_accum_dev);
 }
 
 int bb_trainer_epoch(bb_trainer* t, const float* x_dev, int64_t n_rows, int batch, const bb_train_hyper* h,
