@@ -633,13 +633,21 @@ int launch_one(const bb_ctx* ctx, Tc4Params p, cudaStream_t stream) {
   const size_t out_b = ((size_t)TILE * p.out_dim * 4 + 127) & ~(size_t)127;
   const size_t smem_bytes = ((P::W_BYTES + 127u) & ~127u) + NPIPE * (2 * in_b + out_b);
   auto k = chain_tc4_kernel<ENC, KA, NL, TRACE>;
-  static bool attr_set = false;  // per instantiation
-  static uint32_t smem_off = 0;
+  // per instantiation and per device (function attributes belong to a device's context)
+  constexpr int MAX_DEV = 64;
+  static bool attr_set_d[MAX_DEV] = {};
+  static uint32_t smem_off_d[MAX_DEV] = {};
+  static size_t static_smem_d[MAX_DEV] = {};
+  if (ctx->device < 0 || ctx->device >= MAX_DEV) return BB_ERR_UNSUPPORTED;
+  bool& attr_set = attr_set_d[ctx->device];
+  uint32_t& smem_off = smem_off_d[ctx->device];
+  size_t& static_smem = static_smem_d[ctx->device];
   if (!attr_set) {
     cudaFuncAttributes fa;
     BB_CUDA(cudaFuncGetAttributes(&fa, k));
-    if (smem_bytes + fa.sharedSizeBytes > ctx->smem_optin) return BB_ERR_UNSUPPORTED;
-    BB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - fa.sharedSizeBytes)));
+    static_smem = fa.sharedSizeBytes;
+    if (smem_bytes + static_smem > ctx->smem_optin) return BB_ERR_UNSUPPORTED;
+    BB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - static_smem)));
     // where the dynamic shared memory of THIS kernel starts (a link-time constant the host cannot query): one probe launch
     uint32_t* probe_dev = nullptr;
     BB_CUDA(cudaMalloc(&probe_dev, 4));
@@ -651,6 +659,7 @@ int launch_one(const bb_ctx* ctx, Tc4Params p, cudaStream_t stream) {
     BB_CUDA(cudaFree(probe_dev));
     attr_set = true;
   }
+  if (smem_bytes + static_smem > ctx->smem_optin) return BB_ERR_UNSUPPORTED;  // wide rows: the table-driven kernel (one pipeline) takes over
   p.smem_off = smem_off;
   p.tmem0 = 0;
   p.probe = nullptr;

@@ -124,3 +124,30 @@ def test_range_guard(ae):
     z = codec.encode(torch.from_numpy(x).cuda(), precision="auto").cpu().numpy()
     assert np.isfinite(z).all()
     assert rel_max(z, zr) <= 1e-5
+
+
+@pytest.mark.parametrize("n_features,z_dim", [(4, 2), (15, 15), (16, 8), (24, 15), (10, 20), (31, 16), (31, 31)])
+def test_tc_shape_family_vs_oracle(n_features, z_dim):
+    """every instantiation of the statically shaped tcgen05 kernel (padded first K 16 / 32, padded last N 16 / 32, both
+    directions): random reference-initialised AE(n_features, z_dim), fused normalisation / un-normalisation, ragged row
+    counts (single rows, tile tails whose byte count is not a multiple of 16, fewer tiles than SMs, many tiles)"""
+    torch.manual_seed(100 * n_features + z_dim)
+    m = models.AE(n_features, z_dim).eval()
+    sd = {k: v.numpy().astype(np.float64) for k, v in m.state_dict().items()}
+    codec = m.codec()
+    assert codec.auto_precision == "split16"
+    rng = np.random.default_rng(n_features * 7 + z_dim)
+    for n in (1, 3, 129, 300, 4097, 50021):
+        raw = (rng.lognormal(0.0, 1.0, size=(n, n_features)) + rng.integers(0, 5, size=(1, n_features))).astype(np.float32)
+        mn = raw.min(axis=0) - 0.25
+        rg = (raw.max(axis=0) - mn + 0.5).astype(np.float32)
+        xn = ((raw - mn) / rg).astype(np.float64)  # numpy float32 normalisation, then the float64 reference chain
+        zr = orc.ae_encode(sd, xn)
+        yr = orc.ae_decode(sd, zr) * rg.astype(np.float64) + mn.astype(np.float64)
+        x_dev = torch.from_numpy(raw).cuda()
+        mn_d, rg_d = torch.from_numpy(mn).cuda(), torch.from_numpy(rg).cuda()
+        z = codec.encode(x_dev, mn_d, rg_d, precision="split16")
+        assert rel_max(z.cpu().numpy(), zr) <= 1e-5 and rel_l2(z.cpu().numpy(), zr) <= 1e-5, (n, rel_max(z.cpu().numpy(), zr))
+        y = codec.decode(torch.from_numpy(zr.astype(np.float32)).cuda(), mn_d, rg_d, precision="split16")
+        assert rel_max(y.cpu().numpy(), yr) <= 1e-5 and rel_l2(y.cpu().numpy(), yr) <= 1e-5, (n, rel_max(y.cpu().numpy(), yr))
+    assert not codec.range_flag()
