@@ -64,6 +64,15 @@ _SIGNATURES = {
     "bb_trainer_validate": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.POINTER(C.c_double), _P]),
     "bb_trainer_activation_means": (C.c_int, [_P, _P]),
     "bb_mse_sum_f32": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "bb_ltrainer_create": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, _PP]),
+    "bb_ltrainer_destroy": (C.c_int, [_P]),
+    "bb_ltrainer_param_count": (C.c_int, [_P]),
+    "bb_ltrainer_params_dev": (_P, [_P]),
+    "bb_ltrainer_grads_dev": (_P, [_P]),
+    "bb_ltrainer_get_params": (C.c_int, [_P, _P, _P]),
+    "bb_ltrainer_step": (C.c_int, [_P, _P, C.c_int, C.POINTER(TrainHyper), C.c_int, _P, _P]),
+    "bb_ltrainer_epoch": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.POINTER(TrainHyper), C.POINTER(C.c_double), _P]),
+    "bb_ltrainer_validate": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.POINTER(C.c_double), _P]),
 }
 
 _handle = None

@@ -304,5 +304,68 @@ class Trainer:
         return w, b
 
 
+class LayeredTrainer:
+    """bb_ltrainer: the layer-by-layer trainer for dense autoencoders too wide for the fused training kernels
+    (CFD_dense_AE on 2500-feature snapshots).  Same surface as Trainer for what training.train uses."""
+
+    _ACT = {"none": 0, "leaky": 1, "relu": 2}
+
+    def __init__(self, weights, biases, acts, max_batch, device=None):
+        self.ctx = get_context(device)
+        self.handle = C.c_void_p()
+        self._bn = None
+        self._w = [np.ascontiguousarray(w, dtype=np.float64) for w in weights]
+        self._b = [np.ascontiguousarray(b, dtype=np.float64) for b in biases]
+        dims = (C.c_int * (len(self._w) + 1))(*([self._w[0].shape[1]] + [w.shape[0] for w in self._w]))
+        acts_c = (C.c_int * len(self._w))(*[self._ACT[a] for a in acts])
+        with torch.cuda.device(self.ctx.device):
+            check(_lib.lib().bb_ltrainer_create(self.ctx.handle, len(self._w), dims, acts_c, _host_ptrs(self._w),
+                                                _host_ptrs(self._b), max_batch, C.byref(self.handle)), "bb_ltrainer_create")
+        self.n_params = _lib.lib().bb_ltrainer_param_count(self.handle)
+        self.loss_accum = torch.zeros(1, dtype=torch.float64, device=self.ctx.device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                _lib.lib().bb_ltrainer_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    _flat = Trainer._flat
+
+    def params_view(self):
+        return self._flat(_lib.lib().bb_ltrainer_params_dev(self.handle))
+
+    def grads_view(self):
+        return self._flat(_lib.lib().bb_ltrainer_grads_dev(self.handle), self.n_params + 1)
+
+    def step(self, x, hyper, phase=0):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        check(_lib.lib().bb_ltrainer_step(self.handle, _ptr(x), x.shape[0], C.byref(hyper), phase, _ptr(self.loss_accum),
+                                          _stream(self.ctx)), "bb_ltrainer_step")
+
+    def epoch(self, x, batch, hyper):
+        out = C.c_double()
+        check(_lib.lib().bb_ltrainer_epoch(self.handle, _ptr(x), x.shape[0], batch, C.byref(hyper), C.byref(out),
+                                           _stream(self.ctx)), "bb_ltrainer_epoch")
+        return out.value
+
+    def validate(self, x, batch):
+        out = C.c_double()
+        check(_lib.lib().bb_ltrainer_validate(self.handle, _ptr(x), x.shape[0], batch, C.byref(out), _stream(self.ctx)),
+              "bb_ltrainer_validate")
+        return out.value
+
+    def get_params(self):
+        w = [np.empty_like(a) for a in self._w]
+        b = [np.empty_like(a) for a in self._b]
+        check(_lib.lib().bb_ltrainer_get_params(self.handle, _host_ptrs(w), _host_ptrs(b)), "bb_ltrainer_get_params")
+        return w, b
+
+    def activation_means(self):
+        raise NotImplementedError("activation extraction is implemented for the fused trainer (n_features <= 31)")
+
+
 def make_hyper(lr=1e-3, reg_param=0.0, l1=False, world_size=1, beta1=0.9, beta2=0.999, eps=1e-8):
     return _lib.TrainHyper(lr, beta1, beta2, eps, reg_param, int(bool(l1)), world_size)

@@ -26,6 +26,9 @@ def dist_env():
     return 0, 1
 
 
+FUSED_TRAINER_MAX_FEATURES = 100  # bb_trainer stages whole weight matrices in shared memory (widest: 200 x 100)
+
+
 class DeviceBatches:
     """Stands in for the reference's DataLoader(shuffle=False, drop_last=False) (training.py:253-263):
     the whole (normalised, float32) table resident in HBM plus the batch size."""
@@ -45,8 +48,17 @@ class DeviceAdam:
         w, b = model.linear_tensors()
         self.model = model
         self.has_bn = hasattr(model, "bn_tensors")
-        self.trainer = engine.Trainer(w, b, model.n_features, model.z_dim, max_batch,
-                                      bn=model.bn_tensors() if self.has_bn else None)
+        self.trainer = None
+        if self.has_bn or model.n_features <= FUSED_TRAINER_MAX_FEATURES:
+            try:
+                self.trainer = engine.Trainer(w, b, model.n_features, model.z_dim, max_batch,
+                                              bn=model.bn_tensors() if self.has_bn else None)
+            except Exception:
+                if self.has_bn:
+                    raise
+        if self.trainer is None:
+            # wide rows (CFD_dense_AE on flattened 2-D snapshots): the layer-by-layer GEMM trainer
+            self.trainer = engine.LayeredTrainer(w, b, ["leaky", "leaky", "leaky", "none"] * 2, max_batch)
         self.rank, self.world = dist_env()
         if self.has_bn:
             self.trainer.set_dropout(seed=dropout_seed + self.rank)  # every rank draws its own dropout stream

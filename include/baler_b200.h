@@ -234,6 +234,28 @@ int bb_trainer_validate(bb_trainer* t, const float* x_dev, int64_t n_rows, int b
  */
 int bb_trainer_activation_means(bb_trainer* t, double* out_host_6x200);
 
+/*
+ * Layer-by-layer trainer for dense autoencoders whose weights do not fit the fused training kernels: CFD_dense_AE on
+ * 2500-feature snapshots (models.py:186-226) or any chain of up to 8 Linears with dims[0] == dims[n_layers].  Same
+ * contract as bb_trainer_* (training.fit training.py:31-101, Adam training.py:266, sum-MSE / n_columns
+ * utils.py:195-199), one fp32 GEMM launch per matrix product.  `weights[l]` = (dims[l+1], dims[l]) row-major float64,
+ * `acts[l]` = BB_ACT_*.  MSE only (h->l1 must be 0); phase as in bb_trainer_step.
+ */
+typedef struct bb_ltrainer bb_ltrainer;
+int bb_ltrainer_create(bb_ctx* ctx, int n_layers, const int* dims, const int* acts, const double* const* weights_host,
+                       const double* const* biases_host, int max_batch, bb_ltrainer** out);
+int bb_ltrainer_destroy(bb_ltrainer* t);
+int bb_ltrainer_param_count(const bb_ltrainer* t);
+float* bb_ltrainer_params_dev(bb_ltrainer* t);
+float* bb_ltrainer_grads_dev(bb_ltrainer* t);  /* n_params gradient entries, then the batch loss */
+int bb_ltrainer_get_params(bb_ltrainer* t, double* const* weights_host, double* const* biases_host);
+int bb_ltrainer_step(bb_ltrainer* t, const float* x_dev, int batch_rows, const bb_train_hyper* h, int phase,
+                     double* loss_accum_dev, bb_stream_t stream);
+int bb_ltrainer_epoch(bb_ltrainer* t, const float* x_dev, int64_t n_rows, int batch, const bb_train_hyper* h,
+                      double* epoch_loss_host, bb_stream_t stream);
+int bb_ltrainer_validate(bb_ltrainer* t, const float* x_dev, int64_t n_rows, int batch, double* epoch_loss_host,
+                         bb_stream_t stream);
+
 /* sum((a - b)^2) over n float32 elements, ADDED to *out_dev (double): nn.MSELoss(reduction="sum") of
  * utils.mse_sum_loss_l1 (utils.py:195-196) on loose tensors. */
 int bb_mse_sum_f32(bb_ctx* ctx, const float* a_dev, const float* b_dev, int64_t n, double* out_dev, bb_stream_t stream);

@@ -298,3 +298,81 @@ def test_dropout_bn_data_parallel_step_matches_oracle(golden):
     assert torch.equal(ranks[0].params_view(), ranks[1].params_view())  # replicas stay bit-identical
     rm, rv = ranks[0].bn_running_views()
     assert rm.numel() == 200 + 100 + 50 + 24 and torch.isfinite(rm).all() and torch.isfinite(rv).all()
+
+
+# ------------------------------------------------------------------ layer-by-layer trainer (wide rows: CFD_dense_AE)
+AE_ACTS = ["leaky", "leaky", "leaky", "none"] * 2
+
+
+def _layered(sd, max_batch):
+    return engine.LayeredTrainer([sd[n + ".weight"] for n in NAMES], [sd[n + ".bias"] for n in NAMES], AE_ACTS, max_batch)
+
+
+def test_layered_trainer_cfd_dense_step_matches_oracle():
+    """CFD_dense_AE(2500, 25) (models.py:186-226; the shipped CFD_project_animation: 60 snapshots of 50 x 50): one fit
+    step - loss, every gradient, Adam update - against the float64 oracle"""
+    torch.manual_seed(3)
+    m = models.CFD_dense_AE(2500, 25)
+    sd = {k: v.numpy().astype(np.float64) for k, v in m.state_dict().items()}
+    rng = np.random.default_rng(5)
+    x = rng.random((60, 2500), dtype=np.float32)
+    tr = _layered(sd, 64)
+    assert tr.n_params == sum(v.size for v in sd.values())
+    tr.step(torch.from_numpy(x).cuda(), engine.make_hyper(lr=1e-3), phase=1)
+    loss_ref, _, _, g = orc.ae_loss_and_grads(sd, x.astype(np.float64))
+    got = tr.grads_view().cpu().numpy()
+    ref = np.concatenate([np.concatenate([g[n + ".weight"].ravel(), g[n + ".bias"].ravel()]) for n in NAMES])
+    assert abs(got[-1] - loss_ref) <= 1e-5 * loss_ref
+    assert rel_max(got[:-1], ref) <= 1e-5 and rel_l2(got[:-1], ref) <= 1e-5, (rel_max(got[:-1], ref), rel_l2(got[:-1], ref))
+    # full step from the same start: Adam's first update is lr * sign(g) wherever |g| >> eps
+    tr2 = _layered(sd, 64)
+    tr2.step(torch.from_numpy(x).cuda(), engine.make_hyper(lr=1e-3))
+    p0 = np.concatenate([np.concatenate([sd[n + ".weight"].ravel(), sd[n + ".bias"].ravel()]) for n in NAMES])
+    opt = orc.Adam({k: v.copy() for k, v in sd.items()}, lr=1e-3)
+    opt.step(g)
+    p1 = np.concatenate([np.concatenate([opt.params[n + ".weight"].ravel(), opt.params[n + ".bias"].ravel()]) for n in NAMES])
+    p = tr2.params_view().cpu().numpy().astype(np.float64)
+    big = np.abs(ref) > 1e-3 * np.abs(ref).max()
+    assert rel_max((p - p0)[big], (p1 - p0)[big]) <= 1e-3
+    assert abs(tr2.loss_accum.item() - loss_ref) <= 1e-5 * loss_ref
+
+
+def test_layered_trainer_equals_fused_trainer_on_the_cms_shape(golden):
+    """same model, same batch: the GEMM-per-layer trainer and the fused kernels give the same gradients, and a few
+    epochs give the same loss curve"""
+    g = golden("ae_train.npz")
+    sd0 = sub_sd(g, "sd0")
+    x = torch.from_numpy(np.ascontiguousarray(g["x_norm"][:2048])).cuda()
+    a, b = make_trainer(sd0, 512), _layered(sd0, 512)
+    h = engine.make_hyper(lr=1e-3)
+    a.step(x[:512].contiguous(), h, phase=1)
+    b.step(x[:512].contiguous(), h, phase=1)
+    ga, gb = a.grads_view().cpu().numpy(), b.grads_view().cpu().numpy()
+    assert rel_max(gb, ga) <= 1e-5 and rel_l2(gb, ga) <= 1e-5
+    a, b = make_trainer(sd0, 512), _layered(sd0, 512)
+    la = [a.epoch(x, 512, h) for _ in range(3)]
+    lb = [b.epoch(x, 512, h) for _ in range(3)]
+    assert np.allclose(la, lb, rtol=1e-3), (la, lb)
+    assert abs(b.validate(x, 512) - a.validate(x, 512)) <= 1e-3 * a.validate(x, 512)
+
+
+def test_cfd_dense_training_through_the_training_module(tmp_path):
+    """training.train on a 2-D dense project (flattened 50 x 50 snapshots -> CFD_dense_AE(2500, z)): the loss curve goes
+    down and the files of the reference's train mode are written"""
+    from types import SimpleNamespace
+    from baler_b200.modules import training
+    rng = np.random.default_rng(1)
+    t = np.linspace(0, 1, 50, dtype=np.float32)
+    snaps = np.stack([np.outer(np.sin(2 * np.pi * (t + 0.01 * i)), np.cos(2 * np.pi * t * (1 + 0.02 * i))) for i in range(60)])
+    snaps = ((snaps - snaps.min()) / (snaps.max() - snaps.min())).astype(np.float32) + 0.01 * rng.random(snaps.shape, dtype=np.float32)
+    cfg = SimpleNamespace(deterministic_algorithm=True, batch_size=20, data_dimension=2, model_type="dense", lr=1e-3, reg_param=0.001,
+                          early_stopping=False, early_stopping_patience=100, min_delta=0, lr_scheduler=False, lr_scheduler_patience=50,
+                          epochs=12, test_size=0, intermittent_model_saving=False, intermittent_saving_patience=100, RHO=0.05, l1=True,
+                          activation_extraction=False)
+    torch.manual_seed(0)
+    model = models.CFD_dense_AE(2500, 25)
+    w0 = model.state_dict()["en1.weight"].clone()
+    training.train(model, 50, snaps, snaps, str(tmp_path), cfg)
+    losses = np.load(tmp_path / "loss_data.npy")
+    assert losses.shape == (2, 12) and np.isfinite(losses).all() and losses[0, -1] < 0.7 * losses[0, 0]
+    assert not torch.equal(model.state_dict()["en1.weight"], w0) and model.state_dict()["en1.weight"].dtype == torch.float32
