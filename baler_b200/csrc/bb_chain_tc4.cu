@@ -25,7 +25,8 @@
 namespace {
 
 constexpr int TILE = 128;
-constexpr int EPI_WARPS = 8;            // per pipeline
+constexpr int EPI_GROUPS = 2;           // column groups per pipeline: group h drains sub-chunks h, h + EPI_GROUPS, ...
+constexpr int EPI_WARPS = 4 * EPI_GROUPS;  // per pipeline: one warp per TMEM lane quarter and column group
 constexpr int NPIPE = 2;
 constexpr int NTHREADS = NPIPE * (EPI_WARPS + 1) * 32;
 constexpr int REG_X = 0, REG_Y = 112, REG_Z = 224, PIPE_COLS = 256;
@@ -466,22 +467,24 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
       int i = h;
       if (i < n_sub) tmem_ld16(col + 16u * (uint32_t)i, va);
 #pragma unroll 1
-      for (; i < n_sub; i += 4) {
+      for (; i < n_sub; i += 2 * EPI_GROUPS) {
         tc_wait_ld();
-        if (i + 2 < n_sub) tmem_ld16(col + 16u * (uint32_t)(i + 2), vb);
+        if (i + EPI_GROUPS < n_sub) tmem_ld16(col + 16u * (uint32_t)(i + EPI_GROUPS), vb);
         convert16(va, c1, c2, pk);
         finish(i);
         if (i == h) trace(lt, 4 + 4 * s);
-        if (i + 2 < n_sub) {
+        if (i + EPI_GROUPS < n_sub) {
           tc_wait_ld();
-          if (i + 4 < n_sub) tmem_ld16(col + 16u * (uint32_t)(i + 4), va);
+          if (i + 2 * EPI_GROUPS < n_sub) tmem_ld16(col + 16u * (uint32_t)(i + 2 * EPI_GROUPS), va);
           convert16(vb, c1, c2, pk);
-          finish(i + 2);
+          finish(i + EPI_GROUPS);
           if (i == h) trace(lt, 5 + 4 * s);
         }
       }
     }
-    if (h == 1) {
+    if (h >= 2) {
+      // nothing to do in the last step for the extra column groups
+    } else if (h == 1) {
       // the last accumulator is drained by the h == 0 warps; meanwhile the first operand of the next tile (its TMEM
       // region has been idle since step 1 / step 3, which this warp has seen complete)
       trace(lt, 1);
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
       const uint32_t b0 = bars_base + 8u * (1 + g * BARS_PER_PIPE);
       mbar_init(b0 + 8u * BAR_FULL, 1);             // one tcgen05.commit per step (even tiles)
       mbar_init(b0 + 8u * (BAR_FULL + 1), 1);       // (odd tiles)
-      mbar_init(b0 + 8u * BAR_A1, EPI_WARPS / 2);   // the four h == 1 warps
+      mbar_init(b0 + 8u * BAR_A1, 4);               // the four h == 1 warps
       mbar_init(b0 + 8u * BAR_IN, 1);               // the loader's expect_tx
       mbar_init(b0 + 8u * (BAR_IN + 1), 1);
       for (int c = 0; c < MAX_SUB; ++c) mbar_init(b0 + 8u * (BAR_SUB + c), 4);  // the 4 lane-quarter warps of one half
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
 
   if (warp == NPIPE * EPI_WARPS) run_issuer<ENC, KA, NL, TRACE, 0>(p, smem_base, bars_base, in_stage_bytes, in0_off);
   else if (warp == NPIPE * EPI_WARPS + 1) run_issuer<ENC, KA, NL, TRACE, 1>(p, smem_base, bars_base, in_stage_bytes, in0_off);
-  else run_epilogue<ENC, KA, NL, TRACE>(p, warp / EPI_WARPS, warp & 3, (warp >> 2) & 1, smem_base, smem, bars_base, in_stage_bytes,
+  else run_epilogue<ENC, KA, NL, TRACE>(p, warp / EPI_WARPS, warp & 3, (warp >> 2) % EPI_GROUPS, smem_base, smem, bars_base, in_stage_bytes,
                                         in0_off, out0_off, out_stage_bytes, norm_s);
 
   tc_fence_before();
