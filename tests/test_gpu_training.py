@@ -376,3 +376,28 @@ def test_cfd_dense_training_through_the_training_module(tmp_path):
     losses = np.load(tmp_path / "loss_data.npy")
     assert losses.shape == (2, 12) and np.isfinite(losses).all() and losses[0, -1] < 0.7 * losses[0, 0]
     assert not torch.equal(model.state_dict()["en1.weight"], w0) and model.state_dict()["en1.weight"].dtype == torch.float32
+
+
+def test_layered_trainer_data_parallel_phases():
+    """the layered trainer has the same two-phase step as the fused one: gradients of two half batches sum to the full
+    batch's gradient (the loss is a sum over rows), and phase 2 applies Adam on the summed buffer"""
+    torch.manual_seed(4)
+    m = models.CFD_dense_AE(400, 20)
+    sd = {k: v.numpy().astype(np.float64) for k, v in m.state_dict().items()}
+    x = torch.rand((64, 400), device="cuda")
+    h1, h2 = engine.make_hyper(lr=1e-3), engine.make_hyper(lr=1e-3, world_size=2)
+    full = _layered(sd, 64)
+    full.step(x, h1, phase=1)
+    ranks = [_layered(sd, 64) for _ in range(2)]
+    for tr, xs in zip(ranks, (x[:32].contiguous(), x[32:].contiguous())):
+        tr.step(xs, h2, phase=1)
+    total = ranks[0].grads_view() + ranks[1].grads_view()
+    ref = full.grads_view()
+    assert rel_max(total.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+    for tr, xs in zip(ranks, (x[:32].contiguous(), x[32:].contiguous())):
+        tr.grads_view().copy_(total)
+        tr.step(xs, h2, phase=2)
+    full.step(x, h1, phase=2)
+    assert torch.equal(ranks[0].params_view(), ranks[1].params_view())
+    assert rel_max(ranks[0].params_view().cpu().numpy(), full.params_view().cpu().numpy()) <= 1e-5
+    assert abs(ranks[0].loss_accum.item() - full.loss_accum.item()) <= 1e-5 * full.loss_accum.item()
