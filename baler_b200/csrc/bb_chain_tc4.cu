@@ -355,7 +355,7 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t sm
     trace(lt, 33);
     const uint32_t bar_full = bar_p + 8u * (BAR_FULL + (uint32_t)(lt & 1));
     uint32_t* tr = nullptr;  // second half of the trace buffer: per k-step (wait passed, issued) clocks of the issuer
-    if constexpr (TRACE) { if (blockIdx.x == 0 && G == p.trace_pipe && lane0 && lt < 16) tr = p.trace + 1024 + lt * 64; }
+    if constexpr (TRACE) { if (blockIdx.x == 0 && lane0 && lt < 16) tr = p.trace + 1024 * (1 + G) + lt * 64; }  // both pipelines' issuers
     auto after_commit = [&](int s_done) {
       trace(lt, 34 + 5 * s_done + 4);
       if (s_done == 0) load_tile(tile + 2 * tile_stride, lt);  // this tile's stage was consumed before a1_ready; off the s0 critical path

@@ -16,14 +16,16 @@ x = torch.rand((n, 24), device='cuda')
 for decode, dim_in, dim_out in ((0, 24, 15), (1, 15, 24)):
     xin = x if not decode else torch.rand((n, 15), device='cuda')
     out = torch.empty((n, dim_out), device='cuda')
-    dbg = torch.zeros(2 * 16 * 64, dtype=torch.int32, device='cuda')
+    dbg = torch.zeros(3 * 16 * 64, dtype=torch.int32, device='cuda')
     for it in range(2):
         rc = fn(codec.handle, decode, xin.data_ptr(), n, out.data_ptr(), 0, -2, dbg.data_ptr(), GROUPS, None)
         assert rc == 0
         torch.cuda.synchronize()
     full = dbg.cpu().numpy().astype(np.int64) & 0xffffffff
     t = full[:1024].reshape(16, 64)
-    ks = full[1024:].reshape(16, 64)
+    import os
+    pipe = int(os.environ.get('BALER_B200_TRACE_PIPE', '0'))
+    ks = full[1024 * (1 + pipe):1024 * (2 + pipe)].reshape(16, 64)
     print('decode' if decode else 'encode', 'tile period (cycles):', np.diff(t[2:12, 0]))
     for lt in (5, 6):
         rel = lambda v: int((v - t[lt, 0]) & 0xffffffff) if v else -1
