@@ -146,6 +146,18 @@ void narrow_f64_f32(const double* src, float* dst, size_t n) {
 }
 
 constexpr int64_t PIPE_CHUNK_ROWS = 1 << 21;  // rows per pipeline chunk (2 Mi rows: 192 MiB in, 120 MiB out for 24 -> 15)
+constexpr int64_t PIPE_MIN_CHUNK_ROWS = 1 << 18;
+
+// Chunking of a host table: at least ~16 chunks so that filling and draining the H2D / kernel / D2H pipeline stays a small
+// part of the call (a 12.5M-row shard cut into 2Mi-row chunks spends a third of its time in fill and drain), but never
+// below 256 Ki rows (per-chunk launch and event overhead) nor above 2 Mi rows (staging memory)
+inline int64_t pipe_chunk_rows(int64_t n_rows) {
+  int64_t c = (n_rows + 15) / 16;
+  c = std::max<int64_t>(c, PIPE_MIN_CHUNK_ROWS);
+  c = std::min<int64_t>(c, PIPE_CHUNK_ROWS);
+  c = (c + 127) & ~(int64_t)127;  // whole 128-row tiles: chunk boundaries stay 16-byte aligned for any row width
+  return std::max<int64_t>(1, std::min<int64_t>(n_rows, c));
+}
 
 int pipe_init(bb_model* m, size_t in_bytes, size_t out_bytes) {
   if (!m->s_compute) {
@@ -338,7 +350,7 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
   BB_CUDA(cudaSetDevice(m->ctx->device));
   const int F = m->enc.desc.in_dim, Z = m->enc.desc.out_dim;
   const int dev_dtype = (z_dtype == BB_F16) ? BB_F16 : BB_F32;
-  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_rows, PIPE_CHUNK_ROWS));
+  const int64_t chunk = pipe_chunk_rows(n_rows);
   const int64_t n_chunks = n_rows ? (n_rows + chunk - 1) / chunk : 0;
   const size_t in_b = (size_t)chunk * F * sizeof(float), out_b = (size_t)chunk * Z * dtype_size(dev_dtype);
   int rc = pipe_init(m, in_b, out_b);
@@ -434,7 +446,7 @@ int bb_decompress_host(bb_model* m, const void* z_host, int z_dtype, int64_t n_r
   BB_CUDA(cudaSetDevice(m->ctx->device));
   const int F = m->dec.desc.out_dim, Z = m->dec.desc.in_dim;
   const int dev_in = (z_dtype == BB_F16) ? BB_F16 : BB_F32;
-  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_rows, PIPE_CHUNK_ROWS));
+  const int64_t chunk = pipe_chunk_rows(n_rows);
   const int64_t n_chunks = n_rows ? (n_rows + chunk - 1) / chunk : 0;
   const size_t in_b = (size_t)chunk * Z * dtype_size(dev_in), out_b = (size_t)chunk * F * sizeof(float);
   int rc = pipe_init(m, in_b, out_b);

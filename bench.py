@@ -162,6 +162,30 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def bind_to_gpu_numa_node(local):
+    """one process per GPU: run on (and first-touch pinned host buffers from) the CPUs next to that GPU's PCIe root, so that
+    eight ranks' host <-> device streams do not all cross the socket interconnect.  Best effort: silently skipped when the
+    topology files are not there."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -175,6 +199,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        bind_to_gpu_numa_node(local)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL logs (even its version banner at WARN) go to stderr, and only on request
         os.environ.pop("NCCL_DEBUG", None)
