@@ -18,6 +18,9 @@ __all__ = ("perform_compression", "perform_decompression", "perform_training", "
 
 def main():
     config, mode, workspace_name, project_name, verbose = helper.get_arguments()
+    if os.environ.get("BALER_B200_SEED"):  # reproducible initial weights (the reference seeds only inside train(), after the
+        import torch                       # model has been constructed: training.py:168-174)
+        torch.manual_seed(int(os.environ["BALER_B200_SEED"]))
     project_path = os.path.join("workspaces", workspace_name, project_name)
     output_path = os.path.join(project_path, "output")
     if mode == "newProject":

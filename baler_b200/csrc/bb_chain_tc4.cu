@@ -43,7 +43,6 @@ struct Tc4Params {
   int epi_col[4], epi_nsub[4];      // steps 0..3: accumulator region (pipeline-relative column) and its 16-column sub-chunks
   float epi_c1[4], epi_c2[4];       // the multipliers of the layer that step drains
   int in_dim, out_dim;
-  int fast;
   int* flag;
   uint32_t* trace;      // optional: SM-clock timestamps of CTA 0 / pipeline trace_pipe (64 slots per tile, first 16 tiles)
   int trace_pipe;
@@ -222,14 +221,12 @@ __device__ __forceinline__ void mma_f16(uint32_t d, uint32_t a, uint64_t b, uint
                ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void issue_kstep(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                            uint32_t idesc, uint32_t acc, int fast) {
+                                            uint32_t idesc, uint32_t acc) {
   if (elect_one()) {
     const uint64_t bh = (uint64_t)b_hi | ((uint64_t)B_DESC_HI << 32), bl = (uint64_t)b_lo | ((uint64_t)B_DESC_HI << 32);
     mma_f16(d, a_hi, bh, idesc, acc);
-    if (!fast) {
-      mma_f16(d, a_hi, bl, idesc, 1u);
-      mma_f16(d, a_lo, bh, idesc, 1u);
-    }
+    mma_f16(d, a_hi, bl, idesc, 1u);
+    mma_f16(d, a_lo, bh, idesc, 1u);
   }
   __syncwarp();
 }
@@ -254,8 +251,7 @@ constexpr int kstep_index(const SStep* st, int S, int M) {  // running k-step nu
   return n;
 }
 template <class P, int S, int M, bool TRACE>
-__device__ __forceinline__ void issue_mma(const uint32_t tcol, const uint32_t bar_p, const uint32_t sb4, uint32_t& par_sub, const int fast,
-                                          uint32_t* tr) {
+__device__ __forceinline__ void issue_mma(const uint32_t tcol, const uint32_t bar_p, const uint32_t sb4, uint32_t& par_sub, uint32_t* tr) {
   constexpr SMma mm = P::step(S).mma[M];
   constexpr SStep all[5] = {P::step(0), P::step(1), P::step(2), P::step(3), P::step(4)};
   constexpr int k_index0 = kstep_index(all, S, M);
@@ -280,7 +276,7 @@ __device__ __forceinline__ void issue_mma(const uint32_t tcol, const uint32_t ba
     const uint32_t b_hi = sb4 + ((b_off >> 4) | lbo_f);
     const uint32_t b_lo = sb4 + (((b_off + mat) >> 4) | lbo_f);
     const uint32_t a_hi = tcol + (uint32_t)mm.a_col + 16u * (uint32_t)k;
-    issue_kstep(tcol + (uint32_t)mm.d_col, a_hi, a_hi + 8u, b_hi, b_lo, idesc, (k > 0 || mm.acc) ? 1u : 0u, fast);
+    issue_kstep(tcol + (uint32_t)mm.d_col, a_hi, a_hi + 8u, b_hi, b_lo, idesc, (k > 0 || mm.acc) ? 1u : 0u);
     if constexpr (TRACE) { if (tr) tr[2 * (k_index0 + k) + 1] = (uint32_t)clock64(); }
   }
 }
@@ -291,9 +287,9 @@ __device__ __forceinline__ void issue_mma(const uint32_t tcol, const uint32_t ba
 // the slow tcgen05.mma issue sequence (4x slower).  Net effect: -1 % .. -75 %.
 template <class P, int S, bool TRACE>
 __device__ __forceinline__ void issue_step(const uint32_t tcol, const uint32_t bar_p, const uint32_t bar_full, const uint32_t sb4,
-                                           uint32_t& par_sub, const int fast, uint32_t* tr) {
-  issue_mma<P, S, 0, TRACE>(tcol, bar_p, sb4, par_sub, fast, tr);
-  if constexpr (P::step(S).n_mma > 1) issue_mma<P, S, 1, TRACE>(tcol, bar_p, sb4, par_sub, fast, tr);
+                                           uint32_t& par_sub, uint32_t* tr) {
+  issue_mma<P, S, 0, TRACE>(tcol, bar_p, sb4, par_sub, tr);
+  if constexpr (P::step(S).n_mma > 1) issue_mma<P, S, 1, TRACE>(tcol, bar_p, sb4, par_sub, tr);
   issue_commit(bar_full);
 }
 
@@ -302,8 +298,9 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t sm
                                            const uint32_t in_stage_bytes, const uint32_t in0_off) {
   using P = Prog<ENC, KA, NL>;
   // Everything below is warp-uniform.  TMEM: this CTA owns all 512 columns of the SM (one CTA per SM), so the
-  // allocation base is column 0 / lane 0 (checked by the caller).  One copy of this code serves both pipelines
-  // (the unrolled step program is ~1.5k instructions; two copies pushed the kernel past the instruction cache).
+  // allocation base is column 0 / lane 0 (checked by the caller).  The pipeline index is a template parameter (one copy
+  // of the unrolled step program, ~1.3k instructions, per pipeline): with it every TMEM address is parameter + constant.
+  // The single-product FAST16 mode stays on the table-driven kernel.
   const uint32_t tcol = p.tmem0 + (uint32_t)G * PIPE_COLS;
   const uint32_t bar_w = bars_base;
   const uint32_t bar_p = bars_base + 8u * (1 + G * BARS_PER_PIPE);
@@ -346,7 +343,6 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t sm
   mbar_wait(bar_w, 0);  // weights resident
   uint32_t par_a1 = 0, par_sub = 0;
   int64_t lt = 0;
-  constexpr int fast = 0;  // the single-product mode stays on the table-driven kernel
   for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, ++lt) {
     trace(lt, 32);
     mbar_wait(bar_p + 8u * BAR_A1, par_a1);
@@ -360,11 +356,11 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t sm
       trace(lt, 34 + 5 * s_done + 4);
       if (s_done == 0) load_tile(tile + 2 * tile_stride, lt);  // this tile's stage was consumed before a1_ready; off the s0 critical path
     };
-    issue_step<P, 0, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(0);
-    issue_step<P, 1, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(1);
-    issue_step<P, 2, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(2);
-    issue_step<P, 3, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(3);
-    issue_step<P, 4, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, fast, tr); after_commit(4);
+    issue_step<P, 0, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(0);
+    issue_step<P, 1, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(1);
+    issue_step<P, 2, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(2);
+    issue_step<P, 3, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(3);
+    issue_step<P, 4, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(4);
   }
 }
 
@@ -692,7 +688,7 @@ int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int64_t n_rows, c
   p.pre_min = pre_min; p.pre_range = pre_range; p.post_min = post_min; p.post_range = post_range;
   for (int l = 0; l < 4; ++l) { p.c1[l] = t.c1[l]; p.c2[l] = t.c2[l]; }
   p.in_dim = c->desc.in_dim; p.out_dim = c->desc.out_dim;
-  p.fast = fast; p.flag = flag_dev; p.trace = trace;
+  p.flag = flag_dev; p.trace = trace;
   p.pipes = getenv("BALER_B200_TC4_PIPES") ? atoi(getenv("BALER_B200_TC4_PIPES")) : NPIPE;
   p.trace_pipe = getenv("BALER_B200_TRACE_PIPE") ? atoi(getenv("BALER_B200_TRACE_PIPE")) : 0;
   if (trace != nullptr) {  // SM-clock trace build: the two CMS shapes only

@@ -29,6 +29,21 @@ def dist_env():
 FUSED_TRAINER_MAX_FEATURES = 100  # bb_trainer stages whole weight matrices in shared memory (widest: 200 x 100)
 
 
+def broadcast_initial_state(model):
+    """data-parallel runs start every replica from rank 0's freshly initialised model (what DistributedDataParallel does
+    at construction): each process draws its own random initial weights otherwise"""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"  # gloo: the CPU tests of the host logic
+    sd = model.state_dict()
+    for k in sd:
+        t = sd[k].to(dev)
+        dist.broadcast(t, src=0)
+        sd[k] = t.cpu()
+    model.load_state_dict(sd)
+
+
 class DeviceBatches:
     """Stands in for the reference's DataLoader(shuffle=False, drop_last=False) (training.py:253-263):
     the whole (normalised, float32) table resident in HBM plus the batch size."""
@@ -45,6 +60,8 @@ class DeviceAdam:
     the bb_trainer; `lr` is what LRScheduler adjusts."""
 
     def __init__(self, model, lr, max_batch, l1=False, reg_param=0.0, dropout_seed=0):
+        self.rank, self.world = dist_env()
+        broadcast_initial_state(model)
         w, b = model.linear_tensors()
         self.model = model
         self.has_bn = hasattr(model, "bn_tensors")
@@ -59,7 +76,6 @@ class DeviceAdam:
         if self.trainer is None:
             # wide rows (CFD_dense_AE on flattened 2-D snapshots): the layer-by-layer GEMM trainer
             self.trainer = engine.LayeredTrainer(w, b, ["leaky", "leaky", "leaky", "none"] * 2, max_batch)
-        self.rank, self.world = dist_env()
         if self.has_bn:
             self.trainer.set_dropout(seed=dropout_seed + self.rank)  # every rank draws its own dropout stream
         self.dp = sharded.DataParallelTrainer(self.trainer) if self.world > 1 else None
@@ -119,6 +135,7 @@ def train(model, variables, train_data, test_data, project_path, config):
     optional `model_{epoch}.pt`, `activations.npy`; returns the trained model."""
     from . import helper
 
+    dist_env()  # under torchrun: pick this rank's GPU before anything is allocated on a device
     if config.deterministic_algorithm:
         import random
 

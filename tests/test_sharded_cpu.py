@@ -76,6 +76,15 @@ def _worker(rank, world, port, out_dir):
             off += grads[k].size
         opt.step(summed)
         np.save(os.path.join(out_dir, "params_rank%d.npy" % rank), np.concatenate([opt.params[k].ravel() for k in keys]))
+        # --- every replica starts from rank 0's initial model (each process draws its own random weights otherwise)
+        from baler_b200.modules import models, training
+        torch.manual_seed(100 + rank)
+        m = models.AE_Dropout_BN(24, 15)
+        before = torch.cat([v.double().ravel() for v in m.state_dict().values()])
+        training.broadcast_initial_state(m)
+        after = torch.cat([v.double().ravel() for v in m.state_dict().values()])
+        assert (rank == 0) == bool(torch.equal(before, after))
+        np.save(os.path.join(out_dir, "init_rank%d.npy" % rank), after.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -84,3 +93,4 @@ def test_world_size_2_gloo(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     p0, p1 = np.load(tmp_path / "params_rank0.npy"), np.load(tmp_path / "params_rank1.npy")
     assert np.array_equal(p0, p1)  # replicated optimizer state stays bit-identical across ranks
+    assert np.array_equal(np.load(tmp_path / "init_rank0.npy"), np.load(tmp_path / "init_rank1.npy"))

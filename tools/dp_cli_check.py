@@ -1,0 +1,71 @@
+"""End-to-end check of data-parallel training through the CLI (run on a box with >= 2 GPUs):
+    python tools/dp_cli_check.py
+makes a CMS workspace with a synthetic table, trains it once with one process and once under torchrun with two ranks
+(same global batch), and compares the loss curves and the files written."""
+import os, subprocess, sys, tempfile
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from baler_b200 import synth
+from baler_b200.modules import helper
+
+CONFIG = '''
+def set_config(c):
+    c.input_path = "workspaces/CMS_workspace/data/example_CMS_data.npz"
+    c.data_dimension = 1
+    c.compression_ratio = 1.6
+    c.apply_normalization = True
+    c.model_name = "%s"
+    c.epochs = 3
+    c.lr = 0.001
+    c.batch_size = 512
+    c.early_stopping = True
+    c.lr_scheduler = True
+    c.early_stopping_patience = 100
+    c.min_delta = 0
+    c.lr_scheduler_patience = 50
+    c.custom_norm = False
+    c.reg_param = 0.001
+    c.RHO = 0.05
+    c.test_size = 0
+    c.extra_compression = False
+    c.intermittent_model_saving = False
+    c.intermittent_saving_patience = 100
+    c.activation_extraction = False
+    c.deterministic_algorithm = True
+    c.separate_model_saving = False
+    c.l1 = True
+    c.mse_avg = False
+    c.mse_sum = True
+    c.emd = False
+    c.save_error_bounded_deltas = False
+'''
+
+def main():
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), BALER_B200_SEED="7")
+    for model in ("AE", "AE_Dropout_BN"):
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)
+            losses = {}
+            for proj, launch in (("single", [sys.executable, "-m", "baler_b200"]),
+                                 ("dp2", [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                                          "--master-addr", "127.0.0.1", "--master-port", "29531", "-m", "baler_b200"])):
+                helper.create_new_project("CMS_workspace", proj)
+                np.savez("workspaces/CMS_workspace/data/example_CMS_data.npz", data=synth.cms_table(40_000, seed=3), names=synth.CMS_NAMES)
+                with open("workspaces/CMS_workspace/%s/config/%s_config.py" % (proj, proj), "w") as f:
+                    f.write(CONFIG % model)
+                r = subprocess.run(launch + ["--project", "CMS_workspace", proj, "--mode", "train"], env=env, capture_output=True, text=True)
+                assert r.returncode == 0, "\n".join(l for l in (r.stdout + r.stderr).splitlines() if not l.startswith(('W1', 'I1', '***', 'Setting OMP')))[:6000]
+                out = "workspaces/CMS_workspace/%s/output" % proj
+                losses[proj] = np.load(out + "/training/loss_data.npy")
+                assert os.path.exists(out + "/compressed_output/model.pt") and os.path.exists(out + "/training/normalization_features.npy")
+            a, b = losses["single"][0], losses["dp2"][0]
+            print(model, "single", a, "dp2", b, "rel diff", np.abs(a - b) / a)
+            assert np.all(np.isfinite(b)) and b[-1] < b[0]
+            if model == "AE":
+                assert np.all(np.abs(a - b) <= 0.01 * a)  # same global batch, summed gradients: the reference curve within 1 %
+    print("dp cli check ok")
+
+if __name__ == "__main__":
+    main()
