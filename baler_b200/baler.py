@@ -93,6 +93,8 @@ def perform_compression(output_path, config, verbose):
     compressed, _, _, _ = helper.compress(
         model_path=os.path.join(output_path, "compressed_output", "model.pt"), config=config)
     print("Compression took:", f"{(time.time() - start) / 60:.3} minutes")
+    if compressed is None:
+        return  # sharded launch (torchrun): rank 0 holds the gathered latent and writes the file
     names = np.load(config.input_path)["names"]
     save = np.savez_compressed if config.extra_compression else np.savez
     save(os.path.join(output_path, "compressed_output", "compressed.npz"), data=compressed, names=names,
@@ -119,6 +121,8 @@ def perform_decompression(output_path, config, verbose):
         input_batch_index=os.path.join(output_path, "compressed_output", "compressed_batch_index_metadata.npz.gz"),
         model_name=config.model_name, config=config, output_path=output_path, original_shape=original_shape,
         renormalize_features=flat_features)
+    if decompressed is None:
+        return  # sharded launch (torchrun): rank 0 holds the gathered rows and writes the file
     if blocks:
         decompressed = decompressed.reshape(original_shape if config.model_type == "dense"
                                             else (original_shape[0], 1, original_shape[1], original_shape[2]))

@@ -157,6 +157,8 @@ def _latent_np_dtype(model, config):
 def compress(model_path, config):
     """reference helper.py:473-616 -> (compressed ndarray, eb_batch, eb_deltas, eb_index).
     Normalisation uses THIS file's column min/max (helper.py:500-502), fused into the encode kernel."""
+    from .. import sharded
+    rank, world = sharded.dist_env()  # under torchrun: this rank's GPU, before anything touches a device
     loaded = np.load(config.input_path)
     data_before = loaded["data"]
     original_shape = data_before.shape
@@ -189,10 +191,22 @@ def compress(model_path, config):
     if config.apply_normalization:
         print("Normalizing...")
     codec = model.codec(data_before.shape[1], data_before.shape[2]) if conv else model.codec()
-    compressed, _ = codec.compress_host(table, recompute_minmax=normalise,
-                                        z_dtype=_latent_np_dtype(model, config),
-                                        precision=getattr(config, "precision", "auto"))
-    return compressed, [], [], []
+    if world == 1:
+        compressed, _ = codec.compress_host(table, recompute_minmax=normalise,
+                                            z_dtype=_latent_np_dtype(model, config),
+                                            precision=getattr(config, "precision", "auto"))
+        return compressed, [], [], []
+    # launched under torchrun: rows are sharded contiguously over the ranks; the only exchange on the way in is the
+    # 2 x C column min / max of the whole file, rank 0 collects the latent rows (the other ranks return None)
+    lo, hi = sharded.row_range(len(table), rank, world)
+    shard = table[lo:hi]
+    feats = sharded.global_minmax(shard) if normalise else None
+    if len(shard):
+        z, _ = codec.compress_host(shard, features=feats, z_dtype=_latent_np_dtype(model, config),
+                                   precision=getattr(config, "precision", "auto"))
+    else:
+        z = np.empty((0, config.latent_space_size), dtype=_latent_np_dtype(model, config))
+    return sharded.gather_rows_to_rank0(z, len(table)), [], [], []
 
 
 def decompress(model_path, input_path, input_path_deltas, input_batch_index, model_name, config, output_path,
@@ -200,6 +214,8 @@ def decompress(model_path, input_path, input_path_deltas, input_batch_index, mod
     """reference helper.py:619-733 -> (decompressed ndarray, names, normalization_features).
     `renormalize_features` ([min; range], optional, not in the reference signature) fuses the
     un-normalisation of baler.py:410-424 into the decode kernel."""
+    from .. import sharded
+    rank, world = sharded.dist_env()  # under torchrun: this rank's GPU, before anything touches a device
     loaded = np.load(input_path)
     data, names, normalization_features = loaded["data"], loaded["names"], loaded["normalization_features"]
     if getattr(config, "save_error_bounded_deltas", False):
@@ -222,8 +238,17 @@ def decompress(model_path, input_path, input_path_deltas, input_batch_index, mod
         codec = model.codec(h, w)
     else:
         codec = model.codec()
-    decompressed = codec.decompress_host(data, features=renormalize_features, y_dtype=out_dtype,
-                                         precision=getattr(config, "precision", "auto"))
+    if world == 1:
+        decompressed = codec.decompress_host(data, features=renormalize_features, y_dtype=out_dtype,
+                                             precision=getattr(config, "precision", "auto"))
+    else:  # under torchrun: every rank decodes its contiguous row range, rank 0 collects (the others return None data)
+        lo, hi = sharded.row_range(len(data), rank, world)
+        part = (codec.decompress_host(np.ascontiguousarray(data[lo:hi]), features=renormalize_features, y_dtype=out_dtype,
+                                      precision=getattr(config, "precision", "auto"))
+                if hi > lo else np.empty((0, codec.n_features), dtype=out_dtype))
+        decompressed = sharded.gather_rows_to_rank0(part, len(data))
+        if decompressed is None:
+            return None, names, normalization_features
     if conv:
         decompressed = decompressed.reshape(len(decompressed), 1, h, w)
     if config.data_dimension == 2 and config.model_type == "dense":

@@ -10,22 +10,7 @@ from .. import engine, sharded
 from . import utils
 
 
-def dist_env():
-    """(rank, world).  Launched under torchrun (`python -m torch.distributed.run --nproc-per-node N -m baler_b200
-    --mode train ...`) the run is data-parallel: one process per GPU, NCCL; otherwise (1 process) rank 0 of 1.
-    The reference has no distributed code; the global batch stays `config.batch_size`, cut into `world` contiguous
-    slices in the reference's batch order (sharded.dp_batch_slices), gradients are summed."""
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1 and not dist.is_initialized():
-        local = int(os.environ.get("LOCAL_RANK", "0"))
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
-    return 0, 1
-
-
+dist_env = sharded.dist_env
 FUSED_TRAINER_MAX_FEATURES = 100  # bb_trainer stages whole weight matrices in shared memory (widest: 200 x 100)
 
 

@@ -12,6 +12,21 @@ import torch
 import torch.distributed as dist
 
 
+def dist_env():
+    """(rank, world).  Launched under torchrun (`python -m torch.distributed.run --nproc-per-node N -m baler_b200 ...`)
+    the CLI modes run one process per GPU over NCCL; otherwise (one process) rank 0 of 1.  Picks this rank's GPU before
+    anything is allocated on a device."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def row_range(n_rows, rank, world):
     """contiguous shard [lo, hi) of n_rows rows for `rank` (first n_rows % world ranks get one extra row)"""
     base, extra = divmod(n_rows, world)
@@ -83,3 +98,46 @@ class DataParallelTrainer:
             self.step(xb, hyper)
         self.sync_running_stats()
         return self.trainer.loss_accum.item() / max(len(x_local_batches), 1)
+
+
+def global_minmax(shard, group=None):
+    """per-column [min; max - min] of the WHOLE table from this rank's row shard (numpy, any float dtype): local min / max,
+    then the 2 x C exchange.  Same arithmetic as data_processing.find_minmax (data_processing.py:113-130) on the full
+    table: min and max are exact, the range is one subtraction in the table's dtype."""
+    import numpy as np
+    c = shard.shape[1]
+    dev = "cuda" if dist.is_initialized() and dist.get_backend(group) == "nccl" else "cpu"
+    if len(shard):
+        mn, mx = torch.from_numpy(shard.min(axis=0)).to(dev), torch.from_numpy(shard.max(axis=0)).to(dev)
+    else:  # more ranks than rows
+        mn = torch.full((c,), float("inf"), dtype=torch.from_numpy(shard[:0]).dtype, device=dev)
+        mx = -mn
+    combine_minmax_(mn, mx, group)
+    mn, mx = mn.cpu().numpy(), mx.cpu().numpy()
+    return np.stack([mn, mx - mn])
+
+
+def gather_rows_to_rank0(shard, n_rows, group=None, chunk_rows=1 << 22):
+    """contiguous row shards (numpy [rows_r, C], rank order = row order) -> the full [n_rows, C] array on rank 0, None on
+    the other ranks.  Point to point in chunks through a device staging buffer, so no rank ever holds more than its own
+    shard plus one chunk on the GPU."""
+    import numpy as np
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    if world == 1:
+        return shard
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    c = shard.shape[1]
+    if rank == 0:
+        out = np.empty((n_rows, c), dtype=shard.dtype)
+        out[:len(shard)] = shard
+        for src in range(1, world):
+            lo, hi = row_range(n_rows, src, world)
+            for r0 in range(lo, hi, chunk_rows):
+                r1 = min(hi, r0 + chunk_rows)
+                buf = torch.empty((r1 - r0, c), dtype=torch.from_numpy(shard[:0]).dtype, device=dev)
+                dist.recv(buf, src=src, group=group)
+                out[r0:r1] = buf.cpu().numpy()
+        return out
+    for r0 in range(0, len(shard), chunk_rows):
+        dist.send(torch.from_numpy(np.ascontiguousarray(shard[r0:r0 + chunk_rows])).to(dev), dst=0, group=group)
+    return None

@@ -76,6 +76,16 @@ def _worker(rank, world, port, out_dir):
             off += grads[k].size
         opt.step(summed)
         np.save(os.path.join(out_dir, "params_rank%d.npy" % rank), np.concatenate([opt.params[k].ravel() for k in keys]))
+        # --- sharded CLI compress / decompress: global [min; range] from row shards, rows gathered on rank 0 in row order
+        for n in (10_001, 1):  # 1 row: rank 1's shard is empty
+            t = synth.cms_table(max(n, 2), seed=6)[:n]
+            lo, hi = sharded.row_range(n, rank, world)
+            f = sharded.global_minmax(t[lo:hi])
+            assert f.dtype == np.float32 and np.array_equal(f, orc.find_minmax(t))
+            full = sharded.gather_rows_to_rank0(np.ascontiguousarray(t[lo:hi, :15]).astype(np.float64), n, chunk_rows=1000)
+            assert (full is None) == (rank != 0)
+            if rank == 0:
+                assert full.dtype == np.float64 and np.array_equal(full, t[:, :15].astype(np.float64))
         # --- every replica starts from rank 0's initial model (each process draws its own random weights otherwise)
         from baler_b200.modules import models, training
         torch.manual_seed(100 + rank)

@@ -60,6 +60,21 @@ def main():
                 out = "workspaces/CMS_workspace/%s/output" % proj
                 losses[proj] = np.load(out + "/training/loss_data.npy")
                 assert os.path.exists(out + "/compressed_output/model.pt") and os.path.exists(out + "/training/normalization_features.npy")
+                if model == "AE":  # then compress + decompress with the same launcher, on the model the single-process run trained
+                    if proj == "dp2":
+                        import shutil
+                        for f in ("compressed_output/model.pt", "training/normalization_features.npy"):
+                            shutil.copy("workspaces/CMS_workspace/single/output/" + f, out + "/" + f)
+                    for mode in ("compress", "decompress"):
+                        r = subprocess.run(launch + ["--project", "CMS_workspace", proj, "--mode", mode], env=env, capture_output=True, text=True)
+                        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+            if model == "AE":
+                for f, key in (("compressed_output/compressed.npz", "data"), ("compressed_output/compressed.npz", "normalization_features"),
+                               ("decompressed_output/decompressed.npz", "data")):
+                    s1 = np.load("workspaces/CMS_workspace/single/output/" + f)[key]
+                    s2 = np.load("workspaces/CMS_workspace/dp2/output/" + f)[key]
+                    assert s1.shape == s2.shape and s1.dtype == s2.dtype and np.array_equal(s1, s2), (f, key)
+                print("sharded compress / decompress (2 ranks) == single process, bit for bit")
             a, b = losses["single"][0], losses["dp2"][0]
             print(model, "single", a, "dp2", b, "rel diff", np.abs(a - b) / a)
             assert np.all(np.isfinite(b)) and b[-1] < b[0]
