@@ -5,6 +5,8 @@
 #include <new>
 #include <thread>
 
+#include <cstdlib>
+
 #include "bb_common.cuh"
 
 extern "C" {
@@ -201,6 +203,7 @@ int pinned_init(bb_model* m, int io, size_t bytes) {
 
 // device copy of the whole table between the two passes of bb_compress_host, when it fits in half of the free memory
 float* resident_get(bb_model* m, size_t bytes) {
+  if (getenv("BALER_B200_NO_RESIDENT")) return nullptr;  // test hook: take the two-pass streaming path of tables that do not fit
   if (m->resident_bytes >= bytes) return m->resident_dev;
   if (m->resident_dev) { cudaFree(m->resident_dev); m->resident_dev = nullptr; m->resident_bytes = 0; }
   size_t free_b = 0, total_b = 0;

@@ -263,3 +263,19 @@ def test_cli_roundtrip_matches_reference_files(golden, tmp_path, monkeypatch):
     assert mism.mean() <= 1e-3 and np.all(np.abs(dec[:, it] - ref[:, it])[mism] == 1), mism.mean()
     np.save(os.path.join(out, "training", "loss_data.npy"), g["loss_data"])
     baler.print_info(out, type("c", (), {"input_path": path}))
+
+
+def test_host_pipeline_streaming_path(ae, monkeypatch):
+    """tables that do not fit next to their latent in HBM (BASELINE configs[4]: 1B rows = 96 GB) are read from the host
+    twice - once for the column min / max, once for the encode - instead of staying resident between the passes; the
+    test hook forces that path on a small table and the result must equal the resident path bit for bit"""
+    m, sd, _ = ae
+    n = (1 << 20) + 777
+    table = synth.cms_table(n, seed=31)
+    z_res, f_res = m.codec().compress_host(table, recompute_minmax=True, z_dtype=np.float32)
+    monkeypatch.setenv("BALER_B200_NO_RESIDENT", "1")
+    z_str, f_str = m.codec().compress_host(table, recompute_minmax=True, z_dtype=np.float32)
+    assert np.array_equal(f_res, f_str) and np.array_equal(f_res, orc.find_minmax(table))
+    assert np.array_equal(z_res, z_str)
+    z64, _ = m.codec().compress_host(table, recompute_minmax=True, z_dtype=np.float64)
+    assert z64.dtype == np.float64 and np.array_equal(z64, z_res.astype(np.float64))
