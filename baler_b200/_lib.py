@@ -64,6 +64,7 @@ _SIGNATURES = {
     "bb_trainer_validate": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.POINTER(C.c_double), _P]),
     "bb_trainer_activation_means": (C.c_int, [_P, _P]),
     "bb_mse_sum_f32": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "bb_error_bounded_deltas_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P, _P, C.c_double, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "bb_ltrainer_create": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, _PP]),
     "bb_ltrainer_destroy": (C.c_int, [_P]),
     "bb_ltrainer_param_count": (C.c_int, [_P]),

@@ -90,7 +90,7 @@ def perform_compression(output_path, config, verbose):
     normalization_features = []
     if config.apply_normalization:
         normalization_features = np.load(os.path.join(output_path, "training", "normalization_features.npy"))
-    compressed, _, _, _ = helper.compress(
+    compressed, error_bound_batch, error_bound_deltas, error_bound_index = helper.compress(
         model_path=os.path.join(output_path, "compressed_output", "model.pt"), config=config)
     print("Compression took:", f"{(time.time() - start) / 60:.3} minutes")
     if compressed is None:
@@ -99,6 +99,23 @@ def perform_compression(output_path, config, verbose):
     save = np.savez_compressed if config.extra_compression else np.savez
     save(os.path.join(output_path, "compressed_output", "compressed.npz"), data=compressed, names=names,
          normalization_features=normalization_features)
+    if getattr(config, "save_error_bounded_deltas", False):
+        # reference baler.py:316-338: two gzip'd np.save files of object arrays (per batch: the deltas; the batch indices
+        # and the (row-in-batch, column) index arrays)
+        import gzip
+
+        def obj(items):
+            a = np.empty(len(items), dtype=object)
+            for i, it in enumerate(items):
+                a[i] = it
+            return a
+
+        index = np.empty(2, dtype=object)
+        index[0], index[1] = np.asarray(error_bound_batch), obj(error_bound_index)
+        for name, arr in (("compressed_deltas.npz.gz", obj([np.asarray(d, dtype=np.float16) for d in error_bound_deltas])),
+                          ("compressed_batch_index_metadata.npz.gz", index)):
+            with gzip.GzipFile(os.path.join(output_path, "compressed_output", name), "w") as f:
+                np.save(file=f, arr=arr, allow_pickle=True)
 
 
 def perform_decompression(output_path, config, verbose):

@@ -304,6 +304,26 @@ class Trainer:
         return w, b
 
 
+def error_bounded_deltas(x, y, mn, rg, bound_percent, row0=0):
+    """helper.save_error_bounded_requirement on device tensors: x raw rows, y decoded normalised rows (float32 CUDA),
+    mn / rg the normalisation features (or None).  Returns (rows int64, cols int64, deltas float16) sorted row-major."""
+    ctx = get_context()
+    assert x.is_cuda and y.is_cuda and x.dtype == torch.float32 and y.dtype == torch.float32 and x.shape == y.shape
+    n, c = x.shape
+    cap = n * c
+    count = torch.zeros(1, dtype=torch.int64, device=x.device)
+    rows = torch.empty(cap, dtype=torch.int64, device=x.device)
+    cols = torch.empty(cap, dtype=torch.int32, device=x.device)
+    deltas = torch.empty(cap, dtype=torch.float16, device=x.device)
+    check(_lib.lib().bb_error_bounded_deltas_f32(ctx.handle, _ptr(x.contiguous()), _ptr(y.contiguous()), n, c, _ptr(mn), _ptr(rg),
+                                                 float(bound_percent), int(row0), cap, _ptr(count), _ptr(rows), _ptr(cols),
+                                                 _ptr(deltas), _stream(ctx)), "bb_error_bounded_deltas_f32")
+    k = int(count.item())
+    r, cc, d = rows[:k].cpu().numpy(), cols[:k].cpu().numpy().astype(np.int64), deltas[:k].cpu().numpy()
+    order = np.lexsort((cc, r))
+    return r[order], cc[order], d[order]
+
+
 class LayeredTrainer:
     """bb_ltrainer: the layer-by-layer trainer for dense autoencoders too wide for the fused training kernels
     (CFD_dense_AE on 2500-feature snapshots).  Same surface as Trainer for what training.train uses."""

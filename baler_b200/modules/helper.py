@@ -164,8 +164,6 @@ def compress(model_path, config):
     original_shape = data_before.shape
     if hasattr(config, "convert_to_blocks") and config.convert_to_blocks:
         data_before = data_processing.convert_to_blocks_util(config.convert_to_blocks, data_before)
-    if getattr(config, "save_error_bounded_deltas", False):
-        raise NotImplementedError("error-bounded deltas: listed as a next row in DESIGN.md")
     conv = False
     if config.data_dimension == 1:
         number_of_columns = len(loaded["names"])
@@ -191,6 +189,10 @@ def compress(model_path, config):
     if config.apply_normalization:
         print("Normalizing...")
     codec = model.codec(data_before.shape[1], data_before.shape[2]) if conv else model.codec()
+    if getattr(config, "save_error_bounded_deltas", False):
+        if world > 1:
+            raise NotImplementedError("error-bounded deltas are collected by a single process")
+        return _compress_with_deltas(codec, model, table, normalise, config)
     if world == 1:
         compressed, _ = codec.compress_host(table, recompute_minmax=normalise,
                                             z_dtype=_latent_np_dtype(model, config),
@@ -209,6 +211,66 @@ def compress(model_path, config):
     return sharded.gather_rows_to_rank0(z, len(table)), [], [], []
 
 
+def _compress_with_deltas(codec, model, table, normalise, config):
+    """reference helper.py:583-611 with config.save_error_bounded_deltas: every batch is encoded, decoded again and
+    compared with its (normalised) input; elements whose relative error exceeds config.error_bounded_requirement percent
+    get a float16 delta (helper.save_error_bounded_requirement, helper.py:442-470).  Here the table goes through the GPU in
+    row chunks: encode, decode, one scan kernel (bb_error_bounded_deltas_f32); the hits are regrouped per batch of
+    config.batch_size rows on the host, in the reference's (batch index, deltas, (row-in-batch, column)) lists."""
+    from .. import engine
+    n, bs = len(table), int(config.batch_size)
+    z_dtype = _latent_np_dtype(model, config)
+    compressed = np.empty((n, codec.z_dim), dtype=z_dtype)
+    mn = rg = None
+    if normalise and n:
+        feats = data_processing.find_minmax(table)  # this file's own [min; range] (helper.py:500-502)
+        mn, rg = torch.from_numpy(np.ascontiguousarray(feats[0])).cuda(), torch.from_numpy(np.ascontiguousarray(feats[1])).cuda()
+    rows, cols, deltas = [], [], []
+    chunk = 1 << 20
+    for r0 in range(0, n, chunk):
+        x = torch.from_numpy(table[r0:r0 + chunk]).cuda()
+        z = codec.encode(x, mn, rg, precision=getattr(config, "precision", "auto"))
+        y = codec.decode(z, precision=getattr(config, "precision", "auto"))  # still normalised, as upstream compares it
+        r, c, d = engine.error_bounded_deltas(x, y, mn, rg, config.error_bounded_requirement, row0=r0)
+        rows.append(r); cols.append(c); deltas.append(d)
+        compressed[r0:r0 + chunk] = z.cpu().numpy().astype(z_dtype, copy=False)
+    rows = np.concatenate(rows) if rows else np.empty(0, np.int64)
+    cols = np.concatenate(cols) if cols else np.empty(0, np.int64)
+    deltas = np.concatenate(deltas) if deltas else np.empty(0, np.float16)
+    print("Total Deltas Found - ", len(rows))
+    # upstream appends an entry for EVERY batch (its `len(index) > 0` test is on a 2-tuple); batches without a hit get
+    # empty lists here (upstream would reuse the previous batch's deltas or crash on the first one)
+    batch_of = rows // bs
+    cuts = np.searchsorted(batch_of, np.arange((n + bs - 1) // bs + 1))
+    eb_batch, eb_deltas, eb_index = [], [], []
+    for b in range(len(cuts) - 1):
+        lo, hi = cuts[b], cuts[b + 1]
+        eb_batch.append(b)
+        eb_deltas.append(list(deltas[lo:hi]))
+        eb_index.append((rows[lo:hi] - b * bs, cols[lo:hi]))
+    return compressed, eb_batch, eb_deltas, eb_index
+
+
+def _apply_deltas(decompressed, input_path_deltas, input_batch_index, batch_size, col_scale):
+    """reference helper.py:655-665, 708-718: out[row][col] -= delta for every stored delta; `col_scale` = the range of each
+    column when un-normalisation is fused into the decode kernel ((y - d) * range + min == y * range + min - d * range)"""
+    import gzip
+    loaded_deltas = np.load(gzip.GzipFile(input_path_deltas, "r"), allow_pickle=True)
+    loaded_index = np.load(gzip.GzipFile(input_batch_index, "r"), allow_pickle=True)
+    batches, index = loaded_index[0], loaded_index[1]
+    added = 0
+    for i, b in enumerate(batches):
+        d = np.asarray(loaded_deltas[i], dtype=np.float64)
+        r, c = np.asarray(index[i][0], dtype=np.int64), np.asarray(index[i][1], dtype=np.int64)
+        if len(d) == 0:
+            continue
+        step = d if col_scale is None else d * np.asarray(col_scale, dtype=np.float64)[c]
+        np.subtract.at(decompressed, (int(b) * batch_size + r, c), step.astype(decompressed.dtype))
+        added += len(d)
+    print("Total Deltas Added - ", added)
+    return decompressed
+
+
 def decompress(model_path, input_path, input_path_deltas, input_batch_index, model_name, config, output_path,
                original_shape, renormalize_features=None):
     """reference helper.py:619-733 -> (decompressed ndarray, names, normalization_features).
@@ -218,8 +280,6 @@ def decompress(model_path, input_path, input_path_deltas, input_batch_index, mod
     rank, world = sharded.dist_env()  # under torchrun: this rank's GPU, before anything touches a device
     loaded = np.load(input_path)
     data, names, normalization_features = loaded["data"], loaded["names"], loaded["normalization_features"]
-    if getattr(config, "save_error_bounded_deltas", False):
-        raise NotImplementedError("error-bounded deltas: listed as a next row in DESIGN.md")
     latent_space_size = data.shape[1]
     model_dict = torch.load(str(model_path), map_location="cpu")
     # the reference reads len() of the last state-dict entry, which crashes on AE_Dropout_BN's
@@ -249,6 +309,11 @@ def decompress(model_path, input_path, input_path_deltas, input_batch_index, mod
         decompressed = sharded.gather_rows_to_rank0(part, len(data))
         if decompressed is None:
             return None, names, normalization_features
+    if getattr(config, "save_error_bounded_deltas", False):
+        if world > 1:
+            raise NotImplementedError("error-bounded deltas are applied by a single process")
+        decompressed = _apply_deltas(decompressed, input_path_deltas, input_batch_index, int(config.batch_size),
+                                     None if renormalize_features is None else renormalize_features[1])
     if conv:
         decompressed = decompressed.reshape(len(decompressed), 1, h, w)
     if config.data_dimension == 2 and config.model_type == "dense":

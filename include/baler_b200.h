@@ -256,6 +256,18 @@ int bb_ltrainer_epoch(bb_ltrainer* t, const float* x_dev, int64_t n_rows, int ba
 int bb_ltrainer_validate(bb_ltrainer* t, const float* x_dev, int64_t n_rows, int batch, double* epoch_loss_host,
                          bb_stream_t stream);
 
+/*
+ * Error-bounded deltas: helper.save_error_bounded_requirement (helper.py:442-470) for n_rows rows at once.  `x_dev` raw
+ * rows (normalised here with [min; range] when given, exactly as helper.normalize does), `y_dev` their decoded, still
+ * normalised reconstruction.  An element is a hit when |(y - x) / x * 100| > bound_percent (x == 0 never is); for every
+ * hit the global row (row0 + r), the column and float16(y) - float16(x) are appended in arbitrary order; *count_dev
+ * receives the number of hits (it may exceed `capacity`: entries beyond it are dropped, call again with more room).
+ */
+int bb_error_bounded_deltas_f32(bb_ctx* ctx, const float* x_dev, const float* y_dev, int64_t n_rows, int n_cols,
+                                const float* min_dev, const float* range_dev, double bound_percent, int64_t row0,
+                                int64_t capacity, unsigned long long* count_dev, long long* rows_out_dev,
+                                int* cols_out_dev, void* deltas_f16_out_dev, bb_stream_t stream);
+
 /* sum((a - b)^2) over n float32 elements, ADDED to *out_dev (double): nn.MSELoss(reduction="sum") of
  * utils.mse_sum_loss_l1 (utils.py:195-196) on loose tensors. */
 int bb_mse_sum_f32(bb_ctx* ctx, const float* a_dev, const float* b_dev, int64_t n, double* out_dev, bb_stream_t stream);

@@ -370,3 +370,29 @@ def decompress(sd, latent, norm_features=None, type_list=None, batch_size=None, 
         for c, t in enumerate(type_list):
             out[:, c] = out[:, c].astype(t)
     return out
+
+
+# --------------------------------------------------------------------------- error-bounded deltas
+def error_bounded_deltas(decoded, data, bound_percent):
+    """helper.save_error_bounded_requirement (helper.py:442-470) on one batch of NORMALISED rows.
+
+    relative error in percent (decoded - data) / data * 100; +-inf (data == 0) is set to 0, NaN stays NaN and never
+    exceeds; the stored delta is np.subtract(decoded, data, dtype=float16), i.e. BOTH operands are rounded to float16
+    first and subtracted in float16.  Returns (rows, cols, deltas float16) in np.where (row-major) order.  (Upstream
+    leaves `deltas` unbound when nothing exceeds the bound - a crash this restatement does not reproduce.)"""
+    decoded = np.asarray(decoded, dtype=np.float64)
+    data = np.asarray(data, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        err = (decoded - data) / data * 100.0
+    err[np.isinf(err)] = 0.0
+    rows, cols = np.where(np.abs(err) > bound_percent)
+    deltas = (decoded.astype(np.float16) - data.astype(np.float16))[rows, cols].astype(np.float16)
+    return rows, cols, deltas
+
+
+def apply_error_bounded_deltas(decoded, rows, cols, deltas):
+    """helper.decompress (helper.py:708-718): out[row][col] -= delta for every stored delta of the batch"""
+    out = np.array(decoded, copy=True)
+    for r, c, d in zip(rows, cols, deltas):
+        out[r][c] -= d
+    return out

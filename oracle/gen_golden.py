@@ -20,6 +20,7 @@ Fixtures (all float64 unless noted; state-dict tensors stored under "<prefix>/<k
   schedules.npz     LRScheduler / EarlyStopping decision sequences
   conv_ae.npz       Conv_AE(5, 250) on 5x5 blocks: eval encode / decode (weights by seed + checksums)
   cfd_dense.npz     CFD_dense_AE(2500, 25) on 50x50 snapshots: encode / decode (weights by seed + checksums)
+  eb_deltas.npz     helper.save_error_bounded_requirement on 4 batches of the trained CMS AE + delta re-application
 """
 import os
 import sys
@@ -368,8 +369,37 @@ def gen_cfd_dense():
     print("cfd_dense", z.shape, y.shape, os.path.getsize(os.path.join(OUT, "cfd_dense.npz")) / 1e6, "MB")
 
 
+def gen_eb_deltas():
+    """helper.save_error_bounded_requirement (helper.py:442-470) on the trained CMS AE: per batch of normalised rows,
+    which elements exceed the relative-error bound and the float16 deltas stored for them (2 batches of 256 rows); then the reference's own
+    delta re-application of helper.decompress (helper.py:708-718) on those batches."""
+    g = np.load(os.path.join(OUT, "ae_cms.npz"))
+    model = ref_models.AE(24, 15)
+    model.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")})
+    model.eval()
+    table = synth.cms_table(512, seed=41)
+    norm = ref_helper.normalize(table, False)
+    cfg = make_config()
+    cfg.error_bounded_requirement = 25.0  # percent
+    d = dict(table=table, bound=np.float64(cfg.error_bounded_requirement))
+    with torch.no_grad():
+        for b in range(2):
+            data = torch.tensor(norm[256 * b:256 * (b + 1)], dtype=torch.float64)
+            dec = model.decode(model.encode(data)).numpy()
+            deltas, index = ref_helper.save_error_bounded_requirement(cfg, dec, data.numpy())
+            rows, cols = index
+            fixed = dec.copy()
+            for i in range(len(rows)):  # helper.py:714-716
+                fixed[rows[i]][cols[i]] -= deltas[i]
+            d["rows%d" % b], d["cols%d" % b] = rows.astype(np.int64), cols.astype(np.int64)
+            d["deltas%d" % b] = np.array(deltas, dtype=np.float16)
+            d["decoded%d" % b], d["fixed%d" % b] = dec, fixed
+    np.savez_compressed(os.path.join(OUT, "eb_deltas.npz"), **d)
+    print("eb_deltas", [len(d["rows%d" % b]) for b in range(2)])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules", "conv_ae", "cfd_dense"]
+    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules", "conv_ae", "cfd_dense", "eb_deltas"]
     for name in which:
         globals()["gen_" + name]()

@@ -279,3 +279,61 @@ def test_host_pipeline_streaming_path(ae, monkeypatch):
     assert np.array_equal(z_res, z_str)
     z64, _ = m.codec().compress_host(table, recompute_minmax=True, z_dtype=np.float64)
     assert z64.dtype == np.float64 and np.array_equal(z64, z_res.astype(np.float64))
+
+
+def test_error_bounded_deltas_vs_reference(golden, tmp_path, monkeypatch):
+    """config.save_error_bounded_deltas: hits, float16 deltas and their re-application against what the reference
+    functions produced for the same model and rows (tests/golden/eb_deltas.npz, batches of 256 rows, bound 25 %).
+    The reconstruction here differs from the float64 one by ~1e-6, so elements within that distance of the bound may flip:
+    counted budget."""
+    import gzip
+    from baler_b200 import baler
+    from baler_b200.modules import helper
+    g, ga = golden("eb_deltas.npz"), golden("ae_cms.npz")
+    table, bound, bs = g["table"], float(g["bound"]), 256
+    ref_hits = {}
+    for b in range(2):
+        for r, c, d in zip(g["rows%d" % b], g["cols%d" % b], g["deltas%d" % b]):
+            ref_hits[(int(r) + bs * b, int(c))] = d
+    monkeypatch.chdir(tmp_path)
+    helper.create_new_project("CMS_workspace", "CMS_project_v1")
+    path = os.path.join("workspaces", "CMS_workspace", "data", "example_CMS_data.npz")
+    np.savez(path, data=table, names=synth.CMS_NAMES)
+    out = os.path.join("workspaces", "CMS_workspace", "CMS_project_v1", "output")
+    torch.save({k: torch.from_numpy(v) for k, v in sub_sd(ga, "sd").items()}, os.path.join(out, "compressed_output", "model.pt"))
+    feats = orc.find_minmax(table)
+    np.save(os.path.join(out, "training", "normalization_features.npy"), feats)
+
+    class cfg(helper.Config):
+        input_path = path
+        data_dimension, compression_ratio, apply_normalization, model_name = 1, 1.6, True, "AE"
+        batch_size, custom_norm, extra_compression, separate_model_saving = bs, False, False, False
+        save_error_bounded_deltas, error_bounded_requirement, convert_to_blocks = True, bound, False
+
+    baler.perform_compression(out, cfg, False)
+    deltas = np.load(gzip.GzipFile(os.path.join(out, "compressed_output", "compressed_deltas.npz.gz"), "r"), allow_pickle=True)
+    index = np.load(gzip.GzipFile(os.path.join(out, "compressed_output", "compressed_batch_index_metadata.npz.gz"), "r"), allow_pickle=True)
+    assert list(index[0]) == [0, 1] and len(deltas) == 2  # one entry per batch, as upstream writes them
+    got = {}
+    for b in range(2):
+        rows, cols = index[1][b]
+        assert np.all(np.diff(rows * 24 + cols) > 0)  # np.where order: row-major
+        for r, c, d in zip(rows, cols, deltas[b]):
+            got[(int(r) + bs * b, int(c))] = d
+    both = set(got) & set(ref_hits)
+    assert len(set(got) ^ set(ref_hits)) <= 0.005 * len(ref_hits), (len(got), len(ref_hits))
+    off = [k for k in both if got[k] != ref_hits[k]]
+    assert len(off) <= 0.01 * len(both)
+    # the delta is float16(y) - float16(x) with x, y in [0, 1]: a reconstruction that differs in the 7th digit can round
+    # to the neighbouring float16, which moves the delta by one float16 ulp of y
+    assert all(abs(float(got[k]) - float(ref_hits[k])) <= 2.0 ** -10 for k in off)
+    # decompression applies the deltas: compare with the reference's corrected reconstruction, un-normalised
+    baler.perform_decompression(out, cfg, False)
+    dec = np.load(os.path.join(out, "decompressed_output", "decompressed.npz"))["data"]
+    fixed = np.concatenate([g["fixed0"], g["fixed1"]])
+    ref = orc.renormalize(fixed, feats[0], feats[1])
+    same = np.ones(dec.shape, dtype=bool)
+    for r, c in set(got) ^ set(ref_hits):
+        same[r, c] = False
+    scale = np.abs(ref).max(axis=0)
+    assert (np.abs(dec - ref)[same] <= 1e-3 * np.broadcast_to(scale, dec.shape)[same]).all()  # float16 deltas: 2^-11 relative
