@@ -314,6 +314,23 @@ def run_ours(args):
                "rows_per_gpu": ne, "steps": args.e2e_steps,
                "note": "bb_compress_host + bb_decompress_host, pinned host buffers, fp32 latent; timed on the host clock "
                        "around blocking calls (the copies are part of the call)"}
+        # the same pass with the reference's on-disk dtypes (helper.py:565: float64 latent in compressed.npz, float64
+        # reconstruction): the library widens / narrows on host threads around float32 PCIe copies; smaller sample
+        if world == 1:
+            nf = min(ne, 20_000_000)
+            z64 = np.empty((nf, 15), dtype=np.float64)
+            y64 = np.empty((nf, 24), dtype=np.float64)
+
+            def f64_step():
+                _, feats = codec.compress_host(xn[:nf], recompute_minmax=True, z_dtype=np.float64, precision=precision, out=z64)
+                codec.decompress_host(z64, features=feats, y_dtype=np.float64, precision=precision, out=y64)
+
+            f64_step()
+            t0 = time.perf_counter()
+            f64_step()
+            e2e["reference_file_dtypes"] = {"value": nf / (time.perf_counter() - t0), "unit": "rows/s", "rows": nf,
+                                            "note": "float64 latent and float64 reconstruction in pageable host arrays"}
+            del z64, y64
         del xh, zh, yh
 
     # ---- training line (secondary): one epoch of AE on a 600k-row normalised table, bs 512 per GPU
