@@ -382,7 +382,6 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
   const uint8_t* in_s = smem + in0_off + (uint32_t)g * 2u * in_stage_bytes;
   float* out_s = reinterpret_cast<float*>(smem + out0_off + (uint32_t)g * out_stage_bytes) + (size_t)wq * 32 * out_dim;  // this warp's 32 rows
   const uint32_t out_s_addr = smem_base + out0_off + (uint32_t)g * out_stage_bytes + (uint32_t)(wq * 32 * out_dim) * 4u;
-  const bool has_pre = p.pre_min != nullptr, has_post = p.post_min != nullptr;
   auto trace = [&](int64_t lt, int slot) {
     if constexpr (TRACE) {
       if (blockIdx.x == 0 && g == p.trace_pipe && wq == 0 && lane == 0 && lt < 16 && (h == 0) != (slot == 1 || slot == 2 || (slot >= 29 && slot <= 31))) p.trace[lt * 64 + slot] = (uint32_t)clock64();
@@ -411,13 +410,14 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
 #pragma unroll
         for (int j = 0; j < 16; ++j) xv[j] = (k0 + j < in_dim && row < rows) ? xr[k0 + j] : 0.f;
       }
+      // numpy float32 (x - min) / range (data_processing.py:151); here the quotient is x * rcp_rn(range): within 1 ulp of
+      // the IEEE quotient, far inside the 1e-5 budget of the latent.  Branch-free: without normalisation (and beyond the
+      // real features) the table holds min = 0, 1 / range = 1; the bias slot k == in_dim gets the constant one.
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int k = k0 + j;
-        // numpy float32 (x - min) / range (data_processing.py:151); here the quotient is x * rcp_rn(range):
-        // within 1 ulp of the IEEE quotient, far inside the 1e-5 budget of the latent
-        if (k < in_dim) { if (has_pre && row < rows) xv[j] = __fsub_rn(xv[j], norm_s[0][k]) * norm_s[1][k]; }
-        else xv[j] = k == in_dim ? 1.f : 0.f;
+        const float xn = __fsub_rn(xv[j], norm_s[0][k]) * norm_s[1][k];
+        xv[j] = k < in_dim ? xn : (k == in_dim ? 1.f : 0.f);
       }
       uint32_t pk[16];
 #pragma unroll
@@ -514,18 +514,22 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
         __syncwarp();
       }
       trace(lt, 28);
-      bool bad = false;
+      // branch-free over the padded width (a runtime `j < out_dim` test per element made this a chain of 16 - 32 dependent
+      // branch blocks, ~70 cycles per element): compute everything, then predicated stores
       const float s1 = p.c1[ep.layer], s2 = p.c2[ep.layer];
+      float ys[NL];
+      uint32_t bad_mask = 0;
 #pragma unroll
       for (int j = 0; j < NL; ++j) {
-        if (j < out_dim) {
-          const float a = __uint_as_float(v[j]);
-          float y = fmaf(fabsf(a), s2, a * s1);
-          bad |= !(fabsf(y) <= 3.0e38f);  // inf / NaN: an fp16 operand overflowed somewhere upstream
-          if (has_post) y = fmaf(y, norm_s[3][j], norm_s[2][j]);  // y * range + min (data_processing.py:203)
-          out_s[lane * out_dim + j] = y;
-        }
+        const float a = __uint_as_float(v[j]);
+        const float y = fmaf(fabsf(a), s2, a * s1);
+        bad_mask |= (fabsf(y) <= 3.0e38f) ? 0u : (1u << j);  // inf / NaN: an fp16 operand overflowed somewhere upstream
+        ys[j] = fmaf(y, norm_s[3][j], norm_s[2][j]);           // y * range + min (data_processing.py:203); 1 and 0 when absent
       }
+      const bool bad = (bad_mask & (out_dim >= 32 ? 0xFFFFFFFFu : ((1u << out_dim) - 1u))) != 0u;
+#pragma unroll
+      for (int j = 0; j < NL; ++j)
+        if (j < out_dim) out_s[lane * out_dim + j] = ys[j];
       if (bad && row < rows) atomicOr(p.flag, 1);
       trace(lt, 26);
       const int my_rows = min(32, max(0, rows - wq * 32));
