@@ -369,7 +369,7 @@ template <bool ENC, int KA, int NL, bool TRACE>
 __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, const int wq, const int h, const uint32_t smem_base,
                                              uint8_t* smem, const uint32_t bars_base, const uint32_t in_stage_bytes,
                                              const uint32_t in0_off, const uint32_t out0_off, const uint32_t out_stage_bytes,
-                                             const float (*norm_s)[32]) {
+                                             const float2 (*norm_s)[32]) {
   using P = Prog<ENC, KA, NL>;
   const int lane = threadIdx.x & 31;
   const int row = wq * 32 + lane;                                      // tile row == TMEM lane
@@ -411,13 +411,12 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
         for (int j = 0; j < 16; ++j) xv[j] = (k0 + j < in_dim && row < rows) ? xr[k0 + j] : 0.f;
       }
       // numpy float32 (x - min) / range (data_processing.py:151); here the quotient is x * rcp_rn(range): within 1 ulp of
-      // the IEEE quotient, far inside the 1e-5 budget of the latent.  Branch-free: without normalisation (and beyond the
-      // real features) the table holds min = 0, 1 / range = 1; the bias slot k == in_dim gets the constant one.
+      // the IEEE quotient, far inside the 1e-5 budget of the latent.  Branch-free: the table also covers "no
+      // normalisation" ({0, 1}) and turns the zero loaded beyond the real features into the bias slot's constant one.
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int k = k0 + j;
-        const float xn = __fsub_rn(xv[j], norm_s[0][k]) * norm_s[1][k];
-        xv[j] = k < in_dim ? xn : (k == in_dim ? 1.f : 0.f);
+        const float2 mr = norm_s[0][k0 + j];
+        xv[j] = __fsub_rn(xv[j], mr.x) * mr.y;
       }
       uint32_t pk[16];
 #pragma unroll
@@ -524,12 +523,19 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
         const float a = __uint_as_float(v[j]);
         const float y = fmaf(fabsf(a), s2, a * s1);
         bad_mask |= (fabsf(y) <= 3.0e38f) ? 0u : (1u << j);  // inf / NaN: an fp16 operand overflowed somewhere upstream
-        ys[j] = fmaf(y, norm_s[3][j], norm_s[2][j]);           // y * range + min (data_processing.py:203); 1 and 0 when absent
+        const float2 rm = norm_s[1][j];
+        ys[j] = fmaf(y, rm.x, rm.y);                           // y * range + min (data_processing.py:203); {1, 0} when absent
       }
       const bool bad = (bad_mask & (out_dim >= 32 ? 0xFFFFFFFFu : ((1u << out_dim) - 1u))) != 0u;
+      if ((out_dim & 3) == 0) {  // rows are 16-byte multiples: 128-bit stores (2-way instead of 8-way bank conflicts at 24 floats per row)
 #pragma unroll
-      for (int j = 0; j < NL; ++j)
-        if (j < out_dim) out_s[lane * out_dim + j] = ys[j];
+        for (int q = 0; q < NL / 4; ++q)
+          if (4 * q < out_dim) reinterpret_cast<float4*>(out_s + lane * out_dim)[q] = make_float4(ys[4 * q], ys[4 * q + 1], ys[4 * q + 2], ys[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NL; ++j)
+          if (j < out_dim) out_s[lane * out_dim + j] = ys[j];
+      }
       if (bad && row < rows) atomicOr(p.flag, 1);
       trace(lt, 26);
       const int my_rows = min(32, max(0, rows - wq * 32));
@@ -559,7 +565,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[1 + NPIPE * BARS_PER_PIPE];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float norm_s[4][32];   // pre_min, 1 / pre_range, post_min, post_range
+  // [0][k] = {pre_min, 1 / pre_range} of input feature k ({0, 1} without normalisation; the bias slot k == in_dim holds
+  // {-1, 1} so that a zero input becomes the constant one; {0, 1} beyond it), [1][j] = {post_range, post_min}
+  __shared__ float2 norm_s[2][32];
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler too (role dispatch below)
@@ -588,12 +596,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 128) {  // column (de)normalisation vectors
+  if (tid < 64) {  // column (de)normalisation vectors
     const int which = tid >> 5, k = tid & 31;
-    const float* src = which == 0 ? p.pre_min : which == 1 ? p.pre_range : which == 2 ? p.post_min : p.post_range;
-    const int dim = which < 2 ? p.in_dim : p.out_dim;
-    float v = (src != nullptr && k < dim) ? src[k] : (which & 1 ? 1.f : 0.f);
-    if (which == 1) v = __frcp_rn(v);  // the loader multiplies by 1 / range
+    float2 v;
+    if (which == 0) {
+      v = make_float2(k == p.in_dim ? -1.f : 0.f, 1.f);
+      if (p.pre_min != nullptr && k < p.in_dim) v = make_float2(p.pre_min[k], __frcp_rn(p.pre_range[k]));  // the loader multiplies by 1 / range
+    } else {
+      v = make_float2(1.f, 0.f);
+      if (p.post_min != nullptr && k < p.out_dim) v = make_float2(p.post_range[k], p.post_min[k]);
+    }
     norm_s[which][k] = v;
   }
   if (warp == 0) {  // warp 0 owns the TMEM allocation
