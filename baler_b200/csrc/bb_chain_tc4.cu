@@ -123,8 +123,9 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // n
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   // a protocol bug must not hang the GPU: trap (-> launch error) after ~1 s of polling
   // back off between polls: hot polling by the ~12 warps that wait at any time took 40 % of the SM's issue slots
+  // (measured 32 / 64 / 128 ns: 5.58 / 5.75 / 5.83 G rows/s encode)
   for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins) {
-    __nanosleep(32);
+    __nanosleep(128);
     if (spins > (1u << 22)) __trap();
   }
 }
