@@ -66,6 +66,9 @@ _SIGNATURES = {
     "bb_mse_sum_f32": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     "bb_error_bounded_deltas_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P, _P, C.c_double, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "bb_ltrainer_create": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, _PP]),
+    "bb_ltrainer_create_ex": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _PP]),
+    "bb_ltrainer_get_bn": (C.c_int, [_P, _P]),
+    "bb_ltrainer_bn_running_dev": (_P, [_P, C.POINTER(C.c_int)]),
     "bb_ltrainer_destroy": (C.c_int, [_P]),
     "bb_ltrainer_param_count": (C.c_int, [_P]),
     "bb_ltrainer_params_dev": (_P, [_P]),

@@ -9,6 +9,18 @@
 //     Adam      torch.optim.Adam single-tensor update (training.py:266)
 // Shapes here are small-batch x wide (60 x 2500): the GEMMs are latency-bound either way, so the kernel is a plain
 // 64 x 64 x 16 shared-memory tile with arbitrary strides (one kernel serves NT, NN and TN), not a tuned one.
+//
+// `Conv_AE` (models.py:316-407) trains through the same chain (bb_ltrainer_create_ex): on a fixed block shape every
+// (transposed) convolution is a linear map of the flattened tensor, i.e. a dense matrix whose entries are shared kernel
+// weights or structural zeros.  Such a layer keeps its TRAINABLE parameters (kernel, per-channel bias) apart from the
+// dense matrix the GEMMs read:
+//     expand    Wd[i] = w[map[i]] (0 where map[i] < 0),  bd[n] = b[n / S]         after every Adam step
+//     reduce    dw[j] = sum of dWd over the entries that share kernel weight j      (CSR lists, fixed order)
+// BatchNorm2d between the affine map and the activation (train mode: batch statistics over rows x positions of a
+// channel, biased variance, eps 1e-5, running statistics with momentum 0.1 and the unbiased variance; eval mode: the
+// running statistics), one block per channel:
+//     forward   xhat = (z - mean) * rstd,  y = gamma * xhat + beta
+//     backward  dgamma = sum(dy * xhat),  dbeta = sum(dy),  dz = gamma * rstd * (dy - dbeta / M - xhat * dgamma / M)
 #include <cmath>
 #include <vector>
 
@@ -109,6 +121,109 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
   db[n] = s;
 }
 
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  __syncthreads();
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  return red[0];
+}
+
+constexpr float LBN_EPS = 1e-5f, LBN_MOMENTUM = 0.1f;
+
+// BatchNorm over channel c = blockIdx.x of Z[rows][N] (channel c = columns c*S .. c*S + S - 1), then the activation, in
+// place.  training: batch statistics (saved for the backward pass in mean_rstd, running statistics updated);
+// otherwise the running statistics.  xhat (nullable) receives the normalised values.
+__global__ void __launch_bounds__(256) bn_fwd_kernel(float* __restrict__ Z, float* __restrict__ xhat, const int rows, const int N,
+                                                     const int S, const int C, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* __restrict__ running,
+                                                     float* __restrict__ mean_rstd, const int training, const int act) {
+  __shared__ float red[256];
+  const int c = blockIdx.x, M = rows * S;
+  float mean, rstd;
+  if (training) {
+    float s = 0.f;
+    for (int e = threadIdx.x; e < M; e += 256) s += Z[(int64_t)(e / S) * N + c * S + e % S];
+    mean = block_sum_256(s, red) / M;
+    s = 0.f;
+    for (int e = threadIdx.x; e < M; e += 256) {
+      const float d = Z[(int64_t)(e / S) * N + c * S + e % S] - mean;
+      s += d * d;
+    }
+    const float var = block_sum_256(s, red) / M;
+    rstd = 1.f / sqrtf(var + LBN_EPS);
+    if (threadIdx.x == 0) {
+      running[c] = (1.f - LBN_MOMENTUM) * running[c] + LBN_MOMENTUM * mean;
+      running[C + c] = (1.f - LBN_MOMENTUM) * running[C + c] + LBN_MOMENTUM * (M > 1 ? var * M / (M - 1) : var);
+      mean_rstd[c] = mean;
+      mean_rstd[C + c] = rstd;
+    }
+  } else {
+    mean = running[c];
+    rstd = 1.f / sqrtf(running[C + c] + LBN_EPS);
+  }
+  const float g = gamma[c], b = beta[c];
+  for (int e = threadIdx.x; e < M; e += 256) {
+    const int64_t i = (int64_t)(e / S) * N + c * S + e % S;
+    const float xh = (Z[i] - mean) * rstd;
+    if (xhat) xhat[i] = xh;
+    Z[i] = act_fwd(g * xh + b, act);
+  }
+}
+
+// dY (already multiplied by act') -> dZ in place; dgamma, dbeta of channel c
+__global__ void __launch_bounds__(256) bn_bwd_kernel(float* __restrict__ dY, const float* __restrict__ xhat, const int rows,
+                                                     const int N, const int S, const int C, const float* __restrict__ gamma,
+                                                     const float* __restrict__ mean_rstd, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta) {
+  __shared__ float red[256];
+  const int c = blockIdx.x, M = rows * S;
+  float s1 = 0.f, s2 = 0.f;
+  for (int e = threadIdx.x; e < M; e += 256) {
+    const int64_t i = (int64_t)(e / S) * N + c * S + e % S;
+    s1 += dY[i];
+    s2 += dY[i] * xhat[i];
+  }
+  s1 = block_sum_256(s1, red);
+  s2 = block_sum_256(s2, red);
+  if (threadIdx.x == 0) { dgamma[c] = s2; dbeta[c] = s1; }
+  const float k = gamma[c] * mean_rstd[C + c], m1 = s1 / M, m2 = s2 / M;
+  for (int e = threadIdx.x; e < M; e += 256) {
+    const int64_t i = (int64_t)(e / S) * N + c * S + e % S;
+    dY[i] = k * (dY[i] - m1 - xhat[i] * m2);
+  }
+}
+
+// dense matrix / bias of a weight-sharing layer from its trainable kernel and per-channel bias
+__global__ void __launch_bounds__(256) tied_expand_kernel(const int32_t* __restrict__ map, const float* __restrict__ w,
+                                                          float* __restrict__ Wd, const int n_dense, const float* __restrict__ b,
+                                                          float* __restrict__ bd, const int N, const int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_dense) Wd[i] = map[i] >= 0 ? w[map[i]] : 0.f;
+  if (i < N) bd[i] = b[i / S];
+}
+
+// gradient of the shared weights: sum of the dense gradient over the entries that use weight j (ascending entry order)
+__global__ void __launch_bounds__(256) tied_reduce_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                          const float* __restrict__ gWd, float* __restrict__ gw, const int n_w,
+                                                          const float* __restrict__ gbd, float* __restrict__ gb, const int n_b,
+                                                          const int S) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_w) {
+    float s = 0.f;
+    for (int e = ptr[j]; e < ptr[j + 1]; ++e) s += gWd[idx[e]];
+    gw[j] = s;
+  }
+  if (j < n_b) {
+    float s = 0.f;
+    for (int q = 0; q < S; ++q) s += gbd[j * S + q];
+    gb[j] = s;
+  }
+}
+
 // mode 0: Adam update + fold the loss partials into grads[n_params] and *loss_accum; 1: only the loss fold (phase 1 of a
 // data-parallel step / validation); 2: Adam update with the (all-reduced) grads, loss from grads[n_params]
 __global__ void __launch_bounds__(256) ladam_kernel(const int n_params, const int mode, float* __restrict__ grads,
@@ -140,14 +255,26 @@ constexpr int LOSS_BLOCKS = 64;
 
 }  // namespace
 
+constexpr int LT_MAX_LAYERS = 16;
+
+struct LLayer {
+  int K = 0, N = 0, act = 0;
+  int n_w = 0, n_b = 0, bn_c = 0;            // trainable weights / biases, BatchNorm channels (0: none)
+  int w_off = 0, b_off = 0, g_off = 0;       // offsets into the trainable vectors (weights, biases, gamma then beta)
+  bool tied = false;                         // weight sharing: dense matrix / bias kept apart from the trainable vector
+  float *Wd = nullptr, *bd = nullptr, *gWd = nullptr, *gbd = nullptr;  // what the GEMMs read / write (alias when !tied)
+  float* dense = nullptr;                    // owns Wd | bd | gWd | gbd when tied
+  int32_t *map = nullptr, *csr_ptr = nullptr, *csr_idx = nullptr;
+  float *xhat = nullptr, *mean_rstd = nullptr, *running = nullptr;  // BatchNorm: saved xhat, batch (mean, rstd), running (mean | var)
+};
+
 struct bb_ltrainer {
   bb_ctx* ctx = nullptr;
-  int n_layers = 0, max_batch = 0, n_params = 0, max_dim = 0;
-  int dims[BB_MAX_LAYERS + 1] = {0};
-  int acts[BB_MAX_LAYERS] = {0};
-  int w_off[BB_MAX_LAYERS] = {0}, b_off[BB_MAX_LAYERS] = {0};
-  size_t a_off[BB_MAX_LAYERS + 1] = {0};  // float offsets of A_0 .. A_L in `act` (max_batch rows each)
+  int n_layers = 0, max_batch = 0, n_params = 0, max_dim = 0, loss_columns = 0, n_running = 0;
+  LLayer lay[LT_MAX_LAYERS];
+  size_t a_off[LT_MAX_LAYERS + 1] = {0};  // float offsets of A_0 .. A_L in `act` (max_batch rows each)
   float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *act = nullptr, *dz[2] = {nullptr, nullptr};
+  float* running_all = nullptr;           // running statistics of all BatchNorm layers, layer after layer
   float* loss_part = nullptr;
   double* loss_accum = nullptr;
   long long step = 0;
@@ -161,68 +288,114 @@ void lgemm(cudaStream_t s, const float* A, int64_t sam, int64_t sak, const float
   gemm_strided_kernel<<<grid, GT, 0, s>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act);
 }
 
-// forward (+ loss, + backward into grads when `backward`)
+void expand_tied(bb_ltrainer* t, cudaStream_t s) {
+  for (int l = 0; l < t->n_layers; ++l) {
+    const LLayer& y = t->lay[l];
+    if (!y.tied) continue;
+    const int n = y.N * y.K;
+    tied_expand_kernel<<<(n + 255) / 256, 256, 0, s>>>(y.map, t->params + y.w_off, y.Wd, n, t->params + y.b_off, y.bd, y.N, y.N / y.n_b);
+  }
+}
+
+// forward (+ loss, + backward into grads when `backward`); BatchNorm layers use batch statistics iff `backward`
 int lforward_backward(bb_ltrainer* t, const float* x, int rows, bool backward, cudaStream_t s) {
   const int L = t->n_layers;
-  BB_CUDA(cudaMemcpyAsync(t->act + t->a_off[0], x, sizeof(float) * (size_t)rows * t->dims[0], cudaMemcpyDeviceToDevice, s));
+  BB_CUDA(cudaMemcpyAsync(t->act + t->a_off[0], x, sizeof(float) * (size_t)rows * t->lay[0].K, cudaMemcpyDeviceToDevice, s));
   for (int l = 0; l < L; ++l) {
-    const int K = t->dims[l], N = t->dims[l + 1];
+    const LLayer& y = t->lay[l];
     // A_{l+1}[rows x N] = act(A_l[rows x K] . W_l[N x K]^T + b_l)
-    lgemm(s, t->act + t->a_off[l], K, 1, t->params + t->w_off[l], 1, K, t->act + t->a_off[l + 1], N, rows, N, K,
-          t->params + t->b_off[l], t->acts[l]);
+    lgemm(s, t->act + t->a_off[l], y.K, 1, y.Wd, 1, y.K, t->act + t->a_off[l + 1], y.N, rows, y.N, y.K, y.bd,
+          y.bn_c ? BB_ACT_NONE : y.act);
+    if (y.bn_c)
+      bn_fwd_kernel<<<y.bn_c, 256, 0, s>>>(t->act + t->a_off[l + 1], backward ? y.xhat : nullptr, rows, y.N, y.N / y.bn_c, y.bn_c,
+                                           t->params + y.g_off, t->params + y.g_off + y.bn_c, y.running, y.mean_rstd,
+                                           backward ? 1 : 0, y.act);
   }
-  const int C = t->dims[L];
+  const int C = t->lay[L - 1].N;
   float* dA = t->dz[0];
-  loss_seed_kernel<<<LOSS_BLOCKS, 256, 0, s>>>(t->act + t->a_off[L], x, (int64_t)rows * C, 1.f / C, backward ? dA : nullptr, t->loss_part);
+  loss_seed_kernel<<<LOSS_BLOCKS, 256, 0, s>>>(t->act + t->a_off[L], x, (int64_t)rows * C, 1.f / t->loss_columns,
+                                                backward ? dA : nullptr, t->loss_part);
   if (!backward) return (int)cudaGetLastError();
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
-    const int K = t->dims[l], N = t->dims[l + 1];
+    const LLayer& y = t->lay[l];
+    const int K = y.K, N = y.N;
     float* dZ = t->dz[cur];
-    act_bwd_kernel<<<t->ctx->sm_count * 2, 256, 0, s>>>(dZ, t->act + t->a_off[l + 1], (int64_t)rows * N, t->acts[l]);
+    act_bwd_kernel<<<t->ctx->sm_count * 2, 256, 0, s>>>(dZ, t->act + t->a_off[l + 1], (int64_t)rows * N, y.act);
+    if (y.bn_c)
+      bn_bwd_kernel<<<y.bn_c, 256, 0, s>>>(dZ, y.xhat, rows, N, N / y.bn_c, y.bn_c, t->params + y.g_off, y.mean_rstd,
+                                           t->grads + y.g_off, t->grads + y.g_off + y.bn_c);
     // dW_l[N x K] = dZ^T[N x rows] . A_l[rows x K]
-    lgemm(s, dZ, 1, N, t->act + t->a_off[l], K, 1, t->grads + t->w_off[l], K, N, K, rows, nullptr, BB_ACT_NONE);
-    colsum_kernel<<<(N + 255) / 256, 256, 0, s>>>(dZ, rows, N, t->grads + t->b_off[l]);
+    lgemm(s, dZ, 1, N, t->act + t->a_off[l], K, 1, y.gWd, K, N, K, rows, nullptr, BB_ACT_NONE);
+    colsum_kernel<<<(N + 255) / 256, 256, 0, s>>>(dZ, rows, N, y.gbd);
+    if (y.tied) {
+      const int n = y.n_w > y.n_b ? y.n_w : y.n_b;
+      tied_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(y.csr_ptr, y.csr_idx, y.gWd, t->grads + y.w_off, y.n_w, y.gbd,
+                                                         t->grads + y.b_off, y.n_b, N / y.n_b);
+    }
     if (l > 0)  // dA_l[rows x K] = dZ[rows x N] . W_l[N x K]
-      lgemm(s, dZ, N, 1, t->params + t->w_off[l], K, 1, t->dz[cur ^ 1], K, rows, K, N, nullptr, BB_ACT_NONE);
+      lgemm(s, dZ, N, 1, y.Wd, K, 1, t->dz[cur ^ 1], K, rows, K, N, nullptr, BB_ACT_NONE);
     cur ^= 1;
   }
   return (int)cudaGetLastError();
+}
+
+template <typename T>
+int dev_upload(T** dst, const std::vector<T>& src) {
+  int rc = (int)cudaMalloc(dst, sizeof(T) * (src.empty() ? 1 : src.size()));
+  if (rc == BB_OK && !src.empty()) rc = (int)cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice);
+  return rc;
 }
 
 }  // namespace
 
 extern "C" {
 
-int bb_ltrainer_create(bb_ctx* ctx, int n_layers, const int* dims, const int* acts, const double* const* weights_host,
-                       const double* const* biases_host, int max_batch, bb_ltrainer** out) {
-  if (!ctx || !dims || !acts || !weights_host || !biases_host || !out || n_layers < 1 || n_layers > BB_MAX_LAYERS || max_batch < 1)
+int bb_ltrainer_create_ex(bb_ctx* ctx, int n_layers, const int* dims, const int* acts, const int* n_shared_w,
+                          const int32_t* const* w_maps, const int* n_bias, const int* bn_channels,
+                          const double* const* weights_host, const double* const* biases_host, const double* const* bn_host,
+                          int loss_columns, int max_batch, bb_ltrainer** out) {
+  if (!ctx || !dims || !acts || !weights_host || !biases_host || !out || n_layers < 1 || n_layers > LT_MAX_LAYERS || max_batch < 1)
     return BB_ERR_INVALID;
   if (dims[0] != dims[n_layers]) return BB_ERR_INVALID;  // an autoencoder: the loss compares the output with the input
   BB_CUDA(cudaSetDevice(ctx->device));
   bb_ltrainer* t = new (std::nothrow) bb_ltrainer();
   if (!t) return BB_ERR_NOMEM;
   t->ctx = ctx; t->n_layers = n_layers; t->max_batch = max_batch;
+  t->loss_columns = loss_columns > 0 ? loss_columns : dims[n_layers];
   int p = 0;
   size_t a = 0;
   for (int l = 0; l <= n_layers; ++l) {
-    t->dims[l] = dims[l];
     if (dims[l] < 1) { delete t; return BB_ERR_INVALID; }
     t->max_dim = dims[l] > t->max_dim ? dims[l] : t->max_dim;
     t->a_off[l] = a;
     a += (size_t)max_batch * dims[l];
   }
   for (int l = 0; l < n_layers; ++l) {
-    t->acts[l] = acts[l];
-    t->w_off[l] = p; p += dims[l] * dims[l + 1];
-    t->b_off[l] = p; p += dims[l + 1];
+    LLayer& y = t->lay[l];
+    y.K = dims[l]; y.N = dims[l + 1]; y.act = acts[l];
+    y.tied = n_shared_w && n_shared_w[l] > 0;
+    y.n_w = y.tied ? n_shared_w[l] : y.K * y.N;
+    y.n_b = y.tied && n_bias && n_bias[l] > 0 ? n_bias[l] : y.N;
+    y.bn_c = bn_channels ? bn_channels[l] : 0;
+    const bool bad = (y.tied && (!w_maps || !w_maps[l])) || y.N % y.n_b != 0 || (!y.tied && y.n_b != y.N) || y.bn_c < 0 ||
+                     (y.bn_c && (y.N % y.bn_c != 0 || !bn_host || !bn_host[l]));
+    if (bad) { delete t; return BB_ERR_INVALID; }
+    y.w_off = p; p += y.n_w;
+    y.b_off = p; p += y.n_b;
+    y.g_off = p; p += 2 * y.bn_c;
+    t->n_running += 2 * y.bn_c;
   }
   t->n_params = p;
-  std::vector<float> hp(p);
+  std::vector<float> hp(p), hrun(t->n_running);
+  int roff = 0;
   for (int l = 0; l < n_layers; ++l) {
-    const int K = dims[l], N = dims[l + 1];
-    for (int i = 0; i < N * K; ++i) hp[t->w_off[l] + i] = (float)weights_host[l][i];
-    for (int n = 0; n < N; ++n) hp[t->b_off[l] + n] = (float)biases_host[l][n];
+    const LLayer& y = t->lay[l];
+    for (int i = 0; i < y.n_w; ++i) hp[y.w_off + i] = (float)weights_host[l][i];
+    for (int n = 0; n < y.n_b; ++n) hp[y.b_off + n] = (float)biases_host[l][n];
+    for (int c = 0; c < 2 * y.bn_c; ++c) hp[y.g_off + c] = (float)bn_host[l][c];                     // gamma | beta
+    for (int c = 0; c < 2 * y.bn_c; ++c) hrun[roff + c] = (float)bn_host[l][2 * y.bn_c + c];         // running mean | var
+    roff += 2 * y.bn_c;
   }
   int rc = (int)cudaMalloc(&t->params, sizeof(float) * p);
   if (rc == BB_OK) rc = (int)cudaMalloc(&t->grads, sizeof(float) * (p + 1));
@@ -232,21 +405,71 @@ int bb_ltrainer_create(bb_ctx* ctx, int n_layers, const int* dims, const int* ac
   for (int i = 0; i < 2 && rc == BB_OK; ++i) rc = (int)cudaMalloc(&t->dz[i], sizeof(float) * (size_t)max_batch * t->max_dim);
   if (rc == BB_OK) rc = (int)cudaMalloc(&t->loss_part, sizeof(float) * LOSS_BLOCKS);
   if (rc == BB_OK) rc = (int)cudaMalloc(&t->loss_accum, sizeof(double));
+  if (rc == BB_OK) rc = dev_upload(&t->running_all, hrun);
   if (rc == BB_OK) rc = (int)cudaMemcpy(t->params, hp.data(), sizeof(float) * p, cudaMemcpyHostToDevice);
   if (rc == BB_OK) rc = (int)cudaMemset(t->m, 0, sizeof(float) * p);
   if (rc == BB_OK) rc = (int)cudaMemset(t->v, 0, sizeof(float) * p);
   if (rc == BB_OK) rc = (int)cudaMemset(t->grads, 0, sizeof(float) * (p + 1));
   if (rc == BB_OK) rc = (int)cudaMemset(t->loss_accum, 0, sizeof(double));
+  roff = 0;
+  for (int l = 0; l < n_layers && rc == BB_OK; ++l) {
+    LLayer& y = t->lay[l];
+    if (y.bn_c) {
+      y.running = t->running_all + roff;
+      roff += 2 * y.bn_c;
+      rc = (int)cudaMalloc(&y.xhat, sizeof(float) * (size_t)max_batch * y.N);
+      if (rc == BB_OK) rc = (int)cudaMalloc(&y.mean_rstd, sizeof(float) * 2 * y.bn_c);
+      if (rc != BB_OK) break;
+    }
+    if (!y.tied) {
+      y.Wd = t->params + y.w_off; y.bd = t->params + y.b_off;
+      y.gWd = t->grads + y.w_off; y.gbd = t->grads + y.b_off;
+      continue;
+    }
+    const int n = y.N * y.K;
+    std::vector<int32_t> map(w_maps[l], w_maps[l] + n), ptr(y.n_w + 1, 0), idx;
+    for (int i = 0; i < n; ++i) {
+      if (map[i] >= y.n_w) { rc = BB_ERR_INVALID; break; }
+      if (map[i] >= 0) ptr[map[i] + 1] += 1;
+    }
+    if (rc != BB_OK) break;
+    for (int j = 0; j < y.n_w; ++j) ptr[j + 1] += ptr[j];
+    idx.resize(ptr[y.n_w]);
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int i = 0; i < n; ++i)
+      if (map[i] >= 0) idx[fill[map[i]]++] = i;
+    rc = dev_upload(&y.map, map);
+    if (rc == BB_OK) rc = dev_upload(&y.csr_ptr, ptr);
+    if (rc == BB_OK) rc = dev_upload(&y.csr_idx, idx);
+    if (rc == BB_OK) rc = (int)cudaMalloc(&y.dense, sizeof(float) * 2 * (size_t)(n + y.N));
+    if (rc == BB_OK) { y.Wd = y.dense; y.bd = y.Wd + n; y.gWd = y.bd + y.N; y.gbd = y.gWd + n; }
+  }
+  if (rc == BB_OK) {
+    expand_tied(t, nullptr);
+    rc = (int)cudaDeviceSynchronize();
+  }
   if (rc != BB_OK) { bb_ltrainer_destroy(t); return rc; }
   *out = t;
   return BB_OK;
 }
 
+int bb_ltrainer_create(bb_ctx* ctx, int n_layers, const int* dims, const int* acts, const double* const* weights_host,
+                       const double* const* biases_host, int max_batch, bb_ltrainer** out) {
+  return bb_ltrainer_create_ex(ctx, n_layers, dims, acts, nullptr, nullptr, nullptr, nullptr, weights_host, biases_host, nullptr, 0,
+                               max_batch, out);
+}
+
 int bb_ltrainer_destroy(bb_ltrainer* t) {
   if (!t) return BB_OK;
-  void* ptrs[] = {t->params, t->grads, t->m, t->v, t->act, t->dz[0], t->dz[1], t->loss_part, t->loss_accum};
+  void* ptrs[] = {t->params, t->grads, t->m, t->v, t->act, t->dz[0], t->dz[1], t->loss_part, t->loss_accum, t->running_all};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int l = 0; l < t->n_layers; ++l) {
+    LLayer& y = t->lay[l];
+    void* lp[] = {y.dense, y.map, y.csr_ptr, y.csr_idx, y.xhat, y.mean_rstd};
+    for (void* p : lp)
+      if (p) cudaFree(p);
+  }
   delete t;
   return BB_OK;
 }
@@ -254,15 +477,36 @@ int bb_ltrainer_destroy(bb_ltrainer* t) {
 int bb_ltrainer_param_count(const bb_ltrainer* t) { return t ? t->n_params : 0; }
 float* bb_ltrainer_params_dev(bb_ltrainer* t) { return t ? t->params : nullptr; }
 float* bb_ltrainer_grads_dev(bb_ltrainer* t) { return t ? t->grads : nullptr; }
+float* bb_ltrainer_bn_running_dev(bb_ltrainer* t, int* n_floats) {
+  if (n_floats) *n_floats = t ? t->n_running : 0;
+  return t ? t->running_all : nullptr;
+}
 
 int bb_ltrainer_get_params(bb_ltrainer* t, double* const* weights_host, double* const* biases_host) {
   if (!t || !weights_host || !biases_host) return BB_ERR_INVALID;
   std::vector<float> hp(t->n_params);
   BB_CUDA(cudaMemcpy(hp.data(), t->params, sizeof(float) * hp.size(), cudaMemcpyDeviceToHost));
   for (int l = 0; l < t->n_layers; ++l) {
-    const int K = t->dims[l], N = t->dims[l + 1];
-    for (int i = 0; i < N * K; ++i) weights_host[l][i] = (double)hp[t->w_off[l] + i];
-    for (int n = 0; n < N; ++n) biases_host[l][n] = (double)hp[t->b_off[l] + n];
+    const LLayer& y = t->lay[l];
+    for (int i = 0; i < y.n_w; ++i) weights_host[l][i] = (double)hp[y.w_off + i];
+    for (int n = 0; n < y.n_b; ++n) biases_host[l][n] = (double)hp[y.b_off + n];
+  }
+  return BB_OK;
+}
+
+int bb_ltrainer_get_bn(bb_ltrainer* t, double* const* bn_host) {
+  if (!t || !bn_host) return BB_ERR_INVALID;
+  std::vector<float> hp(t->n_params), hr(t->n_running);
+  BB_CUDA(cudaMemcpy(hp.data(), t->params, sizeof(float) * hp.size(), cudaMemcpyDeviceToHost));
+  if (t->n_running) BB_CUDA(cudaMemcpy(hr.data(), t->running_all, sizeof(float) * hr.size(), cudaMemcpyDeviceToHost));
+  int roff = 0;
+  for (int l = 0; l < t->n_layers; ++l) {
+    const LLayer& y = t->lay[l];
+    if (!y.bn_c) continue;
+    if (!bn_host[l]) return BB_ERR_INVALID;
+    for (int c = 0; c < 2 * y.bn_c; ++c) bn_host[l][c] = (double)hp[y.g_off + c];
+    for (int c = 0; c < 2 * y.bn_c; ++c) bn_host[l][2 * y.bn_c + c] = (double)hr[roff + c];
+    roff += 2 * y.bn_c;
   }
   return BB_OK;
 }
@@ -285,6 +529,7 @@ int bb_ltrainer_step(bb_ltrainer* t, const float* x_dev, int batch_rows, const b
   ladam_kernel<<<(t->n_params + 255) / 256, 256, 0, s>>>(t->n_params, phase, t->grads, t->params, t->m, t->v, lr_bc1, inv_sqrt_bc2,
                                                         (float)h->beta1, (float)h->beta2, (float)h->eps, t->loss_part, LOSS_BLOCKS,
                                                         loss_accum_dev);
+  if (phase != 1) expand_tied(t, s);
   return (int)cudaGetLastError();
 }
 
@@ -297,7 +542,7 @@ int bb_ltrainer_epoch(bb_ltrainer* t, const float* x_dev, int64_t n_rows, int ba
   int64_t n_batches = 0;
   for (int64_t r0 = 0; r0 < n_rows; r0 += batch, ++n_batches) {
     const int rows = (int)(n_rows - r0 < batch ? n_rows - r0 : batch);
-    const int rc = bb_ltrainer_step(t, x_dev + (size_t)r0 * t->dims[0], rows, h, 0, t->loss_accum, s);
+    const int rc = bb_ltrainer_step(t, x_dev + (size_t)r0 * t->lay[0].K, rows, h, 0, t->loss_accum, s);
     if (rc != BB_OK) return rc;
   }
   double total = 0.0;
@@ -315,7 +560,7 @@ int bb_ltrainer_validate(bb_ltrainer* t, const float* x_dev, int64_t n_rows, int
   int64_t n_batches = 0;
   for (int64_t r0 = 0; r0 < n_rows; r0 += batch, ++n_batches) {
     const int rows = (int)(n_rows - r0 < batch ? n_rows - r0 : batch);
-    int rc = lforward_backward(t, x_dev + (size_t)r0 * t->dims[0], rows, false, s);
+    int rc = lforward_backward(t, x_dev + (size_t)r0 * t->lay[0].K, rows, false, s);
     if (rc != BB_OK) return rc;
     // mode 1 folds the loss partials into grads[n_params]; mode 2 with zero parameters adds that slot to the accumulator
     ladam_kernel<<<1, 256, 0, s>>>(t->n_params, 1, t->grads, nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, t->loss_part,

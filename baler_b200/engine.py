@@ -330,17 +330,38 @@ class LayeredTrainer:
 
     _ACT = {"none": 0, "leaky": 1, "relu": 2}
 
-    def __init__(self, weights, biases, acts, max_batch, device=None):
+    def __init__(self, weights, biases, acts, max_batch, device=None, dims=None, w_maps=None, bn=None, loss_columns=0):
+        """plain Linears: weights[l] is the (out, in) matrix.  Conv_AE (weight sharing, BatchNorm2d; see
+        bb_ltrainer_create_ex): `dims` gives the layer widths, w_maps[l] (int32 (out * in,), or None) maps dense entries to
+        the flat kernel weights[l], biases[l] is per channel; bn[l] = None or a (4, channels) array gamma / beta /
+        running_mean / running_var."""
         self.ctx = get_context(device)
         self.handle = C.c_void_p()
-        self._bn = None
+        n = len(weights)
         self._w = [np.ascontiguousarray(w, dtype=np.float64) for w in weights]
         self._b = [np.ascontiguousarray(b, dtype=np.float64) for b in biases]
-        dims = (C.c_int * (len(self._w) + 1))(*([self._w[0].shape[1]] + [w.shape[0] for w in self._w]))
-        acts_c = (C.c_int * len(self._w))(*[self._ACT[a] for a in acts])
+        self._maps = [None if m is None else np.ascontiguousarray(m, dtype=np.int32) for m in (w_maps or [None] * n)]
+        self._bn = None if bn is None or all(b is None for b in bn) else \
+            [None if b is None else np.ascontiguousarray(b, dtype=np.float64) for b in bn]
+        if dims is None:
+            dims = [self._w[0].shape[1]] + [w.shape[0] for w in self._w]
+        self.dims = list(dims)
+        dims_c = (C.c_int * (n + 1))(*self.dims)
+        acts_c = (C.c_int * n)(*[self._ACT[a] for a in acts])
+        shared = (C.c_int * n)(*[0 if m is None else self._w[l].size for l, m in enumerate(self._maps)])
+        n_bias = (C.c_int * n)(*[0 if m is None else self._b[l].size for l, m in enumerate(self._maps)])
+        bn_ch = (C.c_int * n)(*[0 if self._bn is None or self._bn[l] is None else self._bn[l].shape[1] for l in range(n)])
+        maps_c, bn_c = (C.c_void_p * n)(), (C.c_void_p * n)()
+        for l in range(n):
+            if self._maps[l] is not None:
+                assert self._maps[l].size == self.dims[l] * self.dims[l + 1]
+                maps_c[l] = self._maps[l].ctypes.data
+            if bn_ch[l]:
+                bn_c[l] = self._bn[l].ctypes.data
         with torch.cuda.device(self.ctx.device):
-            check(_lib.lib().bb_ltrainer_create(self.ctx.handle, len(self._w), dims, acts_c, _host_ptrs(self._w),
-                                                _host_ptrs(self._b), max_batch, C.byref(self.handle)), "bb_ltrainer_create")
+            check(_lib.lib().bb_ltrainer_create_ex(self.ctx.handle, n, dims_c, acts_c, shared, maps_c, n_bias, bn_ch,
+                                                   _host_ptrs(self._w), _host_ptrs(self._b), bn_c, loss_columns, max_batch,
+                                                   C.byref(self.handle)), "bb_ltrainer_create_ex")
         self.n_params = _lib.lib().bb_ltrainer_param_count(self.handle)
         self.loss_accum = torch.zeros(1, dtype=torch.float64, device=self.ctx.device)
 
@@ -382,6 +403,22 @@ class LayeredTrainer:
         b = [np.empty_like(a) for a in self._b]
         check(_lib.lib().bb_ltrainer_get_params(self.handle, _host_ptrs(w), _host_ptrs(b)), "bb_ltrainer_get_params")
         return w, b
+
+    def get_bn(self):
+        """per layer None or (4, channels): gamma / beta / running_mean / running_var"""
+        out = [None if b is None else np.empty_like(b) for b in self._bn]
+        ptrs = (C.c_void_p * len(out))()
+        for l, a in enumerate(out):
+            if a is not None:
+                ptrs[l] = a.ctypes.data
+        check(_lib.lib().bb_ltrainer_get_bn(self.handle, ptrs), "bb_ltrainer_get_bn")
+        return out
+
+    def bn_running_views(self):
+        """zero-copy view of the running statistics of all BatchNorm layers (one tensor; DataParallelTrainer averages it)"""
+        n = C.c_int()
+        ptr = _lib.lib().bb_ltrainer_bn_running_dev(self.handle, C.byref(n))
+        return (self._flat(ptr, n.value),)
 
     def activation_means(self):
         raise NotImplementedError("activation extraction is implemented for the fused trainer (n_features <= 31)")

@@ -276,7 +276,11 @@ class Conv_AE:
         decode  z -> 2000 -> 128 -> 16x.. (BN folded) -> 8x.. (BN folded) -> HW      (ReLU except the output)
     whose matrices are built once on the host (float64, by pushing an identity basis through torch's own conv on
     the CPU - weight preprocessing, not the data path) and run by the CUDA GEMM chain (96 % of the FLOPs are the
-    two 2000-wide Linears either way).  Training of Conv_AE is not part of this round."""
+    two 2000-wide Linears either way).
+
+    Training (training.train -> engine.LayeredTrainer, bb_ltrainer_create_ex): the same chain with the convolutions
+    as weight-sharing dense layers (`training_spec`: entry -> kernel-weight index maps) and BatchNorm2d on batch
+    statistics; only the kernels, channel biases, Linears and BatchNorm affine parameters are trained."""
 
     dtype = torch.float32
 
@@ -380,6 +384,58 @@ class Conv_AE:
         dec.append((m, b, "none"))
         return enc, dec, conv_out
 
+    # -- training: the chain as weight-sharing dense layers
+    _CONV = [("q_z_conv.0", "conv", 1, None), ("q_z_conv.2", "conv", 1, "q_z_conv.3"), ("q_z_conv.5", "conv", 0, None),
+             ("q_z_lin.0", "lin", 0, None), ("q_z_lin.2", "lin", 0, None), ("p_x_lin.0", "lin", 0, None),
+             ("p_x_lin.2", "lin", 0, None), ("p_x_conv.0", "convT", 0, "p_x_conv.1"), ("p_x_conv.3", "convT", 1, "p_x_conv.4"),
+             ("p_x_conv.6", "convT", 1, None)]
+
+    def training_spec(self, h=5, w=5):
+        """dict(dims, acts, weights, biases, w_maps, bn) for engine.LayeredTrainer.  w_maps[l][i] is the flat index of the
+        kernel weight that dense entry i of layer l repeats (-1: structural zero), found by pushing an identity basis
+        through torch's own (transposed) convolution with the kernel entries replaced by their 1-based flat indices: at
+        stride 1 every (output, input) pair meets at most one kernel entry."""
+        F = torch.nn.functional
+        dims, acts, weights, biases, maps, bn = [h * w], [], [], [], [], []
+        shape = (1, h, w)
+        for i, (name, kind, pad, bn_name) in enumerate(self._CONV):
+            wt, bs = self._t(name + ".weight"), self._t(name + ".bias")
+            if kind == "lin":
+                if dims[-1] != wt.shape[1]:
+                    raise RuntimeError("Conv_AE: a %dx%d block flattens to %d values, the model's Linear expects %d "
+                                       "(reference models.py:320-343)" % (h, w, dims[-1], wt.shape[1]))
+                weights.append(wt.numpy()); biases.append(bs.numpy()); maps.append(None)
+                dims.append(wt.shape[0])
+                if name == "q_z_lin.0":
+                    conv_out = shape
+                if name == "p_x_lin.2":
+                    shape = conv_out
+            else:
+                op = F.conv2d if kind == "conv" else F.conv_transpose2d
+                codes = torch.arange(1, wt.numel() + 1, dtype=torch.float64).reshape(wt.shape)
+                m, _, shape = self._as_matrix(lambda x: op(x, codes, None, padding=pad), shape)
+                maps.append(np.rint(m).astype(np.int32).reshape(-1) - 1)
+                weights.append(wt.reshape(-1).numpy()); biases.append(bs.numpy())
+                dims.append(int(np.prod(shape)))
+            acts.append("none" if i == len(self._CONV) - 1 else "relu")
+            bn.append(None if bn_name is None else np.stack([self._t(bn_name + "." + k).numpy()
+                                                             for k in ("weight", "bias", "running_mean", "running_var")]))
+        self._conv_out = conv_out
+        return dict(dims=dims, acts=acts, weights=weights, biases=biases, w_maps=maps, bn=bn)
+
+    def load_trained(self, weights, biases, bn, steps):
+        """write the trainer's parameters (training_spec order) back into the state_dict; `steps` training forward passes
+        were made (num_batches_tracked)"""
+        for (name, kind, pad, bn_name), wt, bs, b4 in zip(self._CONV, weights, biases, bn):
+            dt = self._sd[name + ".weight"].dtype
+            self._sd[name + ".weight"] = torch.from_numpy(np.asarray(wt)).reshape(self._sd[name + ".weight"].shape).to(dt)
+            self._sd[name + ".bias"] = torch.from_numpy(np.asarray(bs)).reshape(-1).to(dt)
+            if bn_name is not None:
+                for k, row in zip(("weight", "bias", "running_mean", "running_var"), b4):
+                    self._sd[bn_name + "." + k] = torch.from_numpy(np.asarray(row)).to(dt)
+                self._sd[bn_name + ".num_batches_tracked"] = self._sd[bn_name + ".num_batches_tracked"] + int(steps)
+        self._codec = None
+
     def codec(self, h=5, w=5):
         if self._codec is None or self._codec_hw != (h, w):
             enc, dec, conv_out = self._chains(h, w)
@@ -388,7 +444,7 @@ class Conv_AE:
 
     def encode(self, x, precision="auto"):
         if self.training:
-            raise NotImplementedError("Conv_AE training (batch-statistics BatchNorm2d) is not part of this round")
+            raise NotImplementedError("the train-mode forward of Conv_AE (batch statistics) runs inside training.train")
         x = _as_cuda_f32(x)
         h, w = x.shape[-2], x.shape[-1]
         z = self.codec(h, w).encode(x.reshape(-1, h * w), precision=precision)
@@ -397,7 +453,7 @@ class Conv_AE:
 
     def decode(self, z, precision="auto"):
         if self.training:
-            raise NotImplementedError("Conv_AE training (batch-statistics BatchNorm2d) is not part of this round")
+            raise NotImplementedError("the train-mode forward of Conv_AE (batch statistics) runs inside training.train")
         h, w = self._codec_hw if self._codec_hw else (5, 5)
         y = self.codec(h, w).decode(_as_cuda_f32(z).reshape(-1, self.z_dim), precision=precision)
         return y.reshape(-1, 1, h, w)  # any batch size: the reference's view() to the LAST TRAINING batch (F7c) is not reproduced

@@ -44,13 +44,23 @@ class DeviceAdam:
     """Stands in for torch.optim.Adam(model.parameters(), lr) (training.py:266): Adam state lives in
     the bb_trainer; `lr` is what LRScheduler adjusts."""
 
-    def __init__(self, model, lr, max_batch, l1=False, reg_param=0.0, dropout_seed=0):
+    def __init__(self, model, lr, max_batch, l1=False, reg_param=0.0, dropout_seed=0, block_hw=None):
         self.rank, self.world = dist_env()
         broadcast_initial_state(model)
-        w, b = model.linear_tensors()
         self.model = model
         self.has_bn = hasattr(model, "bn_tensors")
-        self.trainer = None
+        self.conv = hasattr(model, "training_spec")
+        self.trainer, self.steps = None, 0
+        self.lr, self.l1, self.reg_param = lr, l1, reg_param
+        if self.conv:
+            # Conv_AE: (transposed) convolutions as weight-sharing dense layers, BatchNorm2d on batch statistics; the loss
+            # divisor is true_data.shape[1] = 1 channel (utils.py:197)
+            sp = model.training_spec(*block_hw)
+            self.trainer = engine.LayeredTrainer(sp["weights"], sp["biases"], sp["acts"], max_batch, dims=sp["dims"],
+                                                 w_maps=sp["w_maps"], bn=sp["bn"], loss_columns=1)
+            self.dp = sharded.DataParallelTrainer(self.trainer) if self.world > 1 else None
+            return
+        w, b = model.linear_tensors()
         if self.has_bn or model.n_features <= FUSED_TRAINER_MAX_FEATURES:
             try:
                 self.trainer = engine.Trainer(w, b, model.n_features, model.z_dim, max_batch,
@@ -64,7 +74,6 @@ class DeviceAdam:
         if self.has_bn:
             self.trainer.set_dropout(seed=dropout_seed + self.rank)  # every rank draws its own dropout stream
         self.dp = sharded.DataParallelTrainer(self.trainer) if self.world > 1 else None
-        self.lr, self.l1, self.reg_param = lr, l1, reg_param
 
     def hyper(self, world_size=None):
         return engine.make_hyper(lr=self.lr, reg_param=self.reg_param, l1=self.l1,
@@ -72,12 +81,18 @@ class DeviceAdam:
 
     def epoch(self, data, batch_size):
         """one pass over `data` in the reference's batch order; data-parallel when launched with several ranks"""
+        self.steps += (data.shape[0] + batch_size - 1) // batch_size
         if self.dp is None:
             return self.trainer.epoch(data, batch_size, self.hyper())
         slices = sharded.dp_batch_slices(data.shape[0], batch_size, self.rank, self.world)
         return self.dp.epoch([data[lo:hi] for lo, hi in slices], self.hyper())
 
     def sync_model(self):
+        if self.conv:
+            w, b = self.trainer.get_params()
+            self.model.load_trained(w, b, self.trainer.get_bn(), self.steps)
+            self.steps = 0
+            return
         w, b = self.trainer.get_params()
         self.model.set_linear_tensors(w, b)
         if self.has_bn:
@@ -109,8 +124,9 @@ def validate(model, test_dl, model_children, reg_param, optimizer=None):
 def _to_device_table(data, config):
     arr = np.asarray(data)
     if config.data_dimension == 2:
-        if config.model_type != "dense":
-            raise NotImplementedError("convolutional models: see DESIGN.md (next rows)")
+        if config.model_type == "convolutional" and config.model_name != "Conv_AE":
+            raise NotImplementedError("convolutional models other than Conv_AE: see DESIGN.md (out of scope)")
+        # dense: (N, H * W) rows (training.py:195-204); Conv_AE: (N, 1, H, W) batches (:222-228), the same memory
         arr = arr.reshape(arr.shape[0], arr.shape[1] * arr.shape[2])
     return torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).cuda()
 
@@ -132,8 +148,10 @@ def train(model, variables, train_data, test_data, project_path, config):
     valid_ds = train_ds if test_data is train_data else _to_device_table(test_data, config)
     train_dl, valid_dl = DeviceBatches(train_ds, bs), DeviceBatches(valid_ds, bs)
     model_children = list(model.children())
+    conv = config.data_dimension == 2 and config.model_type == "convolutional"
     optimizer = DeviceAdam(model, config.lr, max_batch=bs, l1=bool(getattr(config, "l1_in_training", False)),
-                           reg_param=config.reg_param, dropout_seed=int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF)
+                           reg_param=config.reg_param, dropout_seed=int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF,
+                           block_hw=tuple(np.asarray(train_data).shape[1:3]) if conv else None)
     early_stopping = utils.EarlyStopping(config.early_stopping_patience, config.min_delta) if config.early_stopping else None
     lr_scheduler = utils.LRScheduler(optimizer, config.lr_scheduler_patience) if config.lr_scheduler else None
     train_loss, val_loss = [], []
@@ -165,5 +183,12 @@ def train(model, variables, train_data, test_data, project_path, config):
         if getattr(config, "activation_extraction", False):
             np.save(os.path.join(project_path, "activations.npy"), optimizer.trainer.activation_means())
         np.save(os.path.join(project_path, "loss_data.npy"), np.array([train_loss, val_loss]))
+        if conv:
+            # reference training.py:344-346: the conv-stack output shape of the LAST forward, which is validate()'s last
+            # batch when test_size > 0, else the last training batch; decompress reads its batch size back (helper.py:650-688)
+            last = valid_dl if config.test_size else train_dl
+            rows = last.data.shape[0] - (last.data.shape[0] - 1) // bs * bs
+            model.set_final_layer_dims(torch.Size((rows,) + tuple(model._conv_out)))
+            np.save(os.path.join(project_path, "final_layer.npy"), np.array(model.get_final_layer_dims()))
     print(f"{(end - start) / 60:.3} minutes")
     return model

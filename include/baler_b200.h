@@ -244,6 +244,25 @@ int bb_trainer_activation_means(bb_trainer* t, double* out_host_6x200);
 typedef struct bb_ltrainer bb_ltrainer;
 int bb_ltrainer_create(bb_ctx* ctx, int n_layers, const int* dims, const int* acts, const double* const* weights_host,
                        const double* const* biases_host, int max_batch, bb_ltrainer** out);
+/*
+ * The same trainer for Conv_AE (models.py:316-407, float32) on a fixed block shape.  A (transposed) convolution is a
+ * layer with n_shared_w[l] > 0: its dense (dims[l+1], dims[l]) matrix is w_maps[l][i] -> index of the kernel weight entry
+ * i repeats (-1: structural zero), its bias is one value per channel (n_bias[l] channels of dims[l+1] / n_bias[l]
+ * consecutive outputs); `weights_host[l]` / `biases_host[l]` then hold the n_shared_w[l] kernel weights / n_bias[l]
+ * channel biases, and only those are trained.  bn_channels[l] > 0 puts nn.BatchNorm2d(bn_channels[l]) between the
+ * affine map and the activation (training steps: batch statistics, eps 1e-5, running statistics with momentum 0.1;
+ * bb_ltrainer_validate: running statistics); `bn_host[l]` = gamma | beta | running_mean | running_var, 4 x channels.
+ * loss_columns: the divisor of the summed squared error (utils.py:197 `true_data.shape[1]`: 1 for (B, 1, H, W)
+ * batches); 0 = dims[n_layers].  Any of n_shared_w, w_maps, n_bias, bn_channels, bn_host may be NULL (plain Linears).
+ * Up to 16 layers.  The flat vector behind params_dev / grads_dev holds, layer after layer, weights | biases | gamma |
+ * beta of the TRAINABLE parameters.
+ */
+int bb_ltrainer_create_ex(bb_ctx* ctx, int n_layers, const int* dims, const int* acts, const int* n_shared_w,
+                          const int32_t* const* w_maps, const int* n_bias, const int* bn_channels,
+                          const double* const* weights_host, const double* const* biases_host, const double* const* bn_host,
+                          int loss_columns, int max_batch, bb_ltrainer** out);
+int bb_ltrainer_get_bn(bb_ltrainer* t, double* const* bn_host); /* per BatchNorm layer: gamma | beta | running_mean | running_var */
+float* bb_ltrainer_bn_running_dev(bb_ltrainer* t, int* n_floats); /* running (mean | var) of every BatchNorm layer, layer after layer */
 int bb_ltrainer_destroy(bb_ltrainer* t);
 int bb_ltrainer_param_count(const bb_ltrainer* t);
 float* bb_ltrainer_params_dev(bb_ltrainer* t);

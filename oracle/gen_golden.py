@@ -20,6 +20,9 @@ Fixtures (all float64 unless noted; state-dict tensors stored under "<prefix>/<k
   schedules.npz     LRScheduler / EarlyStopping decision sequences
   conv_ae.npz       Conv_AE(5, 250) on 5x5 blocks: eval encode / decode (weights by seed + checksums)
   cfd_dense.npz     CFD_dense_AE(2500, 25) on 50x50 snapshots: encode / decode (weights by seed + checksums)
+  conv_train.npz    Conv_AE(5, 250) training on 600 5x5 blocks, batch 300: loss, gradients and parameters after 1 and 3 Adam
+                    steps (the four 2000-wide Linear weights as every 101st entry + l2 norm), BatchNorm2d running statistics,
+                    then training.train() for 2 epochs: loss_data, final_layer, eval-mode reconstruction of 64 blocks
   eb_deltas.npz     helper.save_error_bounded_requirement on 4 batches of the trained CMS AE + delta re-application
 """
 import os
@@ -353,6 +356,79 @@ def gen_conv_ae():
     print("conv_ae", z.shape, y.shape, os.path.getsize(os.path.join(OUT, "conv_ae.npz")) / 1e6, "MB")
 
 
+CONV_BIG = ("q_z_lin.0.weight", "q_z_lin.2.weight", "p_x_lin.0.weight", "p_x_lin.2.weight")
+CONV_STRIDE = 101
+
+
+def _conv_pack(named, prefix):
+    """tensors by name; the four big Linear weights as a strided sample + l2 norm (6 MB each step otherwise)"""
+    d = {}
+    for k, v in named:
+        a = v.detach().double().numpy().reshape(-1) if v.dim() else v.detach().numpy().copy()
+        if k in CONV_BIG:
+            d[f"{prefix}/{k}#sample"] = a[::CONV_STRIDE].copy()
+            d[f"{prefix}/{k}#norm"] = np.array(np.sqrt((a * a).sum()))
+        else:
+            d[f"{prefix}/{k}"] = a.copy() if v.dim() else a
+    return d
+
+
+def conv_train_blocks():
+    snaps = synth.cfd_snapshots(6)
+    blocks = ref_helper.data_processing.convert_to_blocks_util([1, 5, 5], snaps).astype(np.float32)
+    return ((blocks - blocks.min()) / (blocks.max() - blocks.min())).astype(np.float32)  # 600 x 5 x 5 in [0, 1]
+
+
+def gen_conv_train():
+    """Conv_AE training steps exactly as training.fit runs them (training.py:62-95: forward in train mode,
+    mse_sum_loss_l1(validate=True) - whose divisor is true_data.shape[1] = 1 for (B, 1, 5, 5) batches -, backward, Adam),
+    from torch.manual_seed(0) initial weights + randomise_bn2d (reproduced by the test through the drop-in class)."""
+    blocks = conv_train_blocks()
+    xs = torch.tensor(blocks, dtype=torch.float32).view(-1, 1, 5, 5)
+    d = dict(blocks=blocks.reshape(-1, 25))
+    torch.manual_seed(0)
+    model = ref_models.Conv_AE(5, 250)
+    randomise_bn2d(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    model.train()
+    losses = []
+    for step, lo in enumerate((0, 300, 0)):
+        xb = xs[lo:lo + 300]
+        opt.zero_grad()
+        loss, _, _ = ref_utils.mse_sum_loss_l1(list(model.children()), xb, model(xb), 0.001, True)
+        loss.backward()
+        if step == 0:
+            d.update(_conv_pack([(k, p.grad) for k, p in model.named_parameters()], "g0"))
+        opt.step()
+        losses.append(float(loss))
+        if step in (0, 2):
+            d.update(_conv_pack(model.state_dict().items(), f"sd{step + 1}"))
+    d["losses"] = np.array(losses)
+    model.eval()
+    with torch.no_grad():
+        d["eval_loss"] = np.array(float(ref_utils.mse_sum_loss_l1(None, xs[:300], model(xs[:300]), 0.001, True)[0]))
+    # training.train(): 2 epochs, batch 300, validation on the training blocks (test_size = 0 -> val = train loss)
+    cfg = make_config(epochs=2, batch_size=300, data_dimension=2, model_type="convolutional", model_name="Conv_AE",
+                      early_stopping=False, lr_scheduler=False, convert_to_blocks=[1, 5, 5], latent_space_size=250)
+    tmp = tempfile.mkdtemp()
+    try:
+        torch.manual_seed(0)
+        model = ref_models.Conv_AE(5, 250)
+        randomise_bn2d(model)
+        trained = ref_training.train(model, 5, blocks, blocks, tmp, cfg)
+        d["loss_data"] = np.load(os.path.join(tmp, "loss_data.npy"))
+        d["final_layer"] = np.load(os.path.join(tmp, "final_layer.npy"), allow_pickle=True)
+        d.update(_conv_pack(trained.state_dict().items(), "sd_final"))
+        trained.eval()
+        with torch.no_grad():
+            d["recon_final"] = trained(xs[:64]).numpy().reshape(64, 25)
+    finally:
+        shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(OUT, "conv_train.npz"), **d)
+    print("conv_train", d["losses"], d["eval_loss"], d["loss_data"], d["final_layer"],
+          os.path.getsize(os.path.join(OUT, "conv_train.npz")) / 1e6, "MB")
+
+
 def gen_cfd_dense():
     """CFD_dense_AE(2500, 25) (float32) on 50x50 snapshots, as CFD_project_animation configures it."""
     snaps = synth.cfd_snapshots(60)
@@ -400,6 +476,6 @@ def gen_eb_deltas():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules", "conv_ae", "cfd_dense", "eb_deltas"]
+    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules", "conv_ae", "conv_train", "cfd_dense", "eb_deltas"]
     for name in which:
         globals()["gen_" + name]()

@@ -113,3 +113,125 @@ def test_conv_cli_compress_decompress(golden, tmp_path, monkeypatch):
     dec = np.load(os.path.join(out, "decompressed_output", "decompressed.npz"))["data"]
     assert dec.shape == (6, 1, 50, 50) and dec.dtype == np.float32
     assert rel_max(dec.reshape(600, 25), g["recon_eval"].reshape(600, 25)) <= 1e-5
+
+
+# ---- Conv_AE training (tests/golden/conv_train.npz: the reference's own steps, oracle/gen_golden.py::gen_conv_train)
+
+CONV_BIG = ("q_z_lin.0.weight", "q_z_lin.2.weight", "p_x_lin.0.weight", "p_x_lin.2.weight")
+# a bias in front of a BatchNorm2d has a mathematically zero gradient (the mean subtraction removes it): both sides hold
+# rounding noise there, which Adam's first steps turn into +-lr moves.  It does not change the function.
+CONV_DEAD = ("q_z_conv.2.bias", "p_x_conv.0.bias", "p_x_conv.3.bias")
+
+
+def _conv_model():
+    torch.manual_seed(0)
+    m = models.Conv_AE(5, 250)
+    m.load_state_dict(randomise_bn2d(m.state_dict()))
+    return m
+
+
+def _conv_trainer(m, max_batch=300):
+    from baler_b200 import engine
+    sp = m.training_spec(5, 5)
+    tr = engine.LayeredTrainer(sp["weights"], sp["biases"], sp["acts"], max_batch, dims=sp["dims"], w_maps=sp["w_maps"],
+                               bn=sp["bn"], loss_columns=1)
+    return tr, sp
+
+
+def _named_flat(m, sp, flat):
+    """trainer's flat vector (layer after layer: weights | biases | gamma | beta) -> {state_dict key: float64 array}"""
+    out, off = {}, 0
+    for (name, kind, pad, bn_name), w, b, bn in zip(m._CONV, sp["weights"], sp["biases"], sp["bn"]):
+        out[name + ".weight"] = flat[off:off + w.size]; off += w.size
+        out[name + ".bias"] = flat[off:off + b.size]; off += b.size
+        if bn is not None:
+            c = bn.shape[1]
+            out[bn_name + ".weight"] = flat[off:off + c]; off += c
+            out[bn_name + ".bias"] = flat[off:off + c]; off += c
+    assert off == flat.size
+    return out
+
+
+def _check_packed(g, prefix, named, tol, skip=()):
+    scale = max(float(np.abs(g[f"{prefix}/{k}#sample" if k in CONV_BIG else f"{prefix}/{k}"]).max()) for k in named)
+    bad = {}
+    for k, a in named.items():
+        if k in skip:
+            continue
+        a = np.asarray(a, dtype=np.float64).reshape(-1)
+        if k in CONV_BIG:
+            ref = g[f"{prefix}/{k}#sample"]
+            if abs(np.sqrt((a * a).sum()) - float(g[f"{prefix}/{k}#norm"])) > tol * float(g[f"{prefix}/{k}#norm"]):
+                bad[k + "#norm"] = np.sqrt((a * a).sum()) / float(g[f"{prefix}/{k}#norm"]) - 1
+            a = a[::101]
+        else:
+            ref = g[f"{prefix}/{k}"].reshape(-1)
+        floor = max(float(np.abs(ref).max()), 1e-2 * scale)
+        err = float(np.abs(a - ref).max()) / floor
+        if err > tol:
+            bad[k] = err
+    assert not bad, (prefix, bad)
+
+
+def test_conv_ae_train_steps_match_reference(golden):
+    """one training step of Conv_AE as training.fit runs it (train-mode BatchNorm2d, sum-MSE / 1 channel, backward, Adam):
+    loss, every gradient and the parameters after 1 and 3 steps against the reference's own values"""
+    from baler_b200 import engine
+    g = golden("conv_train.npz")
+    m = _conv_model()
+    tr, sp = _conv_trainer(m)
+    x = torch.from_numpy(g["blocks"]).cuda()
+    h = engine.make_hyper(lr=1e-3)
+    tr.step(x[:300].contiguous(), h, phase=1)
+    grads = tr.grads_view().cpu().numpy().astype(np.float64)
+    assert abs(grads[-1] - g["losses"][0]) <= 1e-5 * g["losses"][0]
+    skip = CONV_DEAD
+    _check_packed(g, "g0", _named_flat(m, sp, grads[:-1]), 1e-5, skip)
+    tr.step(x[:300].contiguous(), h, phase=2)
+    _check_packed(g, "sd1", _named_flat(m, sp, tr.params_view().cpu().numpy().astype(np.float64)), 1e-5, skip)
+    tr.loss_accum.zero_()
+    tr.step(x[300:].contiguous(), h)
+    tr.step(x[:300].contiguous(), h)
+    # fp32 on both sides and three steps apart: Adam moves an entry by ~lr * g / |g| whatever its size, so entries whose
+    # gradient is cancellation noise (weights behind mostly-dead ReLU units) differ by a fraction of lr = 1e-3 (observed
+    # 5e-5 absolute on p_x_lin.0, 9e-4 of the tensor's largest weight); the one-step gates above are the 1e-5 ones
+    _check_packed(g, "sd3", _named_flat(m, sp, tr.params_view().cpu().numpy().astype(np.float64)), 2e-3, skip)
+    assert abs(tr.loss_accum.item() - g["losses"][1:].sum()) <= 1e-4 * g["losses"][1:].sum()
+    bn = tr.get_bn()
+    for (name, kind, pad, bn_name), b4 in zip(m._CONV, bn):
+        if bn_name is not None:
+            # the batch mean contains the dead bias in front of the BatchNorm (see CONV_DEAD): +-lr per step of noise
+            assert np.abs(b4[2] - g[f"sd3/{bn_name}.running_mean"]).max() <= 1e-3
+            assert rel_max(b4[3], g[f"sd3/{bn_name}.running_var"]) <= 1e-4
+    # eval mode (running statistics): the validation loss of the first 300 blocks
+    assert abs(tr.validate(x[:300].contiguous(), 300) - float(g["eval_loss"])) <= 1e-3 * float(g["eval_loss"])
+
+
+def test_conv_ae_training_through_the_training_module(golden, tmp_path):
+    """training.train on a convolutional 2-D project: loss_data.npy within 1 % of the reference's two epochs from the same
+    initial weights, final_layer.npy as the reference writes it, and the trained model's eval-mode reconstruction"""
+    from types import SimpleNamespace
+    from baler_b200.modules import training
+    g = golden("conv_train.npz")
+    blocks = g["blocks"].reshape(-1, 5, 5)
+    cfg = SimpleNamespace(deterministic_algorithm=False, batch_size=300, data_dimension=2, model_type="convolutional",
+                          model_name="Conv_AE", lr=1e-3, reg_param=0.001, early_stopping=False, early_stopping_patience=100,
+                          min_delta=0, lr_scheduler=False, lr_scheduler_patience=50, epochs=2, test_size=0,
+                          intermittent_model_saving=False, intermittent_saving_patience=100, RHO=0.05, l1=True,
+                          activation_extraction=False)
+    m = _conv_model()
+    training.train(m, 5, blocks, blocks, str(tmp_path), cfg)
+    losses = np.load(tmp_path / "loss_data.npy")
+    assert losses.shape == (2, 2)
+    assert np.abs(losses - g["loss_data"]).max() <= 1e-2 * np.abs(g["loss_data"]).max()
+    assert np.abs(losses[0] - g["loss_data"][0]).max() <= 1e-4 * g["loss_data"][0, 0]
+    assert list(np.load(tmp_path / "final_layer.npy")) == list(g["final_layer"]) == [300, 32, 4, 1]
+    sd = m.state_dict()
+    assert int(sd["p_x_conv.1.num_batches_tracked"]) == 4 == int(g["sd_final/p_x_conv.1.num_batches_tracked"])
+    assert rel_max(sd["q_z_conv.3.running_var"].numpy(), g["sd_final/q_z_conv.3.running_var"]) <= 1e-3
+    m.eval()
+    y = m(torch.from_numpy(g["blocks"][:64]).view(-1, 1, 5, 5)).cpu().numpy().reshape(64, 25)
+    # eval mode reads bias - running_mean of the three dead biases (CONV_DEAD): Adam moves them by +-lr per step on rounding
+    # noise and the running mean follows with momentum 0.1, so after 4 steps the two sides differ by a few 1e-3 there
+    # (observed 1.3e-2 of the largest output); the train-mode losses above, which do not see those biases, agree to 4e-6
+    assert rel_max(y, g["recon_final"]) <= 4e-2 and rel_l2(y, g["recon_final"]) <= 4e-2
