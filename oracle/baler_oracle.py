@@ -396,3 +396,70 @@ def apply_error_bounded_deltas(decoded, rows, cols, deltas):
     for r, c, d in zip(rows, cols, deltas):
         out[r][c] -= d
     return out
+
+
+# --------------------------------------------------------------------------- Conv_AE training
+def conv_chain_train_step(spec, x, loss_columns=1):
+    """One train-mode forward + loss + backward of models.Conv_AE (models.py:316-407) on flattened blocks x [B, H*W], as
+    training.fit runs it (training.py:62-92).  `spec` describes the network as a chain of affine layers (what the product's
+    Conv_AE.training_spec returns, plain numpy): dims, acts ("relu" / "none"), weights[l] / biases[l] (a Linear's (out, in)
+    matrix, or a (transposed) convolution's flat kernel with w_maps[l][i] = kernel index of dense entry i, -1 = zero, and a
+    per-channel bias), bn[l] = None or (4, C) gamma / beta / running_mean / running_var of the nn.BatchNorm2d that follows.
+    nn.BatchNorm2d in train mode: per-channel mean and BIASED variance over batch x positions, eps 1e-5.
+    Loss: nn.MSELoss(reduction="sum") / true_data.shape[1] (utils.py:195-199), and shape[1] of a (B, 1, H, W) batch is 1.
+    Returns (loss, grads) with grads[l] = dict(weight, bias[, gamma, beta]) in the layers' TRAINABLE parametrisation, plus
+    the batch statistics [(mean, biased var)] per BatchNorm layer."""
+    x = np.asarray(x, dtype=np.float64)
+    L = len(spec["weights"])
+    dense, a, saved, stats = [], x, [], []
+    for l in range(L):
+        k, n = spec["dims"][l], spec["dims"][l + 1]
+        w = np.asarray(spec["weights"][l], dtype=np.float64)
+        b = np.asarray(spec["biases"][l], dtype=np.float64)
+        mp = spec["w_maps"][l]
+        wd = w.reshape(n, k) if mp is None else np.where(mp >= 0, w.reshape(-1)[np.clip(mp, 0, None)], 0.0).reshape(n, k)
+        bd = np.repeat(b, n // b.size)
+        dense.append(wd)
+        z = a @ wd.T + bd
+        bn = spec["bn"][l]
+        xhat = rstd = None
+        if bn is not None:
+            c = bn.shape[1]
+            zc = z.reshape(z.shape[0], c, n // c)
+            mean, var = zc.mean(axis=(0, 2)), zc.var(axis=(0, 2))
+            stats.append((mean, var))
+            rstd = 1.0 / np.sqrt(var + BN_EPS)
+            xhat = (zc - mean[None, :, None]) * rstd[None, :, None]
+            z = (xhat * bn[0][None, :, None] + bn[1][None, :, None]).reshape(z.shape)
+        out = np.maximum(z, 0.0) if spec["acts"][l] == "relu" else z
+        saved.append((a, out, xhat, rstd))
+        a = out
+    diff = a - x
+    loss = float((diff * diff).sum() / loss_columns)
+    d = 2.0 * diff / loss_columns
+    grads = [None] * L
+    for l in reversed(range(L)):
+        a_in, out, xhat, rstd = saved[l]
+        n = spec["dims"][l + 1]
+        if spec["acts"][l] == "relu":
+            d = d * (out > 0)
+        g = {}
+        bn = spec["bn"][l]
+        if bn is not None:
+            c = bn.shape[1]
+            dc = d.reshape(d.shape[0], c, n // c)
+            g["gamma"], g["beta"] = (dc * xhat).sum(axis=(0, 2)), dc.sum(axis=(0, 2))
+            m = dc.shape[0] * dc.shape[2]
+            dc = (bn[0] * rstd)[None, :, None] * (dc - g["beta"][None, :, None] / m - xhat * g["gamma"][None, :, None] / m)
+            d = dc.reshape(d.shape)
+        gw, gb = d.T @ a_in, d.sum(axis=0)
+        mp = spec["w_maps"][l]
+        nb = np.asarray(spec["biases"][l]).size
+        g["bias"] = gb.reshape(nb, n // nb).sum(axis=1)
+        if mp is None:
+            g["weight"] = gw
+        else:
+            g["weight"] = np.bincount(mp[mp >= 0], weights=gw.reshape(-1)[mp >= 0], minlength=np.asarray(spec["weights"][l]).size)
+        grads[l] = g
+        d = d @ dense[l]
+    return loss, grads, stats

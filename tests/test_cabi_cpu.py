@@ -155,3 +155,37 @@ def test_new_project_skeleton(tmp_path):
 
     ns["set_config"](C)
     assert C.model_name == "AE" and C.batch_size == 512 and C.input_path.endswith("proj_data.npz")
+
+
+def test_conv_ae_training_spec_maps_reproduce_the_convolutions():
+    """Conv_AE.training_spec: expanding a layer's kernel through its entry -> weight map gives the dense matrix torch's own
+    (transposed) convolution applies to a flattened block; every kernel weight is used, per-channel bias layout"""
+    torch.manual_seed(3)
+    m = models.Conv_AE(5, 250)
+    sp = m.training_spec(5, 5)
+    assert sp["dims"] == [25, 144, 288, 128, 2000, 250, 2000, 128, 288, 144, 25]
+    assert sp["acts"] == ["relu"] * 9 + ["none"]
+    assert [None if b is None else b.shape for b in sp["bn"]] == [None, (4, 16), None, None, None, None, None, (4, 16), (4, 8), None]
+    F = torch.nn.functional
+    x = torch.randn(7, 25, dtype=torch.float64)
+    shapes = [(1, 5, 5), (8, 6, 3), (16, 6, 3), None, None, None, None, (32, 4, 1), (16, 6, 3), (8, 6, 3)]
+    for l, ((name, kind, pad, bn_name), mp, w, b) in enumerate(zip(m._CONV, sp["w_maps"], sp["weights"], sp["biases"])):
+        if mp is None:
+            assert w.shape == (sp["dims"][l + 1], sp["dims"][l])
+            continue
+        assert mp.dtype == np.int32 and mp.shape == (sp["dims"][l] * sp["dims"][l + 1],)
+        assert set(np.unique(mp[mp >= 0])) == set(range(w.size))  # every kernel weight appears
+        dense = np.where(mp >= 0, w[np.clip(mp, 0, None)], 0.0).reshape(sp["dims"][l + 1], sp["dims"][l])
+        bias = np.repeat(b, sp["dims"][l + 1] // b.size)
+        xin = torch.randn((7,) + shapes[l], dtype=torch.float64)
+        op = F.conv2d if kind == "conv" else F.conv_transpose2d
+        ref = op(xin, m._t(name + ".weight"), m._t(name + ".bias"), padding=pad).reshape(7, -1).numpy()
+        got = xin.reshape(7, -1).numpy() @ dense.T + bias
+        assert np.abs(got - ref).max() <= 1e-12
+    # load_trained writes the kernels back in their tensor shapes and counts the batches
+    before = int(m.state_dict()["p_x_conv.4.num_batches_tracked"])
+    m.load_trained([w * 2 for w in sp["weights"]], sp["biases"], sp["bn"], steps=5)
+    sd = m.state_dict()
+    assert sd["p_x_conv.6.weight"].shape == (8, 1, 2, 5) and sd["p_x_conv.6.weight"].dtype == torch.float32
+    assert np.allclose(sd["q_z_conv.0.weight"].numpy().reshape(-1), 2 * sp["weights"][0], rtol=1e-6)
+    assert int(sd["p_x_conv.4.num_batches_tracked"]) == before + 5

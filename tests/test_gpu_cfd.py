@@ -235,3 +235,68 @@ def test_conv_ae_training_through_the_training_module(golden, tmp_path):
     # noise and the running mean follows with momentum 0.1, so after 4 steps the two sides differ by a few 1e-3 there
     # (observed 1.3e-2 of the largest output); the train-mode losses above, which do not see those biases, agree to 4e-6
     assert rel_max(y, g["recon_final"]) <= 4e-2 and rel_l2(y, g["recon_final"]) <= 4e-2
+
+
+def test_conv_cli_train_compress_decompress(tmp_path, monkeypatch):
+    """--mode train / compress / decompress of a convolutional project (convert_to_blocks = [1, 5, 5]): the files of the
+    reference's train mode, then a round trip through the trained model"""
+    from baler_b200 import baler
+
+    monkeypatch.chdir(tmp_path)
+    helper.create_new_project("CFD_workspace", "CFD_project_train")
+    snaps = synth.cfd_snapshots(6)
+    snaps = (snaps - snaps.min()) / (snaps.max() - snaps.min())
+    path = os.path.join("workspaces", "CFD_workspace", "data", "CFD_blocks.npz")
+    np.savez(path, data=snaps, names=np.array(["snapshot"]))
+    out = os.path.join("workspaces", "CFD_workspace", "CFD_project_train", "output")
+
+    class cfg(helper.Config):
+        input_path = path
+        data_dimension, compression_ratio, apply_normalization, model_name, model_type = 2, 10, False, "Conv_AE", "convolutional"
+        batch_size, custom_norm, extra_compression, separate_model_saving = 200, True, False, False
+        save_error_bounded_deltas, convert_to_blocks = False, [1, 5, 5]
+        epochs, lr, reg_param, RHO, l1, test_size = 30, 1e-3, 0.001, 0.05, True, 0
+        early_stopping, early_stopping_patience, min_delta = False, 100, 0
+        lr_scheduler, lr_scheduler_patience = False, 50
+        intermittent_model_saving, intermittent_saving_patience = False, 100
+        activation_extraction, deterministic_algorithm = False, True
+
+    baler.perform_training(out, cfg, False)
+    losses = np.load(os.path.join(out, "training", "loss_data.npy"))
+    assert losses.shape == (2, 30) and np.isfinite(losses).all() and losses[0, -1] < 0.2 * losses[0, 0]
+    assert list(np.load(os.path.join(out, "training", "final_layer.npy"))) == [200, 32, 4, 1]
+    sd = torch.load(os.path.join(out, "compressed_output", "model.pt"))
+    assert len(sd) == 35 and sd["q_z_conv.5.weight"].shape == (32, 16, 3, 3) and sd["q_z_conv.5.weight"].dtype == torch.float32
+    assert int(sd["q_z_conv.3.num_batches_tracked"]) == 90
+    baler.perform_compression(out, cfg, False)
+    baler.perform_decompression(out, cfg, False)
+    dec = np.load(os.path.join(out, "decompressed_output", "decompressed.npz"))["data"]
+    assert dec.shape == (6, 1, 50, 50)
+    err = float(((dec.reshape(6, 50, 50) - snaps) ** 2).mean())
+    assert err < 0.5 * float(((snaps - snaps.mean()) ** 2).mean())  # better than predicting the mean after 30 epochs
+
+
+def test_conv_ae_train_step_vs_oracle_ragged_batch():
+    """a ragged batch (77 blocks, trainer sized for 128) and other weights against the float64 restatement
+    (oracle.conv_chain_train_step, itself pinned to the reference's step in tests/test_oracle_golden.py)"""
+    from baler_b200 import engine
+    from oracle import baler_oracle as orc
+    torch.manual_seed(5)
+    m = models.Conv_AE(5, 250)
+    m.load_state_dict(randomise_bn2d(m.state_dict(), seed=9))
+    tr, sp = _conv_trainer(m, max_batch=128)
+    x = torch.rand((77, 25), generator=torch.Generator().manual_seed(6))
+    tr.step(x.cuda(), engine.make_hyper(lr=1e-3), phase=1)
+    flat = tr.grads_view().cpu().numpy().astype(np.float64)
+    loss, grads, _ = orc.conv_chain_train_step(sp, x.numpy())
+    assert abs(flat[-1] - loss) <= 1e-5 * loss
+    got = _named_flat(m, sp, flat[:-1])
+    scale = max(float(np.abs(g["weight"]).max()) for g in grads)
+    for (name, kind, pad, bn_name), g in zip(m._CONV, grads):
+        pairs = [(name + ".weight", g["weight"]), (name + ".bias", g["bias"])]
+        if bn_name:
+            pairs += [(bn_name + ".weight", g["gamma"]), (bn_name + ".bias", g["beta"])]
+        for key, ref in pairs:
+            ref = np.asarray(ref).reshape(-1)
+            floor = max(float(np.abs(ref).max()), 1e-2 * scale)
+            assert np.abs(got[key] - ref).max() <= (1e-4 if key in CONV_DEAD else 1e-5) * floor, key
