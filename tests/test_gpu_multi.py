@@ -56,6 +56,23 @@ def _worker(rank, world, port, out_dir):
         rm, rv = trb.bn_running_views()
         np.save(os.path.join(out_dir, "dbn_%d.npy" % rank),
                 np.concatenate([trb.params_view().cpu().numpy(), rm.cpu().numpy(), rv.cpu().numpy(), np.array(losses, dtype=np.float32)]))
+        # Conv_AE, data parallel through the layer-by-layer trainer: per-rank BatchNorm2d statistics, SUM all-reduce of the
+        # trainable (kernel-level) gradient, identical Adam step + dense re-expansion on every rank
+        torch.manual_seed(0)
+        cm = models.Conv_AE(5, 250)
+        from test_gpu_cfd import randomise_bn2d
+        cm.load_state_dict(randomise_bn2d(cm.state_dict()))  # the initial state of tests/golden/conv_train.npz
+        sp = cm.training_spec(5, 5)
+        trc = engine.LayeredTrainer(sp["weights"], sp["biases"], sp["acts"], 150, dims=sp["dims"], w_maps=sp["w_maps"],
+                                    bn=sp["bn"], loss_columns=1)
+        dpc = sharded.DataParallelTrainer(trc)
+        gc = np.load(os.path.join(GOLDEN, "conv_train.npz"))
+        xc = torch.from_numpy(np.ascontiguousarray(gc["blocks"])).cuda()
+        slc = sharded.dp_batch_slices(600, 300, rank, world)
+        closs = [dpc.epoch([xc[lo:hi].contiguous() for lo, hi in slc], hyper) for _ in range(3)]
+        np.save(os.path.join(out_dir, "conv_%d.npy" % rank),
+                np.concatenate([trc.params_view().cpu().numpy(), trc.bn_running_views()[0].cpu().numpy(),
+                                np.array(closs, dtype=np.float32)]))
         # sharded compress: local min/max -> exchange -> encode of the local rows with the global features
         table = synth.cms_table(40_001, seed=8)
         lo, hi = sharded.row_range(len(table), rank, world)
@@ -82,6 +99,11 @@ def test_data_parallel_equals_single_gpu(tmp_path):
     d0, d1 = np.load(tmp_path / "dbn_0.npy"), np.load(tmp_path / "dbn_1.npy")
     assert np.array_equal(d0, d1) and np.isfinite(d0).all()  # AE_Dropout_BN replicas: parameters, running statistics, losses
     assert d0[-1] < d0[-3]  # three epochs: the loss goes down
+    c0, c1 = np.load(tmp_path / "conv_0.npy"), np.load(tmp_path / "conv_1.npy")
+    assert np.array_equal(c0, c1) and np.isfinite(c0).all() and c0[-1] < c0[-3]  # Conv_AE replicas stay identical and learn
+    gc = np.load(os.path.join(GOLDEN, "conv_train.npz"))
+    # first epoch = the reference's first two steps at batch 300, up to the per-rank (150-block) BatchNorm statistics
+    assert abs(c0[-3] - gc["loss_data"][0, 0]) <= 0.05 * gc["loss_data"][0, 0]
     g = np.load(os.path.join(GOLDEN, "ae_train.npz"))
     sd0 = {k[4:]: np.asarray(g[k], order="C") for k in g.files if k.startswith("sd0/")}
     names = models.AE.names
