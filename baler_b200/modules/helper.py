@@ -190,9 +190,7 @@ def compress(model_path, config):
         print("Normalizing...")
     codec = model.codec(data_before.shape[1], data_before.shape[2]) if conv else model.codec()
     if getattr(config, "save_error_bounded_deltas", False):
-        if world > 1:
-            raise NotImplementedError("error-bounded deltas are collected by a single process")
-        return _compress_with_deltas(codec, model, table, normalise, config)
+        return _compress_with_deltas(codec, model, table, normalise, config, rank, world)
     if world == 1:
         compressed, _ = codec.compress_host(table, recompute_minmax=normalise,
                                             z_dtype=_latent_np_dtype(model, config),
@@ -211,32 +209,43 @@ def compress(model_path, config):
     return sharded.gather_rows_to_rank0(z, len(table)), [], [], []
 
 
-def _compress_with_deltas(codec, model, table, normalise, config):
+def _compress_with_deltas(codec, model, table, normalise, config, rank=0, world=1):
     """reference helper.py:583-611 with config.save_error_bounded_deltas: every batch is encoded, decoded again and
     compared with its (normalised) input; elements whose relative error exceeds config.error_bounded_requirement percent
     get a float16 delta (helper.save_error_bounded_requirement, helper.py:442-470).  Here the table goes through the GPU in
     row chunks: encode, decode, one scan kernel (bb_error_bounded_deltas_f32); the hits are regrouped per batch of
-    config.batch_size rows on the host, in the reference's (batch index, deltas, (row-in-batch, column)) lists."""
-    from .. import engine
+    config.batch_size rows on the host, in the reference's (batch index, deltas, (row-in-batch, column)) lists.
+    Launched under torchrun every rank scans its contiguous row range (hits carry GLOBAL row numbers), rank 0 collects the
+    latent rows and the hit lists and regroups them; the other ranks return (None, [], [], [])."""
+    from .. import engine, sharded
     n, bs = len(table), int(config.batch_size)
     z_dtype = _latent_np_dtype(model, config)
-    compressed = np.empty((n, codec.z_dim), dtype=z_dtype)
+    lo, hi = sharded.row_range(n, rank, world)
+    shard = table[lo:hi]
+    compressed = np.empty((hi - lo, codec.z_dim), dtype=z_dtype)
     mn = rg = None
     if normalise and n:
-        feats = data_processing.find_minmax(table)  # this file's own [min; range] (helper.py:500-502)
+        # this file's own [min; range] (helper.py:500-502), over all ranks' rows
+        feats = data_processing.find_minmax(table) if world == 1 else sharded.global_minmax(shard)
         mn, rg = torch.from_numpy(np.ascontiguousarray(feats[0])).cuda(), torch.from_numpy(np.ascontiguousarray(feats[1])).cuda()
     rows, cols, deltas = [], [], []
     chunk = 1 << 20
-    for r0 in range(0, n, chunk):
-        x = torch.from_numpy(table[r0:r0 + chunk]).cuda()
+    for r0 in range(0, hi - lo, chunk):
+        x = torch.from_numpy(shard[r0:r0 + chunk]).cuda()
         z = codec.encode(x, mn, rg, precision=getattr(config, "precision", "auto"))
         y = codec.decode(z, precision=getattr(config, "precision", "auto"))  # still normalised, as upstream compares it
-        r, c, d = engine.error_bounded_deltas(x, y, mn, rg, config.error_bounded_requirement, row0=r0)
+        r, c, d = engine.error_bounded_deltas(x, y, mn, rg, config.error_bounded_requirement, row0=lo + r0)
         rows.append(r); cols.append(c); deltas.append(d)
         compressed[r0:r0 + chunk] = z.cpu().numpy().astype(z_dtype, copy=False)
     rows = np.concatenate(rows) if rows else np.empty(0, np.int64)
     cols = np.concatenate(cols) if cols else np.empty(0, np.int64)
     deltas = np.concatenate(deltas) if deltas else np.empty(0, np.float16)
+    if world > 1:
+        compressed = sharded.gather_rows_to_rank0(compressed, n)
+        hits = sharded.gather_objects_to_rank0((rows, cols, deltas))
+        if rank != 0:
+            return None, [], [], []
+        rows, cols, deltas = (np.concatenate([h[i] for h in hits]) for i in range(3))  # rank order = row order
     print("Total Deltas Found - ", len(rows))
     # upstream appends an entry for EVERY batch (its `len(index) > 0` test is on a 2-tuple); batches without a hit get
     # empty lists here (upstream would reuse the previous batch's deltas or crash on the first one)
@@ -309,9 +318,7 @@ def decompress(model_path, input_path, input_path_deltas, input_batch_index, mod
         decompressed = sharded.gather_rows_to_rank0(part, len(data))
         if decompressed is None:
             return None, names, normalization_features
-    if getattr(config, "save_error_bounded_deltas", False):
-        if world > 1:
-            raise NotImplementedError("error-bounded deltas are applied by a single process")
+    if getattr(config, "save_error_bounded_deltas", False):  # host step; under torchrun rank 0 holds the gathered rows
         decompressed = _apply_deltas(decompressed, input_path_deltas, input_batch_index, int(config.batch_size),
                                      None if renormalize_features is None else renormalize_features[1])
     if conv:

@@ -141,3 +141,14 @@ def gather_rows_to_rank0(shard, n_rows, group=None, chunk_rows=1 << 22):
     for r0 in range(0, len(shard), chunk_rows):
         dist.send(torch.from_numpy(np.ascontiguousarray(shard[r0:r0 + chunk_rows])).to(dev), dst=0, group=group)
     return None
+
+
+def gather_objects_to_rank0(obj, group=None):
+    """[obj of rank 0, obj of rank 1, ...] on rank 0, None on the other ranks (variable-length host data: the
+    error-bounded-delta hit lists)"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return [obj]
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(obj, out, dst=0, group=group)
+    return out

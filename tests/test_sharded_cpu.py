@@ -86,6 +86,14 @@ def _worker(rank, world, port, out_dir):
             assert (full is None) == (rank != 0)
             if rank == 0:
                 assert full.dtype == np.float64 and np.array_equal(full, t[:, :15].astype(np.float64))
+        # --- variable-length host lists (error-bounded-delta hits with global row numbers) collected in rank order
+        hits = (np.arange(rank * 5, rank * 5 + 3 + rank, dtype=np.int64), np.full(3 + rank, rank, dtype=np.int64),
+                np.full(3 + rank, 0.5 * rank, dtype=np.float16))
+        got = sharded.gather_objects_to_rank0(hits)
+        assert (got is None) == (rank != 0)
+        if rank == 0:
+            assert [len(h[0]) for h in got] == [3, 4] and got[1][2].dtype == np.float16
+            assert np.array_equal(np.concatenate([h[0] for h in got]), [0, 1, 2, 5, 6, 7, 8])
         # --- every replica starts from rank 0's initial model (each process draws its own random weights otherwise)
         from baler_b200.modules import models, training
         torch.manual_seed(100 + rank)

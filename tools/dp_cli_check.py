@@ -39,7 +39,8 @@ def set_config(c):
     c.mse_avg = False
     c.mse_sum = True
     c.emd = False
-    c.save_error_bounded_deltas = False
+    c.save_error_bounded_deltas = %s
+    c.error_bounded_requirement = 25
 '''
 
 def main():
@@ -54,7 +55,7 @@ def main():
                 helper.create_new_project("CMS_workspace", proj)
                 np.savez("workspaces/CMS_workspace/data/example_CMS_data.npz", data=synth.cms_table(40_000, seed=3), names=synth.CMS_NAMES)
                 with open("workspaces/CMS_workspace/%s/config/%s_config.py" % (proj, proj), "w") as f:
-                    f.write(CONFIG % model)
+                    f.write(CONFIG % (model, "False"))
                 r = subprocess.run(launch + ["--project", "CMS_workspace", proj, "--mode", "train"], env=env, capture_output=True, text=True)
                 assert r.returncode == 0, "\n".join(l for l in (r.stdout + r.stderr).splitlines() if not l.startswith(('W1', 'I1', '***', 'Setting OMP')))[:6000]
                 out = "workspaces/CMS_workspace/%s/output" % proj
@@ -75,6 +76,35 @@ def main():
                     s2 = np.load("workspaces/CMS_workspace/dp2/output/" + f)[key]
                     assert s1.shape == s2.shape and s1.dtype == s2.dtype and np.array_equal(s1, s2), (f, key)
                 print("sharded compress / decompress (2 ranks) == single process, bit for bit")
+                # the same with the error-bounded-deltas side channel (helper.py:442-470, baler.py:316-338): every rank scans
+                # its rows, rank 0 regroups the hits per batch and writes the two gzip'd files
+                import gzip
+                launches = {"single": [sys.executable, "-m", "baler_b200"],
+                            "dp2": [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                                    "--master-addr", "127.0.0.1", "--master-port", "29532", "-m", "baler_b200"]}
+                for proj, launch in launches.items():
+                    with open("workspaces/CMS_workspace/%s/config/%s_config.py" % (proj, proj), "w") as f:
+                        f.write(CONFIG % (model, "True"))
+                    for mode in ("compress", "decompress"):
+                        r = subprocess.run(launch + ["--project", "CMS_workspace", proj, "--mode", mode], env=env, capture_output=True, text=True)
+                        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+                n_hits = 0
+                for f in ("compressed_deltas.npz.gz", "compressed_batch_index_metadata.npz.gz"):
+                    a1 = np.load(gzip.GzipFile("workspaces/CMS_workspace/single/output/compressed_output/" + f), allow_pickle=True)
+                    a2 = np.load(gzip.GzipFile("workspaces/CMS_workspace/dp2/output/compressed_output/" + f), allow_pickle=True)
+                    assert len(a1) == len(a2)
+                    if f.startswith("compressed_deltas"):
+                        for d1, d2 in zip(a1, a2):
+                            assert np.array_equal(np.asarray(d1), np.asarray(d2))
+                            n_hits += len(d1)
+                    else:
+                        assert np.array_equal(a1[0], a2[0])
+                        for (r1, c1), (r2, c2) in zip(a1[1], a2[1]):
+                            assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
+                s1 = np.load("workspaces/CMS_workspace/single/output/decompressed_output/decompressed.npz")["data"]
+                s2 = np.load("workspaces/CMS_workspace/dp2/output/decompressed_output/decompressed.npz")["data"]
+                assert np.array_equal(s1, s2) and n_hits > 0
+                print("error-bounded deltas: %d hits, files and corrected reconstruction of the 2-rank run == single process" % n_hits)
             a, b = losses["single"][0], losses["dp2"][0]
             print(model, "single", a, "dp2", b, "rel diff", np.abs(a - b) / a)
             assert np.all(np.isfinite(b)) and b[-1] < b[0]
