@@ -369,8 +369,11 @@ def run_ours(args):
             xs = xt[:512 * 64].cpu().numpy()
             torch_port.fit_steps(sd0, xs, 512, 10)
             _, sec = torch_port.fit_steps(sd0, xs, 512, 300)
+            _, sec_dl = torch_port.fit_steps(sd0, xs, 512, 64, as_shipped=True)
             cpu_train = {"samples_per_s": 300 * 512 / sec, "cores": int(torch.get_num_threads()), "kind": "port",
-                         "sample": "300 steps of bs 512, reference loop body restated on torch CPU float64 (oracle/torch_port.py)"}
+                         "sample": "300 steps of bs 512, reference loop body restated on torch CPU float64 (oracle/torch_port.py)",
+                         "as_shipped_loop_samples_per_s": 64 * 512 / sec_dl,
+                         "as_shipped_note": "64 steps with the batches drawn through torch DataLoader as training.py:253-263 does"}
         train = {"cpu_baseline": cpu_train, "samples_per_s": tn * world / dt, "us_per_step": 1e6 * dt / steps, "steps": steps,
                  "global_batch": 512 * world, "epoch_loss": loss, "model": "AE 24-200-100-50-15-50-100-200-24",
                  "flop_per_sample": 357000, "tflops": tn * world * 357000 / dt / 1e12}

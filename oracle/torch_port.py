@@ -50,11 +50,29 @@ def decompress(sd, z, feats, block=BLOCK):
     return out.numpy()
 
 
-def fit_steps(sd, x_norm, batch, n_steps, lr=1e-3):
+def fit_steps(sd, x_norm, batch, n_steps, lr=1e-3, as_shipped=False):
     """Timing port of the reference's training loop body (training.py:64-97) on torch CPU float64:
     zero_grad -> forward -> sum-MSE / n_cols -> backward -> Adam.step -> loss.item() per batch.
+    as_shipped: the batches come out of torch.utils.data.DataLoader(tensor, batch_size, shuffle=False, drop_last=False) as in
+    training.py:253-263 (row-by-row indexing + collation per batch) instead of tensor slices.
     Returns (mean loss, seconds)."""
     import time
+
+    if as_shipped:
+        from torch.utils.data import DataLoader
+        params = {k: v.clone().requires_grad_(True) for k, v in to_torch(sd).items()}
+        opt = torch.optim.Adam(list(params.values()), lr=lr)
+        x = torch.from_numpy(np.ascontiguousarray(x_norm)).to(torch.float64)[:batch * n_steps]
+        total, n = 0.0, 0
+        t0 = time.perf_counter()
+        for xb in DataLoader(x, batch_size=batch, shuffle=False, drop_last=False):
+            opt.zero_grad()
+            loss = ((_chain(params, DEC, _chain(params, ENC, xb)) - xb) ** 2).sum() / xb.shape[1]
+            loss.backward()
+            opt.step()
+            total += loss.item()
+            n += 1
+        return total / max(n, 1), time.perf_counter() - t0
 
     params = {k: v.clone().requires_grad_(True) for k, v in to_torch(sd).items()}
     opt = torch.optim.Adam(list(params.values()), lr=lr)
