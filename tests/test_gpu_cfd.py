@@ -299,4 +299,5 @@ def test_conv_ae_train_step_vs_oracle_ragged_batch():
         for key, ref in pairs:
             ref = np.asarray(ref).reshape(-1)
             floor = max(float(np.abs(ref).max()), 1e-2 * scale)
-            assert np.abs(got[key] - ref).max() <= (1e-4 if key in CONV_DEAD else 1e-5) * floor, key
+            # a dead bias (exactly 0 in float64) holds fp32 cancellation noise of the 77 x 18 summed dZ values: ~5e-4 of floor
+            assert np.abs(got[key] - ref).max() <= (5e-3 if key in CONV_DEAD else 1e-5) * floor, key
