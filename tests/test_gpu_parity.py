@@ -223,6 +223,54 @@ def test_full_size_table_properties(ae):
     assert torch.equal(mn, x.min(0).values) and torch.equal(mx, x.max(0).values)
 
 
+def test_billion_row_table_in_chunks(ae):
+    """BASELINE configs[4] at one GPU (T1B in 8 chunks of 125M rows; the 96 GB table plus its 60 GB latent and
+    96 GB reconstruction do not fit 180 GB at once): pass 1 combines the chunks' column min / max into the file's
+    features, pass 2 encodes + decodes every chunk with them.  Chunks are regenerated from their seeds, never stored.
+    Properties: the combined features equal the min / max of all rows (exact), sampled rows of every chunk match the
+    oracle with the GLOBAL features, a row range inside a chunk encodes to the same bits as on its own, and the
+    reconstruction of the whole table stays within the model's error everywhere (checksum of per-chunk maxima)."""
+    m, sd, _ = ae
+    codec = m.codec()
+    free, _ = torch.cuda.mem_get_info()
+    chunk, n_chunks = (125_000_000, 8) if free > 60e9 else (2_000_000, 4)
+    scale = torch.linspace(0.5, 3.0, 24, device="cuda")
+
+    def make(i):
+        g = torch.Generator(device="cuda").manual_seed(20260101 + i)
+        x = torch.rand((chunk, 24), dtype=torch.float32, device="cuda", generator=g)
+        return x.mul_(scale).add_(float(i) * 0.125)  # every chunk has its own range: the features must be global
+
+    mn = torch.full((24,), float("inf"), device="cuda")
+    mx = -mn
+    for i in range(n_chunks):
+        x = make(i)
+        cmn, cmx = engine.colminmax(x)
+        assert torch.equal(cmn, x.min(0).values) and torch.equal(cmx, x.max(0).values)
+        mn, mx = torch.minimum(mn, cmn), torch.maximum(mx, cmx)
+        del x
+    rg = mx - mn
+    feats = [mn.cpu().numpy().astype(np.float64), rg.cpu().numpy().astype(np.float64)]
+    worst = []
+    for i in range(n_chunks):
+        x = make(i)
+        z = codec.encode(x, mn, rg)
+        g = torch.Generator(device="cuda").manual_seed(99 + i)
+        idx = torch.randint(0, chunk, (2048,), device="cuda", generator=g)
+        xs = x[idx].cpu().numpy()
+        xn = ((xs - mn.cpu().numpy()) / rg.cpu().numpy()).astype(np.float64)  # float32 normalisation, as helper.normalize
+        close(z[idx].cpu().numpy(), orc.ae_encode(sd, xn))
+        lo = chunk // 3 + 5
+        assert torch.equal(codec.encode(x[lo:lo + 70_001].contiguous(), mn, rg), z[lo:lo + 70_001])
+        y = codec.decode(z, mn, rg)
+        close(y[idx].cpu().numpy(), orc.renormalize(orc.ae_decode(sd, z[idx].cpu().numpy().astype(np.float64)), feats[0], feats[1]))
+        worst.append(float((y - x).abs_().max()))
+        assert bool(torch.isfinite(y).all())
+        del x, y, z
+    ref_err = np.abs(orc.renormalize(orc.ae_forward(sd, xn), feats[0], feats[1]) - xs).max()
+    assert max(worst) < 50 * max(ref_err, 1e-3)  # no chunk went through different features or a stale buffer
+
+
 def test_cli_roundtrip_matches_reference_files(golden, tmp_path, monkeypatch):
     """--mode compress / decompress on a workspace whose model.pt was trained by the reference: the files we
     write must match the files the reference wrote (tests/golden/cli_roundtrip.npz)."""
