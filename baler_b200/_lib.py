@@ -75,6 +75,7 @@ _SIGNATURES = {
     "bb_ltrainer_grads_dev": (_P, [_P]),
     "bb_ltrainer_get_params": (C.c_int, [_P, _P, _P]),
     "bb_ltrainer_step": (C.c_int, [_P, _P, C.c_int, C.POINTER(TrainHyper), C.c_int, _P, _P]),
+    "bb_ltrainer_step_swae": (C.c_int, [_P, _P, C.c_int, C.POINTER(TrainHyper), C.c_int, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "bb_ltrainer_epoch": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.POINTER(TrainHyper), C.POINTER(C.c_double), _P]),
     "bb_ltrainer_validate": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.POINTER(C.c_double), _P]),
 }

@@ -224,6 +224,70 @@ __global__ void __launch_bounds__(256) tied_reduce_kernel(const int32_t* __restr
   }
 }
 
+// ---- sliced-Wasserstein term of utils.loss_function_swae (utils.py:27-76), one block per projection s:
+//   w_i = sort(lat[:, s])_i - sort(pri[:, s])_i;  part[s] = sum_i w_i^2;  d lat[perm_i, s] = 2 w_i * coef
+// lat / pri are [rows][S] (projections of the latent batch and of the prior draws); lat is overwritten by its gradient.
+constexpr int SWD_MAX_ROWS = 2048;
+
+__device__ void bitonic_sort_smem(float* key, int* idx, const int n) {
+  for (int k = 2; k <= n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int p = i ^ j;
+        if (p > i) {
+          const bool up = (i & k) == 0;
+          const float a = key[i], b = key[p];
+          if ((a > b) == up) {
+            key[i] = b; key[p] = a;
+            if (idx) { const int t = idx[i]; idx[i] = idx[p]; idx[p] = t; }
+          }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) swd_sort_kernel(float* __restrict__ lat, const float* __restrict__ pri, const int rows,
+                                                       const int S, const int n_pow2, const float coef,
+                                                       float* __restrict__ part) {
+  extern __shared__ float sw[];
+  float* lk = sw;                       // n_pow2 latent projections
+  float* pk = lk + n_pow2;              // n_pow2 prior projections
+  int* li = (int*)(pk + n_pow2);        // row of every latent projection
+  __shared__ float red[256];
+  const int s = blockIdx.x;
+  for (int i = threadIdx.x; i < n_pow2; i += 256) {
+    lk[i] = i < rows ? lat[(int64_t)i * S + s] : INFINITY;
+    pk[i] = i < rows ? pri[(int64_t)i * S + s] : INFINITY;
+    li[i] = i;
+  }
+  __syncthreads();
+  bitonic_sort_smem(lk, li, n_pow2);
+  bitonic_sort_smem(pk, nullptr, n_pow2);
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < rows; i += 256) {
+    const float w = lk[i] - pk[i];
+    acc += w * w;
+    lat[(int64_t)li[i] * S + s] = 2.f * w * coef;
+  }
+  acc = block_sum_256(acc, red);
+  if (threadIdx.x == 0) part[s] = acc;
+}
+
+// loss_part[0] += coef * sum_s part[s] (fixed order);  dst[e] += src[e]
+__global__ void __launch_bounds__(256) swd_fold_kernel(const float* __restrict__ part, const int S, const float coef,
+                                                       float* __restrict__ loss_part) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < S; i += 256) acc += part[i];
+  acc = block_sum_256(acc, red);
+  if (threadIdx.x == 0) loss_part[0] += coef * acc;
+}
+
+__global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, const int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) dst[e] += src[e];
+}
+
 // mode 0: Adam update + fold the loss partials into grads[n_params] and *loss_accum; 1: only the loss fold (phase 1 of a
 // data-parallel step / validation); 2: Adam update with the (all-reduced) grads, loss from grads[n_params]
 __global__ void __launch_bounds__(256) ladam_kernel(const int n_params, const int mode, float* __restrict__ grads,
@@ -275,6 +339,9 @@ struct bb_ltrainer {
   size_t a_off[LT_MAX_LAYERS + 1] = {0};  // float offsets of A_0 .. A_L in `act` (max_batch rows each)
   float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *act = nullptr, *dz[2] = {nullptr, nullptr};
   float* running_all = nullptr;           // running statistics of all BatchNorm layers, layer after layer
+  // loss_function_swae: projections of the latent batch / of the prior draws [max_batch][S], latent gradient, partials
+  float *sw_lat = nullptr, *sw_pri = nullptr, *sw_dz = nullptr, *sw_part = nullptr;
+  int sw_S = 0;
   float* loss_part = nullptr;
   double* loss_accum = nullptr;
   long long step = 0;
@@ -298,7 +365,13 @@ void expand_tied(bb_ltrainer* t, cudaStream_t s) {
 }
 
 // forward (+ loss, + backward into grads when `backward`); BatchNorm layers use batch statistics iff `backward`
-int lforward_backward(bb_ltrainer* t, const float* x, int rows, bool backward, cudaStream_t s) {
+struct SwaeArgs {
+  const float *prior, *proj;   // [rows][D] prior draws, [S][D] unit projection directions (device)
+  int S, latent_layer;         // the latent is the output of layer `latent_layer`
+  float reg_weight;
+};
+
+int lforward_backward(bb_ltrainer* t, const float* x, int rows, bool backward, cudaStream_t s, const SwaeArgs* sw = nullptr) {
   const int L = t->n_layers;
   BB_CUDA(cudaMemcpyAsync(t->act + t->a_off[0], x, sizeof(float) * (size_t)rows * t->lay[0].K, cudaMemcpyDeviceToDevice, s));
   for (int l = 0; l < L; ++l) {
@@ -315,12 +388,28 @@ int lforward_backward(bb_ltrainer* t, const float* x, int rows, bool backward, c
   float* dA = t->dz[0];
   loss_seed_kernel<<<LOSS_BLOCKS, 256, 0, s>>>(t->act + t->a_off[L], x, (int64_t)rows * C, 1.f / t->loss_columns,
                                                 backward ? dA : nullptr, t->loss_part);
+  if (sw) {
+    // utils.compute_swd (utils.py:56-76): reg_weight / (B (B - 1)) * mean_{s, i} (sort(z P)_{s,i} - sort(prior P)_{s,i})^2
+    const int D = t->lay[sw->latent_layer].N, S = sw->S;
+    const float* Z = t->act + t->a_off[sw->latent_layer + 1];
+    lgemm(s, Z, D, 1, sw->proj, 1, D, t->sw_lat, S, rows, S, D, nullptr, BB_ACT_NONE);
+    lgemm(s, sw->prior, D, 1, sw->proj, 1, D, t->sw_pri, S, rows, S, D, nullptr, BB_ACT_NONE);
+    int n_pow2 = 1;
+    while (n_pow2 < rows) n_pow2 <<= 1;
+    const float coef = sw->reg_weight / ((float)rows * (float)(rows - 1)) / ((float)S * (float)rows);
+    swd_sort_kernel<<<S, 256, sizeof(float) * 3 * n_pow2, s>>>(t->sw_lat, t->sw_pri, rows, S, n_pow2, coef, t->sw_part);
+    swd_fold_kernel<<<1, 256, 0, s>>>(t->sw_part, S, coef, t->loss_part);
+    // d latent = d(z P) . P^T... as [rows][S] . [S][D]
+    if (backward) lgemm(s, t->sw_lat, S, 1, sw->proj, D, 1, t->sw_dz, D, rows, D, S, nullptr, BB_ACT_NONE);
+  }
   if (!backward) return (int)cudaGetLastError();
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
     const LLayer& y = t->lay[l];
     const int K = y.K, N = y.N;
     float* dZ = t->dz[cur];
+    if (sw && l == sw->latent_layer)  // the encoder sees the decoder's gradient plus the sliced-Wasserstein one
+      add_inplace_kernel<<<t->ctx->sm_count, 256, 0, s>>>(dZ, t->sw_dz, (int64_t)rows * N);
     act_bwd_kernel<<<t->ctx->sm_count * 2, 256, 0, s>>>(dZ, t->act + t->a_off[l + 1], (int64_t)rows * N, y.act);
     if (y.bn_c)
       bn_bwd_kernel<<<y.bn_c, 256, 0, s>>>(dZ, y.xhat, rows, N, N / y.bn_c, y.bn_c, t->params + y.g_off, y.mean_rstd,
@@ -461,7 +550,8 @@ int bb_ltrainer_create(bb_ctx* ctx, int n_layers, const int* dims, const int* ac
 
 int bb_ltrainer_destroy(bb_ltrainer* t) {
   if (!t) return BB_OK;
-  void* ptrs[] = {t->params, t->grads, t->m, t->v, t->act, t->dz[0], t->dz[1], t->loss_part, t->loss_accum, t->running_all};
+  void* ptrs[] = {t->params, t->grads, t->m, t->v, t->act, t->dz[0], t->dz[1], t->loss_part, t->loss_accum, t->running_all,
+                  t->sw_lat, t->sw_pri, t->sw_dz, t->sw_part};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int l = 0; l < t->n_layers; ++l) {
@@ -511,13 +601,13 @@ int bb_ltrainer_get_bn(bb_ltrainer* t, double* const* bn_host) {
   return BB_OK;
 }
 
-int bb_ltrainer_step(bb_ltrainer* t, const float* x_dev, int batch_rows, const bb_train_hyper* h, int phase,
-                     double* loss_accum_dev, bb_stream_t stream) {
+static int lstep(bb_ltrainer* t, const float* x_dev, int batch_rows, const bb_train_hyper* h, int phase, double* loss_accum_dev,
+                 bb_stream_t stream, const SwaeArgs* sw) {
   if (!t || !h || !x_dev || batch_rows < 1 || batch_rows > t->max_batch || phase < 0 || phase > 2) return BB_ERR_INVALID;
   if (h->l1) return BB_ERR_UNSUPPORTED;  // the reference never trains the L1 term (training.py:83-89); fused kernels have the opt-in
   cudaStream_t s = (cudaStream_t)stream;
   if (phase != 2) {
-    const int rc = lforward_backward(t, x_dev, batch_rows, true, s);
+    const int rc = lforward_backward(t, x_dev, batch_rows, true, s, sw);
     if (rc != BB_OK) return rc;
   }
   float lr_bc1 = 0.f, inv_sqrt_bc2 = 0.f;
@@ -531,6 +621,37 @@ int bb_ltrainer_step(bb_ltrainer* t, const float* x_dev, int batch_rows, const b
                                                         loss_accum_dev);
   if (phase != 1) expand_tied(t, s);
   return (int)cudaGetLastError();
+}
+
+int bb_ltrainer_step(bb_ltrainer* t, const float* x_dev, int batch_rows, const bb_train_hyper* h, int phase,
+                     double* loss_accum_dev, bb_stream_t stream) {
+  return lstep(t, x_dev, batch_rows, h, phase, loss_accum_dev, stream, nullptr);
+}
+
+int bb_ltrainer_step_swae(bb_ltrainer* t, const float* x_dev, int batch_rows, const bb_train_hyper* h, int phase,
+                          const float* prior_dev, const float* proj_dev, int n_projections, int latent_layer, float reg_weight,
+                          double* loss_accum_dev, bb_stream_t stream) {
+  if (!t || !prior_dev || !proj_dev || n_projections < 1 || latent_layer < 0 || latent_layer >= t->n_layers - 1)
+    return BB_ERR_INVALID;
+  if (batch_rows < 2 || batch_rows > SWD_MAX_ROWS) return BB_ERR_UNSUPPORTED;  // B (B - 1) in the weight; shared-memory sort
+  for (int l = 0; l < t->n_layers; ++l)
+    if (t->lay[l].bn_c) return BB_ERR_UNSUPPORTED;  // upstream runs the encoder twice per step: BatchNorm statistics move twice
+  if (t->sw_S != n_projections) {
+    BB_CUDA(cudaSetDevice(t->ctx->device));
+    BB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    void* old[] = {t->sw_lat, t->sw_pri, t->sw_dz, t->sw_part};
+    for (void* p : old)
+      if (p) cudaFree(p);
+    t->sw_lat = t->sw_pri = t->sw_dz = t->sw_part = nullptr;
+    t->sw_S = 0;
+    BB_CUDA(cudaMalloc(&t->sw_lat, sizeof(float) * (size_t)t->max_batch * n_projections));
+    BB_CUDA(cudaMalloc(&t->sw_pri, sizeof(float) * (size_t)t->max_batch * n_projections));
+    BB_CUDA(cudaMalloc(&t->sw_dz, sizeof(float) * (size_t)t->max_batch * t->max_dim));
+    BB_CUDA(cudaMalloc(&t->sw_part, sizeof(float) * n_projections));
+    t->sw_S = n_projections;
+  }
+  SwaeArgs sw{prior_dev, proj_dev, n_projections, latent_layer, reg_weight};
+  return lstep(t, x_dev, batch_rows, h, phase, loss_accum_dev, stream, &sw);
 }
 
 int bb_ltrainer_epoch(bb_ltrainer* t, const float* x_dev, int64_t n_rows, int batch, const bb_train_hyper* h,

@@ -386,6 +386,16 @@ class LayeredTrainer:
         check(_lib.lib().bb_ltrainer_step(self.handle, _ptr(x), x.shape[0], C.byref(hyper), phase, _ptr(self.loss_accum),
                                           _stream(self.ctx)), "bb_ltrainer_step")
 
+    def step_swae(self, x, hyper, prior, proj, latent_layer, reg_weight=100.0, phase=0):
+        """one step with utils.loss_function_swae: `prior` [rows, z_dim] standard-normal draws, `proj` [S, z_dim] unit
+        projection directions (float32, device), the latent = output of layer `latent_layer`"""
+        for t in (x, prior, proj):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        assert prior.shape[0] == x.shape[0] and prior.shape[1] == proj.shape[1] == self.dims[latent_layer + 1]
+        check(_lib.lib().bb_ltrainer_step_swae(self.handle, _ptr(x), x.shape[0], C.byref(hyper), phase, _ptr(prior), _ptr(proj),
+                                               proj.shape[0], latent_layer, float(reg_weight), _ptr(self.loss_accum),
+                                               _stream(self.ctx)), "bb_ltrainer_step_swae")
+
     def epoch(self, x, batch, hyper):
         out = C.c_double()
         check(_lib.lib().bb_ltrainer_epoch(self.handle, _ptr(x), x.shape[0], batch, C.byref(hyper), C.byref(out),

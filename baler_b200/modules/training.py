@@ -44,14 +44,17 @@ class DeviceAdam:
     """Stands in for torch.optim.Adam(model.parameters(), lr) (training.py:266): Adam state lives in
     the bb_trainer; `lr` is what LRScheduler adjusts."""
 
-    def __init__(self, model, lr, max_batch, l1=False, reg_param=0.0, dropout_seed=0, block_hw=None):
+    def __init__(self, model, lr, max_batch, l1=False, reg_param=0.0, dropout_seed=0, block_hw=None, swae=False):
         self.rank, self.world = dist_env()
         broadcast_initial_state(model)
         self.model = model
         self.has_bn = hasattr(model, "bn_tensors")
         self.conv = hasattr(model, "training_spec")
         self.trainer, self.steps = None, 0
-        self.lr, self.l1, self.reg_param = lr, l1, reg_param
+        self.lr, self.l1, self.reg_param, self.swae = lr, l1, reg_param, swae
+        if swae and (self.conv or self.has_bn or self.world > 1):
+            # upstream encodes twice per step with this loss (training.py:66-72): BatchNorm / dropout state would move twice
+            raise NotImplementedError("loss_function_swae: dense models without BatchNorm / dropout, one process")
         if self.conv:
             # Conv_AE: (transposed) convolutions as weight-sharing dense layers, BatchNorm2d on batch statistics; the loss
             # divisor is true_data.shape[1] = 1 channel (utils.py:197)
@@ -61,7 +64,7 @@ class DeviceAdam:
             self.dp = sharded.DataParallelTrainer(self.trainer) if self.world > 1 else None
             return
         w, b = model.linear_tensors()
-        if self.has_bn or model.n_features <= FUSED_TRAINER_MAX_FEATURES:
+        if not swae and (self.has_bn or model.n_features <= FUSED_TRAINER_MAX_FEATURES):
             try:
                 self.trainer = engine.Trainer(w, b, model.n_features, model.z_dim, max_batch,
                                               bn=model.bn_tensors() if self.has_bn else None)
@@ -87,6 +90,26 @@ class DeviceAdam:
         slices = sharded.dp_batch_slices(data.shape[0], batch_size, self.rank, self.world)
         return self.dp.epoch([data[lo:hi] for lo, hi in slices], self.hyper())
 
+    SWAE_PROJECTIONS, SWAE_REG_WEIGHT = 2000, 100.0  # defaults of utils.loss_function_swae (utils.py:27-36)
+
+    def epoch_swae(self, data, batch_size, latent_dim):
+        """one pass with config.custom_loss_function = "loss_function_swae" (training.py:70-78).  The two random inputs of
+        utils.compute_swd are drawn here from torch's global CPU generator in the reference's order - randn_like(z), then
+        randn(num_projections, latent_dim) normalised per row (utils.py:57-90) - in float32 (upstream cannot run this loss on
+        the float64 AE: its float32 projections meet a double latent), and handed to the device step."""
+        tr = self.trainer
+        tr.loss_accum.zero_()
+        n_batches = 0
+        for r0 in range(0, data.shape[0], batch_size):
+            xb = data[r0:r0 + batch_size]
+            prior = torch.randn((xb.shape[0], latent_dim), dtype=torch.float32)
+            proj = torch.randn(self.SWAE_PROJECTIONS, latent_dim)
+            proj = proj / proj.norm(dim=1).view(-1, 1)
+            tr.step_swae(xb, self.hyper(), prior.cuda(), proj.cuda(), latent_layer=3, reg_weight=self.SWAE_REG_WEIGHT)
+            n_batches += 1
+        self.steps += n_batches
+        return tr.loss_accum.item() / n_batches
+
     def sync_model(self):
         if self.conv:
             w, b = self.trainer.get_params()
@@ -106,8 +129,9 @@ def fit(config, model, train_dl, model_children, regular_param, optimizer, laten
     print("### Beginning Training")
     model.train()
     if hasattr(config, "custom_loss_function") and config.custom_loss_function == "loss_function_swae":
-        raise NotImplementedError("loss_function_swae is outside the B200 hot path")
-    epoch_loss = optimizer.epoch(train_dl.data, train_dl.batch_size)
+        epoch_loss = optimizer.epoch_swae(train_dl.data, train_dl.batch_size, latent_dim)
+    else:
+        epoch_loss = optimizer.epoch(train_dl.data, train_dl.batch_size)
     print(f"# Finished. Training Loss: {epoch_loss:.6f}")
     return epoch_loss, epoch_loss, 0, model
 
@@ -151,7 +175,8 @@ def train(model, variables, train_data, test_data, project_path, config):
     conv = config.data_dimension == 2 and config.model_type == "convolutional"
     optimizer = DeviceAdam(model, config.lr, max_batch=bs, l1=bool(getattr(config, "l1_in_training", False)),
                            reg_param=config.reg_param, dropout_seed=int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF,
-                           block_hw=tuple(np.asarray(train_data).shape[1:3]) if conv else None)
+                           block_hw=tuple(np.asarray(train_data).shape[1:3]) if conv else None,
+                           swae=getattr(config, "custom_loss_function", None) == "loss_function_swae")
     early_stopping = utils.EarlyStopping(config.early_stopping_patience, config.min_delta) if config.early_stopping else None
     lr_scheduler = utils.LRScheduler(optimizer, config.lr_scheduler_patience) if config.lr_scheduler else None
     train_loss, val_loss = [], []

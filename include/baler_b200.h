@@ -270,6 +270,19 @@ float* bb_ltrainer_grads_dev(bb_ltrainer* t);  /* n_params gradient entries, the
 int bb_ltrainer_get_params(bb_ltrainer* t, double* const* weights_host, double* const* biases_host);
 int bb_ltrainer_step(bb_ltrainer* t, const float* x_dev, int batch_rows, const bb_train_hyper* h, int phase,
                      double* loss_accum_dev, bb_stream_t stream);
+/*
+ * One training step with config.custom_loss_function = "loss_function_swae" (training.py:70-78, utils.py:27-91):
+ * loss = sum-MSE / n_columns + reg_weight / (B (B - 1)) * mean over projections s and ranks i of
+ * (sort(z P)[s][i] - sort(prior P)[s][i])^2, z the latent batch (output of layer `latent_layer`).  The two random
+ * inputs of utils.compute_swd are the caller's: `prior_dev` [batch_rows][z_dim] (torch.randn_like(z)) and `proj_dev`
+ * [n_projections][z_dim] unit rows (utils.get_random_projections), so a caller that draws them from torch's generator
+ * in the reference's order reproduces the reference's stream.  Upstream encodes twice per step (model(inputs), then
+ * model.encode(inputs)): identical values for a model without dropout / BatchNorm, which is what is accepted here
+ * (BatchNorm layers: BB_ERR_UNSUPPORTED).  2 <= batch_rows <= 2048.  phase as in bb_ltrainer_step.
+ */
+int bb_ltrainer_step_swae(bb_ltrainer* t, const float* x_dev, int batch_rows, const bb_train_hyper* h, int phase,
+                          const float* prior_dev, const float* proj_dev, int n_projections, int latent_layer, float reg_weight,
+                          double* loss_accum_dev, bb_stream_t stream);
 int bb_ltrainer_epoch(bb_ltrainer* t, const float* x_dev, int64_t n_rows, int batch, const bb_train_hyper* h,
                       double* epoch_loss_host, bb_stream_t stream);
 int bb_ltrainer_validate(bb_ltrainer* t, const float* x_dev, int64_t n_rows, int batch, double* epoch_loss_host,

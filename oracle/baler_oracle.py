@@ -93,13 +93,31 @@ def mse_sum_loss(recon, x):
     return float(np.sum((recon - x) ** 2) / x.shape[1])
 
 
-def ae_loss_and_grads(sd, x, reg_param=0.0, l1=False):
+def swd_term(z, prior, proj, reg_weight=100.0):
+    """utils.compute_swd as utils.loss_function_swae calls it (utils.py:27-76) with p = 2: `prior` = the torch.randn_like(z)
+    draws, `proj` [S, D] = utils.get_random_projections (unit rows).  reg_weight / (B (B - 1)) * mean over projections and
+    ranks of (sort(z P^T) - sort(prior P^T))^2, sorted along the batch.  Returns (value, d value / d z)."""
+    z, prior, proj = (np.asarray(a, dtype=np.float64) for a in (z, prior, proj))
+    b, s = z.shape[0], proj.shape[0]
+    lat, pri = z @ proj.T, prior @ proj.T                        # [B, S]
+    order = np.argsort(lat, axis=0, kind="stable")
+    w = np.take_along_axis(lat, order, axis=0) - np.sort(pri, axis=0)
+    coef = reg_weight / (b * (b - 1)) / (s * b)
+    dlat = np.zeros_like(lat)
+    np.put_along_axis(dlat, order, 2.0 * w * coef, axis=0)
+    return float(coef * (w * w).sum()), dlat @ proj
+
+
+def ae_loss_and_grads(sd, x, reg_param=0.0, l1=False, swae=None):
     """Loss and parameter gradients of one `fit` step for the dense AE.
 
     loss = mse_sum_loss  (+ reg_param * l1_chain when `l1`, i.e. utils.mse_sum_loss_l1 with
     validate=False, utils.py:201-209: a SECOND chain v = relu(child(v)) over the 8 Linears,
     ReLU not LeakyReLU, also after the latent and the output; l1 += mean|v| per layer).
     `training.fit` always passes validate=True (training.py:83-89), so l1=False is what ships.
+    swae = (prior, proj[, reg_weight]): config.custom_loss_function == "loss_function_swae" (training.py:70-78): the loss is
+    sum-MSE / n_columns + swd_term(latent), and the encoder receives both gradients (upstream runs the encoder a second time
+    for z, the same values for this model).
     Returns (loss, mse, l1_value, grads dict keyed like the state dict).
     """
     x = np.asarray(x, dtype=np.float64)
@@ -116,8 +134,13 @@ def ae_loss_and_grads(sd, x, reg_param=0.0, l1=False):
     mse = float(np.sum((recon - x) ** 2) / n_cols)
     grads = {}
     d = 2.0 * (recon - x) / n_cols
+    swd = 0.0
+    if swae is not None:
+        swd, dz_swd = swd_term(acts[4], *swae)
     for i in range(7, -1, -1):
         name = AE_LAYERS[i]
+        if i == 3 and swae is not None:
+            d = d + dz_swd
         if i not in (3, 7):
             d = d * np.where(pre[i] > 0, 1.0, LEAKY_SLOPE)
         grads[name + ".weight"] = d.T @ acts[i]
@@ -139,7 +162,7 @@ def ae_loss_and_grads(sd, x, reg_param=0.0, l1=False):
             grads[name + ".weight"] = grads[name + ".weight"] + d.T @ vals[i]
             grads[name + ".bias"] = grads[name + ".bias"] + d.sum(axis=0)
             d = d @ sd[name + ".weight"]
-    loss = mse + (reg_param * l1_val if l1 else 0.0)
+    loss = mse + (reg_param * l1_val if l1 else 0.0) + swd
     return loss, mse, l1_val, grads
 
 

@@ -23,6 +23,8 @@ Fixtures (all float64 unless noted; state-dict tensors stored under "<prefix>/<k
   conv_train.npz    Conv_AE(5, 250) training on 600 5x5 blocks, batch 300: loss, gradients and parameters after 1 and 3 Adam
                     steps (the four 2000-wide Linear weights as every 101st entry + l2 norm), BatchNorm2d running statistics,
                     then training.train() for 2 epochs: loss_data, final_layer, eval-mode reconstruction of 64 blocks
+  swae.npz          CFD_dense_AE(64, 10) (float32), batch 48: utils.loss_function_swae after torch.manual_seed(123) - loss, SWD
+                    term, all gradients, parameters after the Adam step; the prior / projection draws replayed from the seed
   eb_deltas.npz     helper.save_error_bounded_requirement on 4 batches of the trained CMS AE + delta re-application
 """
 import os
@@ -429,6 +431,44 @@ def gen_conv_train():
           os.path.getsize(os.path.join(OUT, "conv_train.npz")) / 1e6, "MB")
 
 
+def gen_swae():
+    """One training step with config.custom_loss_function = "loss_function_swae" exactly as training.fit runs it
+    (training.py:62-92): reconstructions = model(inputs); z = model.encode(inputs); utils.loss_function_swae(inputs, z,
+    reconstructions, latent_dim).  Its random inputs come from torch's global generator in the order randn_like(z), then
+    randn(2000, latent_dim) (utils.py:56-90): seeded here and replayed into the fixture."""
+    rng = np.random.default_rng(5)
+    x = rng.random((48, 64), dtype=np.float32)
+    torch.manual_seed(0)
+    model = ref_models.CFD_dense_AE(64, 10)
+    d = dict(x=x)
+    d.update(sd_np(model, "sd0"))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    model.train()
+    xb = torch.from_numpy(x)
+    opt.zero_grad()
+    recon = model(xb)
+    z = model.encode(xb)
+    torch.manual_seed(123)
+    loss, mse, swd = ref_utils.loss_function_swae(xb, z, recon, 10)
+    loss.backward()
+    d.update(grads_np(model, "g"))
+    opt.step()
+    d.update(sd_np(model, "sd1"))
+    d.update(loss=float(loss), mse=float(mse), swd=float(swd), latent=z.detach().numpy())
+    torch.manual_seed(123)
+    d["prior"] = torch.randn_like(z).numpy()
+    d["proj"] = ref_utils.get_random_projections("normal", 10, 2000).numpy()
+    np.savez_compressed(os.path.join(OUT, "swae.npz"), **d)
+    print("swae", d["loss"], d["mse"], d["swd"], os.path.getsize(os.path.join(OUT, "swae.npz")) / 1e6, "MB")
+    try:  # the float64 AE: z (double) @ projections (float) - does upstream run at all?
+        m64 = ref_models.AE(24, 15)
+        x64 = torch.rand(8, 24, dtype=torch.float64)
+        ref_utils.loss_function_swae(x64, m64.encode(x64), m64(x64), 15)
+        print("swae on the float64 AE: runs")
+    except Exception as e:
+        print("swae on the float64 AE upstream:", type(e).__name__, str(e)[:100])
+
+
 def gen_cfd_dense():
     """CFD_dense_AE(2500, 25) (float32) on 50x50 snapshots, as CFD_project_animation configures it."""
     snaps = synth.cfd_snapshots(60)
@@ -476,6 +516,6 @@ def gen_eb_deltas():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules", "conv_ae", "conv_train", "cfd_dense", "eb_deltas"]
+    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules", "conv_ae", "conv_train", "cfd_dense", "swae", "eb_deltas"]
     for name in which:
         globals()["gen_" + name]()

@@ -401,3 +401,65 @@ def test_layered_trainer_data_parallel_phases():
     assert torch.equal(ranks[0].params_view(), ranks[1].params_view())
     assert rel_max(ranks[0].params_view().cpu().numpy(), full.params_view().cpu().numpy()) <= 1e-5
     assert abs(ranks[0].loss_accum.item() - full.loss_accum.item()) <= 1e-5 * full.loss_accum.item()
+
+
+def _flat_named(sd_like):
+    return np.concatenate([np.concatenate([np.asarray(sd_like[n + ".weight"]).ravel(), np.asarray(sd_like[n + ".bias"]).ravel()])
+                           for n in NAMES]).astype(np.float64)
+
+
+def test_swae_step_matches_reference(golden):
+    """config.custom_loss_function = "loss_function_swae" (training.py:70-78, utils.py:27-91): one step on a float32
+    CFD_dense_AE(64, 10) with the reference's own seeded draws (tests/golden/swae.npz) - loss = sum-MSE / C + sliced
+    Wasserstein term, every gradient, parameters after Adam - and the float64 restatement on a ragged batch"""
+    g = golden("swae.npz")
+    sd0 = sub_sd(g, "sd0")
+    tr = _layered(sd0, 64)
+    x = torch.from_numpy(g["x"]).cuda()
+    prior, proj = torch.from_numpy(g["prior"]).cuda(), torch.from_numpy(g["proj"]).cuda()
+    h = engine.make_hyper(lr=1e-3)
+    tr.step_swae(x, h, prior, proj, latent_layer=3, phase=1)
+    flat = tr.grads_view().cpu().numpy().astype(np.float64)
+    assert abs(flat[-1] - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    ref = _flat_named(sub_sd(g, "g"))
+    assert rel_max(flat[:-1], ref) <= 1e-5 and rel_l2(flat[:-1], ref) <= 1e-5
+    tr.step_swae(x, h, prior, proj, latent_layer=3, phase=2)
+    upd = tr.params_view().cpu().numpy().astype(np.float64) - _flat_named(sd0)
+    ref_upd = _flat_named(sub_sd(g, "sd1")) - _flat_named(sd0)
+    # Adam's first step is lr * g / (|g| + eps): entries whose gradient is ~1e-8 (dead units) move by a noise-decided amount
+    big = np.abs(ref) > 1e-6 * np.abs(ref).max()
+    assert np.abs(upd - ref_upd)[big].max() <= 1e-2 * 1e-3 and np.abs(upd - ref_upd).max() <= 2.1e-3
+    # ragged batch (37 of 64 rows), other draws: against the float64 restatement
+    rng = np.random.default_rng(8)
+    x2 = rng.random((37, 64), dtype=np.float32)
+    pr2 = rng.standard_normal((37, 10)).astype(np.float32)
+    pj2 = rng.standard_normal((500, 10)).astype(np.float32)
+    pj2 /= np.linalg.norm(pj2, axis=1, keepdims=True)
+    tr2 = _layered(sd0, 64)
+    tr2.step_swae(torch.from_numpy(x2).cuda(), h, torch.from_numpy(pr2).cuda(), torch.from_numpy(pj2).cuda(), latent_layer=3,
+                  reg_weight=40.0, phase=1)
+    loss, _, _, grads = orc.ae_loss_and_grads(sd0, x2, swae=(pr2, pj2, 40.0))
+    flat2 = tr2.grads_view().cpu().numpy().astype(np.float64)
+    assert abs(flat2[-1] - loss) <= 1e-5 * loss
+    assert rel_max(flat2[:-1], _flat_named(grads)) <= 1e-5 and rel_l2(flat2[:-1], _flat_named(grads)) <= 1e-5
+
+
+def test_swae_training_through_the_training_module(golden, tmp_path):
+    """training.train with the custom loss: the first epoch (one batch of 48 rows) draws the reference's stream after
+    torch.manual_seed(123) and reproduces its loss; the loss goes down over the epochs"""
+    from types import SimpleNamespace
+    from baler_b200.modules import training
+    g = golden("swae.npz")
+    cfg = SimpleNamespace(deterministic_algorithm=False, batch_size=48, data_dimension=1, model_type="dense", lr=1e-3, reg_param=0.001,
+                          early_stopping=False, early_stopping_patience=100, min_delta=0, lr_scheduler=False, lr_scheduler_patience=50,
+                          epochs=20, test_size=0, intermittent_model_saving=False, intermittent_saving_patience=100, RHO=0.05, l1=True,
+                          activation_extraction=False, custom_loss_function="loss_function_swae", latent_space_size=10)
+    m = models.CFD_dense_AE(64, 10)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sub_sd(g, "sd0").items()})
+    torch.manual_seed(123)
+    training.train(m, 64, g["x"], g["x"], str(tmp_path), cfg)
+    losses = np.load(tmp_path / "loss_data.npy")
+    assert abs(losses[0, 0] - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert np.isfinite(losses).all() and losses[0, -1] < 0.9 * losses[0, 0]
+    with pytest.raises(NotImplementedError):
+        training.DeviceAdam(models.AE_Dropout_BN(24, 15), 1e-3, 64, swae=True)
