@@ -189,3 +189,23 @@ def test_conv_ae_training_spec_maps_reproduce_the_convolutions():
     assert sd["p_x_conv.6.weight"].shape == (8, 1, 2, 5) and sd["p_x_conv.6.weight"].dtype == torch.float32
     assert np.allclose(sd["q_z_conv.0.weight"].numpy().reshape(-1), 2 * sp["weights"][0], rtol=1e-6)
     assert int(sd["p_x_conv.4.num_batches_tracked"]) == before + 5
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): exactly one JSON line on stdout with the
+    contract's keys; under torchrun only rank 0 prints"""
+    import json
+    import sys
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-rows", "20000"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "rows/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["metric"].startswith("compress+decompress rows/s")
+    r1 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=300)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
