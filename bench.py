@@ -398,7 +398,21 @@ def run_ours(args):
                "decode_blocks_per_s": nb / (c1.elapsed_time(c2) * 1e-3),
                "encode_tflops_fp32": nb * flop / (c0.elapsed_time(c1) * 1e-3) / 1e12,
                "note": "layered fp32 GEMM path (CUDA cores); nominal FFMA peak 74.5 TFLOP/s"}
-        del blocks, zc, yc
+        # one training pass over 60k blocks, batch 600 (train-mode BatchNorm2d, sum-MSE, Adam): the layer-by-layer trainer
+        # with the convolutions as weight-sharing dense layers
+        sp = cm.training_spec(5, 5)
+        ctr = engine.LayeredTrainer(sp["weights"], sp["biases"], sp["acts"], 600, dims=sp["dims"], w_maps=sp["w_maps"],
+                                    bn=sp["bn"], loss_columns=1)
+        tb = blocks[:60_000].reshape(-1, 25).contiguous()
+        ctr.epoch(tb[:6000], 600, engine.make_hyper(lr=1e-3))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        closs = ctr.epoch(tb, 600, engine.make_hyper(lr=1e-3))
+        torch.cuda.synchronize()
+        cdt = time.perf_counter() - t0
+        cfd.update(train_blocks_per_s=len(tb) / cdt, train_us_per_step=1e6 * cdt / (len(tb) // 600), train_batch=600,
+                   train_epoch_loss=closs)
+        del blocks, zc, yc, tb, ctr
 
     if world > 1:
         dist.barrier()
