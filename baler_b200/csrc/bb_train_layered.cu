@@ -37,47 +37,53 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
 }
 
 // C[m][n] = sum_k A(m, k) * B(k, n) with A(m, k) = A[m * sam + k * sak], B(k, n) = B[k * sbk + n * sbn];
-// epilogue: + bias[n], activation; fixed summation order (k ascending), one thread per 4 x 4 outputs
+// epilogue: + bias[n], activation; fixed summation order (k ascending: the same bits whatever the tile size), one thread
+// per (TM_ / 16) x (TN_ / 16) outputs.  64 x 64 tiles by default, 32 x 32 when those would leave most SMs without a CTA
+// (the K = 2000 products of Conv_AE have N = 128 or 250: 20 - 40 CTAs with a 125-iteration k loop otherwise).
+template <int TM_, int TN_>
 __global__ void __launch_bounds__(GT)
 gemm_strided_kernel(const float* __restrict__ A, const int64_t sam, const int64_t sak, const float* __restrict__ B,
                     const int64_t sbk, const int64_t sbn, float* __restrict__ C, const int64_t ldc, const int M, const int N,
                     const int K, const float* __restrict__ bias, const int act) {
-  __shared__ float As[TK][TM + 1];
-  __shared__ float Bs[TK][TN + 1];
-  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  constexpr int RM = TM_ / 16, RN = TN_ / 16;
+  __shared__ float As[TK][TM_ + 1];
+  __shared__ float Bs[TK][TN_ + 1];
+  const int m0 = blockIdx.y * TM_, n0 = blockIdx.x * TN_;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  float acc[4][4] = {};
+  float acc[RM][RN] = {};
   for (int k0 = 0; k0 < K; k0 += TK) {
-    for (int e = tid; e < TK * TM; e += GT) {
-      const int kk = e / TM, mm = e - kk * TM;
+    for (int e = tid; e < TK * TM_; e += GT) {
+      const int kk = e / TM_, mm = e - kk * TM_;
       const int m = m0 + mm, k = k0 + kk;
       As[kk][mm] = (m < M && k < K) ? __ldg(A + (int64_t)m * sam + (int64_t)k * sak) : 0.f;
     }
-    for (int e = tid; e < TK * TN; e += GT) {
-      const int kk = e / TN, nn = e - kk * TN;
+    for (int e = tid; e < TK * TN_; e += GT) {
+      const int kk = e / TN_, nn = e - kk * TN_;
       const int n = n0 + nn, k = k0 + kk;
       Bs[kk][nn] = (n < N && k < K) ? __ldg(B + (int64_t)k * sbk + (int64_t)n * sbn) : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
-      float a[4], b[4];
+      float a[RM], b[RN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+      for (int i = 0; i < RM; ++i) a[i] = As[kk][ty * RM + i];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < RN; ++j) b[j] = Bs[kk][tx * RN + j];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < RN; ++j) {
+      const int n = n0 + tx * RN + j;
       if (n < N) C[(int64_t)m * ldc + n] = act_fwd(acc[i][j] + (bias ? __ldg(bias + n) : 0.f), act);
     }
   }
@@ -349,10 +355,17 @@ struct bb_ltrainer {
 
 namespace {
 
+constexpr int SMALL_TILE_BELOW = 148;  // 64 x 64 grids with fewer CTAs than one per SM use 32 x 32 tiles
+
 void lgemm(cudaStream_t s, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
            int M, int N, int K, const float* bias, int act) {
   const dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
-  gemm_strided_kernel<<<grid, GT, 0, s>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act);
+  if ((int)(grid.x * grid.y) >= SMALL_TILE_BELOW) {
+    gemm_strided_kernel<TM, TN><<<grid, GT, 0, s>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act);
+  } else {
+    const dim3 grid32((N + 31) / 32, (M + 31) / 32);
+    gemm_strided_kernel<32, 32><<<grid32, GT, 0, s>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act);
+  }
 }
 
 void expand_tied(bb_ltrainer* t, cudaStream_t s) {
