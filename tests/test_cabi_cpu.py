@@ -209,3 +209,13 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert "workload" in d["config"] and d["metric"].startswith("compress+decompress rows/s")
     r1 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=300)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_header_is_plain_c_and_cxx():
+    """include/baler_b200.h is the drop-in boundary: it must compile on its own as C99 and as C++ (no torch / CUDA types)"""
+    hdr = os.path.join(ROOT, "include", "baler_b200.h")
+    for cc, lang, std in (("gcc", "c", "-std=c99"), ("g++", "c++", "-std=c++17")):
+        r = subprocess.run([cc, std, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", lang, hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    src = open(hdr).read()
+    assert "#include <cuda" not in src and "at::" not in src
