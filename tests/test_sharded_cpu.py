@@ -86,6 +86,53 @@ def _worker(rank, world, port, out_dir):
             assert (full is None) == (rank != 0)
             if rank == 0:
                 assert full.dtype == np.float64 and np.array_equal(full, t[:, :15].astype(np.float64))
+        # --- sharded.DataParallelTrainer itself (the class the GPU trainers run under) on a CPU stand-in trainer built on the
+        # oracle: phase 1 fills [grads | loss], SUM all-reduce, phase 2 applies Adam; a rank with an empty slice of the last
+        # batch contributes zeros; BatchNorm running statistics (one tensor, as the layer-by-layer trainer exposes them)
+        # are averaged over ranks at the end of the epoch
+        class OracleTrainer:
+            def __init__(self):
+                self.opt = orc.Adam({k: sd0[k].copy() for k in keys})
+                self.n = sum(sd0[k].size for k in keys)
+                self.grads = torch.zeros(self.n + 1, dtype=torch.float64)
+                self.loss_accum = torch.zeros(1, dtype=torch.float64)
+                self._bn = True
+                self.running = torch.full((6,), float(rank + 1), dtype=torch.float64)
+
+            def grads_view(self):
+                return self.grads
+
+            def bn_running_views(self):
+                return (self.running,)
+
+            def step(self, xb, hyper, phase):
+                if phase == 1:
+                    l, _, _, gr = orc.ae_loss_and_grads(self.opt.params, xb.numpy())
+                    self.grads.copy_(torch.from_numpy(np.concatenate([gr[k].ravel() for k in keys] + [[l]])))
+                else:
+                    off, summed = 0, {}
+                    for k in keys:
+                        summed[k] = self.grads.numpy()[off:off + sd0[k].size].reshape(sd0[k].shape)
+                        off += sd0[k].size
+                    self.opt.step(summed)
+                    self.loss_accum += self.grads[-1]
+
+        tr = OracleTrainer()
+        dp = sharded.DataParallelTrainer(tr)
+        xt = torch.from_numpy(x[:513])  # global batch 512: the last batch is ONE row, rank 1's slice of it is empty
+        slices = sharded.dp_batch_slices(513, 512, rank, world)
+        assert (slices[-1][1] - slices[-1][0] == 0) == (rank == 1)
+        epoch_loss = dp.epoch([xt[a:b] for a, b in slices], None)
+        single = orc.Adam({k: sd0[k].copy() for k in keys})
+        ref_loss = 0.0
+        for a, b in ((0, 512), (512, 513)):
+            l, _, _, gr = orc.ae_loss_and_grads(single.params, x[a:b])
+            single.step(gr)
+            ref_loss += l
+        assert abs(epoch_loss - ref_loss / 2) < 1e-9 * ref_loss
+        for k in keys:
+            assert rel_max(tr.opt.params[k], single.params[k]) < 1e-9, k
+        assert torch.equal(tr.running, torch.full((6,), 1.5, dtype=torch.float64))
         # --- variable-length host lists (error-bounded-delta hits with global row numbers) collected in rank order
         hits = (np.arange(rank * 5, rank * 5 + 3 + rank, dtype=np.int64), np.full(3 + rank, rank, dtype=np.int64),
                 np.full(3 + rank, 0.5 * rank, dtype=np.float16))
