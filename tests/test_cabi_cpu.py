@@ -219,3 +219,37 @@ def test_header_is_plain_c_and_cxx():
         assert r.returncode == 0, r.stderr
     src = open(hdr).read()
     assert "#include <cuda" not in src and "at::" not in src
+
+
+def test_apply_deltas_host_step_matches_reference(golden, tmp_path):
+    """helper._apply_deltas (the host half of decompress with save_error_bounded_deltas: reads the two gzip'd object-array
+    files baler.py:316-338 writes and subtracts every delta, helper.py:655-665, 708-718) against the reference's corrected
+    batches (tests/golden/eb_deltas.npz), with and without the fused un-normalisation scale"""
+    import gzip
+    from baler_b200.modules import helper
+    g = golden("eb_deltas.npz")
+    bs = g["decoded0"].shape[0]
+    n_b = 2
+
+    def obj(items):
+        a = np.empty(len(items), dtype=object)
+        for i, it in enumerate(items):
+            a[i] = it
+        return a
+
+    index = np.empty(2, dtype=object)
+    index[0] = np.arange(n_b)
+    index[1] = obj([(g["rows%d" % b], g["cols%d" % b]) for b in range(n_b)])
+    paths = [str(tmp_path / "compressed_deltas.npz.gz"), str(tmp_path / "compressed_batch_index_metadata.npz.gz")]
+    for path, arr in zip(paths, (obj([g["deltas%d" % b] for b in range(n_b)]), index)):
+        with gzip.GzipFile(path, "w") as f:
+            np.save(file=f, arr=arr, allow_pickle=True)
+    decoded = np.concatenate([g["decoded%d" % b] for b in range(n_b)])
+    fixed = np.concatenate([g["fixed%d" % b] for b in range(n_b)])
+    out = helper._apply_deltas(decoded.copy(), paths[0], paths[1], bs, None)
+    assert np.array_equal(out, fixed)
+    # un-normalisation fused into the decode kernel: (y - d) * range + min == (y * range + min) - d * range
+    rng = np.linspace(0.5, 4.0, decoded.shape[1])
+    mn = np.linspace(-1.0, 1.0, decoded.shape[1])
+    out2 = helper._apply_deltas(decoded * rng + mn, paths[0], paths[1], bs, rng)
+    assert np.abs(out2 - (fixed * rng + mn)).max() <= 1e-12 * np.abs(fixed * rng + mn).max()
