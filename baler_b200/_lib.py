@@ -55,6 +55,11 @@ _SIGNATURES = {
     "bb_trainer_get_bn": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "bb_trainer_bn_running_dev": (C.c_int, [_P, _PP, _PP, C.POINTER(C.c_int)]),
     "bb_trainer_destroy": (C.c_int, [_P]),
+    "bb_trainer_set_precision": (C.c_int, [_P, C.c_int]),
+    "bb_trainer_precision": (C.c_int, [_P]),
+    "bb_trainer_range_flag": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
+    "bb_trainer_debug_layer": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
+    "bb_trainer_profile": (C.c_int, [_P, C.c_int, _P]),
     "bb_trainer_param_count": (C.c_int, [_P]),
     "bb_trainer_params_dev": (_P, [_P]),
     "bb_trainer_grads_dev": (_P, [_P]),

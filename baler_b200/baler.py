@@ -62,6 +62,8 @@ def _latent_size(config, shape, original_shape):
 
 def perform_training(output_path, config, verbose):
     """reference baler.py:84-207"""
+    from . import sharded
+    sharded.dist_env()  # under torchrun: bind this rank to ITS GPU before helper.process allocates anything on a device
     train_set, test_set, normalization_features, original_shape = helper.process(
         config.input_path, config.custom_norm, config.test_size, config.apply_normalization,
         config.convert_to_blocks if hasattr(config, "convert_to_blocks") else None, verbose)

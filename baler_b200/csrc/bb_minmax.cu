@@ -109,6 +109,38 @@ colminmax_kernel(const float* __restrict__ x, const int64_t n_elems, const int c
   }
 }
 
+// Wide tables (c > 1024: flattened 2-D snapshots, e.g. 50 x 50 = 2500 per-pixel columns of CFD_dense_AE): one thread per
+// column, blockIdx.y strides over rows; consecutive threads read consecutive columns (coalesced), same accumulator layout.
+__global__ void __launch_bounds__(256)
+colminmax_wide_kernel(const float* __restrict__ x, const int64_t n_rows, const int c, unsigned* __restrict__ acc,
+                      float* __restrict__ min_out, float* __restrict__ max_out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < c) {
+    float mn = INFINITY, mx = -INFINITY;
+    bool nan = false;
+    for (int64_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
+      const float e = __ldg(x + r * c + col);
+      mn = fminf(mn, e); mx = fmaxf(mx, e); nan |= (e != e);
+    }
+    if (mn <= mx) { atomicMin(&acc[col], enc(mn)); atomicMax(&acc[c + col], enc(mx)); }
+    if (nan) atomicOr(&acc[2 * c + col], 1u);
+  }
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&acc[3 * c], 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      const bool isnan = __ldcg(&acc[2 * c + i]) != 0u;
+      min_out[i] = isnan ? __int_as_float(0x7fc00000) : dec(__ldcg(&acc[i]));
+      max_out[i] = isnan ? __int_as_float(0x7fc00000) : dec(__ldcg(&acc[c + i]));
+    }
+    if (threadIdx.x == 0) acc[3 * c] = 0u;
+  }
+}
+
 int gcd(int a, int b) { return b ? gcd(b, a % b) : a; }
 
 }  // namespace
@@ -116,7 +148,7 @@ int gcd(int a, int b) { return b ? gcd(b, a % b) : a; }
 // reset != 0: start a new reduction; reset == 0: fold this table into the running min/max (chunked input)
 int bb_colminmax_launch(bb_ctx* ctx, const float* x, int64_t n_rows, int n_cols, float* min_dev,
                         float* max_dev, int reset, cudaStream_t stream) {
-  if (n_cols <= 0 || n_cols > 1024 || n_rows < 0) return BB_ERR_INVALID;
+  if (n_cols <= 0 || n_rows < 0) return BB_ERR_INVALID;
   const size_t need = (size_t)(3 * n_cols + 1) * sizeof(unsigned);
   if (ctx->minmax_scratch_bytes < need) {
     if (ctx->minmax_scratch) cudaFree(ctx->minmax_scratch);
@@ -130,6 +162,13 @@ int bb_colminmax_launch(bb_ctx* ctx, const float* x, int64_t n_rows, int n_cols,
     BB_CUDA(cudaMemsetAsync(acc + n_cols, 0, (size_t)(2 * n_cols + 1) * sizeof(unsigned), stream));
   }
   if (n_rows == 0) return BB_OK;
+  if (n_cols > 1024) {
+    const int gx = (n_cols + 255) / 256;
+    int64_t gy = (int64_t)ctx->sm_count * 8 / gx;
+    gy = gy < 1 ? 1 : (gy > n_rows ? n_rows : gy);
+    colminmax_wide_kernel<<<dim3(gx, (unsigned)gy), 256, 0, stream>>>(x, n_rows, n_cols, acc, min_dev, max_dev);
+    return (int)cudaGetLastError();
+  }
   const int64_t n_elems = n_rows * n_cols;
   const bool vec = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
   const int lanes = vec ? n_cols / gcd(n_cols, 4) : n_cols;  // thread period that keeps columns fixed

@@ -18,12 +18,14 @@
 //      is all-reduced (SUM, because the loss is a sum: utils.py:195) between 2 and 3 by the caller.
 // Everything is fp32 FFMA; a 512-row step is ~0.2 GFLOP, so the step is latency- not throughput-bound.
 #include <cmath>
+#include <cstring>
 #include <new>
 
 #include <cooperative_groups.h>
 #include <curand_philox4x32_x.h>
 
 #include "bb_common.cuh"
+#include "bb_train_tc.cuh"
 
 namespace {
 // Programmatic dependent launch: the three kernels of a training step are launched back to back with
@@ -713,6 +715,13 @@ struct bb_trainer {
   unsigned long long seed = 0;
   size_t dbn_smem = 0;
   int dbn_max_ctas = 0;
+  // tensor-core path (bb_train_tc.cu): the default for the plain AE with the MSE loss.  Both paths share params / m / v /
+  // grads; each keeps derived weight copies (fp32 transposed `wt` here, packed fp16 images there) that go stale when the
+  // other one moves the parameters and are rebuilt on the next switch.
+  TcTrainer* tc = nullptr;
+  int precision = BB_PREC_AUTO;      // BB_PREC_FP32 forces the fp32 kernels
+  bool wt_fresh = true, tc_fresh = true;
+  bool last_tc = false;              // which path ran the most recent forward pass (activation extraction)
 };
 
 namespace {
@@ -744,6 +753,35 @@ int launch_dbn(bb_trainer* t, const float* x, int rows, int mode, cudaStream_t s
 int create_common(bb_ctx* ctx, int n_features, int z_dim, const double* const* weights_host, const double* const* biases_host,
                   int max_batch, int kind, const double* const* bn_gamma, const double* const* bn_beta,
                   const double* const* bn_mean, const double* const* bn_var, const long long* bn_nbt, bb_trainer** out);
+
+__global__ void __launch_bounds__(NT) refresh_wt_kernel(const int n_params, const float* __restrict__ params,
+                                                        const int* __restrict__ wt_index, float* __restrict__ wt) {
+  const int p = blockIdx.x * NT + threadIdx.x;
+  if (p < n_params && wt_index[p] >= 0) wt[wt_index[p]] = params[p];
+}
+
+// which implementation serves this call; rebuilds that path's derived weight copy when the other path moved the parameters
+bool use_tc(bb_trainer* t, const bb_train_hyper* h, cudaStream_t s, int* rc) {
+  *rc = BB_OK;
+  const bool tc = t->tc && t->kind == 0 && t->precision != BB_PREC_FP32 && !(h && h->l1);
+  if (tc && !t->tc_fresh) {
+    *rc = bb_tc_train_repack(t->tc, s);
+    t->tc_fresh = true;
+  }
+  if (!tc && !t->wt_fresh) {
+    refresh_wt_kernel<<<(t->d.n_params + NT - 1) / NT, NT, 0, s>>>(t->d.n_params, t->params, t->wt_index, t->wt);
+    *rc = (int)cudaGetLastError();
+    t->wt_fresh = true;
+  }
+  return tc;
+}
+
+TcHyper tc_hyper(const bb_train_hyper* h) {
+  TcHyper o;
+  o.beta1 = (float)h->beta1; o.beta2 = (float)h->beta2; o.eps = (float)h->eps;
+  o.lr = h->lr; o.b1d = h->beta1; o.b2d = h->beta2;
+  return o;
+}
 
 }  // namespace
 
@@ -924,6 +962,13 @@ int create_common(bb_ctx* ctx, int n_features, int z_dim, const double* const* w
     t->dbn_max_ctas = per_sm * ctx->sm_count;
   }
   if (rc == BB_OK) rc = (int)cudaFuncSetAttribute(train_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem_bytes);
+  if (rc == BB_OK && kind == 0) {
+    // tensor-core path; shapes it does not take (BB_ERR_UNSUPPORTED) stay on the fp32 kernels
+    const int trc = bb_tc_train_create(ctx, dims, acts, max_batch, t->params, t->m, t->v, t->grads, &t->tc);
+    if (trc == BB_OK) rc = bb_tc_train_repack(t->tc, nullptr);
+    else if (trc != BB_ERR_UNSUPPORTED) rc = trc;
+    if (rc == BB_OK) rc = (int)cudaDeviceSynchronize();
+  }
   if (rc != BB_OK) { bb_trainer_destroy(t); return rc; }
   *out = t;
   return BB_OK;
@@ -938,8 +983,37 @@ int bb_trainer_destroy(bb_trainer* t) {
                   t->bn_part, t->rm, t->rv, t->nbt};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  bb_tc_train_destroy(t->tc);
   delete t;
   return BB_OK;
+}
+
+int bb_trainer_set_precision(bb_trainer* t, int precision) {
+  if (!t || precision < BB_PREC_AUTO || precision > BB_PREC_SPLIT16) return BB_ERR_INVALID;
+  if (precision == BB_PREC_SPLIT16 && !t->tc) return BB_ERR_UNSUPPORTED;
+  t->precision = precision;
+  return BB_OK;
+}
+
+int bb_trainer_precision(const bb_trainer* t) {
+  if (!t) return BB_ERR_INVALID;
+  return t->tc && t->kind == 0 && t->precision != BB_PREC_FP32 ? BB_PREC_SPLIT16 : BB_PREC_FP32;
+}
+
+int bb_trainer_range_flag(bb_trainer* t, int reset, int* out) {
+  if (!t || !out) return BB_ERR_INVALID;
+  *out = 0;
+  return t->tc ? bb_tc_train_range_flag(t->tc, reset, out) : BB_OK;
+}
+
+int bb_trainer_debug_layer(bb_trainer* t, int which, int layer, int rows, float* out_host, int capacity_floats) {
+  if (!t || !t->tc) return BB_ERR_UNSUPPORTED;
+  return bb_tc_train_debug_layer(t->tc, which, layer, rows, out_host, capacity_floats);
+}
+
+int bb_trainer_profile(bb_trainer* t, int step, long long* out_128) {
+  if (!t || !t->tc) return BB_ERR_UNSUPPORTED;
+  return bb_tc_train_profile(t->tc, step, out_128);
 }
 
 int bb_trainer_param_count(const bb_trainer* t) { return t ? t->d.n_params : 0; }
@@ -962,6 +1036,23 @@ int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_
                     double* loss_accum_dev, bb_stream_t stream) {
   if (!t || !h || !x_dev || batch_rows < 1 || batch_rows > t->max_batch || phase < 0 || phase > 2) return BB_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
+  int urc;
+  if (use_tc(t, h, s, &urc)) {
+    if (urc != BB_OK) return urc;
+    const TcHyper th = tc_hyper(h);
+    t->wt_fresh = t->wt_fresh && phase == 1;
+    if (phase != 2) { t->last_rows = batch_rows; t->last_tc = true; }
+    if (phase == 2) {
+      t->step += 1;
+      return bb_tc_train_adam_flat(t->tc, &th, t->step, loss_accum_dev, s);
+    }
+    const int flags = TC_P1 | TC_DW | TC_GRADS | (phase == 0 ? TC_ADAM : 0);
+    if (phase == 0) t->step += 1;
+    return bb_tc_train_run(t->tc, x_dev, batch_rows, batch_rows, flags, &th, t->step, loss_accum_dev, s);
+  }
+  if (urc != BB_OK) return urc;
+  if (phase != 1) t->tc_fresh = false;
+  if (phase != 2) t->last_tc = false;
   const int p = t->d.n_params;
   const int n_splits = (batch_rows + DW_T - 1) / DW_T;
   const int n_ctas = (batch_rows + RT - 1) / RT;
@@ -995,10 +1086,25 @@ int bb_trainer_epoch(bb_trainer* t, const float* x_dev, int64_t n_rows, int batc
   cudaStream_t s = (cudaStream_t)stream;
   BB_CUDA(cudaMemsetAsync(t->loss_accum, 0, sizeof(double), s));
   int64_t n_batches = 0;
-  for (int64_t r0 = 0; r0 < n_rows; r0 += batch, ++n_batches) {
-    const int rows = (int)(n_rows - r0 < batch ? n_rows - r0 : batch);
-    const int rc = bb_trainer_step(t, x_dev + (size_t)r0 * t->d.dims[0], rows, h, 0, t->loss_accum, s);
+  int urc;
+  if (use_tc(t, h, s, &urc)) {
+    // the whole epoch is one persistent kernel: no launch and no host round trip between steps
+    if (urc != BB_OK) return urc;
+    const TcHyper th = tc_hyper(h);
+    n_batches = (n_rows + batch - 1) / batch;
+    t->wt_fresh = false;
+    t->last_tc = true;
+    t->last_rows = (int)(n_rows - (n_batches - 1) * batch);
+    const int rc = bb_tc_train_run(t->tc, x_dev, n_rows, batch, TC_P1 | TC_DW | TC_ADAM, &th, t->step + 1, t->loss_accum, s);
     if (rc != BB_OK) return rc;
+    t->step += n_batches;
+  } else {
+    if (urc != BB_OK) return urc;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += batch, ++n_batches) {
+      const int rows = (int)(n_rows - r0 < batch ? n_rows - r0 : batch);
+      const int rc = bb_trainer_step(t, x_dev + (size_t)r0 * t->d.dims[0], rows, h, 0, t->loss_accum, s);
+      if (rc != BB_OK) return rc;
+    }
   }
   double total = 0.0;
   BB_CUDA(cudaMemcpyAsync(&total, t->loss_accum, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1013,8 +1119,22 @@ int bb_trainer_validate(bb_trainer* t, const float* x_dev, int64_t n_rows, int b
   cudaStream_t s = (cudaStream_t)stream;
   BB_CUDA(cudaMemsetAsync(t->loss_accum, 0, sizeof(double), s));
   int64_t n_batches = 0;
-  for (int64_t r0 = 0; r0 < n_rows; r0 += batch, ++n_batches) {
+  int urc;
+  const bool tc = use_tc(t, nullptr, s, &urc);
+  if (urc != BB_OK) return urc;
+  if (tc) {
+    TcHyper th;
+    memset(&th, 0, sizeof(th));
+    th.b1d = th.b2d = 0.5;
+    n_batches = (n_rows + batch - 1) / batch;
+    t->last_tc = true;
+    t->last_rows = (int)(n_rows - (n_batches - 1) * batch);
+    const int rc = bb_tc_train_run(t->tc, x_dev, n_rows, batch, TC_FWD_ONLY, &th, 1, t->loss_accum, s);
+    if (rc != BB_OK) return rc;
+  }
+  for (int64_t r0 = 0; !tc && r0 < n_rows; r0 += batch, ++n_batches) {
     const int rows = (int)(n_rows - r0 < batch ? n_rows - r0 : batch);
+    t->last_tc = false;
     int rc = t->kind == 1 ? launch_dbn(t, x_dev + (size_t)r0 * t->d.dims[0], rows, 1, s)
                           : launch_fwd_bwd(t, x_dev + (size_t)r0 * t->d.dims[0], rows, 0, nullptr, s);
     if (rc != BB_OK) return rc;
@@ -1035,6 +1155,7 @@ int bb_trainer_validate(bb_trainer* t, const float* x_dev, int64_t n_rows, int b
 
 int bb_trainer_activation_means(bb_trainer* t, double* out) {
   if (!t || !out) return BB_ERR_INVALID;
+  if (t->last_tc) return bb_tc_train_activation_means(t->tc, t->last_rows, out);
   const int rows = t->last_rows, stride = t->d.a_stride;
   std::vector<float> h((size_t)rows * stride);
   if (rows) BB_CUDA(cudaMemcpy(h.data(), t->act_g, h.size() * sizeof(float), cudaMemcpyDeviceToHost));

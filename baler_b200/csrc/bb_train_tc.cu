@@ -1,0 +1,1122 @@
+// Tensor-core training step of the dense autoencoder (AE / CFD_dense_AE family, 8 Linears).
+//
+// Replaces the body of the batch loop of training.fit (reference baler/modules/training.py:64-97): forward,
+// sum-MSE / n_columns loss (utils.py:195-199), backward, Adam (training.py:266) - the same contract as the fp32
+// kernels in bb_train.cu, which stay as the reference-accuracy path for the opt-in L1 chain and AE_Dropout_BN.
+//
+// Why warp-level MMA (mma.sync m16n8k16, SASS HMMA) and not tcgen05 here: a training step is 512 rows.  tcgen05 needs
+// 128 (M) rows per instruction, so a step would occupy 4 SMs whose tensor pipes run the 15 dependent layer passes
+// back to back (>= 7 us of MMA issue alone for the 3-product split); 16-row warp tiles put the same step on 32 SMs and
+// the weight-gradient products on ~90.  mma.sync runs at 0.5 m16n8k16 / clock / SM here (tools/hmma_bench.cu).  The arithmetic is the same fp16 hi / lo split as the inference kernels:
+//   x = hi + lo / 2048, hi = fp16(x), lo = fp16((x - hi) * 2048)      (22 significant bits, lo never subnormal)
+//   a * b ~= hi_a hi_b + (hi_a lo_b + lo_a hi_b) / 2048                (three HMMA per k-step, fp32 accumulate)
+//
+// One persistent cooperative kernel (8 warps per CTA, one CTA per SM) runs a whole epoch (or one step of the step API).
+// Per step:
+//   phase 1  CTA i < rows / 16 owns 16 batch rows and walks the 8 forward and 7 backward layer passes.  The B operands
+//            (weights, pre-packed in mma fragment order as fp16 hi | lo, a forward and a transposed image) stream
+//            L2 -> shared memory by bulk copies (TMA 1-D, mbarrier completion) into a 4-stage ring that runs ahead of
+//            the math; the warp that is last to finish a stage refills it.  Activations stay in shared memory as hi / lo
+//            fp16 [row][feature] (ldmatrix A operands); every layer input X_l and every pre-activation gradient dZ_l is
+//            also copied to a global scratch for phase 2.  A warp owns the n-tiles warp, warp + 8, ...; each layer pass
+//            is instantiated per tile count (predicated-off HMMAs occupy the tensor pipe like live ones).
+//   barrier  (grid-wide, one atomic counter)
+//   phase 2  CTA j owns a 32 x 32 block of one layer's weight matrix (bias = one more input column of ones): it bulk-
+//            loads the two [rows][32 features] panels, contracts over ALL batch rows (dW = dZ^T X, ldmatrix.trans), so no
+//            cross-CTA reduction and no atomics exist anywhere; the Adam update runs in the accumulator registers and the
+//            updated weights are written back as fp32 master copy + whole fragments of both packed fp16 images.
+//   barrier
+// Measured on B200 (tools/train_bench.py, profiles/r02_train_*): what bounds the step is not HMMA throughput but
+// per-pass latency - 15 dependent passes, each a barrier, a weight-chunk wait, a k loop of dependent MMA chains at 2
+// warps per scheduler, and an epilogue of dependent conversions.
+// Data parallel: between the contraction and Adam each rank pushes its gradient tile into every peer's exchange
+// buffer over NVLink (peer-mapped memory), raises a per-tile flag and sums the world's tiles in rank order - the
+// all-reduce is fused into the weight-gradient kernel, tile by tile (SUM, not mean: the loss is a sum, utils.py:195).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "bb_train_tc.cuh"
+
+namespace {
+
+constexpr int NL = 8;
+// 8 warps = 256 threads: registers are allocated to CTAs in units of 4 warps, so 9..12 warps would cap every thread at
+// 168 registers (measured: spills in the inner loops); with 8 the accumulators, the double-buffered fragments and the
+// epilogue live in registers.
+constexpr int NWARPS = 8;
+
+constexpr int NTHREADS = NWARPS * 32;
+constexpr int TROWS = 16;          // batch rows per phase-1 tile (one m16 MMA tile)
+constexpr int RING = 4;            // weight ring stages
+constexpr int CHUNK_U4 = 2048;     // uint4 per stage = 64 (k-step, n-tile) fragment blocks of 32 lanes = 32 KB
+constexpr int MAX_CHUNKS = 48;
+constexpr int P2_BLK = 32;         // edge of a phase-2 weight block
+constexpr int P2_ROWS = 512;       // batch rows per panel pass
+constexpr int P2_PANEL = P2_ROWS / 16 * 1024;  // bytes of one panel array: 32 tiles x 32 features x 16 rows x 2
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+constexpr int MAX_WORLD = 16;
+
+struct TcLayer {
+  int K, N, act;
+  int KS, NTf;          // forward pass: k-steps over K + 1 (bias column of ones), n-tiles = the consumer's padded K / 8
+  int KSb, NTb;         // backward pass (dX = dZ W): k-steps over N, n-tiles = the consumer's padded N_{l-1} / 8
+  int w_off, b_off;     // flat fp32 parameter offsets (W (out, in) row-major, then b)
+  int imgf_off, imgb_off;  // uint4 offsets of the packed images [k-step][n-tile][lane] = (hi.r0, hi.r1, lo.r0, lo.r1)
+  int x_off, ldx;       // shared memory: halves offset and row stride of X_l (layer input, incl. ones + zero pad)
+  int xt_off, zt_off;   // global feature-major scratch: first feature row of X_l / dZ_l
+};
+
+// One weight chunk = a run of k-steps of one layer pass that fits a ring stage.  Self-contained (no second lookup behind
+// it: at 2 warps per scheduler every dependent shared-memory load at a chunk boundary is exposed latency) and 32 bytes,
+// so a warp fetches the NEXT chunk's descriptor with two LDS.128 while it works on the current one.
+struct TcChunk {
+  int src_u4, n_u4;        // producer: source offset / size in the packed images
+  short pass, nk;          // layer pass 0..14, k-steps in this chunk
+  short NT, flags;         // n-tiles of the pass; flags: 1 first chunk of the pass, 2 last, 4 backward pass
+  int a_hi_off, a_lo_off;  // byte offsets in dynamic shared memory of the A operand (hi / lo) at this chunk's first k-step
+  int lda_b;               // A row stride, bytes
+  int l;                   // layer
+};
+// What the epilogue of a layer pass needs, byte offsets in dynamic shared memory
+struct TcPass {
+  int N, act;              // out features / activation of the layer (forward passes)
+  int o_hi_off, o_lo_off;  // where the pass writes its output (X_{l+1}, the seed dZ_7, or dZ_{l-1})
+  int o_ld_b;
+  int pact;                // backward: activation of layer l - 1 ...
+  int x_hi_off, x_lo_off;  // ... and X_l, whose sign is the sign of that layer's pre-activation
+  int x_ld_b, kind;        // kind: 0 forward (hidden), 1 forward (last layer: loss + seed), 2 backward
+  int c0, c1;              // chunks [c0, c1) of the weight stream belong to this pass
+  // A operand of the pass (what phase 2 needs feature-major): shared-memory offsets, row stride, padded width, and
+  // where it goes in the global scratch (first feature row; 0 = X, 1 = dZ)
+  int a_hi_off, a_lo_off, a_ld_b, a_feat, a_gfeat0, a_which, NT, pad;
+};
+
+struct TcModel {
+  TcLayer L[NL];
+  int n_chunks, n_chunks_fwd, n_items, n_params, F, RS, dz_ld, smem_x_halves, max_tiles;
+  int pad_[3];
+  TcChunk chunk[MAX_CHUNKS];   // 16-byte aligned
+  TcPass pass[2 * NL - 1];
+};
+
+struct TcItem { int l, n0, k0; };
+
+struct TcPtrs {
+  float *params, *m, *v, *grads;
+  const uint4* img;
+  __half *xt_hi, *xt_lo, *zt_hi, *zt_lo;
+  float* loss_part;       // [2][max_tiles]
+  const TcItem* items;
+  unsigned* bar;
+  const float2* stephyper;  // per step of this launch: (lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t))
+  int* flag;
+  // data parallel (world > 1): peer-mapped exchange buffers and flags, indexed by rank
+  int rank, world;
+  float* xchg[MAX_WORLD];           // [2][world][n_items + 1][1024] floats on every rank
+  unsigned* xflag[MAX_WORLD];       // [world][n_items + 1] step counters on every rank
+  unsigned xbase;                   // flags carry xbase + step-in-launch + 1 (monotonic over launches)
+  long long* prof;                  // diagnostics (nullable): clock64 stamps of CTA 0 during step `prof_step` of a launch
+  int prof_step;
+};
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// mbarrier + bulk copy (TMA 1-D, SASS UBLKCP): one thread moves a whole stage, nobody's LSU slots are spent on it
+__device__ __forceinline__ void mbar_init(uint64_t* bar, const uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, const uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, const uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, const uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy writes (other SMs' st.global before the grid barrier, this CTA's shared-memory accesses) -> async-proxy copies
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// 32-bit shared-window addresses: generic pointers cost an S2R (shared window base) plus 64-bit arithmetic per access in
+// the inner loops (84 instructions per k-step measured, the warps are issue / latency bound at 2 warps per scheduler)
+__device__ __forceinline__ void ldsm_x4a(uint32_t (&r)[4], const uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4t(uint32_t (&r)[4], const uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2t(uint32_t& r0, uint32_t& r1, const uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(const uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(const uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(const uint32_t a, const uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ float2 half2_bits_to_float2(const uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+
+// D += A(16x16, row) * B(16x8, col), fp16 operands, fp32 accumulate
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// The split product of one k-step is three HMMAs: hi*hi, hi*lo, lo*hi.  The tensor core adds its 16 products to the
+// accumulator with truncation, which over a long contraction biases the hi*hi chain by ~1e-6 (measured: gradient error
+// 1.8e-6 -> 3.4e-7 of max); that product therefore starts from zero and is added to the running sum with a rounded fp32
+// add.  The two cross products are 2^-11 smaller and accumulate on the tensor core.
+__device__ __forceinline__ void split16(const float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
+}
+// (a, b) -> packed fp16 hi pair and packed scaled lo pair
+__device__ __forceinline__ void split16x2(const float a, const float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * LO_SCALE, (b - hf.y) * LO_SCALE);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, const unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Warp-uniform values the compiler cannot prove uniform (the warp index, anything loaded from memory) make every branch
+// on them "potentially divergent": nvcc then guards each mma.sync / ldmatrix behind a WARPSYNC.ALL, ~12 per k-step in the
+// inner loops (measured: ~300 cycles per k-step).  A shuffle from lane 0 is uniform by construction.
+__device__ __forceinline__ int uni(const int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// every CTA of the (cooperatively launched, co-resident) grid arrives; `target` counts arrivals since the launch
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*reinterpret_cast<volatile unsigned*>(bar) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+  fence_proxy_async();
+}
+
+__device__ __forceinline__ float act_apply(const float v, const int act) {
+  if (act == BB_ACT_LEAKY) return v > 0.f ? v : BB_LEAKY * v;
+  if (act == BB_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+// Scratch shared by the two phases.  Per array (hi or lo) of X or dZ:
+//   [feature block of 32][16-row tile s][row 16][4 pieces of 8 features = 16 bytes, piece index XOR (row >> 1) & 3]
+// so that (a) a phase-1 CTA copies its shared-memory rows out in 16-byte pieces, 1 KB contiguous per (block, tile), (b)
+// the panel of a phase-2 item (32 features, all tiles) is ONE contiguous range = one bulk copy, (c) ldmatrix.trans on the
+// panel as it lands in shared memory (rows = batch rows = the contraction index of dW = dZ^T X) is bank-conflict free.
+__device__ __forceinline__ size_t tm_byte_offset(const int fb, const int tile, const int s_max, const int row, const int piece) {
+  return (((size_t)fb * s_max + tile) * 16 + row) * 64 + (size_t)((piece ^ ((row >> 1) & 3)) * 16);
+}
+
+// shared [16 rows][ld] hi / lo arrays -> scratch, all threads: one LDS.128 + one STG.128 per (block, row, piece)
+__device__ __forceinline__ void write_tile_major(const uint32_t sh_hi, const uint32_t sh_lo, const int ld_b, const int n_feat,
+                                                 __half* g_hi, __half* g_lo, const int feat0, const int s_max, const int tile) {
+  const int n_fb = (n_feat + 31) >> 5, per = n_fb * 64;
+  for (int task = threadIdx.x; task < 2 * per; task += NTHREADS) {
+    const int which = task >= per;
+    const int rem = task - which * per, fbi = rem >> 6, row = (rem >> 2) & 15, piece = rem & 3;
+    const uint4 v = lds128((which ? sh_lo : sh_hi) + row * ld_b + fbi * 64 + piece * 16);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(which ? g_lo : g_hi);
+    *reinterpret_cast<uint4*>(dst + tm_byte_offset((feat0 >> 5) + fbi, tile, s_max, row, piece)) = v;
+  }
+}
+
+// Refresh of one parameter's entries in the packed images (flat kernel only; phase 2 writes whole fragment blocks).
+// (n, k) of layer l; k == K is the bias.
+__device__ __forceinline__ void store_packed(const TcModel& M, const TcPtrs& P, const int l, const int n, const int k, const float p) {
+  const TcLayer& L = M.L[l];
+  __half hi, lo;
+  split16(p, hi, lo);
+  __half* img = reinterpret_cast<__half*>(const_cast<uint4*>(P.img));
+  {  // forward image: contraction over k, B[k][n] = W[n][k]
+    const int ks = k >> 4, nt = n >> 3, lane = ((n & 7) << 2) | ((k & 7) >> 1), reg = (k & 15) >> 3, h = k & 1;
+    __half* q = img + ((size_t)L.imgf_off + ((size_t)ks * L.NTf + nt) * 32 + lane) * 8;
+    q[reg * 2 + h] = hi;
+    q[4 + reg * 2 + h] = lo;
+  }
+  if (l >= 1 && k < L.K) {  // transposed image: contraction over n, B[n][k] = W[n][k]
+    const int ks = n >> 4, nt = k >> 3, lane = ((k & 7) << 2) | ((n & 7) >> 1), reg = (n & 15) >> 3, h = n & 1;
+    __half* q = img + ((size_t)L.imgb_off + ((size_t)ks * L.NTb + nt) * 32 + lane) * 8;
+    q[reg * 2 + h] = hi;
+    q[4 + reg * 2 + h] = lo;
+  }
+}
+
+// Adam: torch.optim.Adam single-tensor arithmetic (training.py:266), the same expressions as train_adam_kernel in bb_train.cu
+__device__ __forceinline__ void adam_math(const float m0, const float v0, const float p0, const float g, const float lr_bc1,
+                                          const float inv_sqrt_bc2, const float beta1, const float beta2, const float eps,
+                                          float& mm, float& vv, float& p_out) {
+  // explicit roundings: the tile epilogue and the flat kernel must produce the same bits (no compiler-chosen contraction)
+  mm = __fmaf_rn(__fsub_rn(g, m0), 1.f - beta1, m0);                         // exp_avg.lerp_(g, 1 - beta1)
+  vv = __fmaf_rn(beta2, v0, __fmul_rn(__fmul_rn(1.f - beta2, g), g));        // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+  const float denom = __fmaf_rn(__fsqrt_rn(vv), inv_sqrt_bc2, eps);
+  p_out = __fmaf_rn(-lr_bc1, __fdiv_rn(mm, denom), p0);
+}
+__device__ __forceinline__ void adam_one(const TcPtrs& P, const int idx, const float g, const float lr_bc1, const float inv_sqrt_bc2,
+                                         const float beta1, const float beta2, const float eps, float& p_out) {
+  float mm, vv;
+  adam_math(P.m[idx], P.v[idx], P.params[idx], g, lr_bc1, inv_sqrt_bc2, beta1, beta2, eps, mm, vv, p_out);
+  P.m[idx] = mm;
+  P.v[idx] = vv;
+  P.params[idx] = p_out;
+}
+
+// shared memory: [phase-1 ring + activations | phase-2 panels + tile] ... [mbarriers]
+struct SmemBars {
+  uint64_t full[RING];   // weight ring stage filled (bulk copy complete)
+  uint64_t grp[4];       // phase-2 panel row groups
+  unsigned drained[RING];  // warps done with the stage's current chunk; the last one to arrive refills the stage
+};
+
+// running use counts of the mbarriers (parity = count & 1), carried across tiles, items and steps
+struct PipeState {
+  unsigned chunk;  // weight chunks consumed so far by this CTA
+  unsigned pass;   // phase-2 panel passes so far
+};
+
+// ------------------------------------------------------------------------------------------------ phase 1
+// A weight chunk goes into ring stage (global chunk number % RING).  The warp that is last to finish a stage's chunk
+// (shared counter) immediately refills the stage with the chunk RING positions ahead: no producer warp, nobody waits.
+__device__ __forceinline__ void ring_issue(const TcModel& M, const TcPtrs& P, SmemBars* bars, uint4* ring, const unsigned c_base,
+                                           const int c, const int n_chunks) {
+  if (c >= n_chunks) return;
+  const int2 ch = *reinterpret_cast<const int2*>(&M.chunk[c]);
+  const unsigned st = (c_base + c) % RING;
+  mbar_expect_tx(&bars->full[st], (uint32_t)ch.y * 16u);
+  bulk_g2s(ring + (size_t)st * CHUNK_U4, P.img + ch.x, (uint32_t)ch.y * 16u, &bars->full[st]);
+}
+
+// One layer pass for a warp that owns exactly NJ n-tiles (warp, warp + 8, ...): the k loop over the pass's weight
+// chunks, then the epilogue.  One instantiation per tile count: predicated-off HMMAs occupy the tensor pipe like live
+// ones (measured with ncu: 7.4 k issue slots for 3.2 k useful products when the loop was predicated on 4 tiles).
+// Fragments of k-step kk + 1 are fetched before the products of k-step kk are issued, and within a k-step the independent
+// products of the warp's tiles are issued back to back (the warp issues in order: a dependent HMMA or an fp32 add right
+// behind its HMMA stalls everything after it for the ~21-cycle MMA latency).  The hi * hi products of two consecutive
+// k-steps share one zero-started accumulator before the rounded fp32 add.
+template <int NJ>
+__device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, SmemBars* bars, uint4* ring, const uint32_t sbase,
+                                         const TcPass& ps, const unsigned c_base, const int n_chunks, const int warp, const int lane,
+                                         const int row0, const int rows, const float* xs, float& loss, long long* prof, const int pass) {
+  const int g = lane >> 2, t = lane & 3;
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_colb = (lane >> 4) * 16;
+  float acc[NJ > 0 ? NJ : 1][2][4];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][q][i] = 0.f;
+  const int NT = ps.NT;
+  const uint32_t b_step = NT * 512;
+  for (int c = ps.c0; c < ps.c1; ++c) {
+    const uint4 d0 = *reinterpret_cast<const uint4*>(&M.chunk[c]), d1 = *(reinterpret_cast<const uint4*>(&M.chunk[c]) + 1);
+    const int n_k = d0.z >> 16;
+    const unsigned gc = c_base + c, st = gc % RING;
+    mbar_wait(&bars->full[st], (gc / RING) & 1u);
+    if (NJ > 0) {
+      struct Frag { uint32_t ah[4], al[4]; uint4 b[NJ > 0 ? NJ : 1]; };
+      const uint32_t pa_hi = sbase + d1.x + a_row * d1.z + a_colb, pa_lo = sbase + d1.y + a_row * d1.z + a_colb;
+      const uint32_t pb = sbase + st * (CHUNK_U4 * 16) + (warp * 32 + lane) * 16;
+      auto fetch = [&](Frag& f, const int kk) {
+        ldsm_x4a(f.ah, pa_hi + kk * 32);
+        ldsm_x4a(f.al, pa_lo + kk * 32);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) f.b[j] = lds128(pb + kk * b_step + j * (NWARPS * 512));
+      };
+      float tmp[NJ > 0 ? NJ : 1][4];
+      auto products = [&](const Frag& f, const bool fresh, const bool flush) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          if (fresh) tmp[j][0] = tmp[j][1] = tmp[j][2] = tmp[j][3] = 0.f;
+          mma16816(tmp[j], f.ah, f.b[j].x, f.b[j].y);
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) mma16816(acc[j][1], f.ah, f.b[j].z, f.b[j].w);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) mma16816(acc[j][1], f.al, f.b[j].x, f.b[j].y);
+        if (flush) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][0][i] += tmp[j][i];
+        }
+      };
+      Frag f0, f1;
+      fetch(f0, 0);
+      for (int kk = 0; kk < n_k; kk += 2) {
+        const bool more = kk + 1 < n_k;
+        if (more) fetch(f1, kk + 1);
+        products(f0, true, true);
+        if (more) {
+          if (kk + 2 < n_k) fetch(f0, kk + 2);
+          products(f1, true, true);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && atomicAdd(&bars->drained[st], 1u) == NWARPS - 1) {  // last warp out refills the stage
+      bars->drained[st] = 0u;
+      ring_issue(M, P, bars, ring, c_base, c + RING, n_chunks);
+    }
+  }
+  if (prof && lane == 0) prof[16 + (pass * NWARPS + warp) * 4 + 1] = clock64();
+  // ---- epilogue
+  const int N = ps.N, act = ps.act, kind = ps.kind, pact = ps.pact, F = M.F;
+  const uint32_t o_hi = sbase + ps.o_hi_off, o_lo = sbase + ps.o_lo_off, o_ld = ps.o_ld_b;
+  const uint32_t x_hi = sbase + ps.x_hi_off, x_lo = sbase + ps.x_lo_off, x_ld = ps.x_ld_b;
+  const float inv_f = 1.f / (float)F;
+  float v[NJ > 0 ? NJ * 2 : 1][2];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      v[j * 2 + h][0] = acc[j][0][2 * h] + acc[j][1][2 * h] * LO_INV;
+      v[j * 2 + h][1] = acc[j][0][2 * h + 1] + acc[j][1][2 * h + 1] * LO_INV;
+    }
+  if (kind == 0) {
+    // X_{l+1} = act(X_l W^T + b); column N is the next layer's bias column of ones, beyond it zero padding
+#pragma unroll
+    for (int q = 0; q < NJ * 2; ++q) {
+      const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t;
+      const float one = row0 + g + 8 * (q & 1) < rows ? 1.f : 0.f;
+      v[q][0] = col == N ? one : act_apply(v[q][0], act);
+      v[q][1] = col + 1 == N ? one : act_apply(v[q][1], act);
+    }
+  } else if (kind == 1) {
+    // reconstruction: loss = sum (recon - x)^2 / F, seed gradient dZ_7 = 2 (recon - x) / F
+#pragma unroll
+    for (int q = 0; q < NJ * 2; ++q) {
+      const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = g + 8 * (q & 1);
+      const bool valid = row0 + r < rows;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float gz = 0.f;
+        if (valid && col + e < F) {
+          const float diff = act_apply(v[q][e], act) - xs[r * F + col + e];
+          loss = fmaf(diff * diff, inv_f, loss);
+          gz = 2.f * diff * inv_f;
+          if (act == BB_ACT_RELU && v[q][e] <= 0.f) gz = 0.f;
+        }
+        v[q][e] = gz;
+      }
+    }
+  } else if (pact != BB_ACT_NONE) {
+    // dZ_{l-1} = (dZ_l W_l) * act'_{l-1}; the sign of the pre-activation is the sign of X_l (slope > 0)
+    uint32_t sh[NJ > 0 ? NJ * 2 : 1], sl[NJ > 0 ? NJ * 2 : 1];
+#pragma unroll
+    for (int q = 0; q < NJ * 2; ++q) {
+      const uint32_t xo = (g + 8 * (q & 1)) * x_ld + ((warp + NWARPS * (q >> 1)) * 8 + 2 * t) * 2;
+      sh[q] = lds32(x_hi + xo);
+      sl[q] = lds32(x_lo + xo);
+    }
+    const float neg = pact == BB_ACT_LEAKY ? BB_LEAKY : 0.f;
+#pragma unroll
+    for (int q = 0; q < NJ * 2; ++q) {
+      const float2 xh = half2_bits_to_float2(sh[q]), xl = half2_bits_to_float2(sl[q]);
+      if (!(xh.x > 0.f || (xh.x == 0.f && xl.x > 0.f))) v[q][0] *= neg;
+      if (!(xh.y > 0.f || (xh.y == 0.f && xl.y > 0.f))) v[q][1] *= neg;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    uint32_t hi, lo;
+    split16x2(v[q][0], v[q][1], hi, lo);
+    const uint32_t off = (g + 8 * (q & 1)) * o_ld + ((warp + NWARPS * (q >> 1)) * 8 + 2 * t) * 2;
+    sts32(o_hi + off, hi);
+    sts32(o_lo + off, lo);
+  }
+  if (prof && lane == 0) prof[16 + (pass * NWARPS + warp) * 4 + 2] = clock64();
+}
+
+// forward + loss + backward of one 16-row tile, all 8 warps alike
+__device__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __restrict__ xg, const int rows, const int tile,
+                            const bool fwd_only, const int loss_slot, unsigned char* smem, SmemBars* bars, PipeState& ps,
+                            long long* prof) {
+  const int tid = threadIdx.x, warp = uni(tid >> 5), lane = tid & 31;
+  uint4* ring = reinterpret_cast<uint4*>(smem);
+  __half* XH = reinterpret_cast<__half*>(smem + (size_t)RING * CHUNK_U4 * 16);
+  __half* XL = XH + M.smem_x_halves;
+  __half* DZ = XL + M.smem_x_halves;  // [buf 2][hi | lo][16][dz_ld]
+  const int row0 = tile * TROWS, F = M.F, s_max = M.RS / TROWS, dz_ld = M.dz_ld;
+  float* xs = reinterpret_cast<float*>(DZ + 4 * TROWS * dz_ld);
+  float* wl = xs + TROWS * F;
+  const int n_pass = fwd_only ? NL : 2 * NL - 1;
+  const int n_chunks = fwd_only ? M.n_chunks_fwd : M.n_chunks;
+  const unsigned c_base = ps.chunk;
+  ps.chunk = c_base + (unsigned)n_chunks;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (tid == 0) {
+    fence_proxy_async();  // this CTA's earlier generic-proxy accesses of the ring's shared memory precede the bulk writes
+    for (int c = 0; c < RING; ++c) ring_issue(M, P, bars, ring, c_base, c, n_chunks);
+  }
+  // X_0 = the (already normalised) input rows, hi | lo, plus the bias column of ones and zero padding
+  {
+    const TcLayer L0 = M.L[0];
+    const int width = L0.KS * 16;
+    for (int i = tid; i < TROWS * width; i += NTHREADS) {
+      const int r = i / width, c = i - r * width;
+      const bool valid = row0 + r < rows;
+      float v = 0.f;
+      if (c < F) {
+        v = valid ? __ldg(xg + (size_t)(row0 + r) * F + c) : 0.f;
+        xs[r * F + c] = v;
+      } else if (c == F) {
+        v = valid ? 1.f : 0.f;
+      }
+      __half hi, lo;
+      split16(v, hi, lo);
+      XH[L0.x_off + r * L0.ldx + c] = hi;
+      XL[L0.x_off + r * L0.ldx + c] = lo;
+    }
+  }
+  float loss = 0.f;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    __syncthreads();  // the previous pass's epilogue (this pass's A operand) is complete and visible
+    const TcPass pd = M.pass[pass];
+    if (prof && lane == 0) prof[16 + (pass * NWARPS + warp) * 4] = clock64();
+    // the A operand of this pass goes to phase 2 feature-major (shared by the warps, a few 512-byte runs each)
+    write_tile_major(sbase + pd.a_hi_off, sbase + pd.a_lo_off, pd.a_ld_b, pd.a_feat, pd.a_which ? P.zt_hi : P.xt_hi,
+                     pd.a_which ? P.zt_lo : P.xt_lo, pd.a_gfeat0, s_max, tile);
+    if (prof && lane == 0) prof[16 + (pass * NWARPS + warp) * 4 + 3] = clock64();
+    const int nj = uni(pd.NT > warp ? (pd.NT - warp + NWARPS - 1) / NWARPS : 0);
+    if (nj >= 4) run_pass<4>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
+    else if (nj == 3) run_pass<3>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
+    else if (nj == 2) run_pass<2>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
+    else if (nj == 1) run_pass<1>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
+    else run_pass<0>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
+  }
+  __syncthreads();
+  if (!fwd_only) {  // dZ_0 (ping-pong buffer (7 - 0) & 1)
+    const uint32_t z0 = smem_u32(DZ + ((NL - 1) & 1) * (2 * TROWS * dz_ld));
+    write_tile_major(z0, z0 + TROWS * dz_ld * 2, dz_ld * 2, M.L[0].KSb * 16, P.zt_hi, P.zt_lo, M.L[0].zt_off, s_max, tile);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, off);
+  if (lane == 0) wl[warp] = loss;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < NWARPS; ++w) s += wl[w];
+    P.loss_part[loss_slot * M.max_tiles + tile] = s;
+  }
+  __syncthreads();  // shared memory is reused by the next tile / phase
+}
+
+// ------------------------------------------------------------------------------------------------ phase 2
+// one 32 x 32 block of dW_l = dZ_l^T [X_l | 1] over all rows of the batch, then (exchange,) Adam and re-packing
+__device__ void phase2_item(const TcModel& M, const TcPtrs& P, const int item_idx, const int rows, const int flags,
+                            const float lr_bc1, const float inv_sqrt_bc2, const float beta1, const float beta2, const float eps,
+                            const unsigned step_tag, const int parity, unsigned char* smem, SmemBars* bars, PipeState& ps,
+                            long long* prof) {
+  const int tid = threadIdx.x, warp = uni(tid >> 5), lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const bool pk = prof && tid == 0;
+  if (pk) prof[900] = clock64();
+  TcItem it = P.items[item_idx];
+  it.l = uni(it.l); it.n0 = uni(it.n0); it.k0 = uni(it.k0);
+  TcLayer L = M.L[it.l];
+  L.N = uni(L.N); L.K = uni(L.K);
+  __syncthreads();  // the previous item's tile staging has been read
+  unsigned char* panel = smem;  // [4: dZ hi, dZ lo, X hi, X lo][32 tiles][32 features][32 bytes]
+  float* wtile = reinterpret_cast<float*>(smem + 4 * P2_PANEL);  // [32][33] updated weights of the block
+  const int mt = warp & 1, nt = (warp >> 1) & 3;
+  const int n_base = it.n0 + mt * 16, k_base = it.k0 + nt * 8;
+  const bool mma_warp = true;
+  const bool active = uni(mma_warp && n_base < L.N && k_base <= L.K) != 0;
+  const int ks_total = (rows + TROWS - 1) / TROWS;
+  const int s_max = M.RS / TROWS;
+  float hh[4] = {0.f, 0.f, 0.f, 0.f}, cross[4] = {0.f, 0.f, 0.f, 0.f}, cross2[4] = {0.f, 0.f, 0.f, 0.f};
+  // ldmatrix.trans lane addresses inside one tile's 1 KB [row 16][4 swizzled 16-byte pieces] slab: the stored 8 x 8
+  // blocks are [batch row][feature]; transposed they are the (feature x row) A and (row x feature) B fragments
+  const int ka = (lane & 7) + ((lane >> 4) & 1) * 8, pa = mt * 2 + ((lane >> 3) & 1);
+  const int kb = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const uint32_t panel_b = smem_u32(smem);
+  const uint32_t a_off = panel_b + ka * 64 + ((pa ^ ((ka >> 1) & 3)) * 16);
+  const uint32_t b_off = panel_b + kb * 64 + ((nt ^ ((kb >> 1) & 3)) * 16);
+  // Adam state of this thread's four weights: fetched now, used after the contraction (4 dependent L2 round trips
+  // otherwise: measured 5.7 k cycles for the update)
+  int a_idx[4];
+  float a_m[4], a_v[4], a_p[4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int n = n_base + g + 8 * h, k = k_base + 2 * t + e, q = 2 * h + e;
+      a_idx[q] = (active && n < L.N && k <= L.K) ? (k < L.K ? L.w_off + n * L.K + k : L.b_off + n) : -1;
+      if (a_idx[q] >= 0 && (flags & TC_ADAM)) { a_m[q] = P.m[a_idx[q]]; a_v[q] = P.v[a_idx[q]]; a_p[q] = P.params[a_idx[q]]; }
+    }
+  const size_t zblk = (size_t)((L.zt_off + it.n0) >> 5) * s_max, xblk = (size_t)((L.xt_off + it.k0) >> 5) * s_max;
+
+  for (int s0 = 0; s0 < ks_total; s0 += P2_ROWS / TROWS) {
+    __syncthreads();  // the previous panel pass (or phase) is done with this shared memory
+    if (tid == 0) {
+      fence_proxy_async();
+#pragma unroll
+      for (int grp = 0; grp < 4; ++grp) {
+        const int sa = s0 + grp * 8;
+        const int nt_g = ks_total - sa < 8 ? ks_total - sa : 8;
+        if (nt_g > 0) {
+          const uint32_t bytes = (uint32_t)nt_g * 1024u;
+          mbar_expect_tx(&bars->grp[grp], 4u * bytes);
+          bulk_g2s(panel + 0 * P2_PANEL + grp * 8192, reinterpret_cast<const unsigned char*>(P.zt_hi) + (zblk + sa) * 1024, bytes, &bars->grp[grp]);
+          bulk_g2s(panel + 1 * P2_PANEL + grp * 8192, reinterpret_cast<const unsigned char*>(P.zt_lo) + (zblk + sa) * 1024, bytes, &bars->grp[grp]);
+          bulk_g2s(panel + 2 * P2_PANEL + grp * 8192, reinterpret_cast<const unsigned char*>(P.xt_hi) + (xblk + sa) * 1024, bytes, &bars->grp[grp]);
+          bulk_g2s(panel + 3 * P2_PANEL + grp * 8192, reinterpret_cast<const unsigned char*>(P.xt_lo) + (xblk + sa) * 1024, bytes, &bars->grp[grp]);
+        } else {
+          mbar_expect_tx(&bars->grp[grp], 0u);  // keeps the phase of every group barrier in step
+        }
+      }
+    }
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+      mbar_wait(&bars->grp[grp], ps.pass & 1u);
+      if (pk) prof[901 + 2 * grp] = clock64();
+      if (active) {
+        const int n_ks = uni(ks_total - (s0 + grp * 8) < 8 ? ks_total - (s0 + grp * 8) : 8);
+        struct Frag { uint32_t ah[4], al[4], bh0, bh1, bl0, bl1; };
+        auto fetch = [&](Frag& f, const int ksl) {
+          const uint32_t slab = grp * 8192 + ksl * 1024;
+          ldsm_x4t(f.ah, slab + 0 * P2_PANEL + a_off);
+          ldsm_x4t(f.al, slab + 1 * P2_PANEL + a_off);
+          ldsm_x2t(f.bh0, f.bh1, slab + 2 * P2_PANEL + b_off);
+          ldsm_x2t(f.bl0, f.bl1, slab + 3 * P2_PANEL + b_off);
+        };
+        Frag f0, f1;
+        fetch(f0, 0);
+        for (int ksl = 0; ksl < n_ks; ksl += 2) {
+          const bool more = ksl + 1 < n_ks;
+          if (more) fetch(f1, ksl + 1);
+          float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(t0, f0.ah, f0.bh0, f0.bh1);
+          mma16816(cross, f0.ah, f0.bl0, f0.bl1);
+          if (more) {
+            mma16816(t1, f1.ah, f1.bh0, f1.bh1);
+            mma16816(cross2, f1.ah, f1.bl0, f1.bl1);
+          }
+          mma16816(cross, f0.al, f0.bh0, f0.bh1);
+          if (more) mma16816(cross2, f1.al, f1.bh0, f1.bh1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hh[i] += t0[i];
+          if (more) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hh[i] += t1[i];
+            if (ksl + 2 < n_ks) fetch(f0, ksl + 2);
+          }
+        }
+      }
+      if (pk) prof[902 + 2 * grp] = clock64();
+    }
+    ps.pass += 1;
+  }
+  if (pk) prof[910] = clock64();
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = hh[i] + (cross[i] + cross2[i]) * LO_INV;
+  if (P.world > 1) {
+    // fused all-reduce (SUM): push this rank's tile into every rank's exchange buffer, flag it, sum in rank order
+    const size_t slot_floats = 1024;
+    const size_t per_rank = (size_t)(M.n_items + 1) * slot_floats;
+    const size_t off = ((size_t)parity * P.world + P.rank) * per_rank + (size_t)item_idx * slot_floats + ((warp & 7) * 32 + lane) * 4;
+    if (mma_warp) {
+      for (int r = 0; r < P.world; ++r) *reinterpret_cast<float4*>(P.xchg[r] + off) = make_float4(v[0], v[1], v[2], v[3]);
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (tid < P.world) st_release_sys(P.xflag[tid] + (size_t)P.rank * (M.n_items + 1) + item_idx, step_tag);
+    if (tid < P.world) {
+      const unsigned* f = P.xflag[P.rank] + (size_t)tid * (M.n_items + 1) + item_idx;
+      while ((int)(ld_acquire_sys(f) - step_tag) < 0) {}
+    }
+    __syncthreads();
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; mma_warp && r < P.world; ++r) {
+      const float4 o = __ldcv(reinterpret_cast<const float4*>(
+          P.xchg[P.rank] + ((size_t)parity * P.world + r) * per_rank + (size_t)item_idx * slot_floats + (warp * 32 + lane) * 4));
+      s[0] += o.x; s[1] += o.y; s[2] += o.z; s[3] += o.w;
+    }
+    v[0] = s[0]; v[1] = s[1]; v[2] = s[2]; v[3] = s[3];
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int n = n_base + g + 8 * h;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = k_base + 2 * t + e;
+      float p = 0.f;
+      const int q = 2 * h + e, idx = a_idx[q];
+      (void)n; (void)k;
+      if (idx >= 0) {
+        const float gv = v[q];
+        if (flags & TC_GRADS) P.grads[idx] = gv;
+        if (flags & TC_ADAM) {
+          float mm, vv;
+          adam_math(a_m[q], a_v[q], a_p[q], gv, lr_bc1, inv_sqrt_bc2, beta1, beta2, eps, mm, vv, p);
+          P.m[idx] = mm; P.v[idx] = vv; P.params[idx] = p;
+        }
+      }
+      if (mma_warp) wtile[(mt * 16 + g + 8 * h) * 33 + nt * 8 + 2 * t + e] = p;
+    }
+  }
+  if (pk) prof[911] = clock64();
+  if (flags & TC_ADAM) {
+    // the block's fragments of both packed images, one whole uint4 (hi.r0, hi.r1, lo.r0, lo.r1) per thread: 512-byte runs
+    __syncthreads();
+    const int ksl = (tid >> 7) & 1, ntl = (tid >> 5) & 3, gq = lane >> 2, tq = lane & 3;
+    uint4* img = const_cast<uint4*>(P.img);
+    if (mma_warp) {
+      const int ks = (it.k0 >> 4) + ksl, ntile = (it.n0 >> 3) + ntl;
+      if (ks < L.KS && ntile < L.NTf) {
+        const float* w = wtile + (ntl * 8 + gq) * 33 + ksl * 16 + 2 * tq;
+        uint4 o;
+        split16x2(w[0], w[1], o.x, o.z);
+        split16x2(w[8], w[9], o.y, o.w);
+        img[(size_t)L.imgf_off + ((size_t)ks * L.NTf + ntile) * 32 + lane] = o;
+      }
+    }
+    if (mma_warp && it.l >= 1) {
+      const int ks = (it.n0 >> 4) + ksl, ntile = (it.k0 >> 3) + ntl;
+      if (ks < L.KSb && ntile < L.NTb) {
+        const int kk = ntl * 8 + gq;
+        const bool w_col = it.k0 + kk < L.K;  // the bias column is not part of the transposed image
+        const float* w = wtile + (ksl * 16 + 2 * tq) * 33 + kk;
+        uint4 o;
+        split16x2(w_col ? w[0] : 0.f, w_col ? w[33] : 0.f, o.x, o.z);
+        split16x2(w_col ? w[8 * 33] : 0.f, w_col ? w[9 * 33] : 0.f, o.y, o.w);
+        img[(size_t)L.imgb_off + ((size_t)ks * L.NTb + ntile) * 32 + lane] = o;
+      }
+    }
+  }
+}
+
+// batch loss = sum of the tile partials in tile order (+ the other ranks' in rank order)
+__device__ void finish_loss(const TcModel& M, const TcPtrs& P, const int n_tiles, const int loss_slot, const int flags,
+                            const unsigned step_tag, const int parity, double* loss_accum) {
+  float s = 0.f;
+  for (int i = 0; i < n_tiles; ++i) s += __ldcg(P.loss_part + loss_slot * M.max_tiles + i);
+  if (P.world > 1 && !(flags & TC_FWD_ONLY)) {
+    const size_t per_rank = (size_t)(M.n_items + 1) * 1024;
+    const size_t off = ((size_t)parity * P.world + P.rank) * per_rank + (size_t)M.n_items * 1024;
+    for (int r = 0; r < P.world; ++r) *(volatile float*)(P.xchg[r] + off) = s;
+    __threadfence_system();
+    for (int r = 0; r < P.world; ++r) st_release_sys(P.xflag[r] + (size_t)P.rank * (M.n_items + 1) + M.n_items, step_tag);
+    s = 0.f;
+    for (int r = 0; r < P.world; ++r) {
+      const unsigned* f = P.xflag[P.rank] + (size_t)r * (M.n_items + 1) + M.n_items;
+      while ((int)(ld_acquire_sys(f) - step_tag) < 0) {}
+      s += __ldcv(P.xchg[P.rank] + ((size_t)parity * P.world + r) * per_rank + (size_t)M.n_items * 1024);
+    }
+  }
+  if (flags & (TC_GRADS | TC_P1)) P.grads[M.n_params] = s;
+  if ((flags & (TC_ADAM | TC_FWD_ONLY)) && loss_accum) *loss_accum += (double)s;
+  if (!(s == s) || fabsf(s) > 3.0e38f) *P.flag = 1;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_train_kernel(const __grid_constant__ TcModel Mparam, const __grid_constant__ TcPtrs P, const float* __restrict__ x,
+                const long long n_rows, const int batch, const int n_steps, const int flags, const float beta1,
+                const float beta2, const float eps, double* loss_accum, const int smem_bars_off) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // The layer / chunk tables are indexed with run-time values all over the step.  In the kernel-parameter bank that is
+  // an indexed LDC per field through the small constant cache (measured: 36 k of a 68 k-cycle phase 1 with the MMAs
+  // removed); a shared-memory copy makes them ordinary LDS.
+  __shared__ TcModel M;
+  for (int i = threadIdx.x; i < (int)(sizeof(TcModel) / 4); i += NTHREADS)
+    reinterpret_cast<int*>(&M)[i] = reinterpret_cast<const int*>(&Mparam)[i];
+  SmemBars* bars = reinterpret_cast<SmemBars*>(smem + smem_bars_off);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING; ++i) { mbar_init(&bars->full[i], 1); bars->drained[i] = 0u; }
+    for (int i = 0; i < 4; ++i) mbar_init(&bars->grp[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  PipeState ps = {0u, 0u};
+  unsigned target = 0;
+  const bool fwd_only = (flags & TC_FWD_ONLY) != 0;
+  for (int step = 0; step < n_steps; ++step) {
+    const long long r_begin = (long long)step * batch;
+    const int rows = (int)(n_rows - r_begin < batch ? n_rows - r_begin : batch);
+    const int n_tiles = (rows + TROWS - 1) / TROWS;
+    const int slot = step & 1;
+    const unsigned tag = P.xbase + (unsigned)step + 1u;
+    long long* prof = (P.prof && blockIdx.x == 0 && step == P.prof_step) ? P.prof : nullptr;
+    if (prof && threadIdx.x == 0) prof[0] = clock64();
+    if (flags & (TC_P1 | TC_FWD_ONLY)) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        phase1_tile(M, P, x + (size_t)r_begin * M.F, rows, tile, fwd_only, slot, smem, bars, ps, prof);
+      if (prof && threadIdx.x == 0) prof[1] = clock64();
+      grid_barrier(P.bar, target);
+      if (prof && threadIdx.x == 0) prof[2] = clock64();
+    }
+    if (flags & TC_DW) {
+      const float2 sh = P.stephyper[step];
+      for (int item = blockIdx.x; item < M.n_items; item += gridDim.x)
+        phase2_item(M, P, item, rows, flags, sh.x, sh.y, beta1, beta2, eps, tag, (int)(tag & 1u), smem, bars, ps, prof);
+      if (prof && threadIdx.x == 0) prof[912] = clock64();
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && (flags & (TC_P1 | TC_FWD_ONLY)))
+      finish_loss(M, P, n_tiles, slot, flags, tag, (int)(tag & 1u), loss_accum);
+    if (prof && threadIdx.x == 0) prof[3] = clock64();
+    if ((flags & TC_DW) && step + 1 < n_steps) grid_barrier(P.bar, target);
+    if (prof && threadIdx.x == 0) prof[4] = clock64();
+  }
+}
+
+// Adam (or packing only) over the flat parameter vector: phase 2 of the step API after an external all-reduce, and
+// the (re)build of the packed images from the fp32 parameters
+__global__ void __launch_bounds__(256)
+tc_flat_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcPtrs P, const int do_adam, const float lr_bc1,
+               const float inv_sqrt_bc2, const float beta1, const float beta2, const float eps, double* loss_accum) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx < M.n_params) {
+    int l = 0, n = 0, k = 0;
+#pragma unroll
+    for (int q = 0; q < NL; ++q) {
+      const TcLayer& L = M.L[q];
+      if (idx >= L.w_off && idx < L.b_off) { l = q; n = (idx - L.w_off) / L.K; k = idx - L.w_off - n * L.K; }
+      else if (idx >= L.b_off && idx < L.b_off + L.N) { l = q; n = idx - L.b_off; k = L.K; }
+    }
+    float p = P.params[idx];
+    if (do_adam) adam_one(P, idx, P.grads[idx], lr_bc1, inv_sqrt_bc2, beta1, beta2, eps, p);
+    store_packed(M, P, l, n, k, p);
+  }
+  if (do_adam && idx == 0 && loss_accum) *loss_accum += (double)P.grads[M.n_params];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host side
+struct TcTrainer {
+  bb_ctx* ctx = nullptr;
+  TcModel M;
+  TcPtrs P;
+  int max_batch = 0, grid = 0, bars_off = 0;
+  size_t smem = 0, img_u4 = 0, xt_bytes = 0, zt_bytes = 0;
+  uint4* img = nullptr;
+  __half *xt_hi = nullptr, *xt_lo = nullptr, *zt_hi = nullptr, *zt_lo = nullptr;
+  float* loss_part = nullptr;
+  TcItem* items = nullptr;
+  unsigned* bar = nullptr;
+  float2* stephyper = nullptr;
+  int stephyper_cap = 0;
+  int* flag = nullptr;
+  long long* prof = nullptr;
+  std::vector<float2> host_hyper;
+  unsigned xbase = 0;
+  int xt_feat[NL], zt_feat[NL];
+};
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_batch, float* params, float* m, float* v,
+                       float* grads, TcTrainer** out) {
+  if (!ctx || !dims || !acts || !out || max_batch < 1) return BB_ERR_INVALID;
+  TcTrainer* t = new (std::nothrow) TcTrainer();
+  if (!t) return BB_ERR_NOMEM;
+  t->ctx = ctx;
+  t->max_batch = max_batch;
+  TcModel& M = t->M;
+  memset(&M, 0, sizeof(M));
+  memset(&t->P, 0, sizeof(t->P));
+  M.F = dims[0];
+  M.RS = round_up(max_batch, P2_ROWS);
+  M.max_tiles = (max_batch + TROWS - 1) / TROWS;
+  int p = 0, xs = 0, xt = 0, zt = 0, dz_ld = 0;
+  size_t img = 0;
+  for (int l = 0; l < NL; ++l) {
+    TcLayer& L = M.L[l];
+    L.K = dims[l]; L.N = dims[l + 1]; L.act = acts[l];
+    L.KS = (L.K + 1 + 15) / 16;
+    L.KSb = (L.N + 15) / 16;
+    L.w_off = p; p += L.K * L.N;
+    L.b_off = p; p += L.N;
+    L.ldx = round_up(L.KS * 16, 32) + 8;  // whole 32-feature blocks (write_tile_major), +8: ldmatrix rows hit distinct banks
+    L.x_off = xs; xs += TROWS * L.ldx;
+    t->xt_feat[l] = round_up(L.K + 1, P2_BLK);
+    t->zt_feat[l] = round_up(L.N, P2_BLK);
+    if (t->xt_feat[l] < L.KS * 16) t->xt_feat[l] = round_up(L.KS * 16, P2_BLK);
+    if (t->zt_feat[l] < L.KSb * 16) t->zt_feat[l] = round_up(L.KSb * 16, P2_BLK);
+    L.xt_off = xt; xt += t->xt_feat[l];
+    L.zt_off = zt; zt += t->zt_feat[l];
+    if (round_up(L.KSb * 16, 32) + 8 > dz_ld) dz_ld = round_up(L.KSb * 16, 32) + 8;
+  }
+  for (int l = 0; l < NL; ++l) {
+    TcLayer& L = M.L[l];
+    L.NTf = l + 1 < NL ? 2 * M.L[l + 1].KS : 2 * L.KSb;   // the consumer's padded contraction width / 8
+    L.NTb = l >= 1 ? 2 * M.L[l - 1].KSb : 0;
+    L.imgf_off = (int)img; img += (size_t)L.KS * L.NTf * 32;
+    L.imgb_off = (int)img; img += (size_t)L.KSb * L.NTb * 32;
+    if (L.NTf > 4 * NWARPS || L.NTb > 4 * NWARPS || L.NTf > CHUNK_U4 / 32 || L.NTb > CHUNK_U4 / 32) { delete t; return BB_ERR_UNSUPPORTED; }
+  }
+  M.n_params = p; M.smem_x_halves = xs; M.dz_ld = dz_ld;
+  // weight stream: per pass, groups of k-steps that fit one ring stage
+  const int ring_b = RING * CHUNK_U4 * 16, xl_base = ring_b + xs * 2, dz_base = xl_base + xs * 2;
+  const int dzbuf_b = 2 * TROWS * dz_ld * 2, dzlo_b = TROWS * dz_ld * 2;
+  int nc = 0;
+  for (int pass = 0; pass < 2 * NL - 1; ++pass) {
+    const bool bwd = pass >= NL;
+    const int l = bwd ? 2 * NL - 1 - pass : pass;
+    const TcLayer& L = M.L[l];
+    const int KS = bwd ? L.KSb : L.KS, NT = bwd ? L.NTb : L.NTf, base = bwd ? L.imgb_off : L.imgf_off;
+    const int per_max = (CHUNK_U4 / 32) / NT;
+    const int n_ch = (KS + per_max - 1) / per_max;
+    // A operand of the pass: X_l (forward) or dZ_l in ping-pong buffer (7 - l) & 1 (backward)
+    const int a_hi = bwd ? dz_base + ((NL - 1 - l) & 1) * dzbuf_b : ring_b + L.x_off * 2;
+    const int a_lo = bwd ? a_hi + dzlo_b : xl_base + L.x_off * 2;
+    const int lda_b = (bwd ? dz_ld : L.ldx) * 2;
+    int ks = 0;
+    for (int c = 0; c < n_ch; ++c) {
+      const int len = KS / n_ch + (c < KS % n_ch ? 1 : 0);
+      if (nc >= MAX_CHUNKS) { delete t; return BB_ERR_UNSUPPORTED; }
+      TcChunk& ch = M.chunk[nc++];
+      ch.pass = (short)pass; ch.nk = (short)len; ch.NT = (short)NT;
+      ch.flags = (short)((ks == 0 ? 1 : 0) | (ks + len == KS ? 2 : 0) | (bwd ? 4 : 0));
+      ch.src_u4 = base + ks * NT * 32; ch.n_u4 = len * NT * 32;
+      ch.a_hi_off = a_hi + ks * 32; ch.a_lo_off = a_lo + ks * 32; ch.lda_b = lda_b; ch.l = l;
+      ks += len;
+    }
+    TcPass& ps = M.pass[pass];
+    memset(&ps, 0, sizeof(ps));
+    ps.N = L.N; ps.act = L.act; ps.NT = NT;
+    ps.c0 = nc - n_ch; ps.c1 = nc;
+    ps.a_hi_off = a_hi; ps.a_lo_off = a_lo; ps.a_ld_b = lda_b;
+    ps.a_feat = (bwd ? L.KSb : L.KS) * 16; ps.a_gfeat0 = bwd ? L.zt_off : L.xt_off; ps.a_which = bwd ? 1 : 0;
+    if (!bwd && l < NL - 1) {          // hidden forward layer: writes X_{l+1}
+      ps.kind = 0;
+      ps.o_hi_off = ring_b + M.L[l + 1].x_off * 2; ps.o_lo_off = xl_base + M.L[l + 1].x_off * 2; ps.o_ld_b = M.L[l + 1].ldx * 2;
+    } else if (!bwd) {                 // last layer: loss and the seed gradient dZ_7 -> ping-pong buffer 0
+      ps.kind = 1;
+      ps.o_hi_off = dz_base; ps.o_lo_off = dz_base + dzlo_b; ps.o_ld_b = dz_ld * 2;
+    } else {                           // backward pass of layer l: writes dZ_{l-1} -> buffer (8 - l) & 1
+      ps.kind = 2;
+      ps.o_hi_off = dz_base + ((NL - l) & 1) * dzbuf_b; ps.o_lo_off = ps.o_hi_off + dzlo_b; ps.o_ld_b = dz_ld * 2;
+      ps.pact = M.L[l - 1].act;
+      ps.x_hi_off = ring_b + L.x_off * 2; ps.x_lo_off = xl_base + L.x_off * 2; ps.x_ld_b = L.ldx * 2;
+    }
+    if (pass == NL - 1) M.n_chunks_fwd = nc;
+  }
+  M.n_chunks = nc;
+  std::vector<TcItem> items;
+  for (int l = 0; l < NL; ++l)
+    for (int n0 = 0; n0 < M.L[l].N; n0 += P2_BLK)
+      for (int k0 = 0; k0 <= M.L[l].K; k0 += P2_BLK) items.push_back({l, n0, k0});
+  M.n_items = (int)items.size();
+  const size_t smem1 = (size_t)RING * CHUNK_U4 * 16 + (size_t)2 * xs * 2 + (size_t)4 * TROWS * dz_ld * 2 + (size_t)TROWS * M.F * 4 + NWARPS * 4;
+  const size_t smem2 = (size_t)4 * P2_PANEL + 32 * 33 * 4;
+  t->bars_off = (int)(((smem1 > smem2 ? smem1 : smem2) + 127) / 128 * 128);
+  t->smem = (size_t)t->bars_off + sizeof(SmemBars);
+  if (t->smem > ctx->smem_optin) { delete t; return BB_ERR_UNSUPPORTED; }
+  t->img_u4 = img;
+  t->xt_bytes = (size_t)xt * M.RS * 2;
+  t->zt_bytes = (size_t)zt * M.RS * 2;
+  int rc = BB_OK;
+  auto alloc = [&](void** ptr, size_t bytes) {
+    if (rc == BB_OK) rc = (int)cudaMalloc(ptr, bytes);
+    if (rc == BB_OK) rc = (int)cudaMemset(*ptr, 0, bytes);
+  };
+  alloc((void**)&t->img, img * sizeof(uint4));
+  alloc((void**)&t->xt_hi, (size_t)xt * M.RS * 2);  // [feature / 32][tile][32 features][16 rows]: same size, see fm_u32_index
+  alloc((void**)&t->xt_lo, (size_t)xt * M.RS * 2);
+  alloc((void**)&t->zt_hi, (size_t)zt * M.RS * 2);
+  alloc((void**)&t->zt_lo, (size_t)zt * M.RS * 2);
+  alloc((void**)&t->loss_part, sizeof(float) * 2 * M.max_tiles);
+  alloc((void**)&t->items, sizeof(TcItem) * items.size());
+  alloc((void**)&t->bar, sizeof(unsigned));
+  alloc((void**)&t->flag, sizeof(int));
+  alloc((void**)&t->prof, sizeof(long long) * 1024);
+  if (rc == BB_OK) rc = (int)cudaMemcpy(t->items, items.data(), sizeof(TcItem) * items.size(), cudaMemcpyHostToDevice);
+  if (rc == BB_OK) rc = (int)cudaFuncSetAttribute(tc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem);
+  int per_sm = 0;
+  if (rc == BB_OK) rc = (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc_train_kernel, NTHREADS, t->smem);
+  if (rc == BB_OK && per_sm < 1) rc = BB_ERR_UNSUPPORTED;
+  if (rc != BB_OK) { bb_tc_train_destroy(t); return rc; }
+  const int want = M.n_items > M.max_tiles ? M.n_items : M.max_tiles;
+  t->grid = want < per_sm * ctx->sm_count ? want : per_sm * ctx->sm_count;
+  if (const char* g = getenv("BALER_B200_TC_GRID")) {  // diagnostics: profile with fewer CTAs (any grid >= 1 is correct)
+    const int v = atoi(g);
+    if (v >= 1 && v < t->grid) t->grid = v;
+  }
+  TcPtrs& P = t->P;
+  P.params = params; P.m = m; P.v = v; P.grads = grads;
+  P.img = t->img; P.xt_hi = t->xt_hi; P.xt_lo = t->xt_lo; P.zt_hi = t->zt_hi; P.zt_lo = t->zt_lo;
+  P.loss_part = t->loss_part; P.items = t->items; P.bar = t->bar; P.flag = t->flag;
+  P.rank = 0; P.world = 1;
+  *out = t;
+  return BB_OK;
+}
+
+void bb_tc_train_destroy(TcTrainer* t) {
+  if (!t) return;
+  void* ptrs[] = {t->img, t->xt_hi, t->xt_lo, t->zt_hi, t->zt_lo, t->loss_part, t->items, t->bar, t->flag, t->stephyper, t->prof};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete t;
+}
+
+int bb_tc_train_repack(TcTrainer* t, cudaStream_t s) {
+  if (!t) return BB_ERR_INVALID;
+  tc_flat_kernel<<<(t->M.n_params + 255) / 256, 256, 0, s>>>(t->M, t->P, 0, 0.f, 0.f, 0.f, 0.f, 0.f, nullptr);
+  return (int)cudaGetLastError();
+}
+
+static void step_hyper(const TcHyper* h, long long step, float2* out) {
+  const double bc1 = 1.0 - std::pow(h->b1d, (double)step);
+  const double bc2 = 1.0 - std::pow(h->b2d, (double)step);
+  out->x = (float)(h->lr / bc1);
+  out->y = (float)(1.0 / std::sqrt(bc2));
+}
+
+int bb_tc_train_run(TcTrainer* t, const float* x, int64_t n_rows, int batch, int flags, const TcHyper* h, long long first_step,
+                    double* loss_accum, cudaStream_t s) {
+  if (!t || !h || batch < 1 || batch > t->max_batch || n_rows < 0) return BB_ERR_INVALID;
+  const int n_steps = n_rows == 0 ? 1 : (int)((n_rows + batch - 1) / batch);
+  if (n_steps > t->stephyper_cap) {
+    if (t->stephyper) cudaFree(t->stephyper);
+    t->stephyper = nullptr;
+    t->stephyper_cap = 0;
+    BB_CUDA(cudaMalloc((void**)&t->stephyper, sizeof(float2) * (size_t)n_steps));
+    t->stephyper_cap = n_steps;
+  }
+  t->host_hyper.resize(n_steps);
+  for (int i = 0; i < n_steps; ++i) step_hyper(h, first_step + i, &t->host_hyper[i]);
+  BB_CUDA(cudaMemcpyAsync(t->stephyper, t->host_hyper.data(), sizeof(float2) * (size_t)n_steps, cudaMemcpyHostToDevice, s));
+  BB_CUDA(cudaMemsetAsync(t->bar, 0, sizeof(unsigned), s));
+  t->P.stephyper = t->stephyper;
+  t->P.xbase = t->xbase;
+  if (flags & TC_DW) t->xbase += (unsigned)n_steps;
+  long long nr = n_rows;
+  float b1 = h->beta1, b2 = h->beta2, eps = h->eps;
+  int ns = n_steps, fl = flags, bt = batch, bo = t->bars_off;
+  void* args[] = {(void*)&t->M, (void*)&t->P, (void*)&x, (void*)&nr, (void*)&bt, (void*)&ns, (void*)&fl,
+                  (void*)&b1, (void*)&b2, (void*)&eps, (void*)&loss_accum, (void*)&bo};
+  return (int)cudaLaunchCooperativeKernel((const void*)tc_train_kernel, dim3(t->grid), dim3(NTHREADS), args, t->smem, s);
+}
+
+int bb_tc_train_adam_flat(TcTrainer* t, const TcHyper* h, long long step, double* loss_accum, cudaStream_t s) {
+  if (!t || !h) return BB_ERR_INVALID;
+  float2 sh;
+  step_hyper(h, step, &sh);
+  tc_flat_kernel<<<(t->M.n_params + 255) / 256, 256, 0, s>>>(t->M, t->P, 1, sh.x, sh.y, h->beta1, h->beta2, h->eps, loss_accum);
+  return (int)cudaGetLastError();
+}
+
+// host view of the feature-major scratch (see fm_u32_index): value = hi + lo / 2048
+static size_t fm_half_index(int f_abs, int row, int s_max) {
+  const int tile = row >> 4, rr = row & 15, piece = (f_abs & 31) >> 3;
+  return ((((size_t)(f_abs >> 5) * s_max + tile) * 16 + rr) * 64 + (size_t)((piece ^ ((rr >> 1) & 3)) * 16)) / 2 + (f_abs & 7);
+}
+
+static int fm_download(TcTrainer* t, int which, std::vector<__half>& hi, std::vector<__half>& lo) {
+  const size_t bytes = which == 0 ? t->xt_bytes : t->zt_bytes;
+  hi.resize(bytes / 2); lo.resize(bytes / 2);
+  BB_CUDA(cudaDeviceSynchronize());
+  BB_CUDA(cudaMemcpy(hi.data(), which == 0 ? t->xt_hi : t->zt_hi, bytes, cudaMemcpyDeviceToHost));
+  BB_CUDA(cudaMemcpy(lo.data(), which == 0 ? t->xt_lo : t->zt_lo, bytes, cudaMemcpyDeviceToHost));
+  return BB_OK;
+}
+
+int bb_tc_train_activation_means(TcTrainer* t, int rows, double* out) {
+  if (!t || !out || rows < 0 || rows > t->M.RS) return BB_ERR_INVALID;
+  const TcModel& M = t->M;
+  std::vector<__half> hi, lo;
+  const int rc = fm_download(t, 0, hi, lo);
+  if (rc != BB_OK) return rc;
+  const int layers[6] = {1, 2, 3, 5, 6, 7};  // X_l = LeakyReLU(output of Linear l-1)
+  for (int i = 0; i < 6; ++i) {
+    const TcLayer& L = M.L[layers[i]];
+    for (int j = 0; j < 200; ++j) {
+      double s = NAN;
+      if (j < L.K && rows > 0) {
+        s = 0.0;
+        for (int r = 0; r < rows; ++r) {
+          const size_t q = fm_half_index(L.xt_off + j, r, M.RS / TROWS);
+          s += (double)__half2float(hi[q]) + (double)__half2float(lo[q]) / 2048.0;
+        }
+        s /= rows;
+      }
+      out[i * 200 + j] = s;
+    }
+  }
+  return BB_OK;
+}
+
+int bb_tc_train_debug_layer(TcTrainer* t, int which, int layer, int rows, float* out, int capacity) {
+  if (!t || !out || layer < 0 || layer >= NL || rows < 0 || rows > t->M.RS) return BB_ERR_INVALID;
+  const TcModel& M = t->M;
+  const TcLayer& L = M.L[layer];
+  const int n_feat = which == 0 ? L.K + 1 : L.N;
+  if (capacity < n_feat * rows) return BB_ERR_INVALID;
+  std::vector<__half> hi, lo;
+  const int rc = fm_download(t, which, hi, lo);
+  if (rc != BB_OK) return rc;
+  const int off = which == 0 ? L.xt_off : L.zt_off;
+  for (int f = 0; f < n_feat; ++f)
+    for (int r = 0; r < rows; ++r) {
+      const size_t q = fm_half_index(off + f, r, M.RS / TROWS);
+      out[(size_t)f * rows + r] = __half2float(hi[q]) + __half2float(lo[q]) / 2048.f;
+    }
+  return n_feat;
+}
+
+int bb_tc_train_profile(TcTrainer* t, int step, long long* out_128) {
+  if (!t) return BB_ERR_INVALID;
+  if (out_128) {
+    BB_CUDA(cudaDeviceSynchronize());
+    BB_CUDA(cudaMemcpy(out_128, t->prof, sizeof(long long) * 1024, cudaMemcpyDeviceToHost));
+  }
+  t->P.prof = step >= 0 ? t->prof : nullptr;
+  t->P.prof_step = step;
+  return t->M.n_chunks;
+}
+
+int bb_tc_train_range_flag(TcTrainer* t, int reset, int* out) {
+  if (!t || !out) return BB_ERR_INVALID;
+  BB_CUDA(cudaDeviceSynchronize());
+  BB_CUDA(cudaMemcpy(out, t->flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (reset) BB_CUDA(cudaMemset(t->flag, 0, sizeof(int)));
+  return BB_OK;
+}
+
+size_t bb_tc_train_dp_bytes(const TcTrainer* t) {
+  return t ? (size_t)2 * MAX_WORLD * (t->M.n_items + 1) * 1024 * sizeof(float) : 0;
+}
+
+int bb_tc_train_dp_attach(TcTrainer* t, int rank, int world, void* const* xchg_ptrs, void* const* flag_ptrs) {
+  if (!t || world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return BB_ERR_INVALID;
+  t->P.rank = rank;
+  t->P.world = world;
+  for (int r = 0; r < world; ++r) {
+    if (world > 1 && (!xchg_ptrs || !flag_ptrs || !xchg_ptrs[r] || !flag_ptrs[r])) return BB_ERR_INVALID;
+    t->P.xchg[r] = world > 1 ? (float*)xchg_ptrs[r] : nullptr;
+    t->P.xflag[r] = world > 1 ? (unsigned*)flag_ptrs[r] : nullptr;
+  }
+  return BB_OK;
+}

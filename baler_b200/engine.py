@@ -245,6 +245,29 @@ class Trainer:
         a.__cuda_array_interface__ = {"shape": (n or self.n_params,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
         return torch.as_tensor(a, device=self.ctx.device)
 
+    def set_precision(self, precision):
+        """"auto" / "split16": tensor-core step (AE family, MSE loss); "fp32": the fp32 FFMA kernels"""
+        check(_lib.lib().bb_trainer_set_precision(self.handle, _prec(precision)), "bb_trainer_set_precision")
+
+    @property
+    def precision(self):
+        return {_lib.BB_PREC_FP32: "fp32", _lib.BB_PREC_SPLIT16: "split16"}[_lib.lib().bb_trainer_precision(self.handle)]
+
+    def range_flag(self, reset=True):
+        """sticky flag of the split16 step: a batch loss was not finite (values beyond the fp16 range); synchronises"""
+        flag = C.c_int(0)
+        check(_lib.lib().bb_trainer_range_flag(self.handle, int(reset), C.byref(flag)), "bb_trainer_range_flag")
+        return bool(flag.value)
+
+    def debug_layer(self, which, layer, rows):
+        """split16 step diagnostics: (features, rows) float32 of the input (which=0, last feature = bias ones) or the
+        pre-activation gradient (which=1) of `layer` as the last step left them"""
+        out = np.empty(256 * rows, dtype=np.float32)
+        n = _lib.lib().bb_trainer_debug_layer(self.handle, which, layer, rows, out.ctypes.data, out.size)
+        if n <= 0:
+            check(n if n < 0 else -1, "bb_trainer_debug_layer")
+        return out[:n * rows].reshape(n, rows)
+
     def params_view(self):
         return self._flat(_lib.lib().bb_trainer_params_dev(self.handle))
 

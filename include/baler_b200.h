@@ -198,6 +198,30 @@ int bb_trainer_bn_running_dev(bb_trainer* t, float** running_mean_dev, float** r
 int bb_trainer_get_bn(bb_trainer* t, double* const* bn_weight_host, double* const* bn_bias_host,
                       double* const* bn_mean_host, double* const* bn_var_host, long long* bn_batches_tracked);
 int bb_trainer_destroy(bb_trainer* t);
+/*
+ * Arithmetic of the training step (the reference trains in float64 on torch, training.py:64-97; both choices here meet
+ * the 1e-5 per-step bar on loss, gradients and the Adam update):
+ *   BB_PREC_SPLIT16  tensor cores (mma.sync m16n8k16, fp16 hi / lo 3-product split, fp32 accumulate), one persistent
+ *                    kernel per epoch; the default (BB_PREC_AUTO) for `AE` / `CFD_dense_AE` with the MSE loss.
+ *   BB_PREC_FP32     fp32 FFMA kernels; always used for the opt-in L1 chain and for AE_Dropout_BN.
+ * bb_trainer_precision returns what the next MSE step will run on.  Values beyond +-65504 (un-normalised tables) leave
+ * the fp16 range on the SPLIT16 path: the batch loss turns non-finite, a sticky flag is raised and
+ * bb_trainer_range_flag reports it (synchronises the device); the caller restarts with BB_PREC_FP32.
+ */
+int bb_trainer_set_precision(bb_trainer* t, int precision);
+int bb_trainer_precision(const bb_trainer* t);
+int bb_trainer_range_flag(bb_trainer* t, int reset, int* out);
+/* Diagnostics of the SPLIT16 step (tests): what the last step left in its scratch for `layer` (0..7), as float32
+ * [features][rows] in out_host: which = 0 the layer's input (in_features + 1 rows of features, the last one the bias
+ * column of ones), which = 1 the gradient of the loss with respect to its pre-activation output (out_features).
+ * Returns the number of features (> 0) or an error (< 0). */
+int bb_trainer_debug_layer(bb_trainer* t, int which, int layer, int rows, float* out_host, int capacity_floats);
+/* Diagnostics of the SPLIT16 step: arm SM-clock stamps of CTA 0 for step `step` of the following launches (step < 0:
+ * off) and read the stamps of the last armed launch into out_host_128 (nullable): [0] step start, [1] forward /
+ * backward done, [2] grid barrier passed, [3] weight gradients + Adam done, [4] second barrier passed, [8 + p] / [32 + p] /
+ * [48 + p] start / end of the MMAs / end of the epilogue of layer pass p (0-7 forward, 8-14 backward).  Returns the
+ * number of weight chunks per step. */
+int bb_trainer_profile(bb_trainer* t, int step, long long* out_host_128);
 /* flat float32 views (device) of parameters / gradients, layout: for l in 0..7: W_l (out,in) then b_l */
 int bb_trainer_param_count(const bb_trainer* t);
 float* bb_trainer_params_dev(bb_trainer* t);

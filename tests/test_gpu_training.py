@@ -25,13 +25,15 @@ def make_trainer(sd, max_batch=512):
     return engine.Trainer([sd[n + ".weight"] for n in NAMES], [sd[n + ".bias"] for n in NAMES], 24, 15, max_batch)
 
 
-@pytest.mark.parametrize("tag,l1", [("mse", False), ("l1", True)])
-def test_step_loss_grads_adam(golden, tag, l1):
+@pytest.mark.parametrize("tag,l1,precision", [("mse", False, "split16"), ("mse", False, "fp32"), ("l1", True, "fp32")])
+def test_step_loss_grads_adam(golden, tag, l1, precision):
+    """`precision`: the tensor-core step (default for the MSE loss) and the fp32 FFMA step (always used for the L1 chain)"""
     g = golden("ae_train.npz")
     sd0 = sub_sd(g, "sd0")
     x = torch.from_numpy(g["x_norm"]).cuda()
     tr = make_trainer(sd0)
-    assert tr.n_params == 61839
+    tr.set_precision(precision)
+    assert tr.precision == precision and tr.n_params == 61839
     hyper = engine.make_hyper(lr=1e-3, reg_param=0.001, l1=l1)
     ref_g = flat(sub_sd(g, "g_" + tag))
     p0 = flat(sd0)
@@ -54,7 +56,11 @@ def test_step_loss_grads_adam(golden, tag, l1):
             du, dr = p - p0, ref_p - p0
             assert rel_max(du[big], dr[big]) <= 2e-4 and rel_l2(du, dr) <= 1e-4, (step, rel_max(du[big], dr[big]), rel_l2(du, dr))
             assert np.abs(du - dr).max() <= 0.05 * 1e-3
-            assert rel_max(p, ref_p) <= 1e-5
+            # Adam's first steps move a weight by lr * g / (|g| + 1e-8): where |g| is ~1e-5 of the largest gradient the
+            # update depends on g's absolute rounding error.  The fp32 path (gradients 1e-7 of max) holds 1e-5 of max|w|;
+            # the split16 path (3e-7 of max: the tensor core truncates inside every 16-product sum) measures 1.04e-5 after
+            # one step and 1.2e-5 after three on a handful of such weights, inside the 2e-4 / 1e-4 update bounds above
+            assert rel_max(p, ref_p) <= (1e-5 if precision == "fp32" else 2e-5)
     np.testing.assert_allclose(losses, g["losses_" + tag], rtol=1e-5)
     w, b = tr.get_params()
     assert w[0].shape == (200, 24) and w[0].dtype == np.float64 and b[7].shape == (24,)
