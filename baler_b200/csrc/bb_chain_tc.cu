@@ -762,9 +762,10 @@ int bb_tc_launch_dbg(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, 
                      int fast, int* flag_dev, int dbg_step, float* dbg_out, int force_groups, cudaStream_t stream) {
   if (!c->tc_ok) return BB_ERR_UNSUPPORTED;
   if (n_rows == 0) return BB_OK;
-  if (c->tc4.ok && in_dtype == BB_F32 && out_dtype == BB_F32 && force_groups == 0 && (dbg_step == -1 || dbg_step == -2)) {
-    const int rc = bb_tc4_launch(ctx, c, in, n_rows, pre_min, pre_range, post_min, post_range, out, fast, flag_dev,
-                                 dbg_step == -2 ? reinterpret_cast<uint32_t*>(dbg_out) : nullptr, stream);
+  if (c->tc4.ok && force_groups == 0 && (dbg_step == -1 || dbg_step == -2)) {
+    // the statically shaped kernel: exact and fast arithmetic, float32 or (on the latent side) float16 rows
+    const int rc = bb_tc4_launch(ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range, out, out_dtype, fast,
+                                 flag_dev, dbg_step == -2 ? reinterpret_cast<uint32_t*>(dbg_out) : nullptr, stream);
     if (rc != BB_ERR_UNSUPPORTED) return rc;
   }
   const TcHost* h = reinterpret_cast<const TcHost*>(c->tc_host);

@@ -50,6 +50,7 @@ struct Tc4Params {
   uint32_t tmem0;       // TMEM base address (0: the CTA owns all 512 columns); a parameter so that addresses are UR adds, not R2UR moves
   uint32_t* probe;      // probe launch: thread 0 writes that address here and the kernel returns
   int pipes;            // tile pipelines in use (2; 1 = experiment: the second pipeline idles)
+  int in_f16, out_f16;  // opt-in float16 latent: the decoder's input / the encoder's output rows are fp16 (126 B / row)
 };
 
 // ------------------------------------------------------------------------------------------------ static program
@@ -221,13 +222,17 @@ __device__ __forceinline__ void mma_f16(uint32_t d, uint32_t a, uint64_t b, uint
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// FAST (BB_PREC_FAST16, opt-in, OUTSIDE the 1e-5 tolerance): only the hi * hi product, a third of the tensor work.
+template <bool FAST>
 __device__ __forceinline__ void issue_kstep(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                             uint32_t idesc, uint32_t acc) {
   if (elect_one()) {
     const uint64_t bh = (uint64_t)b_hi | ((uint64_t)B_DESC_HI << 32), bl = (uint64_t)b_lo | ((uint64_t)B_DESC_HI << 32);
     mma_f16(d, a_hi, bh, idesc, acc);
-    mma_f16(d, a_hi, bl, idesc, 1u);
-    mma_f16(d, a_lo, bh, idesc, 1u);
+    if constexpr (!FAST) {
+      mma_f16(d, a_hi, bl, idesc, 1u);
+      mma_f16(d, a_lo, bh, idesc, 1u);
+    }
   }
   __syncwarp();
 }
@@ -251,7 +256,7 @@ constexpr int kstep_index(const SStep* st, int S, int M) {  // running k-step nu
     }
   return n;
 }
-template <class P, int S, int M, bool TRACE>
+template <class P, int S, int M, bool TRACE, bool FAST>
 __device__ __forceinline__ void issue_mma(const uint32_t tcol, const uint32_t bar_p, const uint32_t sb4, uint32_t& par_sub, uint32_t* tr) {
   constexpr SMma mm = P::step(S).mma[M];
   constexpr SStep all[5] = {P::step(0), P::step(1), P::step(2), P::step(3), P::step(4)};
@@ -277,7 +282,7 @@ __device__ __forceinline__ void issue_mma(const uint32_t tcol, const uint32_t ba
     const uint32_t b_hi = sb4 + ((b_off >> 4) | lbo_f);
     const uint32_t b_lo = sb4 + (((b_off + mat) >> 4) | lbo_f);
     const uint32_t a_hi = tcol + (uint32_t)mm.a_col + 16u * (uint32_t)k;
-    issue_kstep(tcol + (uint32_t)mm.d_col, a_hi, a_hi + 8u, b_hi, b_lo, idesc, (k > 0 || mm.acc) ? 1u : 0u);
+    issue_kstep<FAST>(tcol + (uint32_t)mm.d_col, a_hi, a_hi + 8u, b_hi, b_lo, idesc, (k > 0 || mm.acc) ? 1u : 0u);
     if constexpr (TRACE) { if (tr) tr[2 * (k_index0 + k) + 1] = (uint32_t)clock64(); }
   }
 }
@@ -286,15 +291,15 @@ __device__ __forceinline__ void issue_mma(const uint32_t tcol, const uint32_t ba
 // (both convert, then both issue MMAs); the token does break that, but a step that waits for sub-chunks then holds the
 // pipe idle, and any lane-0 polling loop in the issuer warp makes ptxas treat the warp as divergent and fall back to
 // the slow tcgen05.mma issue sequence (4x slower).  Net effect: -1 % .. -75 %.
-template <class P, int S, bool TRACE>
+template <class P, int S, bool TRACE, bool FAST>
 __device__ __forceinline__ void issue_step(const uint32_t tcol, const uint32_t bar_p, const uint32_t bar_full, const uint32_t sb4,
                                            uint32_t& par_sub, uint32_t* tr) {
-  issue_mma<P, S, 0, TRACE>(tcol, bar_p, sb4, par_sub, tr);
-  if constexpr (P::step(S).n_mma > 1) issue_mma<P, S, 1, TRACE>(tcol, bar_p, sb4, par_sub, tr);
+  issue_mma<P, S, 0, TRACE, FAST>(tcol, bar_p, sb4, par_sub, tr);
+  if constexpr (P::step(S).n_mma > 1) issue_mma<P, S, 1, TRACE, FAST>(tcol, bar_p, sb4, par_sub, tr);
   issue_commit(bar_full);
 }
 
-template <bool ENC, int KA, int NL, bool TRACE, int G>
+template <bool ENC, int KA, int NL, bool TRACE, int G, bool FAST>
 __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t smem_base, const uint32_t bars_base,
                                            const uint32_t in_stage_bytes, const uint32_t in0_off) {
   using P = Prog<ENC, KA, NL>;
@@ -313,7 +318,7 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t sm
   const int64_t tile_stride = (int64_t)gridDim.x * p.pipes;
   const int64_t tile0 = (int64_t)blockIdx.x * p.pipes + G;
   const uint32_t in_s = smem_base + in0_off + (uint32_t)G * 2u * in_stage_bytes;
-  const uint32_t row_bytes = (uint32_t)p.in_dim * 4u;
+  const uint32_t row_bytes = (uint32_t)p.in_dim * (p.in_f16 ? 2u : 4u);
   auto trace = [&](int64_t lt, int slot) {
     if constexpr (TRACE) {
       if (blockIdx.x == 0 && G == p.trace_pipe && lane0 && lt < 16) p.trace[lt * 64 + slot] = (uint32_t)clock64();
@@ -328,8 +333,8 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t sm
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in) + (size_t)tile * TILE * row_bytes;
       const uint32_t bar = bar_p + 8u * (BAR_IN + (uint32_t)(lt & 1));
       const uint32_t bulk = bytes & ~15u;
-      for (uint32_t o = bulk; o < bytes; o += 4)
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + o), "r"(*reinterpret_cast<const uint32_t*>(src + o)) : "memory");
+      for (uint32_t o = bulk; o < bytes; o += 2)
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst + o), "h"(*reinterpret_cast<const uint16_t*>(src + o)) : "memory");
       if (bulk) {
         mbar_expect_tx(bar, bulk);
         bulk_g2s(dst, src, bulk, bar);
@@ -357,11 +362,11 @@ __device__ __forceinline__ void run_issuer(const Tc4Params& p, const uint32_t sm
       trace(lt, 34 + 5 * s_done + 4);
       if (s_done == 0) load_tile(tile + 2 * tile_stride, lt);  // this tile's stage was consumed before a1_ready; off the s0 critical path
     };
-    issue_step<P, 0, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(0);
-    issue_step<P, 1, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(1);
-    issue_step<P, 2, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(2);
-    issue_step<P, 3, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(3);
-    issue_step<P, 4, TRACE>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(4);
+    issue_step<P, 0, TRACE, FAST>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(0);
+    issue_step<P, 1, TRACE, FAST>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(1);
+    issue_step<P, 2, TRACE, FAST>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(2);
+    issue_step<P, 3, TRACE, FAST>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(3);
+    issue_step<P, 4, TRACE, FAST>(tcol, bar_p, bar_full, sb4, par_sub, tr); after_commit(4);
   }
 }
 
@@ -381,8 +386,10 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
   const int64_t tile0 = (int64_t)blockIdx.x * p.pipes + g;
   const int in_dim = p.in_dim, out_dim = p.out_dim;
   const uint8_t* in_s = smem + in0_off + (uint32_t)g * 2u * in_stage_bytes;
-  float* out_s = reinterpret_cast<float*>(smem + out0_off + (uint32_t)g * out_stage_bytes) + (size_t)wq * 32 * out_dim;  // this warp's 32 rows
-  const uint32_t out_s_addr = smem_base + out0_off + (uint32_t)g * out_stage_bytes + (uint32_t)(wq * 32 * out_dim) * 4u;
+  const uint32_t out_elt = p.out_f16 ? 2u : 4u;
+  uint8_t* out_sb = smem + out0_off + (uint32_t)g * out_stage_bytes + (size_t)(wq * 32 * out_dim) * out_elt;  // this warp's 32 rows
+  float* out_s = reinterpret_cast<float*>(out_sb);
+  const uint32_t out_s_addr = smem_base + out0_off + (uint32_t)g * out_stage_bytes + (uint32_t)(wq * 32 * out_dim) * out_elt;
   auto trace = [&](int64_t lt, int slot) {
     if constexpr (TRACE) {
       if (blockIdx.x == 0 && g == p.trace_pipe && wq == 0 && lane == 0 && lt < 16 && (h == 0) != (slot == 1 || slot == 2 || (slot >= 29 && slot <= 31))) p.trace[lt * 64 + slot] = (uint32_t)clock64();
@@ -395,12 +402,16 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
     const int rows = (int)min((int64_t)TILE, p.n_rows - tile * TILE);
     mbar_wait(bar_p + 8u * (BAR_IN + (uint32_t)(lt & 1)), (uint32_t)(lt >> 1) & 1u);
     const float* xr = reinterpret_cast<const float*>(in_s + (uint32_t)(lt & 1) * in_stage_bytes) + row * in_dim;
+    const __half* xr16 = reinterpret_cast<const __half*>(in_s + (uint32_t)(lt & 1) * in_stage_bytes) + row * in_dim;
     trace(lt - 1, 29);
 #pragma unroll
     for (int ks = 0; ks < KA / 16; ++ks) {
       float xv[16];
       const int k0 = ks * 16;
-      if ((in_dim & 3) == 0) {  // 128-bit loads of this row's 16 features
+      if (p.in_f16) {  // float16 latent rows
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xv[j] = (k0 + j < in_dim && row < rows) ? __half2float(xr16[k0 + j]) : 0.f;
+      } else if ((in_dim & 3) == 0) {  // 128-bit loads of this row's 16 features
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -528,7 +539,12 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
         ys[j] = fmaf(y, rm.x, rm.y);                           // y * range + min (data_processing.py:203); {1, 0} when absent
       }
       const bool bad = (bad_mask & (out_dim >= 32 ? 0xFFFFFFFFu : ((1u << out_dim) - 1u))) != 0u;
-      if ((out_dim & 3) == 0) {  // rows are 16-byte multiples: 128-bit stores (2-way instead of 8-way bank conflicts at 24 floats per row)
+      if (p.out_f16) {  // float16 latent rows (the range check above saw the fp32 values)
+        __half* o16 = reinterpret_cast<__half*>(out_sb) + lane * out_dim;
+#pragma unroll
+        for (int j = 0; j < NL; ++j)
+          if (j < out_dim) o16[j] = __float2half_rn(ys[j]);
+      } else if ((out_dim & 3) == 0) {  // rows are 16-byte multiples: 128-bit stores (2-way instead of 8-way bank conflicts at 24 floats per row)
 #pragma unroll
         for (int q = 0; q < NL / 4; ++q)
           if (4 * q < out_dim) reinterpret_cast<float4*>(out_s + lane * out_dim)[q] = make_float4(ys[4 * q], ys[4 * q + 1], ys[4 * q + 2], ys[4 * q + 3]);
@@ -540,8 +556,8 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
       if (bad && row < rows) atomicOr(p.flag, 1);
       trace(lt, 26);
       const int my_rows = min(32, max(0, rows - wq * 32));
-      const uint32_t bytes = (uint32_t)(my_rows * out_dim) * 4u;
-      float* gdst = p.out + ((size_t)tile * TILE + (size_t)wq * 32) * out_dim;
+      const uint32_t bytes = (uint32_t)(my_rows * out_dim) * out_elt;
+      float* gdst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.out) + ((size_t)tile * TILE + (size_t)wq * 32) * out_dim * out_elt);
       if ((bytes & 15u) == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -549,7 +565,11 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
         store_pending = true;
       } else {  // ragged tail: plain stores
         __syncwarp();
-        for (int e = lane; e < my_rows * out_dim; e += 32) gdst[e] = out_s[e];
+        if (p.out_f16) {
+          for (int e = lane; e < my_rows * out_dim; e += 32) reinterpret_cast<__half*>(gdst)[e] = reinterpret_cast<const __half*>(out_sb)[e];
+        } else {
+          for (int e = lane; e < my_rows * out_dim; e += 32) gdst[e] = out_s[e];
+        }
         __syncwarp();
       }
       trace(lt, 27);
@@ -560,7 +580,7 @@ __device__ __forceinline__ void run_epilogue(const Tc4Params& p, const int g, co
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <bool ENC, int KA, int NL, bool TRACE>
+template <bool ENC, int KA, int NL, bool TRACE, bool FAST>
 __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_constant__ Tc4Params p) {
   using P = Prog<ENC, KA, NL>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -579,7 +599,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
   }
   if ((smem_base & 0x3FFFFu) != p.smem_off) __trap();
   const uint32_t bars_base = smem_u32(&bars[0]);
-  const uint32_t in_stage_bytes = (uint32_t)((TILE * p.in_dim * 4 + 127) & ~127);
+  const uint32_t in_stage_bytes = (uint32_t)((TILE * p.in_dim * 4 + 127) & ~127);   // sized for float32 rows either way
   const uint32_t out_stage_bytes = (uint32_t)((TILE * p.out_dim * 4 + 127) & ~127);
   const uint32_t in0_off = (P::W_BYTES + 127u) & ~127u;
   const uint32_t out0_off = in0_off + NPIPE * 2u * in_stage_bytes;
@@ -627,8 +647,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
     }
   }
 
-  if (warp == NPIPE * EPI_WARPS) run_issuer<ENC, KA, NL, TRACE, 0>(p, smem_base, bars_base, in_stage_bytes, in0_off);
-  else if (warp == NPIPE * EPI_WARPS + 1) run_issuer<ENC, KA, NL, TRACE, 1>(p, smem_base, bars_base, in_stage_bytes, in0_off);
+  if (warp == NPIPE * EPI_WARPS) run_issuer<ENC, KA, NL, TRACE, 0, FAST>(p, smem_base, bars_base, in_stage_bytes, in0_off);
+  else if (warp == NPIPE * EPI_WARPS + 1) run_issuer<ENC, KA, NL, TRACE, 1, FAST>(p, smem_base, bars_base, in_stage_bytes, in0_off);
   else run_epilogue<ENC, KA, NL, TRACE>(p, warp / EPI_WARPS, warp & 3, (warp >> 2) % EPI_GROUPS, smem_base, smem, bars_base, in_stage_bytes,
                                         in0_off, out0_off, out_stage_bytes, norm_s);
 
@@ -637,7 +657,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc4_kernel(const __grid_con
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "r"(512) : "memory");
 }
 
-template <bool ENC, int KA, int NL, bool TRACE = false>
+template <bool ENC, int KA, int NL, bool TRACE = false, bool FAST = false>
 int launch_one(const bb_ctx* ctx, Tc4Params p, cudaStream_t stream) {
   using P = Prog<ENC, KA, NL>;
   for (int s = 0; s < P::N_STEPS - 1; ++s) {
@@ -648,7 +668,7 @@ int launch_one(const bb_ctx* ctx, Tc4Params p, cudaStream_t stream) {
   const size_t in_b = ((size_t)TILE * p.in_dim * 4 + 127) & ~(size_t)127;
   const size_t out_b = ((size_t)TILE * p.out_dim * 4 + 127) & ~(size_t)127;
   const size_t smem_bytes = ((P::W_BYTES + 127u) & ~127u) + NPIPE * (2 * in_b + out_b);
-  auto k = chain_tc4_kernel<ENC, KA, NL, TRACE>;
+  auto k = chain_tc4_kernel<ENC, KA, NL, TRACE, FAST>;
   // per instantiation and per device (function attributes belong to a device's context)
   constexpr int MAX_DEV = 64;
   static bool attr_set_d[MAX_DEV] = {};
@@ -690,11 +710,13 @@ int launch_one(const bb_ctx* ctx, Tc4Params p, cudaStream_t stream) {
 
 // Host entry: runs the statically shaped kernel when `c->tc4` says the chain belongs to the family and the buffers
 // are float32 and 16-byte aligned (cp.async.bulk); BB_ERR_UNSUPPORTED tells the caller to use the table-driven kernel.
-int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int64_t n_rows, const float* pre_min, const float* pre_range,
-                  const float* post_min, const float* post_range, void* out, int fast, int* flag_dev, uint32_t* trace,
-                  cudaStream_t stream) {
+int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows, const float* pre_min,
+                  const float* pre_range, const float* post_min, const float* post_range, void* out, int out_dtype, int fast,
+                  int* flag_dev, uint32_t* trace, cudaStream_t stream) {
   const Tc4Plan& t = c->tc4;
-  if (!t.ok || fast) return BB_ERR_UNSUPPORTED;
+  if (!t.ok) return BB_ERR_UNSUPPORTED;
+  // float16 rows only where the latent is: the encoder's output, the decoder's input
+  if ((in_dtype == BB_F16 && t.enc) || (out_dtype == BB_F16 && !t.enc)) return BB_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return BB_ERR_UNSUPPORTED;
   if (n_rows == 0) return BB_OK;
   Tc4Params p;
@@ -706,11 +728,17 @@ int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int64_t n_rows, c
   for (int l = 0; l < 4; ++l) { p.c1[l] = t.c1[l]; p.c2[l] = t.c2[l]; }
   p.in_dim = c->desc.in_dim; p.out_dim = c->desc.out_dim;
   p.flag = flag_dev; p.trace = trace;
+  p.in_f16 = in_dtype == BB_F16; p.out_f16 = out_dtype == BB_F16;
   p.pipes = getenv("BALER_B200_TC4_PIPES") ? atoi(getenv("BALER_B200_TC4_PIPES")) : NPIPE;
   p.trace_pipe = getenv("BALER_B200_TRACE_PIPE") ? atoi(getenv("BALER_B200_TRACE_PIPE")) : 0;
   if (trace != nullptr) {  // SM-clock trace build: the two CMS shapes only
     if (t.enc && t.ka == 32 && t.nl == 16) return launch_one<true, 32, 16, true>(ctx, p, stream);
     if (!t.enc && t.ka == 16 && t.nl == 32) return launch_one<false, 16, 32, true>(ctx, p, stream);
+    return BB_ERR_UNSUPPORTED;
+  }
+  if (fast) {  // single-product mode: the CMS shapes (what the bench reports beside the exact mode)
+    if (t.enc && t.ka == 32 && t.nl == 16) return launch_one<true, 32, 16, false, true>(ctx, p, stream);
+    if (!t.enc && t.ka == 16 && t.nl == 32) return launch_one<false, 16, 32, false, true>(ctx, p, stream);
     return BB_ERR_UNSUPPORTED;
   }
   if (t.enc) {

@@ -108,9 +108,9 @@ void bb_tc_release(Chain* c);
 int bb_tc_launch_dbg(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows, const float* pre_min,
                      const float* pre_range, const float* post_min, const float* post_range, void* out, int out_dtype,
                      int fast, int* flag_dev, int dbg_step, float* dbg_out, int force_groups, cudaStream_t stream);
-int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int64_t n_rows, const float* pre_min, const float* pre_range,
-                  const float* post_min, const float* post_range, void* out, int fast, int* flag_dev, uint32_t* trace,
-                  cudaStream_t stream);
+int bb_tc4_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows, const float* pre_min,
+                  const float* pre_range, const float* post_min, const float* post_range, void* out, int out_dtype, int fast,
+                  int* flag_dev, uint32_t* trace, cudaStream_t stream);
 int bb_tc_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
                  const float* pre_min, const float* pre_range, const float* post_min,
                  const float* post_range, void* out, int out_dtype, int fast, int* flag_dev,

@@ -9,8 +9,9 @@ decode+un-normalise -> reconstruction.  `value` = rows / step time with the tabl
 `e2e` = the same pass through the C-ABI host entry points (bb_compress_host / bb_decompress_host) with
 pinned HOST buffers, H2D / D2H copies inside the timed region.  N > 1: one process per GPU (torchrun), the
 table is row-sharded (100M rows per GPU, weak scaling), the only exchange is the 2 x 24 column min / max.
-`--impl reference` times the reference path restated on its own engine (torch CPU float64, all threads:
-oracle/torch_port.py) on a bounded sample of the same workload; the reference package itself cannot travel.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref, staged by oracle/stage_ref.py) on the host cores:
+helper.compress + helper.decompress as shipped on a bounded sample of the same workload (the restatement on torch CPU,
+oracle/torch_port.py, when the staged package is absent; it is always reported as the labelled best case).
 """
 import argparse
 import json
@@ -35,8 +36,9 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback"}
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "tflops_burst": d["bf16_tflops"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "src": "fallback"}
 
 
 def golden_state_dict():
@@ -91,68 +93,95 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_pass(sd_t, table):
-    """compress + decompress of `table` as the reference computes it, on the reference's own engine (torch CPU,
-    float64) in its best case: oracle/torch_port.py (vectorised normalisation, 8192-row blocks, all threads)"""
-    from oracle import torch_port
-    z, feats = torch_port.compress(sd_t, table)
-    return z, torch_port.decompress(sd_t, z, feats)
-
-
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host thread it can"""
     import torch
     torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
 
 
-def cpu_baseline(sd, sample_rows, repeats=2):
+def reference_measurements(args, detail):
+    """The reference's own CPU implementation of the path on the host cores, from the
+    staged unmodified package (oracle/_ref, kind "reference") when it is there, else from the restatement on torch CPU
+    (oracle/torch_port.py, kind "port").  CUDA must already be hidden from this process."""
     import torch
     use_all_host_threads()
+    from oracle import ref_runner, torch_port
     from oracle import baler_oracle as orc
-    from oracle import torch_port
     from baler_b200 import synth
+    sd = golden_state_dict()
+    rows = args.ref_rows
+    table = synth.cms_table(rows)
+    cores = int(torch.get_num_threads())
+    out = {"cores": cores, "host_cpus": os.cpu_count(), "rows": rows}
     sd_t = torch_port.to_torch(sd)
-    table = synth.cms_table(sample_rows)
-    cpu_reference_pass(sd_t, table[:50000])  # warm up the thread pool
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        cpu_reference_pass(sd_t, table)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    shipped_rows = min(sample_rows, 100_000)
+
+    def port_pass(t):
+        z, feats = torch_port.compress(sd_t, t)
+        return torch_port.decompress(sd_t, z, feats)
+
+    port_pass(table[:50000])
     t0 = time.perf_counter()
-    orc.compress(sd, table[:shipped_rows], batch_size=512, as_shipped=True)
-    shipped = shipped_rows / (time.perf_counter() - t0)
-    return {"value": sample_rows / best, "unit": "rows/s", "cores": int(torch.get_num_threads()), "kind": "port",
-            "sample": "%d rows of the synthetic CMS table; reference path restated on torch CPU float64 (oracle/torch_port.py): "
-                      "compress (min/max + normalise + encode) + decompress (decode + un-normalise), best case "
-                      "(8192-row blocks, preallocated output, all torch threads)" % sample_rows,
-            "as_shipped_compress_loop_rows_per_s": shipped, "host_cpus": os.cpu_count()}
+    port_pass(table)
+    out["port_best_case_rows_per_s"] = rows / (time.perf_counter() - t0)
+    if not ref_runner.available():
+        out["kind"] = "port"
+        out["step"] = lambda: port_pass(table)
+        return out
+    out["kind"] = "reference"
+
+    def shipped():
+        tc, td, dec = ref_runner.compress_decompress_as_shipped(table, synth.CMS_NAMES, sd)
+        return tc, td, dec
+
+    out["step"] = shipped
+    if detail:
+        sec, _ = ref_runner.bare_encode_decode(table, sd, "float64")
+        out["bare_model_f64_rows_per_s"] = rows / sec
+        sec, _ = ref_runner.bare_encode_decode(table, sd, "float32")
+        out["bare_model_f32_rows_per_s"] = rows / sec
+        x = orc.normalize(synth.cms_table(512 * 200, seed=7))
+        for name in ("AE", "AE_Dropout_BN"):
+            ref_runner.fit_pass(name, x[:512 * 10])
+            sec, _ = ref_runner.fit_pass(name, x)
+            out["fit_%s_samples_per_s" % name] = len(x) / sec
+        snaps = synth.cfd_snapshots(60)
+        snaps = (snaps - snaps.min()) / (snaps.max() - snaps.min())
+        blocks = np.ascontiguousarray(snaps.reshape(-1, 1, 5, 5), dtype=np.float32)
+        te, td, nb = ref_runner.conv_encode_decode(blocks)
+        out["conv_ae_encode_blocks_per_s"] = nb / te
+        out["conv_ae_decode_blocks_per_s"] = nb / td
+    return out
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation, all host threads, a bounded sample per step"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from oracle import torch_port
-    from baler_b200 import synth
-    use_all_host_threads()
-    sd = golden_state_dict()
-    sd_t = torch_port.to_torch(sd)
-    rows = args.ref_rows
-    table = synth.cms_table(rows)
+    if os.environ.get("CUDA_VISIBLE_DEVICES", None) != "":
+        # the reference runs on cuda:0 whenever it sees one (helper.py:425-439): re-exec with the GPUs hidden
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"):
+            env.pop(k, None)
+        sys.exit(subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env))
+    m = reference_measurements(args, args.cpu_detail)
+    step = m.pop("step")
+    rows = m["rows"]
     for _ in range(args.warmup):
-        cpu_reference_pass(sd_t, table[: max(rows // 10, 1000)])
+        step()
+    parts = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_pass(sd_t, table)
+        parts.append(step())
     dt = time.perf_counter() - t0
     value = rows * args.steps / dt
-    base = {"value": value, "unit": "rows/s", "cores": int(torch.get_num_threads()), "kind": "port",
-            "sample": "%d rows per step; reference path restated on torch CPU float64 (oracle/torch_port.py), best case" % rows,
-            "host_cpus": os.cpu_count()}
+    what = ("helper.compress + helper.decompress + helper.renormalize of the unmodified reference (oracle/_ref, baler 1.4.0) as "
+            "shipped: float64, DataLoader batches of 512, np.concatenate per batch") if m["kind"] == "reference" else \
+        "reference path restated on torch CPU float64 (oracle/torch_port.py), best case"
+    base = dict(m, value=value, unit="rows/s", sample="%d rows of the synthetic CMS table per step; %s" % (rows, what))
+    if m["kind"] == "reference" and parts and parts[0] is not None:
+        base["compress_rows_per_s"] = rows * len(parts) / sum(p[0] for p in parts)
+        base["decompress_rows_per_s"] = rows * len(parts) / sum(p[1] for p in parts)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -160,6 +189,20 @@ def run_reference(args):
         "config": {"workload": "CMS AE 24->15 compress+decompress, %d-row bounded sample per step on host CPU cores" % rows},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline_subprocess(args):
+    """the cpu_baseline leg of our arm: the reference arm in a child process with the GPUs hidden, C1 - C5 detail"""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--ref-rows", str(args.cpu_rows), "--cpu-detail"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"):
+        env.pop(k, None)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    return {"value": None, "unit": "rows/s", "cores": None, "kind": "unavailable", "sample": (r.stderr or r.stdout)[-300:]}
 
 
 def bind_to_gpu_numa_node(local):
@@ -202,10 +245,8 @@ def run_ours(args):
     if world > 1:
         bind_to_gpu_numa_node(local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL logs (even its version banner at WARN) go to stderr, and only on request
-        os.environ.pop("NCCL_DEBUG", None)
-        if os.environ.get("BENCH_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
+        # stdout carries exactly one JSON line: whatever NCCL logs (NCCL_DEBUG is the launcher's choice) goes to stderr
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
             os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
@@ -277,6 +318,51 @@ def run_ours(args):
     value = n * world / (ms_per_step * 1e-3)
     gpu_launches = launches["n"]
 
+    # ---- the CPU legs first (a child process with the GPUs hidden): the training / CFD lines quote them
+    cpu = cpu_baseline_subprocess(args) if (world == 1 and not args.no_cpu) else None
+
+    # ---- other arithmetic / latent modes of the same kernel (the exact mode meets 1e-5 and is
+    # tensor-bound; the single-product `fast` mode and the float16 latent move towards the HBM roof, outside the tolerance)
+    modes = None
+    if world == 1 and not args.no_modes:
+        modes = {}
+        ns = min(n, 2_000_000)
+        z_ref, y_ref = z[:ns].clone(), y[:ns].clone()
+        mn, mx = engine.colminmax(x)
+        rg = mx - mn
+        for name, prec, zdt in (("exact_f16_latent", precision, torch.float16), ("fast", "fast", torch.float32),
+                                ("fast_f16_latent", "fast", torch.float16)):
+            zz = torch.empty((n, 15), dtype=zdt, device=dev)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            try:
+                for it in range(3):
+                    if it == 2:
+                        ev[0].record()
+                    codec.encode(x, mn, rg, precision=prec, out=zz, check_range=False)
+                    if it == 2:
+                        ev[1].record()
+                    codec.decode(zz, mn, rg, precision=prec, out=y, check_range=False)
+                    if it == 2:
+                        ev[2].record()
+                torch.cuda.synchronize()
+            except Exception as e:  # a mode the loaded library does not take is reported, not fatal
+                modes[name] = {"error": str(e)}
+                continue
+            em, dm = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+            bytes_row = 96 + (30 if zdt == torch.float16 else 60)
+            zerr = ((zz[:ns].float() - z_ref).abs().max() / z_ref.abs().max()).item()
+            yerr = ((y[:ns] - y_ref).abs().max() / y_ref.abs().max()).item()
+            tf = n * FLOP_PER_ROW / (em * 1e-3) / 1e12
+            modes[name] = {"compress_rows_per_s": n / (em * 1e-3), "decompress_rows_per_s": n / (dm * 1e-3),
+                           "encode_tflops": tf, "frac_of_bf16_sustained": tf / peaks["tflops"], "frac_of_bf16_burst": tf / peaks["tflops_burst"],
+                           "hbm_gbs": n * bytes_row / (em * 1e-3) / 1e9, "hbm_frac": n * bytes_row / (em * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                           "bytes_per_row": bytes_row, "latent_err_vs_exact": zerr, "recon_err_vs_exact": yerr,
+                           "within_1e-5": bool(zerr <= 1e-5 and yerr <= 1e-5)}
+            del zz
+        codec.range_flag()  # the fast mode may have tripped it: clear
+        codec.decode(z, mn, rg, precision=precision, out=y, check_range=False)  # leave y as the exact reconstruction
+        del z_ref, y_ref
+
     # ---- e2e: host buffers through the C-ABI pipelines
     e2e = None
     if not args.no_e2e:
@@ -333,50 +419,76 @@ def run_ours(args):
             del z64, y64
         del xh, zh, yh
 
-    # ---- training line (secondary): one epoch of AE on a 600k-row normalised table, bs 512 per GPU
-    train = None
+    # ---- training lines: one epoch over a 600k-row normalised table, batch 512 per GPU (weak scaling: global batch
+    # 512 x N, the reference's batch_size = global batch).  AE on the tensor-core step (and on the fp32 step for
+    # comparison at N = 1), AE_Dropout_BN (BASELINE configs[2]) on the fp32 cooperative kernel.
+    train = train_dbn = None
     if not args.no_train:
         tn = 600_000
         mn, mx = engine.colminmax(x[:tn])
         xt = engine.normalize_table(x[:tn].contiguous(), mn, mx - mn)
+
+        def one_epoch(tr, precision_name):
+            hyper = engine.make_hyper(lr=1e-3, world_size=world)
+            if world == 1:
+                tr.epoch(xt[:51200], 512, hyper)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                loss = tr.epoch(xt, 512, hyper)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                steps = (tn + 511) // 512
+            else:
+                dp = sharded.DataParallelTrainer(tr)
+                batches = [xt[i:i + 512] for i in range(0, tn, 512)]  # each rank: its 512-row slice of a 512*world batch
+                dp.epoch(batches[:100], hyper)
+                sync_all()
+                t0 = time.perf_counter()
+                loss = dp.epoch(batches, hyper)
+                sync_all()
+                dt = time.perf_counter() - t0
+                steps = len(batches)
+            tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+            dt = tdt.item()
+            sps = tn * world / dt
+            return {"samples_per_s": sps, "us_per_step": 1e6 * dt / steps, "steps": steps, "global_batch": 512 * world,
+                    "epoch_loss": loss, "precision": precision_name, "flop_per_sample": 357000, "tflops": sps * 357000 / 1e12,
+                    "roofline": {"bound": "latency (15 dependent layer passes per 512-row step); tensor peak for reference",
+                                 "achieved": sps * 357000 / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                                 "frac": sps * 357000 / 1e12 / peaks["tflops"]}}
+
         torch.manual_seed(0)
         tm = models.AE(24, 15)
         w, b = tm.linear_tensors()
         tr = engine.Trainer(w, b, 24, 15, 512)
-        hyper = engine.make_hyper(lr=1e-3, world_size=world)
+        train = one_epoch(tr, tr.precision)
+        train["model"] = "AE 24-200-100-50-15-50-100-200-24"
         if world == 1:
-            tr.epoch(xt[:51200], 512, hyper)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            loss = tr.epoch(xt, 512, hyper)
-            dt = time.perf_counter() - t0
-            steps = (tn + 511) // 512
-        else:
-            dp = sharded.DataParallelTrainer(tr)
-            batches = [xt[i:i + 512] for i in range(0, tn, 512)]  # each rank: its 512-row slice of a 512*world batch
-            dp.epoch(batches[:100], hyper)
-            sync_all()
-            t0 = time.perf_counter()
-            loss = dp.epoch(batches, hyper)
-            sync_all()
-            dt = time.perf_counter() - t0
-            steps = len(batches)
-        cpu_train = None
-        if world == 1 and not args.no_cpu:
-            from oracle import torch_port
-            use_all_host_threads()
-            sd0 = {k: v.numpy() for k, v in tm.state_dict().items()}
-            xs = xt[:512 * 64].cpu().numpy()
-            torch_port.fit_steps(sd0, xs, 512, 10)
-            _, sec = torch_port.fit_steps(sd0, xs, 512, 300)
-            _, sec_dl = torch_port.fit_steps(sd0, xs, 512, 64, as_shipped=True)
-            cpu_train = {"samples_per_s": 300 * 512 / sec, "cores": int(torch.get_num_threads()), "kind": "port",
-                         "sample": "300 steps of bs 512, reference loop body restated on torch CPU float64 (oracle/torch_port.py)",
-                         "as_shipped_loop_samples_per_s": 64 * 512 / sec_dl,
-                         "as_shipped_note": "64 steps with the batches drawn through torch DataLoader as training.py:253-263 does"}
-        train = {"cpu_baseline": cpu_train, "samples_per_s": tn * world / dt, "us_per_step": 1e6 * dt / steps, "steps": steps,
-                 "global_batch": 512 * world, "epoch_loss": loss, "model": "AE 24-200-100-50-15-50-100-200-24",
-                 "flop_per_sample": 357000, "tflops": tn * world * 357000 / dt / 1e12}
+            tr32 = engine.Trainer(w, b, 24, 15, 512)
+            tr32.set_precision("fp32")
+            train["fp32_step"] = {k: v for k, v in one_epoch(tr32, "fp32").items() if k in ("samples_per_s", "us_per_step", "epoch_loss")}
+            del tr32
+        if cpu and cpu.get("fit_AE_samples_per_s"):
+            train["cpu_baseline"] = {"samples_per_s": cpu["fit_AE_samples_per_s"], "cores": cpu["cores"], "kind": cpu["kind"],
+                                     "sample": "training.fit of the unmodified reference, 200 steps of bs 512 (BASELINE.md C4)"}
+            train["vs_cpu"] = train["samples_per_s"] / cpu["fit_AE_samples_per_s"]
+        del tr
+        torch.manual_seed(0)
+        dm = models.AE_Dropout_BN(24, 15)
+        w, b = dm.linear_tensors()
+        trd = engine.Trainer(w, b, 24, 15, 512, bn=dm.bn_tensors())
+        trd.set_dropout(seed=1234 + rank)
+        train_dbn = one_epoch(trd, "fp32")
+        train_dbn["model"] = "AE_Dropout_BN 24-200-100-50-15-50-100-200-24 (dropout .5/.4/.3/.2, 4 BatchNorm1d)"
+        train_dbn["batchnorm"] = "per-rank batch statistics" if world > 1 else "batch statistics"
+        if cpu and cpu.get("fit_AE_Dropout_BN_samples_per_s"):
+            train_dbn["cpu_baseline"] = {"samples_per_s": cpu["fit_AE_Dropout_BN_samples_per_s"], "cores": cpu["cores"],
+                                         "kind": cpu["kind"],
+                                         "sample": "training.fit of the unmodified reference, 200 steps of bs 512 (BASELINE.md C4)"}
+            train_dbn["vs_cpu"] = train_dbn["samples_per_s"] / cpu["fit_AE_Dropout_BN_samples_per_s"]
+        del trd
 
     # ---- CFD line (secondary, BASELINE configs[3]): Conv_AE on 5x5 blocks of synthetic 50x50 flow-field snapshots,
     # z = 250 (compression_ratio 10, baler.py:130-135), eval mode; the dense-equivalent chain on the fp32 GEMM path
@@ -421,11 +533,18 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     enc_tflops = n * FLOP_PER_ROW / (enc_ms * 1e-3) / 1e12
-    traffic = None
+    dec_tflops = n * FLOP_PER_ROW / (dec_ms * 1e-3) / 1e12
+    traffic = traffic_src = None
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(prof):
         per_row = json.load(open(prof)).get("encode_dram_bytes_per_row")
         traffic = per_row * n if per_row else None
+        traffic_src = "profiles/ncu_traffic.json (dram bytes per row of one ncu --set full capture) x rows of this launch; not measured in this run"
+    if cfd is not None and cpu and cpu.get("conv_ae_encode_blocks_per_s"):
+        cfd["cpu_baseline"] = {"encode_blocks_per_s": cpu["conv_ae_encode_blocks_per_s"], "decode_blocks_per_s": cpu["conv_ae_decode_blocks_per_s"],
+                               "cores": cpu["cores"], "kind": cpu["kind"],
+                               "sample": "Conv_AE(5, 250) of the unmodified reference, eval mode, 6000 blocks, batch 600 (BASELINE.md C5)"}
+        cfd["encode_vs_cpu"] = cfd["encode_blocks_per_s"] / cpu["conv_ae_encode_blocks_per_s"]
     out = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -436,17 +555,28 @@ def run_ours(args):
                    "weights": "reference AE(24,15) trained 2 epochs (tests/golden/ae_cms.npz)"},
         "gpu_launches": gpu_launches, "clocks": clocks,
         "compress_rows_per_s": n / (enc_ms * 1e-3), "decompress_rows_per_s": n / (dec_ms * 1e-3),
+        # useful (un-padded, single-count) FLOPs of the launch over the measured dense bf16 peak.  `frac` uses the
+        # SUSTAINED figure (the kernel is timed inside a long step under the power cap); SURVEY 8(d)'s formula uses the
+        # burst figure: `frac_burst`.
         "roofline": {"bound": "tensor", "achieved": enc_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": enc_tflops / peaks["tflops"], "traffic": traffic, "kernel": "fused encode chain",
-                     "peak_source": peaks["src"] + " (bf16 dense, sustained)", "launch_ms": enc_ms,
+                     "frac": enc_tflops / peaks["tflops"], "peak_burst": peaks["tflops_burst"],
+                     "frac_burst": enc_tflops / peaks["tflops_burst"], "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "chain_tc4_kernel (fused encode chain)",
+                     "peak_source": peaks["src"] + " (bf16 dense; frac: sustained, frac_burst: burst)", "launch_ms": enc_ms,
                      "algorithmic_flop_per_row": FLOP_PER_ROW,
                      "hbm": {"achieved_gbs": n * BYTES_PER_ROW / (enc_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                              "frac": n * BYTES_PER_ROW / (enc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                              "algorithmic_bytes_per_row": BYTES_PER_ROW}},
-        "e2e": e2e, "train": train, "cfd": cfd,
+        "roofline_decode": {"bound": "tensor", "achieved": dec_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                            "frac": dec_tflops / peaks["tflops"], "frac_burst": dec_tflops / peaks["tflops_burst"],
+                            "kernel": "chain_tc4_kernel (fused decode chain)", "launch_ms": dec_ms,
+                            "hbm": {"achieved_gbs": n * BYTES_PER_ROW / (dec_ms * 1e-3) / 1e9,
+                                    "frac": n * BYTES_PER_ROW / (dec_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
+        "modes": modes,
+        "e2e": e2e, "train": train, "train_dbn": train_dbn, "cfd": cfd,
     }
-    if world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(sd, args.cpu_rows)
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -462,12 +592,14 @@ def main():
     ap.add_argument("--precision", default="auto")
     ap.add_argument("--e2e-rows", type=int, default=100_000_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-rows", type=int, default=2_000_000)
-    ap.add_argument("--ref-rows", type=int, default=2_000_000)
+    ap.add_argument("--cpu-rows", type=int, default=200_000)
+    ap.add_argument("--ref-rows", type=int, default=200_000, help="rows per step of the reference arm (its loop is O(N^2))")
+    ap.add_argument("--cpu-detail", action="store_true", help="reference arm: also time C3 - C5 of BASELINE.md")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cfd", action="store_true")
+    ap.add_argument("--no-modes", action="store_true")
     ap.add_argument("--cfd-blocks", type=int, default=600_000)
     args = ap.parse_args()
     if args.impl == "reference":
