@@ -60,6 +60,8 @@ _SIGNATURES = {
     "bb_trainer_range_flag": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "bb_trainer_debug_layer": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
     "bb_trainer_profile": (C.c_int, [_P, C.c_int, _P]),
+    "bb_trainer_dp_export": (C.c_int, [_P, C.c_int, _P]),
+    "bb_trainer_dp_connect": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "bb_trainer_param_count": (C.c_int, [_P]),
     "bb_trainer_params_dev": (_P, [_P]),
     "bb_trainer_grads_dev": (_P, [_P]),

@@ -1011,6 +1011,16 @@ int bb_trainer_debug_layer(bb_trainer* t, int which, int layer, int rows, float*
   return bb_tc_train_debug_layer(t->tc, which, layer, rows, out_host, capacity_floats);
 }
 
+int bb_trainer_dp_export(bb_trainer* t, int world_size, unsigned char* handle_out_64) {
+  if (!t || !t->tc) return BB_ERR_UNSUPPORTED;
+  return bb_tc_train_dp_export(t->tc, world_size, handle_out_64);
+}
+
+int bb_trainer_dp_connect(bb_trainer* t, int rank, int world_size, const unsigned char* handles) {
+  if (!t || !t->tc) return BB_ERR_UNSUPPORTED;
+  return bb_tc_train_dp_connect(t->tc, rank, world_size, handles);
+}
+
 int bb_trainer_profile(bb_trainer* t, int step, long long* out_128) {
   if (!t || !t->tc) return BB_ERR_UNSUPPORTED;
   return bb_tc_train_profile(t->tc, step, out_128);
@@ -1048,7 +1058,7 @@ int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_
     }
     const int flags = TC_P1 | TC_DW | TC_GRADS | (phase == 0 ? TC_ADAM : 0);
     if (phase == 0) t->step += 1;
-    return bb_tc_train_run(t->tc, x_dev, batch_rows, batch_rows, flags, &th, t->step, loss_accum_dev, s);
+    return bb_tc_train_run(t->tc, x_dev, batch_rows, batch_rows, flags, &th, t->step, loss_accum_dev, 0, s);
   }
   if (urc != BB_OK) return urc;
   if (phase != 1) t->tc_fresh = false;
@@ -1081,12 +1091,15 @@ int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_
 
 int bb_trainer_epoch(bb_trainer* t, const float* x_dev, int64_t n_rows, int batch, const bb_train_hyper* h,
                      double* epoch_loss_host, bb_stream_t stream) {
-  if (!t || !h || !x_dev || n_rows < 1 || batch < 1 || batch > t->max_batch || !epoch_loss_host) return BB_ERR_INVALID;
-  if (h->world_size > 1) return BB_ERR_INVALID;
+  if (!t || !h || !x_dev || n_rows < 1 || batch < 1 || !epoch_loss_host) return BB_ERR_INVALID;
+  if (h->world_size <= 1 && batch > t->max_batch) return BB_ERR_INVALID;
+  const int dp_world = t->tc ? bb_tc_train_dp_world(t->tc) : 1;
+  if (h->world_size > 1 && h->world_size != dp_world) return BB_ERR_INVALID;  // data parallel needs bb_trainer_dp_connect
   cudaStream_t s = (cudaStream_t)stream;
   BB_CUDA(cudaMemsetAsync(t->loss_accum, 0, sizeof(double), s));
   int64_t n_batches = 0;
   int urc;
+  if (h->world_size > 1 && (batch + dp_world - 1) / dp_world > t->max_batch) return BB_ERR_INVALID;
   if (use_tc(t, h, s, &urc)) {
     // the whole epoch is one persistent kernel: no launch and no host round trip between steps
     if (urc != BB_OK) return urc;
@@ -1095,11 +1108,13 @@ int bb_trainer_epoch(bb_trainer* t, const float* x_dev, int64_t n_rows, int batc
     t->wt_fresh = false;
     t->last_tc = true;
     t->last_rows = (int)(n_rows - (n_batches - 1) * batch);
-    const int rc = bb_tc_train_run(t->tc, x_dev, n_rows, batch, TC_P1 | TC_DW | TC_ADAM, &th, t->step + 1, t->loss_accum, s);
+    const int rc = bb_tc_train_run(t->tc, x_dev, n_rows, batch, TC_P1 | TC_DW | TC_ADAM, &th, t->step + 1, t->loss_accum,
+                                   h->world_size > 1 ? 1 : 0, s);
     if (rc != BB_OK) return rc;
     t->step += n_batches;
   } else {
     if (urc != BB_OK) return urc;
+    if (h->world_size > 1) return BB_ERR_UNSUPPORTED;  // the fused exchange lives in the tensor-core kernel
     for (int64_t r0 = 0; r0 < n_rows; r0 += batch, ++n_batches) {
       const int rows = (int)(n_rows - r0 < batch ? n_rows - r0 : batch);
       const int rc = bb_trainer_step(t, x_dev + (size_t)r0 * t->d.dims[0], rows, h, 0, t->loss_accum, s);
@@ -1129,7 +1144,7 @@ int bb_trainer_validate(bb_trainer* t, const float* x_dev, int64_t n_rows, int b
     n_batches = (n_rows + batch - 1) / batch;
     t->last_tc = true;
     t->last_rows = (int)(n_rows - (n_batches - 1) * batch);
-    const int rc = bb_tc_train_run(t->tc, x_dev, n_rows, batch, TC_FWD_ONLY, &th, 1, t->loss_accum, s);
+    const int rc = bb_tc_train_run(t->tc, x_dev, n_rows, batch, TC_FWD_ONLY, &th, 1, t->loss_accum, 0, s);
     if (rc != BB_OK) return rc;
   }
   for (int64_t r0 = 0; !tc && r0 < n_rows; r0 += batch, ++n_batches) {

@@ -30,8 +30,9 @@
 // per-pass latency - 15 dependent passes, each a barrier, a weight-chunk wait, a k loop of dependent MMA chains at 2
 // warps per scheduler, and an epilogue of dependent conversions.
 // Data parallel: between the contraction and Adam each rank pushes its gradient tile into every peer's exchange
-// buffer over NVLink (peer-mapped memory), raises a per-tile flag and sums the world's tiles in rank order - the
-// all-reduce is fused into the weight-gradient kernel, tile by tile (SUM, not mean: the loss is a sum, utils.py:195).
+// buffer over NVLink (peer-mapped memory) as 8-byte {value, step tag} packets and sums the world's tiles in rank order as
+// they land - the all-reduce is fused into the weight-gradient kernel, tile by tile, with no fence, flag or barrier on the
+// path (SUM, not mean: the loss is a sum, utils.py:195).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -115,9 +116,10 @@ struct TcPtrs {
   int* flag;
   // data parallel (world > 1): peer-mapped exchange buffers and flags, indexed by rank
   int rank, world;
-  float* xchg[MAX_WORLD];           // [2][world][n_items + 1][1024] floats on every rank
-  unsigned* xflag[MAX_WORLD];       // [world][n_items + 1] step counters on every rank
-  unsigned xbase;                   // flags carry xbase + step-in-launch + 1 (monotonic over launches)
+  float* xchg[MAX_WORLD];           // every rank's exchange block: [2][world][n_items][256][4] {value, tag} packets
+  unsigned* xflag[MAX_WORLD];       // (reserved)
+  unsigned xbase;                   // packet tags are xbase + step-in-launch + 1 (monotonic over launches, never 0)
+  int dp_slice;                     // 1: x is the full table, every step takes this rank's share of a global batch
   long long* prof;                  // diagnostics (nullable): clock64 stamps of CTA 0 during step `prof_step` of a launch
   int prof_step;
 };
@@ -194,15 +196,6 @@ __device__ __forceinline__ void split16x2(const float a, const float b, uint32_t
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, const unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // Warp-uniform values the compiler cannot prove uniform (the warp index, anything loaded from memory) make every branch
 // on them "potentially divergent": nvcc then guards each mma.sync / ldmatrix behind a WARPSYNC.ALL, ~12 per k-step in the
 // inner loops (measured: ~300 cycles per k-step).  A shuffle from lane 0 is uniform by construction.
@@ -641,27 +634,39 @@ __device__ void phase2_item(const TcModel& M, const TcPtrs& P, const int item_id
   float v[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = hh[i] + (cross[i] + cross2[i]) * LO_INV;
-  if (P.world > 1) {
-    // fused all-reduce (SUM): push this rank's tile into every rank's exchange buffer, flag it, sum in rank order
-    const size_t slot_floats = 1024;
-    const size_t per_rank = (size_t)(M.n_items + 1) * slot_floats;
-    const size_t off = ((size_t)parity * P.world + P.rank) * per_rank + (size_t)item_idx * slot_floats + ((warp & 7) * 32 + lane) * 4;
-    if (mma_warp) {
-      for (int r = 0; r < P.world; ++r) *reinterpret_cast<float4*>(P.xchg[r] + off) = make_float4(v[0], v[1], v[2], v[3]);
-      __threadfence_system();
+  if (P.world > 1 && (flags & TC_XCHG)) {
+    // Fused all-reduce (SUM) of this tile over NVLink peer memory.  Every value travels as an 8-byte {value, tag}
+    // packet (one atomic store; the tag is the step number): the receiver spins on the packet itself, so there is no
+    // fence, no flag and no CTA barrier on the path - one NVLink store latency.  Slots are double-buffered by step
+    // parity; a slot is rewritten two steps later, which the sender can only reach after the receiver has consumed it
+    // (it needs the receiver's packets of the step in between).  The sum runs in rank order on every rank: replicas
+    // stay bit-identical.
+    const size_t slot = ((size_t)item_idx * NTHREADS + tid) * 4;                      // uint2 index inside one rank's block
+    const size_t per_rank = (size_t)M.n_items * NTHREADS * 4;
+    const size_t mine = ((size_t)parity * P.world + P.rank) * per_rank + slot;
+    for (int r = 0; r < P.world; ++r) {
+      if (r == P.rank) continue;
+      uint2* dst = reinterpret_cast<uint2*>(P.xchg[r]) + mine;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + i), "r"(__float_as_uint(v[i])), "r"(step_tag) : "memory");
     }
-    __syncthreads();
-    if (tid < P.world) st_release_sys(P.xflag[tid] + (size_t)P.rank * (M.n_items + 1) + item_idx, step_tag);
-    if (tid < P.world) {
-      const unsigned* f = P.xflag[P.rank] + (size_t)tid * (M.n_items + 1) + item_idx;
-      while ((int)(ld_acquire_sys(f) - step_tag) < 0) {}
-    }
-    __syncthreads();
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = 0; mma_warp && r < P.world; ++r) {
-      const float4 o = __ldcv(reinterpret_cast<const float4*>(
-          P.xchg[P.rank] + ((size_t)parity * P.world + r) * per_rank + (size_t)item_idx * slot_floats + (warp * 32 + lane) * 4));
-      s[0] += o.x; s[1] += o.y; s[2] += o.z; s[3] += o.w;
+    for (int r = 0; r < P.world; ++r) {
+      if (r == P.rank) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] += v[i];
+        continue;
+      }
+      const uint2* src = reinterpret_cast<const uint2*>(P.xchg[P.rank]) + ((size_t)parity * P.world + r) * per_rank + slot;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t val, tag;
+        do {
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(val), "=r"(tag) : "l"(src + i) : "memory");
+        } while (tag != step_tag);
+        s[i] += __uint_as_float(val);
+      }
     }
     v[0] = s[0]; v[1] = s[1]; v[2] = s[2]; v[3] = s[3];
   }
@@ -717,24 +722,12 @@ __device__ void phase2_item(const TcModel& M, const TcPtrs& P, const int item_id
   }
 }
 
-// batch loss = sum of the tile partials in tile order (+ the other ranks' in rank order)
+// batch loss = sum of the tile partials in tile order.  Data parallel: this rank's share; the caller sums the epoch
+// losses of the ranks (one reduction per epoch instead of one exchange per step)
 __device__ void finish_loss(const TcModel& M, const TcPtrs& P, const int n_tiles, const int loss_slot, const int flags,
                             const unsigned step_tag, const int parity, double* loss_accum) {
   float s = 0.f;
   for (int i = 0; i < n_tiles; ++i) s += __ldcg(P.loss_part + loss_slot * M.max_tiles + i);
-  if (P.world > 1 && !(flags & TC_FWD_ONLY)) {
-    const size_t per_rank = (size_t)(M.n_items + 1) * 1024;
-    const size_t off = ((size_t)parity * P.world + P.rank) * per_rank + (size_t)M.n_items * 1024;
-    for (int r = 0; r < P.world; ++r) *(volatile float*)(P.xchg[r] + off) = s;
-    __threadfence_system();
-    for (int r = 0; r < P.world; ++r) st_release_sys(P.xflag[r] + (size_t)P.rank * (M.n_items + 1) + M.n_items, step_tag);
-    s = 0.f;
-    for (int r = 0; r < P.world; ++r) {
-      const unsigned* f = P.xflag[P.rank] + (size_t)r * (M.n_items + 1) + M.n_items;
-      while ((int)(ld_acquire_sys(f) - step_tag) < 0) {}
-      s += __ldcv(P.xchg[P.rank] + ((size_t)parity * P.world + r) * per_rank + (size_t)M.n_items * 1024);
-    }
-  }
   if (flags & (TC_GRADS | TC_P1)) P.grads[M.n_params] = s;
   if ((flags & (TC_ADAM | TC_FWD_ONLY)) && loss_accum) *loss_accum += (double)s;
   if (!(s == s) || fabsf(s) > 3.0e38f) *P.flag = 1;
@@ -762,8 +755,15 @@ tc_train_kernel(const __grid_constant__ TcModel Mparam, const __grid_constant__ 
   unsigned target = 0;
   const bool fwd_only = (flags & TC_FWD_ONLY) != 0;
   for (int step = 0; step < n_steps; ++step) {
-    const long long r_begin = (long long)step * batch;
-    const int rows = (int)(n_rows - r_begin < batch ? n_rows - r_begin : batch);
+    long long r_begin = (long long)step * batch;
+    int rows = (int)(n_rows - r_begin < batch ? n_rows - r_begin : batch);
+    if (P.dp_slice) {
+      // data parallel: `batch` is the GLOBAL batch (the reference's batch_size) of the full table every rank holds; this
+      // rank takes its contiguous share of it, the first (rows % world) ranks one row more (sharded.row_range)
+      const int base = rows / P.world, extra = rows - base * P.world;
+      r_begin += (long long)P.rank * base + (P.rank < extra ? P.rank : extra);
+      rows = base + (P.rank < extra ? 1 : 0);
+    }
     const int n_tiles = (rows + TROWS - 1) / TROWS;
     const int slot = step & 1;
     const unsigned tag = P.xbase + (unsigned)step + 1u;
@@ -831,10 +831,15 @@ struct TcTrainer {
   long long* prof = nullptr;
   std::vector<float2> host_hyper;
   unsigned xbase = 0;
+  // data parallel: one cudaMalloc'd block [flags | exchange buffers] per rank, mapped into every peer by CUDA IPC
+  void* dp_mem = nullptr;
+  void* dp_peer[MAX_WORLD] = {};
+  size_t dp_flag_bytes = 0;
   int xt_feat[NL], zt_feat[NL];
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static void dp_release(TcTrainer* t);
 
 int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_batch, float* params, float* m, float* v,
                        float* grads, TcTrainer** out) {
@@ -975,6 +980,7 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
 
 void bb_tc_train_destroy(TcTrainer* t) {
   if (!t) return;
+  dp_release(t);
   void* ptrs[] = {t->img, t->xt_hi, t->xt_lo, t->zt_hi, t->zt_lo, t->loss_part, t->items, t->bar, t->flag, t->stephyper, t->prof};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -995,8 +1001,12 @@ static void step_hyper(const TcHyper* h, long long step, float2* out) {
 }
 
 int bb_tc_train_run(TcTrainer* t, const float* x, int64_t n_rows, int batch, int flags, const TcHyper* h, long long first_step,
-                    double* loss_accum, cudaStream_t s) {
-  if (!t || !h || batch < 1 || batch > t->max_batch || n_rows < 0) return BB_ERR_INVALID;
+                    double* loss_accum, int dp_slice, cudaStream_t s) {
+  if (!t || !h || batch < 1 || n_rows < 0) return BB_ERR_INVALID;
+  const int local_max = dp_slice && t->P.world > 1 ? (batch + t->P.world - 1) / t->P.world : batch;
+  if (local_max > t->max_batch) return BB_ERR_INVALID;
+  t->P.dp_slice = dp_slice && t->P.world > 1;
+  if (t->P.dp_slice) flags |= TC_XCHG;
   const int n_steps = n_rows == 0 ? 1 : (int)((n_rows + batch - 1) / batch);
   if (n_steps > t->stephyper_cap) {
     if (t->stephyper) cudaFree(t->stephyper);
@@ -1105,18 +1115,52 @@ int bb_tc_train_range_flag(TcTrainer* t, int reset, int* out) {
   return BB_OK;
 }
 
-size_t bb_tc_train_dp_bytes(const TcTrainer* t) {
-  return t ? (size_t)2 * MAX_WORLD * (t->M.n_items + 1) * 1024 * sizeof(float) : 0;
+static size_t dp_flag_bytes(const TcTrainer*, int) { return 256; }  // reserved
+static size_t dp_total_bytes(const TcTrainer* t, int world) {
+  // [2 step parities][world source ranks][items][256 threads][4 {value, tag} packets of 8 bytes]
+  return dp_flag_bytes(t, world) + (size_t)2 * world * t->M.n_items * NTHREADS * 4 * sizeof(uint2);
 }
 
-int bb_tc_train_dp_attach(TcTrainer* t, int rank, int world, void* const* xchg_ptrs, void* const* flag_ptrs) {
-  if (!t || world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return BB_ERR_INVALID;
+static void dp_release(TcTrainer* t) {
+  for (int r = 0; r < MAX_WORLD; ++r) {
+    if (t->dp_peer[r] && t->dp_peer[r] != t->dp_mem) cudaIpcCloseMemHandle(t->dp_peer[r]);
+    t->dp_peer[r] = nullptr;
+  }
+  if (t->dp_mem) cudaFree(t->dp_mem);
+  t->dp_mem = nullptr;
+  t->P.world = 1; t->P.rank = 0;
+}
+
+int bb_tc_train_dp_export(TcTrainer* t, int world, unsigned char* handle_out_64) {
+  if (!t || world < 2 || world > MAX_WORLD || !handle_out_64) return BB_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  dp_release(t);
+  const size_t bytes = dp_total_bytes(t, world);
+  BB_CUDA(cudaMalloc(&t->dp_mem, bytes));
+  BB_CUDA(cudaMemset(t->dp_mem, 0, bytes));
+  BB_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  BB_CUDA(cudaIpcGetMemHandle(&h, t->dp_mem));
+  memcpy(handle_out_64, &h, 64);
+  t->dp_flag_bytes = dp_flag_bytes(t, world);
+  return BB_OK;
+}
+
+int bb_tc_train_dp_connect(TcTrainer* t, int rank, int world, const unsigned char* handles) {
+  if (!t || !t->dp_mem || !handles || world < 2 || world > MAX_WORLD || rank < 0 || rank >= world) return BB_ERR_INVALID;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { t->dp_peer[r] = t->dp_mem; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    BB_CUDA(cudaIpcOpenMemHandle(&t->dp_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
   t->P.rank = rank;
   t->P.world = world;
   for (int r = 0; r < world; ++r) {
-    if (world > 1 && (!xchg_ptrs || !flag_ptrs || !xchg_ptrs[r] || !flag_ptrs[r])) return BB_ERR_INVALID;
-    t->P.xchg[r] = world > 1 ? (float*)xchg_ptrs[r] : nullptr;
-    t->P.xflag[r] = world > 1 ? (unsigned*)flag_ptrs[r] : nullptr;
+    t->P.xflag[r] = reinterpret_cast<unsigned*>(t->dp_peer[r]);
+    t->P.xchg[r] = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(t->dp_peer[r]) + t->dp_flag_bytes);
   }
   return BB_OK;
 }
+
+int bb_tc_train_dp_world(const TcTrainer* t) { return t ? t->P.world : 1; }

@@ -11,6 +11,7 @@ enum : int {
   TC_GRADS = 4,      // ... stored to the flat gradient vector (+ loss slot)
   TC_ADAM = 8,       // ... and applied (Adam) in the tile epilogue, packed weight images refreshed
   TC_FWD_ONLY = 16,  // validation: forward + loss only
+  TC_XCHG = 32,      // data parallel: sum the gradient tiles (and the loss) of all ranks over peer memory before Adam
 };
 
 struct TcHyper {
@@ -27,8 +28,10 @@ int bb_tc_train_repack(TcTrainer* t, cudaStream_t s);
 // n_steps consecutive batches of `batch` rows starting at x (the last one may be ragged: n_rows total).  `first_step` is
 // the 1-based Adam step number of the first batch.  loss_accum (double, device) receives the sum of batch losses when
 // TC_ADAM or TC_FWD_ONLY is set.
+// dp_slice (data parallel, after bb_tc_train_dp_connect): x is the full table and `batch` the global batch; every rank
+// takes its contiguous share of each global batch.  0: x / batch are this rank's own rows.
 int bb_tc_train_run(TcTrainer* t, const float* x, int64_t n_rows, int batch, int flags, const TcHyper* h, long long first_step,
-                    double* loss_accum, cudaStream_t s);
+                    double* loss_accum, int dp_slice, cudaStream_t s);
 // Adam from the flat gradient vector (data-parallel callers all-reduce it in between); adds the loss slot to loss_accum
 int bb_tc_train_adam_flat(TcTrainer* t, const TcHyper* h, long long step, double* loss_accum, cudaStream_t s);
 // mean over the rows of the last forward pass of the inputs of layers 1,2,3,5,6,7 (hidden activations), NaN padded
@@ -43,6 +46,9 @@ int bb_tc_train_debug_layer(TcTrainer* t, int which, int layer, int rows, float*
 // [4] second barrier passed, [8 + p] / [32 + p] / [48 + p] start / end of MMAs / end of epilogue of layer pass p.
 int bb_tc_train_profile(TcTrainer* t, int step, long long* out_128);
 
-// data parallel over NVLink peer memory (bb_train_tc.cu, "exchange"): see include/baler_b200.h bb_trainer_dp_*
-size_t bb_tc_train_dp_bytes(const TcTrainer* t);
-int bb_tc_train_dp_attach(TcTrainer* t, int rank, int world, void* const* xchg_ptrs, void* const* flag_ptrs);
+// data parallel over NVLink peer memory: every rank exports one cudaMalloc'd block (flags + exchange buffers) as a CUDA
+// IPC handle, the host side all-gathers the handles, connect maps the peers' blocks.  From then on the weight-gradient
+// phase pushes every gradient tile into all ranks' buffers and sums the world's tiles in rank order before Adam.
+int bb_tc_train_dp_export(TcTrainer* t, int world, unsigned char* handle_out_64);
+int bb_tc_train_dp_connect(TcTrainer* t, int rank, int world, const unsigned char* handles);
+int bb_tc_train_dp_world(const TcTrainer* t);

@@ -259,6 +259,22 @@ class Trainer:
         check(_lib.lib().bb_trainer_range_flag(self.handle, int(reset), C.byref(flag)), "bb_trainer_range_flag")
         return bool(flag.value)
 
+    def dp_connect(self, group=None):
+        """data parallel inside the library: exchange the CUDA IPC handles of every rank's exchange block over
+        torch.distributed (host plumbing) and map the peers' blocks; afterwards `epoch(full_table, global_batch, hyper)`
+        with hyper.world_size == world runs the fused gradient exchange (include/baler_b200.h, bb_trainer_dp_connect)"""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = (C.c_ubyte * 64)()
+        check(_lib.lib().bb_trainer_dp_export(self.handle, world, mine), "bb_trainer_dp_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        check(_lib.lib().bb_trainer_dp_connect(self.handle, rank, world, blob), "bb_trainer_dp_connect")
+        dist.barrier(group)
+        self.dp_world = world
+        return world
+
     def debug_layer(self, which, layer, rows):
         """split16 step diagnostics: (features, rows) float32 of the input (which=0, last feature = bias ones) or the
         pre-activation gradient (which=1) of `layer` as the last step left them"""

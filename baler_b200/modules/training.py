@@ -76,7 +76,7 @@ class DeviceAdam:
             self.trainer = engine.LayeredTrainer(w, b, ["leaky", "leaky", "leaky", "none"] * 2, max_batch)
         if self.has_bn:
             self.trainer.set_dropout(seed=dropout_seed + self.rank)  # every rank draws its own dropout stream
-        self.dp = sharded.DataParallelTrainer(self.trainer) if self.world > 1 else None
+        self.dp = sharded.DataParallelTrainer(self.trainer, fused=not l1) if self.world > 1 else None
 
     def hyper(self, world_size=None):
         return engine.make_hyper(lr=self.lr, reg_param=self.reg_param, l1=self.l1,
@@ -87,8 +87,7 @@ class DeviceAdam:
         self.steps += (data.shape[0] + batch_size - 1) // batch_size
         if self.dp is None:
             return self.trainer.epoch(data, batch_size, self.hyper())
-        slices = sharded.dp_batch_slices(data.shape[0], batch_size, self.rank, self.world)
-        return self.dp.epoch([data[lo:hi] for lo, hi in slices], self.hyper())
+        return self.dp.epoch_table(data, batch_size, self.hyper(), self.rank, self.world)
 
     SWAE_PROJECTIONS, SWAE_REG_WEIGHT = 2000, 100.0  # defaults of utils.loss_function_swae (utils.py:27-36)
 

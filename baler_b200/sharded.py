@@ -62,9 +62,18 @@ def allreduce_sum_(flat, group=None):
 class DataParallelTrainer:
     """engine.Trainer on every rank + SUM all-reduce of the flat gradient between backward and Adam."""
 
-    def __init__(self, trainer, group=None):
+    def __init__(self, trainer, group=None, fused=True):
         self.trainer, self.group = trainer, group
         self.grads = trainer.grads_view()  # n_params + 1 floats: gradient, then the batch loss
+        # the tensor-core step of the plain AE exchanges its gradient tiles itself (NVLink peer memory, fused with the
+        # weight-gradient phase): no collective and no host loop per step.  Everything else (fp32 step, BatchNorm models,
+        # the layered trainer, the CPU stand-in of the gloo tests) all-reduces the flat gradient between the two phases.
+        self.fused = False
+        if (fused and hasattr(trainer, "dp_connect") and getattr(trainer, "_bn", None) is None and dist.is_initialized()
+                and dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1
+                and getattr(trainer, "precision", None) == "split16"):
+            trainer.dp_connect(group)
+            self.fused = True
         # AE_Dropout_BN: every rank normalises ITS slice of the batch (per-rank BatchNorm statistics, as torch
         # DistributedDataParallel runs the reference model) and draws its own dropout stream; the running statistics
         # are averaged over ranks at the end of an epoch so that the replicas save the same model.pt
@@ -90,6 +99,16 @@ class DataParallelTrainer:
 
     def _dummy(self, x_local):
         return torch.zeros((1, x_local.shape[1]), dtype=x_local.dtype, device=x_local.device)
+
+    def epoch_table(self, data, batch_size, hyper, rank, world):
+        """one pass over the full (replicated) table in global batches of `batch_size`; returns the epoch loss"""
+        if self.fused:
+            # the library returns this rank's share of every batch loss; one reduction per epoch completes the sum
+            loss = torch.tensor([self.trainer.epoch(data, batch_size, hyper)], dtype=torch.float64, device=data.device)
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+            return loss.item()
+        slices = dp_batch_slices(data.shape[0], batch_size, rank, world)
+        return self.epoch([data[lo:hi] for lo, hi in slices], hyper)
 
     def epoch(self, x_local_batches, hyper):
         """x_local_batches: list of this rank's slices, one per global batch; returns the epoch loss"""

@@ -424,9 +424,17 @@ def run_ours(args):
     # comparison at N = 1), AE_Dropout_BN (BASELINE configs[2]) on the fp32 cooperative kernel.
     train = train_dbn = None
     if not args.no_train:
-        tn = 600_000
-        mn, mx = engine.colminmax(x[:tn])
-        xt = engine.normalize_table(x[:tn].contiguous(), mn, mx - mn)
+        tn = 600_000  # rows per GPU and epoch
+        if world == 1:
+            xsrc = x[:tn].contiguous()
+        else:
+            # data parallel = the reference's run at batch_size = 512 x N on ONE table: every rank holds the same
+            # (tn x N)-row table and processes its 512-row share of every global batch
+            xsrc = synth.cms_table_device(tn * world, seed=synth.CMS_SEED + 77, device=dev)
+        mn, mx = engine.colminmax(xsrc)
+        xt = engine.normalize_table(xsrc, mn, mx - mn)
+        del xsrc
+        gb = 512 * world
 
         def one_epoch(tr, precision_name):
             hyper = engine.make_hyper(lr=1e-3, world_size=world)
@@ -437,27 +445,34 @@ def run_ours(args):
                 loss = tr.epoch(xt, 512, hyper)
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
-                steps = (tn + 511) // 512
+                fused = None
             else:
                 dp = sharded.DataParallelTrainer(tr)
-                batches = [xt[i:i + 512] for i in range(0, tn, 512)]  # each rank: its 512-row slice of a 512*world batch
-                dp.epoch(batches[:100], hyper)
-                sync_all()
-                t0 = time.perf_counter()
-                loss = dp.epoch(batches, hyper)
-                sync_all()
-                dt = time.perf_counter() - t0
-                steps = len(batches)
+                fused = dp.fused
+                dp.epoch_table(xt[:100 * gb], gb, hyper, rank, world)
+                dts = []
+                for _ in range(2):
+                    sync_all()
+                    t0 = time.perf_counter()
+                    loss = dp.epoch_table(xt, gb, hyper, rank, world)
+                    sync_all()
+                    dts.append(time.perf_counter() - t0)
+                dt = min(dts)
+            steps = (xt.shape[0] + gb - 1) // gb
             tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
             dt = tdt.item()
-            sps = tn * world / dt
-            return {"samples_per_s": sps, "us_per_step": 1e6 * dt / steps, "steps": steps, "global_batch": 512 * world,
-                    "epoch_loss": loss, "precision": precision_name, "flop_per_sample": 357000, "tflops": sps * 357000 / 1e12,
-                    "roofline": {"bound": "latency (15 dependent layer passes per 512-row step); tensor peak for reference",
-                                 "achieved": sps * 357000 / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                                 "frac": sps * 357000 / 1e12 / peaks["tflops"]}}
+            sps = xt.shape[0] / dt
+            out = {"samples_per_s": sps, "us_per_step": 1e6 * dt / steps, "steps": steps, "global_batch": gb,
+                   "epoch_loss": loss, "precision": precision_name, "flop_per_sample": 357000, "tflops": sps * 357000 / 1e12,
+                   "roofline": {"bound": "latency (15 dependent layer passes per 512-row step); tensor peak for reference",
+                                "achieved": sps * 357000 / 1e12, "peak": peaks["tflops"] * world, "unit": "TFLOP/s",
+                                "frac": sps * 357000 / 1e12 / (peaks["tflops"] * world)}}
+            if fused is not None:
+                out["gradient_exchange"] = ("fused in the weight-gradient kernel over NVLink peer memory (bb_trainer_dp_connect)"
+                                            if fused else "NCCL SUM all-reduce of the flat gradient between two kernel phases")
+            return out
 
         torch.manual_seed(0)
         tm = models.AE(24, 15)
@@ -475,6 +490,28 @@ def run_ours(args):
                                      "sample": "training.fit of the unmodified reference, 200 steps of bs 512 (BASELINE.md C4)"}
             train["vs_cpu"] = train["samples_per_s"] / cpu["fit_AE_samples_per_s"]
         del tr
+        if world > 1:
+            # data-parallel parity, visible to the driver: replicas bit-identical, and equal to ONE GPU running the same
+            # 20 global batches at batch_size = 512 x N (<= 1e-5 of max|w|)
+            rows_p = 20 * gb
+            hyper = engine.make_hyper(lr=1e-3, world_size=world)
+            trp = engine.Trainer(w, b, 24, 15, 512)
+            dpp = sharded.DataParallelTrainer(trp)
+            dpp.epoch_table(xt[:rows_p], gb, hyper, rank, world)
+            mine = trp.params_view().clone()
+            ref0 = mine.clone()
+            dist.broadcast(ref0, src=0)
+            same = torch.tensor([1 if torch.equal(mine, ref0) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            train["dp_parity"] = {"replicas_identical": bool(same.item()), "global_steps": 20, "fused": dpp.fused}
+            if rank == 0:
+                tr1 = engine.Trainer(w, b, 24, 15, gb)
+                tr1.epoch(xt[:rows_p], gb, engine.make_hyper(lr=1e-3))
+                one = tr1.params_view()
+                train["dp_parity"]["vs_single_gpu_same_global_batch_rel_max"] = ((mine - one).abs().max() / one.abs().max()).item()
+                train["dp_parity"]["ok"] = bool(same.item()) and train["dp_parity"]["vs_single_gpu_same_global_batch_rel_max"] <= 1e-5
+                del tr1
+            del trp, dpp
         torch.manual_seed(0)
         dm = models.AE_Dropout_BN(24, 15)
         w, b = dm.linear_tensors()

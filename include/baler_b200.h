@@ -240,8 +240,23 @@ int bb_trainer_get_params(bb_trainer* t, double* const* weights_host, double* co
 int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_train_hyper* h,
                     int phase, double* loss_accum_dev, bb_stream_t stream);
 /*
+ * Data parallel training inside the library (one process per GPU, NVLink peer memory; the reference is single-process:
+ * this is the run with batch_size = global batch, training.py:253-263, spread over the GPUs).  Every rank
+ *   1. bb_trainer_dp_export: allocates its exchange block and writes its 64-byte CUDA IPC handle,
+ *   2. (host side: all-gather of the handles, e.g. torch.distributed.all_gather_object),
+ *   3. bb_trainer_dp_connect: maps the peers' blocks (`handles` = world_size x 64 bytes in rank order).
+ * Afterwards bb_trainer_epoch with h->world_size == world_size takes the FULL table and the GLOBAL batch: each rank
+ * processes its contiguous share of every global batch; inside the weight-gradient phase of the step kernel each rank
+ * pushes every 32 x 32 gradient tile into all ranks' buffers over NVLink as 8-byte {value, step tag} packets and sums the
+ * world's tiles in rank order as they land, before Adam - a fused SUM all-reduce (the loss is a sum: utils.py:195),
+ * bit-identical replicas, no collective call on the host inside an epoch.  The epoch loss each rank gets back is ITS share
+ * (sum of its rows' terms / number of batches): the caller adds the ranks' values.  SPLIT16 step only (AE family, MSE).
+ */
+int bb_trainer_dp_export(bb_trainer* t, int world_size, unsigned char* handle_out_64);
+int bb_trainer_dp_connect(bb_trainer* t, int rank, int world_size, const unsigned char* handles);
+/*
  * One epoch over n_rows rows in sequential batches of `batch` (last one ragged, drop_last=False,
- * shuffle=False: training.py:253-263).  Single-GPU only (world_size == 1).  Writes the epoch loss
+ * shuffle=False: training.py:253-263).  h->world_size > 1: see bb_trainer_dp_connect.  Writes the epoch loss
  * (mean of batch losses, training.py:99) to *epoch_loss_host after synchronising `stream`.
  */
 int bb_trainer_epoch(bb_trainer* t, const float* x_dev, int64_t n_rows, int batch,

@@ -204,7 +204,12 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "rows/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the unmodified reference when it is staged (oracle/_ref, built by __graft_entry__.build() where /root/reference is
+    # mounted), else the restatement on torch CPU; the restatement is always reported beside it as the best case
+    staged = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "baler"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["port_best_case_rows_per_s"] > d["value"] * (1.0 if staged else 0.0)
     assert d["e2e"] == {"value": d["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["metric"].startswith("compress+decompress rows/s")
     r1 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=300)

@@ -40,6 +40,16 @@ def _worker(rank, world, port, out_dir):
         loss = dp.epoch([x[lo:hi].contiguous() for lo, hi in slices], hyper)
         np.save(os.path.join(out_dir, "dp_params_%d.npy" % rank), tr.params_view().cpu().numpy())
         np.save(os.path.join(out_dir, "dp_loss_%d.npy" % rank), np.array([loss]))
+        # the same two global batches through the library's own exchange (bb_trainer_dp_connect): one persistent kernel per
+        # epoch, gradient tiles summed over NVLink peer memory inside the weight-gradient phase; then a ragged table (1500
+        # rows: global batches of 1024 and 476, the latter 238 rows per rank)
+        trf = engine.Trainer([sd0[n + ".weight"] for n in names], [sd0[n + ".bias"] for n in names], 24, 15, 1024)
+        dpf = sharded.DataParallelTrainer(trf)
+        assert dpf.fused and dp.fused
+        lossf = dpf.epoch_table(x, 1024, hyper, rank, world)
+        np.save(os.path.join(out_dir, "fused_params_%d.npy" % rank), trf.params_view().cpu().numpy())
+        np.save(os.path.join(out_dir, "fused_loss_%d.npy" % rank), np.array([lossf, dpf.epoch_table(x[:1500].contiguous(), 1024, hyper, rank, world)]))
+        np.save(os.path.join(out_dir, "fused_params2_%d.npy" % rank), trf.params_view().cpu().numpy())
         # AE_Dropout_BN, data parallel: per-rank BatchNorm statistics and dropout streams, SUM all-reduce, identical Adam step
         gd = np.load(os.path.join(GOLDEN, "ae_dbn.npz"))
         sdb = {k[4:]: np.asarray(gd[k], order="C") for k in gd.files if k.startswith("sd0/")}
@@ -115,6 +125,18 @@ def test_data_parallel_equals_single_gpu(tmp_path):
     upd, ref = p0 - start, single - start
     assert np.abs(upd - ref).max() <= 0.02 * np.abs(ref).max()  # fp32 summation order differs between 1 and 2 ranks
     assert abs(float(np.load(tmp_path / "dp_loss_0.npy")[0]) - loss) <= 1e-5 * loss
+    # fused exchange inside the library: replicas bit-identical, equal to the single-GPU run at the global batch (<= 1e-5
+    # of max|w| per the data-parallel contract; the two-rank sum of 512-row halves rounds differently from one 1024-row sum)
+    f0, f1 = np.load(tmp_path / "fused_params_0.npy"), np.load(tmp_path / "fused_params_1.npy")
+    assert np.array_equal(f0, f1)
+    assert np.abs(f0 - single).max() <= 1e-5 * np.abs(single).max(), np.abs(f0 - single).max() / np.abs(single).max()
+    fl = np.load(tmp_path / "fused_loss_0.npy")
+    assert abs(fl[0] - loss) <= 1e-5 * loss and np.array_equal(fl, np.load(tmp_path / "fused_loss_1.npy"))
+    loss2 = tr.epoch(x[:1500].contiguous(), 1024, engine.make_hyper(lr=1e-3))
+    assert abs(fl[1] - loss2) <= 1e-5 * loss2
+    g0, g1 = np.load(tmp_path / "fused_params2_0.npy"), np.load(tmp_path / "fused_params2_1.npy")
+    single2 = tr.params_view().cpu().numpy()
+    assert np.array_equal(g0, g1) and np.abs(g0 - single2).max() <= 2e-5 * np.abs(single2).max()
     # sharded compress == one-GPU compress, bit for bit (rows are independent, features are global)
     table = synth.cms_table(40_001, seed=8)
     m = models.AE(24, 15)
