@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(NT) refresh_wt_kernel(const int n_params, cons
 // which implementation serves this call; rebuilds that path's derived weight copy when the other path moved the parameters
 bool use_tc(bb_trainer* t, const bb_train_hyper* h, cudaStream_t s, int* rc) {
   *rc = BB_OK;
-  const bool tc = t->tc && t->kind == 0 && t->precision != BB_PREC_FP32 && !(h && h->l1);
+  const bool tc = t->tc && t->precision != BB_PREC_FP32 && !(h && h->l1);
   if (tc && !t->tc_fresh) {
     *rc = bb_tc_train_repack(t->tc, s);
     t->tc_fresh = true;
@@ -807,6 +807,7 @@ int bb_trainer_set_dropout(bb_trainer* t, unsigned long long seed, const unsigne
   if (!t || t->kind != 1) return BB_ERR_INVALID;
   t->seed = seed;
   for (int i = 0; i < 4; ++i) t->mask_dev[i] = masks_dev ? masks_dev[i] : nullptr;
+  if (t->tc) return bb_tc_train_set_dropout(t->tc, seed, masks_dev);
   return BB_OK;
 }
 
@@ -962,11 +963,19 @@ int create_common(bb_ctx* ctx, int n_features, int z_dim, const double* const* w
     t->dbn_max_ctas = per_sm * ctx->sm_count;
   }
   if (rc == BB_OK) rc = (int)cudaFuncSetAttribute(train_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem_bytes);
-  if (rc == BB_OK && kind == 0) {
+  if (rc == BB_OK) {
     // tensor-core path; shapes it does not take (BB_ERR_UNSUPPORTED) stay on the fp32 kernels
-    const int trc = bb_tc_train_create(ctx, dims, acts, max_batch, t->params, t->m, t->v, t->grads, &t->tc);
-    if (trc == BB_OK) rc = bb_tc_train_repack(t->tc, nullptr);
-    else if (trc != BB_ERR_UNSUPPORTED) rc = trc;
+    int tacts[NL];
+    for (int l = 0; l < NL; ++l) tacts[l] = acts[l];
+    if (kind == 1) tacts[3] = BB_ACT_LEAKY;  // AE_Dropout_BN activates the latent too (models.py:273-275)
+    const int trc = bb_tc_train_create(ctx, dims, tacts, max_batch, t->params, t->m, t->v, t->grads, kind, d.bn_g_off, d.bn_b_off,
+                                       d.n_params, &t->tc);
+    if (trc == BB_OK) {
+      if (kind == 1) rc = bb_tc_train_set_bn(t->tc, t->rm, t->rv, t->nbt);
+      if (rc == BB_OK) rc = bb_tc_train_repack(t->tc, nullptr);
+    } else if (trc != BB_ERR_UNSUPPORTED) {
+      rc = trc;
+    }
     if (rc == BB_OK) rc = (int)cudaDeviceSynchronize();
   }
   if (rc != BB_OK) { bb_trainer_destroy(t); return rc; }
@@ -997,7 +1006,7 @@ int bb_trainer_set_precision(bb_trainer* t, int precision) {
 
 int bb_trainer_precision(const bb_trainer* t) {
   if (!t) return BB_ERR_INVALID;
-  return t->tc && t->kind == 0 && t->precision != BB_PREC_FP32 ? BB_PREC_SPLIT16 : BB_PREC_FP32;
+  return t->tc && t->precision != BB_PREC_FP32 ? BB_PREC_SPLIT16 : BB_PREC_FP32;
 }
 
 int bb_trainer_range_flag(bb_trainer* t, int reset, int* out) {
@@ -1057,6 +1066,7 @@ int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_
       return bb_tc_train_adam_flat(t->tc, &th, t->step, loss_accum_dev, s);
     }
     const int flags = TC_P1 | TC_DW | TC_GRADS | (phase == 0 ? TC_ADAM : 0);
+    bb_tc_train_set_mode(t->tc, 1, (unsigned long long)t->step);
     if (phase == 0) t->step += 1;
     return bb_tc_train_run(t->tc, x_dev, batch_rows, batch_rows, flags, &th, t->step, loss_accum_dev, 0, s);
   }
@@ -1108,6 +1118,7 @@ int bb_trainer_epoch(bb_trainer* t, const float* x_dev, int64_t n_rows, int batc
     t->wt_fresh = false;
     t->last_tc = true;
     t->last_rows = (int)(n_rows - (n_batches - 1) * batch);
+    bb_tc_train_set_mode(t->tc, 1, (unsigned long long)t->step);
     const int rc = bb_tc_train_run(t->tc, x_dev, n_rows, batch, TC_P1 | TC_DW | TC_ADAM, &th, t->step + 1, t->loss_accum,
                                    h->world_size > 1 ? 1 : 0, s);
     if (rc != BB_OK) return rc;
@@ -1144,6 +1155,7 @@ int bb_trainer_validate(bb_trainer* t, const float* x_dev, int64_t n_rows, int b
     n_batches = (n_rows + batch - 1) / batch;
     t->last_tc = true;
     t->last_rows = (int)(n_rows - (n_batches - 1) * batch);
+    bb_tc_train_set_mode(t->tc, 0, 0ull);
     const int rc = bb_tc_train_run(t->tc, x_dev, n_rows, batch, TC_FWD_ONLY, &th, 1, t->loss_accum, 0, s);
     if (rc != BB_OK) return rc;
   }

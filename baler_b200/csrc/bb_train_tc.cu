@@ -39,6 +39,8 @@
 #include <new>
 #include <vector>
 
+#include <curand_philox4x32_x.h>
+
 #include "bb_train_tc.cuh"
 
 namespace {
@@ -59,6 +61,10 @@ constexpr int P2_ROWS = 512;       // batch rows per panel pass
 constexpr int P2_PANEL = P2_ROWS / 16 * 1024;  // bytes of one panel array: 32 tiles x 32 features x 16 rows x 2
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 constexpr int MAX_WORLD = 16;
+constexpr int BN_PW = 208;         // row width (columns) of the per-tile BatchNorm partial-sum packets
+constexpr int BN_TW = 208;         // width of the backward totals scratch in shared memory
+constexpr int RING_DBN = 3;        // AE_Dropout_BN: one ring stage less, its 32 KB hold the BatchNorm inputs
+constexpr float BN_EPS = 1e-5f, BN_MOMENTUM = 0.1f;  // nn.BatchNorm1d defaults (models.py:284-296)
 
 struct TcLayer {
   int K, N, act;
@@ -92,14 +98,24 @@ struct TcPass {
   int c0, c1;              // chunks [c0, c1) of the weight stream belong to this pass
   // A operand of the pass (what phase 2 needs feature-major): shared-memory offsets, row stride, padded width, and
   // where it goes in the global scratch (first feature row; 0 = X, 1 = dZ)
-  int a_hi_off, a_lo_off, a_ld_b, a_feat, a_gfeat0, a_which, NT, pad;
+  int a_hi_off, a_lo_off, a_ld_b, a_feat, a_gfeat0, a_which, NT;
+  // AE_Dropout_BN (models.py:256-313): dropout layer handled in this epilogue (forward pass of encoder layer `drop`; backward
+  // pass that produces dZ of encoder layer `drop`) and BatchNorm (forward pass of decoder layer 4 + bn; backward pass that
+  // produces dZ of decoder layer 4 + bn); -1 = none
+  int drop, bn, pad_[3];
 };
 
 struct TcModel {
   TcLayer L[NL];
   int n_chunks, n_chunks_fwd, n_items, n_params, F, RS, dz_ld, smem_x_halves, max_tiles;
-  int pad_[3];
-  TcChunk chunk[MAX_CHUNKS];   // 16-byte aligned
+  int kind, n_linear;            // 0 AE / 1 AE_Dropout_BN; Linear parameters in the flat vector (BatchNorm gamma / beta follow)
+  // AE_Dropout_BN: flat offsets of gamma / beta, feature offset in the concatenated running statistics, width, the fp32
+  // shared-memory copy U_i of every BatchNorm input (byte offset, row stride in floats), and the per-feature scratch
+  // [mean bn_f_total | 1/sqrt(var + eps) bn_f_total | T1 BN_TW | T2 BN_TW] (byte offset)
+  int bn_g_off[4], bn_b_off[4], bn_f_off[4], bn_n[4], u_off[4], u_ld[4], stat_off, bn_f_total;
+  unsigned keep_thr[4];          // dropout: keep when the 32-bit draw is below this (1 - p of models.py:263-275) ...
+  float keep_scale[4];           // ... and scale the kept value by 1 / (1 - p)
+  alignas(16) TcChunk chunk[MAX_CHUNKS];
   TcPass pass[2 * NL - 1];
 };
 
@@ -120,6 +136,15 @@ struct TcPtrs {
   unsigned* xflag[MAX_WORLD];       // (reserved)
   unsigned xbase;                   // packet tags are xbase + step-in-launch + 1 (monotonic over launches, never 0)
   int dp_slice;                     // 1: x is the full table, every step takes this rank's share of a global batch
+  // AE_Dropout_BN
+  int train;                        // 1: dropout on, batch statistics; 0: eval (running statistics)
+  float *rm, *rv;                   // running mean / variance, bn_f_total each
+  long long* nbt;                   // num_batches_tracked[4]
+  uint4* bn_part;                   // [8 reduction points][max_tiles][BN_PW] packets {a, tag, b, tag} of per-tile column sums
+  uint4* bnx[MAX_WORLD];            // data parallel: every rank's [2 parities][8 points][world][BN_PW] packets of per-rank sums
+  const unsigned char* mask[4];     // injected dropout keep-masks [global batch][width] (parity tests) or nullptr (Philox)
+  unsigned long long seed;
+  unsigned long long drop_step;     // dropout stream position of the launch's first step
   long long* prof;                  // diagnostics (nullable): clock64 stamps of CTA 0 during step `prof_step` of a launch
   int prof_step;
 };
@@ -296,14 +321,281 @@ struct PipeState {
   unsigned pass;   // phase-2 panel passes so far
 };
 
+// what a phase-1 tile needs to know about its step
+struct StepCtx {
+  int rows, n_tiles;         // this rank's rows of the batch / their 16-row tiles
+  int row_base;              // position of this rank's first row in the global batch (dropout and injected masks are keyed by it)
+  int B;                     // rows of the global batch: the BatchNorm population
+  unsigned tag;              // packet tag of the step
+  unsigned long long dstep;  // dropout stream position of the step
+  bool fwd_only;
+};
+
+// ------------------------------------------------------------------------------------------------ AE_Dropout_BN
+// reference baler/modules/models.py:256-313 in train mode:
+//   encoder 4 x (Linear -> Dropout(p = .5,.4,.3,.2) -> LeakyReLU)       [activation also on the latent]
+//   decoder 3 x (Linear -> LeakyReLU -> BatchNorm1d) + Linear -> BatchNorm1d -> ReLU
+// BatchNorm in train mode normalises with the statistics of the WHOLE batch (biased variance, eps 1e-5), which is spread
+// over the phase-1 CTAs (16 rows each) and, data parallel, over the ranks.  At each of the 8 reduction points of a step
+// (4 forward: column mean / variance; 4 backward: sum dY, sum dY xhat) every CTA publishes its tile's column sums as
+// 16-byte {a, tag, b, tag} packets (each 8-byte half carries the step tag, so a reader spins on the data itself: no
+// counter, no fence) and reads all tiles' packets back, thread j owning column j, summing in tile order in double.
+// Data parallel: CTA 0 of every rank pushes the rank's sums into all peers' buffers over NVLink the same way and every
+// CTA combines the ranks' packets in rank order, so all replicas normalise with the same bits - BatchNorm over the
+// global batch, exactly what a single GPU computes at batch_size = global batch.
+// one thread's epilogue values: rows g, g + 8 x column pairs of its NJ n-tiles
+template <int NJ>
+using Vals = float[NJ > 0 ? NJ * 2 : 1][2];
+
+__device__ __forceinline__ uint4 ld_pkt(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_pkt(uint4* p, const float a, const float b, const unsigned tag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(tag), "r"(__float_as_uint(b)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ float sum_over_rows(float s) {  // the 8 lanes that hold one column pair differ in lane bits 2..4
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  return s;
+}
+__device__ __forceinline__ int dp_rank_rows(const int B, const int world, const int r) {
+  const int base = B / world;
+  return base + (r < B - base * world ? 1 : 0);
+}
+
+// Thread j sums column j of reduction point `pt`.  FWD: packets are (sum, sum of squares about the tile mean) and the
+// result is the batch mean and 1 / sqrt(biased variance + eps) (Chan's pairwise combination, no E[x^2] - mean^2
+// cancellation in fp32); otherwise (sum dY, sum dY xhat) and the result is the two totals = d beta, d gamma.
+template <bool FWD>
+__device__ __noinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, const StepCtx& sc, const int bi, const int pt,
+                                       unsigned char* smem) {
+  const int j = threadIdx.x, N = M.bn_n[bi], fo = M.bn_f_off[bi];
+  float* stat = reinterpret_cast<float*>(smem + M.stat_off);
+  if (j < N) {
+    double S1 = 0.0, S2 = 0.0;
+    const uint4* base = P.bn_part + (size_t)pt * M.max_tiles * BN_PW + j;
+    for (int t0 = 0; t0 < sc.n_tiles; t0 += 8) {
+      uint4 pk[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (t0 + u < sc.n_tiles) pk[u] = ld_pkt(base + (size_t)(t0 + u) * BN_PW);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (t0 + u < sc.n_tiles) {
+          while (pk[u].y != sc.tag || pk[u].w != sc.tag) pk[u] = ld_pkt(base + (size_t)(t0 + u) * BN_PW);
+          const double a = (double)__uint_as_float(pk[u].x), b = (double)__uint_as_float(pk[u].z);
+          S1 += a;
+          if (FWD) {
+            const int left = sc.rows - (t0 + u) * TROWS;
+            S2 += b + a * a / (double)(left < TROWS ? left : TROWS);
+          } else {
+            S2 += b;
+          }
+        }
+    }
+    double r1, r2;  // FWD: mean, M2 of the global batch; else the totals
+    if (FWD) {
+      const double n = (double)sc.rows;
+      r1 = S1 / n;
+      r2 = S2 - S1 * S1 / n;
+      r2 = r2 > 0.0 ? r2 : 0.0;
+    } else {
+      r1 = S1;
+      r2 = S2;
+    }
+    if (P.dp_slice) {
+      // this rank's sums travel (and are used locally) rounded to fp32, so every rank combines the same numbers
+      const float fa = (float)r1, fb = (float)r2;
+      const size_t blk = (((size_t)(sc.tag & 1u) * 8 + pt) * P.world) * BN_PW + j;
+      if (blockIdx.x == 0)
+        for (int r = 0; r < P.world; ++r)
+          if (r != P.rank) st_pkt(P.bnx[r] + blk + (size_t)P.rank * BN_PW, fa, fb, sc.tag);
+      double cn = 0.0, c1 = 0.0, c2 = 0.0;
+      for (int r = 0; r < P.world; ++r) {
+        const int nr = dp_rank_rows(sc.B, P.world, r);
+        if (nr == 0) continue;
+        float a = fa, b = fb;
+        if (r != P.rank) {
+          const uint4* src = P.bnx[P.rank] + blk + (size_t)r * BN_PW;
+          uint4 q = ld_pkt(src);
+          while (q.y != sc.tag || q.w != sc.tag) q = ld_pkt(src);
+          a = __uint_as_float(q.x);
+          b = __uint_as_float(q.z);
+        }
+        if (FWD) {
+          const double delta = (double)a - c1, nn = cn + nr;
+          c1 += delta * nr / nn;
+          c2 += (double)b + delta * delta * cn * nr / nn;
+          cn = nn;
+        } else {
+          c1 += (double)a;
+          c2 += (double)b;
+        }
+      }
+      r1 = c1;
+      r2 = c2;
+    }
+    if (FWD) {
+      const double var = r2 / (double)sc.B;
+      stat[fo + j] = (float)r1;
+      stat[M.bn_f_total + fo + j] = (float)(1.0 / sqrt(var + (double)BN_EPS));
+      if (blockIdx.x == 0) {  // running statistics: momentum 0.1, unbiased variance (torch.nn.BatchNorm1d)
+        const double unb = r2 / (double)(sc.B > 1 ? sc.B - 1 : 1);
+        P.rm[fo + j] = (1.f - BN_MOMENTUM) * P.rm[fo + j] + BN_MOMENTUM * (float)r1;
+        P.rv[fo + j] = (1.f - BN_MOMENTUM) * P.rv[fo + j] + BN_MOMENTUM * (float)unb;
+        if (j == 0) P.nbt[bi] += 1;
+      }
+    } else {
+      stat[2 * M.bn_f_total + j] = (float)r1;
+      stat[2 * M.bn_f_total + BN_TW + j] = (float)r2;
+      if (blockIdx.x == 0) {
+        P.grads[M.bn_b_off[bi] + j] = (float)r1;
+        P.grads[M.bn_g_off[bi] + j] = (float)r2;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// eval mode: the running statistics
+__device__ __noinline__ void bn_eval_stats(const TcModel& M, const TcPtrs& P, const int bi, unsigned char* smem) {
+  const int j = threadIdx.x, N = M.bn_n[bi], fo = M.bn_f_off[bi];
+  float* stat = reinterpret_cast<float*>(smem + M.stat_off);
+  if (j < N) {
+    stat[fo + j] = __ldcg(P.rm + fo + j);
+    stat[M.bn_f_total + fo + j] = 1.f / sqrtf(__ldcg(P.rv + fo + j) + BN_EPS);
+  }
+  __syncthreads();
+}
+
+// Dropout of encoder layer l on this thread's values (rows g, g + 8; column pairs of its n-tiles): Philox4x32-10 keyed by
+// (seed, step) with counter (column / 4, global batch row, layer) - the same stream as train_dbn_kernel in bb_train.cu,
+// independent of the launch geometry and of how the batch is split over ranks - or the injected keep-masks.
+template <int NJ>
+__device__ __forceinline__ void dbn_dropout(Vals<NJ>& v, const TcModel& M, const TcPtrs& P, const StepCtx& sc, const int l,
+                                            const int N, const int warp, const int g, const int t, const int row0) {
+  const float ks = M.keep_scale[l];
+  const unsigned thr = M.keep_thr[l];
+  const unsigned char* mk = P.mask[l];
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = row0 + g + 8 * (q & 1);
+    bool k0 = false, k1 = false;
+    if (r < sc.rows && col < N) {
+      const unsigned grow = (unsigned)(sc.row_base + r);
+      if (mk != nullptr) {
+        k0 = mk[(size_t)grow * N + col] != 0;
+        k1 = col + 1 < N && mk[(size_t)grow * N + col + 1] != 0;
+      } else {
+        const uint4 d = curand_Philox4x32_10(make_uint4((unsigned)(col >> 2), grow, (unsigned)l, (unsigned)sc.dstep),
+                                             make_uint2((unsigned)P.seed, (unsigned)(P.seed >> 32) ^ (unsigned)(sc.dstep >> 32)));
+        k0 = ((col & 2) ? d.z : d.x) < thr;
+        k1 = col + 1 < N && ((col & 2) ? d.w : d.y) < thr;
+      }
+    }
+    v[q][0] = k0 ? v[q][0] * ks : 0.f;
+    v[q][1] = k1 ? v[q][1] * ks : 0.f;
+  }
+}
+
+// BatchNorm forward on this thread's values a (the BatchNorm input): keeps a copy U for the backward pass, publishes the
+// tile's column sums, waits for the batch statistics and returns xhat in `xh` (0 outside the valid rows / columns).
+template <int NJ>
+__device__ __forceinline__ void dbn_bn_forward(const Vals<NJ>& a, Vals<NJ>& xh, const TcModel& M, const TcPtrs& P,
+                                               const StepCtx& sc, const int bi, const int tile, const int warp, const int g,
+                                               const int t, const int row0, unsigned char* smem) {
+  const int N = M.bn_n[bi], uld = M.u_ld[bi], fo = M.bn_f_off[bi];
+  float* U = reinterpret_cast<float*>(smem + M.u_off[bi]);
+  const bool vr[2] = {row0 + g < sc.rows, row0 + g + 8 < sc.rows};
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = g + 8 * (q & 1);
+    if (col < N) *reinterpret_cast<float2*>(U + r * uld + col) = make_float2(a[q][0], a[q][1]);
+  }
+  if (P.train) {
+    const int left = sc.rows - row0;
+    const float inv_nt = 1.f / (float)(left < TROWS ? left : TROWS);
+    uint4* part = P.bn_part + ((size_t)bi * M.max_tiles + tile) * BN_PW;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int col = (warp + NWARPS * j) * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float a0 = vr[0] ? a[2 * j][e] : 0.f, a1 = vr[1] ? a[2 * j + 1][e] : 0.f;
+        const float s = sum_over_rows(a0 + a1);
+        const float mean = s * inv_nt;
+        const float d0 = vr[0] ? a0 - mean : 0.f, d1 = vr[1] ? a1 - mean : 0.f;
+        const float m2 = sum_over_rows(d0 * d0 + d1 * d1);
+        if (g == 0 && col + e < N) st_pkt(part + col + e, s, m2, sc.tag);
+      }
+    }
+    bn_reduce<true>(M, P, sc, bi, bi, smem);
+  } else {
+    bn_eval_stats(M, P, bi, smem);
+  }
+  const float* stat = reinterpret_cast<const float*>(smem + M.stat_off);
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float x = 0.f;
+      if (vr[q & 1] && col + e < N) x = (a[q][e] - stat[fo + col + e]) * stat[M.bn_f_total + fo + col + e];
+      xh[q][e] = x;
+    }
+  }
+}
+
+// BatchNorm backward on this thread's values: dy (gradient w.r.t. the BatchNorm output, 0 outside the valid rows /
+// columns) and xhat -> gradient w.r.t. the BatchNorm input, dx = gamma inv / B (B dy - sum dy - xhat sum dy xhat)
+template <int NJ>
+__device__ __forceinline__ void dbn_bn_backward(Vals<NJ>& dy, const Vals<NJ>& xh, const TcModel& M, const TcPtrs& P,
+                                                const StepCtx& sc, const int bi, const int pt, const int tile, const int warp,
+                                                const int g, const int t, const int row0, unsigned char* smem) {
+  const int N = M.bn_n[bi], fo = M.bn_f_off[bi];
+  uint4* part = P.bn_part + ((size_t)pt * M.max_tiles + tile) * BN_PW;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int col = (warp + NWARPS * j) * 8 + 2 * t;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float s1 = sum_over_rows(dy[2 * j][e] + dy[2 * j + 1][e]);
+      const float s2 = sum_over_rows(fmaf(dy[2 * j][e], xh[2 * j][e], dy[2 * j + 1][e] * xh[2 * j + 1][e]));
+      if (g == 0 && col + e < N) st_pkt(part + col + e, s1, s2, sc.tag);
+    }
+  }
+  bn_reduce<false>(M, P, sc, bi, pt, smem);
+  const float* stat = reinterpret_cast<const float*>(smem + M.stat_off);
+  const float inv_b = 1.f / (float)sc.B;
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t;
+    const bool vr = row0 + g + 8 * (q & 1) < sc.rows;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float dx = 0.f;
+      if (vr && col + e < N) {
+        const int c = col + e;
+        const float gam = __ldcg(P.params + M.bn_g_off[bi] + c), inv = stat[M.bn_f_total + fo + c];
+        dx = inv * gam * (dy[q][e] - inv_b * stat[2 * M.bn_f_total + c] - xh[q][e] * inv_b * stat[2 * M.bn_f_total + BN_TW + c]);
+      }
+      dy[q][e] = dx;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ phase 1
 // A weight chunk goes into ring stage (global chunk number % RING).  The warp that is last to finish a stage's chunk
 // (shared counter) immediately refills the stage with the chunk RING positions ahead: no producer warp, nobody waits.
+template <int RN>
 __device__ __forceinline__ void ring_issue(const TcModel& M, const TcPtrs& P, SmemBars* bars, uint4* ring, const unsigned c_base,
                                            const int c, const int n_chunks) {
   if (c >= n_chunks) return;
   const int2 ch = *reinterpret_cast<const int2*>(&M.chunk[c]);
-  const unsigned st = (c_base + c) % RING;
+  const unsigned st = (c_base + c) % RN;
   mbar_expect_tx(&bars->full[st], (uint32_t)ch.y * 16u);
   bulk_g2s(ring + (size_t)st * CHUNK_U4, P.img + ch.x, (uint32_t)ch.y * 16u, &bars->full[st]);
 }
@@ -315,10 +607,13 @@ __device__ __forceinline__ void ring_issue(const TcModel& M, const TcPtrs& P, Sm
 // products of the warp's tiles are issued back to back (the warp issues in order: a dependent HMMA or an fp32 add right
 // behind its HMMA stalls everything after it for the ~21-cycle MMA latency).  The hi * hi products of two consecutive
 // k-steps share one zero-started accumulator before the rounded fp32 add.
-template <int NJ>
+template <int NJ, bool DBN>
 __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, SmemBars* bars, uint4* ring, const uint32_t sbase,
                                          const TcPass& ps, const unsigned c_base, const int n_chunks, const int warp, const int lane,
-                                         const int row0, const int rows, const float* xs, float& loss, long long* prof, const int pass) {
+                                         const int row0, const StepCtx& sc, const int tile, unsigned char* smem, const float* xs,
+                                         float& loss, long long* prof, const int pass) {
+  constexpr int RN = DBN ? RING_DBN : RING;
+  const int rows = sc.rows;
   const int g = lane >> 2, t = lane & 3;
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_colb = (lane >> 4) * 16;
   float acc[NJ > 0 ? NJ : 1][2][4];
@@ -333,8 +628,8 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
   for (int c = ps.c0; c < ps.c1; ++c) {
     const uint4 d0 = *reinterpret_cast<const uint4*>(&M.chunk[c]), d1 = *(reinterpret_cast<const uint4*>(&M.chunk[c]) + 1);
     const int n_k = d0.z >> 16;
-    const unsigned gc = c_base + c, st = gc % RING;
-    mbar_wait(&bars->full[st], (gc / RING) & 1u);
+    const unsigned gc = c_base + c, st = gc % RN;
+    mbar_wait(&bars->full[st], (gc / RN) & 1u);
     if (NJ > 0) {
       struct Frag { uint32_t ah[4], al[4]; uint4 b[NJ > 0 ? NJ : 1]; };
       const uint32_t pa_hi = sbase + d1.x + a_row * d1.z + a_colb, pa_lo = sbase + d1.y + a_row * d1.z + a_colb;
@@ -378,7 +673,7 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
     __syncwarp();
     if (lane == 0 && atomicAdd(&bars->drained[st], 1u) == NWARPS - 1) {  // last warp out refills the stage
       bars->drained[st] = 0u;
-      ring_issue(M, P, bars, ring, c_base, c + RING, n_chunks);
+      ring_issue<RN>(M, P, bars, ring, c_base, c + RN, n_chunks);
     }
   }
   if (prof && lane == 0) prof[16 + (pass * NWARPS + warp) * 4 + 1] = clock64();
@@ -387,7 +682,7 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
   const uint32_t o_hi = sbase + ps.o_hi_off, o_lo = sbase + ps.o_lo_off, o_ld = ps.o_ld_b;
   const uint32_t x_hi = sbase + ps.x_hi_off, x_lo = sbase + ps.x_lo_off, x_ld = ps.x_ld_b;
   const float inv_f = 1.f / (float)F;
-  float v[NJ > 0 ? NJ * 2 : 1][2];
+  Vals<NJ> v;
 #pragma unroll
   for (int j = 0; j < NJ; ++j)
 #pragma unroll
@@ -397,13 +692,59 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
     }
   if (kind == 0) {
     // X_{l+1} = act(X_l W^T + b); column N is the next layer's bias column of ones, beyond it zero padding
+    if (DBN && ps.drop >= 0 && P.train) dbn_dropout<NJ>(v, M, P, sc, ps.drop, N, warp, g, t, row0);
+    if (DBN && ps.bn >= 0) {
+      // decoder layer: LeakyReLU, then BatchNorm over the whole batch
+#pragma unroll
+      for (int q = 0; q < NJ * 2; ++q) {
+        v[q][0] = act_apply(v[q][0], act);
+        v[q][1] = act_apply(v[q][1], act);
+      }
+      Vals<NJ> xh;
+      dbn_bn_forward<NJ>(v, xh, M, P, sc, ps.bn, tile, warp, g, t, row0, smem);
+#pragma unroll
+      for (int q = 0; q < NJ * 2; ++q) {
+        const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t;
+        const bool vr = row0 + g + 8 * (q & 1) < rows;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float y = 0.f;
+          if (vr && col + e < N) y = fmaf(xh[q][e], __ldcg(P.params + M.bn_g_off[ps.bn] + col + e), __ldcg(P.params + M.bn_b_off[ps.bn] + col + e));
+          if (vr && col + e == N) y = 1.f;
+          v[q][e] = y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < NJ * 2; ++q) {
+        const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t;
+        const float one = row0 + g + 8 * (q & 1) < rows ? 1.f : 0.f;
+        v[q][0] = col == N ? one : act_apply(v[q][0], act);
+        v[q][1] = col + 1 == N ? one : act_apply(v[q][1], act);
+      }
+    }
+  } else if (kind == 1 && DBN) {
+    // reconstruction = ReLU(BatchNorm(X_7 W_7^T + b_7)); loss = sum (recon - x)^2 / F; the seed gradient goes back through
+    // the ReLU and the BatchNorm to dZ_7
+    Vals<NJ> xh;
+    dbn_bn_forward<NJ>(v, xh, M, P, sc, 3, tile, warp, g, t, row0, smem);
 #pragma unroll
     for (int q = 0; q < NJ * 2; ++q) {
-      const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t;
-      const float one = row0 + g + 8 * (q & 1) < rows ? 1.f : 0.f;
-      v[q][0] = col == N ? one : act_apply(v[q][0], act);
-      v[q][1] = col + 1 == N ? one : act_apply(v[q][1], act);
+      const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = g + 8 * (q & 1);
+      const bool valid = row0 + r < rows;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float gz = 0.f;
+        if (valid && col + e < F) {
+          const float y = fmaf(xh[q][e], __ldcg(P.params + M.bn_g_off[3] + col + e), __ldcg(P.params + M.bn_b_off[3] + col + e));
+          const float diff = fmaxf(y, 0.f) - xs[r * F + col + e];
+          loss = fmaf(diff * diff, inv_f, loss);
+          gz = y > 0.f ? 2.f * diff * inv_f : 0.f;
+        }
+        v[q][e] = gz;
+      }
     }
+    if (!sc.fwd_only) dbn_bn_backward<NJ>(v, xh, M, P, sc, 3, 4, tile, warp, g, t, row0, smem);
   } else if (kind == 1) {
     // reconstruction: loss = sum (recon - x)^2 / F, seed gradient dZ_7 = 2 (recon - x) / F
 #pragma unroll
@@ -422,22 +763,54 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
         v[q][e] = gz;
       }
     }
-  } else if (pact != BB_ACT_NONE) {
-    // dZ_{l-1} = (dZ_l W_l) * act'_{l-1}; the sign of the pre-activation is the sign of X_l (slope > 0)
-    uint32_t sh[NJ > 0 ? NJ * 2 : 1], sl[NJ > 0 ? NJ * 2 : 1];
+  } else if (DBN && ps.bn >= 0) {
+    // v = gradient w.r.t. the output of BatchNorm ps.bn (= dZ_{l} W_{l}); back through the BatchNorm and the LeakyReLU
+    // in front of it.  The BatchNorm input U is this thread's own copy from the forward pass.
+    const int bi = ps.bn, Nb = M.bn_n[bi], uld = M.u_ld[bi], fo = M.bn_f_off[bi];
+    const float* U = reinterpret_cast<const float*>(smem + M.u_off[bi]);
+    const float* stat = reinterpret_cast<const float*>(smem + M.stat_off);
+    Vals<NJ> xh, u;
 #pragma unroll
     for (int q = 0; q < NJ * 2; ++q) {
-      const uint32_t xo = (g + 8 * (q & 1)) * x_ld + ((warp + NWARPS * (q >> 1)) * 8 + 2 * t) * 2;
-      sh[q] = lds32(x_hi + xo);
-      sl[q] = lds32(x_lo + xo);
+      const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = g + 8 * (q & 1);
+      const bool vr = row0 + r < rows;
+      float2 uu = make_float2(0.f, 0.f);
+      if (col < Nb) uu = *reinterpret_cast<const float2*>(U + r * uld + col);
+      u[q][0] = uu.x; u[q][1] = uu.y;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float x = 0.f;
+        if (vr && col + e < Nb) x = (u[q][e] - stat[fo + col + e]) * stat[M.bn_f_total + fo + col + e];
+        else v[q][e] = 0.f;
+        xh[q][e] = x;
+      }
     }
-    const float neg = pact == BB_ACT_LEAKY ? BB_LEAKY : 0.f;
+    dbn_bn_backward<NJ>(v, xh, M, P, sc, bi, 7 - bi, tile, warp, g, t, row0, smem);
 #pragma unroll
     for (int q = 0; q < NJ * 2; ++q) {
-      const float2 xh = half2_bits_to_float2(sh[q]), xl = half2_bits_to_float2(sl[q]);
-      if (!(xh.x > 0.f || (xh.x == 0.f && xl.x > 0.f))) v[q][0] *= neg;
-      if (!(xh.y > 0.f || (xh.y == 0.f && xl.y > 0.f))) v[q][1] *= neg;
+      if (!(u[q][0] > 0.f)) v[q][0] *= BB_LEAKY;
+      if (!(u[q][1] > 0.f)) v[q][1] *= BB_LEAKY;
     }
+  } else {
+    if (pact != BB_ACT_NONE) {
+      // dZ_{l-1} = (dZ_l W_l) * act'_{l-1}; the sign of the pre-activation is the sign of X_l (slope > 0)
+      uint32_t sh[NJ > 0 ? NJ * 2 : 1], sl[NJ > 0 ? NJ * 2 : 1];
+#pragma unroll
+      for (int q = 0; q < NJ * 2; ++q) {
+        const uint32_t xo = (g + 8 * (q & 1)) * x_ld + ((warp + NWARPS * (q >> 1)) * 8 + 2 * t) * 2;
+        sh[q] = lds32(x_hi + xo);
+        sl[q] = lds32(x_lo + xo);
+      }
+      const float neg = pact == BB_ACT_LEAKY ? BB_LEAKY : 0.f;
+#pragma unroll
+      for (int q = 0; q < NJ * 2; ++q) {
+        const float2 xh = half2_bits_to_float2(sh[q]), xl = half2_bits_to_float2(sl[q]);
+        if (!(xh.x > 0.f || (xh.x == 0.f && xl.x > 0.f))) v[q][0] *= neg;
+        if (!(xh.y > 0.f || (xh.y == 0.f && xl.y > 0.f))) v[q][1] *= neg;
+      }
+    }
+    // encoder layer of AE_Dropout_BN: the same keep-mask and 1 / (1 - p) as in the forward pass
+    if (DBN && ps.drop >= 0 && P.train) dbn_dropout<NJ>(v, M, P, sc, ps.drop, M.L[ps.drop].N, warp, g, t, row0);
   }
 #pragma unroll
   for (int q = 0; q < NJ * 2; ++q) {
@@ -451,12 +824,15 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
 }
 
 // forward + loss + backward of one 16-row tile, all 8 warps alike
-__device__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __restrict__ xg, const int rows, const int tile,
-                            const bool fwd_only, const int loss_slot, unsigned char* smem, SmemBars* bars, PipeState& ps,
-                            long long* prof) {
+template <bool DBN>
+__device__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __restrict__ xg, const StepCtx& sc, const int tile,
+                            const int loss_slot, unsigned char* smem, SmemBars* bars, PipeState& ps, long long* prof) {
+  constexpr int RN = DBN ? RING_DBN : RING;
   const int tid = threadIdx.x, warp = uni(tid >> 5), lane = tid & 31;
+  const int rows = sc.rows;
+  const bool fwd_only = sc.fwd_only;
   uint4* ring = reinterpret_cast<uint4*>(smem);
-  __half* XH = reinterpret_cast<__half*>(smem + (size_t)RING * CHUNK_U4 * 16);
+  __half* XH = reinterpret_cast<__half*>(smem + (size_t)RN * CHUNK_U4 * 16);
   __half* XL = XH + M.smem_x_halves;
   __half* DZ = XL + M.smem_x_halves;  // [buf 2][hi | lo][16][dz_ld]
   const int row0 = tile * TROWS, F = M.F, s_max = M.RS / TROWS, dz_ld = M.dz_ld;
@@ -470,7 +846,7 @@ __device__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __re
 
   if (tid == 0) {
     fence_proxy_async();  // this CTA's earlier generic-proxy accesses of the ring's shared memory precede the bulk writes
-    for (int c = 0; c < RING; ++c) ring_issue(M, P, bars, ring, c_base, c, n_chunks);
+    for (int c = 0; c < RN; ++c) ring_issue<RN>(M, P, bars, ring, c_base, c, n_chunks);
   }
   // X_0 = the (already normalised) input rows, hi | lo, plus the bias column of ones and zero padding
   {
@@ -502,11 +878,11 @@ __device__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __re
                      pd.a_which ? P.zt_lo : P.xt_lo, pd.a_gfeat0, s_max, tile);
     if (prof && lane == 0) prof[16 + (pass * NWARPS + warp) * 4 + 3] = clock64();
     const int nj = uni(pd.NT > warp ? (pd.NT - warp + NWARPS - 1) / NWARPS : 0);
-    if (nj >= 4) run_pass<4>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
-    else if (nj == 3) run_pass<3>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
-    else if (nj == 2) run_pass<2>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
-    else if (nj == 1) run_pass<1>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
-    else run_pass<0>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, rows, xs, loss, prof, pass);
+    if (nj >= 4) run_pass<4, DBN>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, sc, tile, smem, xs, loss, prof, pass);
+    else if (nj == 3) run_pass<3, DBN>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, sc, tile, smem, xs, loss, prof, pass);
+    else if (nj == 2) run_pass<2, DBN>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, sc, tile, smem, xs, loss, prof, pass);
+    else if (nj == 1) run_pass<1, DBN>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, sc, tile, smem, xs, loss, prof, pass);
+    else run_pass<0, DBN>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, sc, tile, smem, xs, loss, prof, pass);
   }
   __syncthreads();
   if (!fwd_only) {  // dZ_0 (ping-pong buffer (7 - 0) & 1)
@@ -733,6 +1109,7 @@ __device__ void finish_loss(const TcModel& M, const TcPtrs& P, const int n_tiles
   if (!(s == s) || fabsf(s) > 3.0e38f) *P.flag = 1;
 }
 
+template <bool DBN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_train_kernel(const __grid_constant__ TcModel Mparam, const __grid_constant__ TcPtrs P, const float* __restrict__ x,
                 const long long n_rows, const int batch, const int n_steps, const int flags, const float beta1,
@@ -753,25 +1130,32 @@ tc_train_kernel(const __grid_constant__ TcModel Mparam, const __grid_constant__ 
   __syncthreads();
   PipeState ps = {0u, 0u};
   unsigned target = 0;
-  const bool fwd_only = (flags & TC_FWD_ONLY) != 0;
+  StepCtx sc;
+  sc.fwd_only = (flags & TC_FWD_ONLY) != 0;
   for (int step = 0; step < n_steps; ++step) {
     long long r_begin = (long long)step * batch;
     int rows = (int)(n_rows - r_begin < batch ? n_rows - r_begin : batch);
+    sc.B = rows;
+    sc.row_base = 0;
     if (P.dp_slice) {
       // data parallel: `batch` is the GLOBAL batch (the reference's batch_size) of the full table every rank holds; this
       // rank takes its contiguous share of it, the first (rows % world) ranks one row more (sharded.row_range)
       const int base = rows / P.world, extra = rows - base * P.world;
-      r_begin += (long long)P.rank * base + (P.rank < extra ? P.rank : extra);
+      sc.row_base = P.rank * base + (P.rank < extra ? P.rank : extra);
+      r_begin += sc.row_base;
       rows = base + (P.rank < extra ? 1 : 0);
     }
     const int n_tiles = (rows + TROWS - 1) / TROWS;
     const int slot = step & 1;
     const unsigned tag = P.xbase + (unsigned)step + 1u;
+    sc.rows = rows; sc.n_tiles = n_tiles; sc.tag = tag; sc.dstep = P.drop_step + (unsigned long long)step;
     long long* prof = (P.prof && blockIdx.x == 0 && step == P.prof_step) ? P.prof : nullptr;
     if (prof && threadIdx.x == 0) prof[0] = clock64();
     if (flags & (TC_P1 | TC_FWD_ONLY)) {
+      // (AE_Dropout_BN in train mode: the tiles of a batch meet at the BatchNorm reduction points, so every tile needs its
+      // own co-resident CTA; the host refuses batches of more than gridDim.x tiles)
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        phase1_tile(M, P, x + (size_t)r_begin * M.F, rows, tile, fwd_only, slot, smem, bars, ps, prof);
+        phase1_tile<DBN>(M, P, x + (size_t)r_begin * M.F, sc, tile, slot, smem, bars, ps, prof);
       if (prof && threadIdx.x == 0) prof[1] = clock64();
       grid_barrier(P.bar, target);
       if (prof && threadIdx.x == 0) prof[2] = clock64();
@@ -780,6 +1164,14 @@ tc_train_kernel(const __grid_constant__ TcModel Mparam, const __grid_constant__ 
       const float2 sh = P.stephyper[step];
       for (int item = blockIdx.x; item < M.n_items; item += gridDim.x)
         phase2_item(M, P, item, rows, flags, sh.x, sh.y, beta1, beta2, eps, tag, (int)(tag & 1u), smem, bars, ps, prof);
+      if (DBN && (flags & TC_ADAM) && blockIdx.x == gridDim.x - 1) {
+        // gamma / beta of the four BatchNorms: their gradients are batch totals every CTA held at the reduction points
+        // (CTA 0 stored them, already summed over the ranks); one CTA applies Adam
+        for (int i = M.n_linear + threadIdx.x; i < M.n_params; i += NTHREADS) {
+          float p;
+          adam_one(P, i, __ldcg(P.grads + i), sh.x, sh.y, beta1, beta2, eps, p);
+        }
+      }
       if (prof && threadIdx.x == 0) prof[912] = clock64();
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && (flags & (TC_P1 | TC_FWD_ONLY)))
@@ -806,7 +1198,7 @@ tc_flat_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcPtrs
     }
     float p = P.params[idx];
     if (do_adam) adam_one(P, idx, P.grads[idx], lr_bc1, inv_sqrt_bc2, beta1, beta2, eps, p);
-    store_packed(M, P, l, n, k, p);
+    if (idx < M.n_linear) store_packed(M, P, l, n, k, p);  // (BatchNorm gamma / beta have no packed image)
   }
   if (do_adam && idx == 0 && loss_accum) *loss_accum += (double)P.grads[M.n_params];
 }
@@ -836,14 +1228,18 @@ struct TcTrainer {
   void* dp_peer[MAX_WORLD] = {};
   size_t dp_flag_bytes = 0;
   int xt_feat[NL], zt_feat[NL];
+  uint4* bn_part = nullptr;      // AE_Dropout_BN: per-tile BatchNorm packets
+  size_t dp_bnx_off = 0;         // ... and where the per-rank packets start inside the data-parallel block
+  int ring = RING;
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static void dp_release(TcTrainer* t);
 
 int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_batch, float* params, float* m, float* v,
-                       float* grads, TcTrainer** out) {
-  if (!ctx || !dims || !acts || !out || max_batch < 1) return BB_ERR_INVALID;
+                       float* grads, int kind, const int* bn_g_off, const int* bn_b_off, int n_params_total, TcTrainer** out) {
+  if (!ctx || !dims || !acts || !out || max_batch < 1 || kind < 0 || kind > 1) return BB_ERR_INVALID;
+  if (kind == 1 && (!bn_g_off || !bn_b_off)) return BB_ERR_INVALID;
   TcTrainer* t = new (std::nothrow) TcTrainer();
   if (!t) return BB_ERR_NOMEM;
   t->ctx = ctx;
@@ -852,6 +1248,8 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
   memset(&M, 0, sizeof(M));
   memset(&t->P, 0, sizeof(t->P));
   M.F = dims[0];
+  M.kind = kind;
+  t->ring = kind == 1 ? RING_DBN : RING;
   M.RS = round_up(max_batch, P2_ROWS);
   M.max_tiles = (max_batch + TROWS - 1) / TROWS;
   int p = 0, xs = 0, xt = 0, zt = 0, dz_ld = 0;
@@ -881,9 +1279,25 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
     L.imgb_off = (int)img; img += (size_t)L.KSb * L.NTb * 32;
     if (L.NTf > 4 * NWARPS || L.NTb > 4 * NWARPS || L.NTf > CHUNK_U4 / 32 || L.NTb > CHUNK_U4 / 32) { delete t; return BB_ERR_UNSUPPORTED; }
   }
-  M.n_params = p; M.smem_x_halves = xs; M.dz_ld = dz_ld;
+  M.n_linear = p;
+  M.n_params = kind == 1 ? n_params_total : p;
+  M.smem_x_halves = xs; M.dz_ld = dz_ld;
+  if (kind == 1) {
+    // dropout keep probabilities 1 - p of models.py:263-275, thresholds exactly as train_dbn_kernel draws them
+    const float keep_p[4] = {0.5f, 0.6f, 0.7f, 0.8f};
+    for (int i = 0; i < 4; ++i) {
+      M.keep_thr[i] = (unsigned)(keep_p[i] * 4294967296.0);
+      M.keep_scale[i] = 1.f / keep_p[i];
+      M.bn_g_off[i] = bn_g_off[i]; M.bn_b_off[i] = bn_b_off[i];
+      M.bn_n[i] = dims[5 + i];
+      M.bn_f_off[i] = M.bn_f_total;
+      M.bn_f_total += dims[5 + i];
+      if (dims[5 + i] > BN_PW || dims[5 + i] > NTHREADS) { delete t; return BB_ERR_UNSUPPORTED; }
+    }
+    if (M.n_params < p + 2 * M.bn_f_total) { delete t; return BB_ERR_INVALID; }
+  }
   // weight stream: per pass, groups of k-steps that fit one ring stage
-  const int ring_b = RING * CHUNK_U4 * 16, xl_base = ring_b + xs * 2, dz_base = xl_base + xs * 2;
+  const int ring_b = t->ring * CHUNK_U4 * 16, xl_base = ring_b + xs * 2, dz_base = xl_base + xs * 2;
   const int dzbuf_b = 2 * TROWS * dz_ld * 2, dzlo_b = TROWS * dz_ld * 2;
   int nc = 0;
   for (int pass = 0; pass < 2 * NL - 1; ++pass) {
@@ -926,6 +1340,13 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
       ps.pact = M.L[l - 1].act;
       ps.x_hi_off = ring_b + L.x_off * 2; ps.x_lo_off = xl_base + L.x_off * 2; ps.x_ld_b = L.ldx * 2;
     }
+    ps.drop = ps.bn = -1;
+    if (kind == 1) {
+      if (!bwd && l < 4) ps.drop = l;                 // encoder layer: Linear -> Dropout -> LeakyReLU
+      if (!bwd && l >= 4 && l < NL - 1) ps.bn = l - 4;  // decoder layer: Linear -> LeakyReLU -> BatchNorm (the last one: kind 1)
+      if (bwd && l - 1 < 4) ps.drop = l - 1;          // backward pass of layer l writes dZ_{l-1}
+      if (bwd && l - 1 >= 4) ps.bn = l - 1 - 4;
+    }
     if (pass == NL - 1) M.n_chunks_fwd = nc;
   }
   M.n_chunks = nc;
@@ -934,7 +1355,18 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
     for (int n0 = 0; n0 < M.L[l].N; n0 += P2_BLK)
       for (int k0 = 0; k0 <= M.L[l].K; k0 += P2_BLK) items.push_back({l, n0, k0});
   M.n_items = (int)items.size();
-  const size_t smem1 = (size_t)RING * CHUNK_U4 * 16 + (size_t)2 * xs * 2 + (size_t)4 * TROWS * dz_ld * 2 + (size_t)TROWS * M.F * 4 + NWARPS * 4;
+  size_t smem1 = (size_t)t->ring * CHUNK_U4 * 16 + (size_t)2 * xs * 2 + (size_t)4 * TROWS * dz_ld * 2 + (size_t)TROWS * M.F * 4 + NWARPS * 4;
+  if (kind == 1) {
+    smem1 = (smem1 + 15) / 16 * 16;
+    for (int i = 0; i < 4; ++i) {
+      M.u_ld[i] = round_up(M.bn_n[i], 8);
+      while (M.u_ld[i] % 32 != 8) M.u_ld[i] += 8;  // rows g = 0..3 of a float2 store land in distinct bank groups
+      M.u_off[i] = (int)smem1;
+      smem1 += (size_t)TROWS * M.u_ld[i] * 4;
+    }
+    M.stat_off = (int)smem1;
+    smem1 += (size_t)(2 * M.bn_f_total + 2 * BN_TW) * 4;
+  }
   const size_t smem2 = (size_t)4 * P2_PANEL + 32 * 33 * 4;
   t->bars_off = (int)(((smem1 > smem2 ? smem1 : smem2) + 127) / 128 * 128);
   t->smem = (size_t)t->bars_off + sizeof(SmemBars);
@@ -957,10 +1389,12 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
   alloc((void**)&t->bar, sizeof(unsigned));
   alloc((void**)&t->flag, sizeof(int));
   alloc((void**)&t->prof, sizeof(long long) * 1024);
+  if (kind == 1) alloc((void**)&t->bn_part, sizeof(uint4) * 8 * (size_t)M.max_tiles * BN_PW);
   if (rc == BB_OK) rc = (int)cudaMemcpy(t->items, items.data(), sizeof(TcItem) * items.size(), cudaMemcpyHostToDevice);
-  if (rc == BB_OK) rc = (int)cudaFuncSetAttribute(tc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem);
+  const void* kern = kind == 1 ? (const void*)tc_train_kernel<true> : (const void*)tc_train_kernel<false>;
+  if (rc == BB_OK) rc = (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem);
   int per_sm = 0;
-  if (rc == BB_OK) rc = (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc_train_kernel, NTHREADS, t->smem);
+  if (rc == BB_OK) rc = (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NTHREADS, t->smem);
   if (rc == BB_OK && per_sm < 1) rc = BB_ERR_UNSUPPORTED;
   if (rc != BB_OK) { bb_tc_train_destroy(t); return rc; }
   const int want = M.n_items > M.max_tiles ? M.n_items : M.max_tiles;
@@ -969,11 +1403,15 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
     const int v = atoi(g);
     if (v >= 1 && v < t->grid) t->grid = v;
   }
+  // AE_Dropout_BN: the tiles of a batch wait for each other at the BatchNorm reduction points: one resident CTA per tile
+  if (kind == 1 && M.max_tiles > t->grid) { bb_tc_train_destroy(t); return BB_ERR_UNSUPPORTED; }
   TcPtrs& P = t->P;
   P.params = params; P.m = m; P.v = v; P.grads = grads;
   P.img = t->img; P.xt_hi = t->xt_hi; P.xt_lo = t->xt_lo; P.zt_hi = t->zt_hi; P.zt_lo = t->zt_lo;
   P.loss_part = t->loss_part; P.items = t->items; P.bar = t->bar; P.flag = t->flag;
   P.rank = 0; P.world = 1;
+  P.bn_part = t->bn_part;
+  P.train = 1;
   *out = t;
   return BB_OK;
 }
@@ -981,7 +1419,8 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
 void bb_tc_train_destroy(TcTrainer* t) {
   if (!t) return;
   dp_release(t);
-  void* ptrs[] = {t->img, t->xt_hi, t->xt_lo, t->zt_hi, t->zt_lo, t->loss_part, t->items, t->bar, t->flag, t->stephyper, t->prof};
+  void* ptrs[] = {t->img, t->xt_hi, t->xt_lo, t->zt_hi, t->zt_lo, t->loss_part, t->items, t->bar, t->flag, t->stephyper, t->prof,
+                  t->bn_part};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete t;
@@ -1027,7 +1466,27 @@ int bb_tc_train_run(TcTrainer* t, const float* x, int64_t n_rows, int batch, int
   int ns = n_steps, fl = flags, bt = batch, bo = t->bars_off;
   void* args[] = {(void*)&t->M, (void*)&t->P, (void*)&x, (void*)&nr, (void*)&bt, (void*)&ns, (void*)&fl,
                   (void*)&b1, (void*)&b2, (void*)&eps, (void*)&loss_accum, (void*)&bo};
-  return (int)cudaLaunchCooperativeKernel((const void*)tc_train_kernel, dim3(t->grid), dim3(NTHREADS), args, t->smem, s);
+  const void* kern = t->M.kind == 1 ? (const void*)tc_train_kernel<true> : (const void*)tc_train_kernel<false>;
+  return (int)cudaLaunchCooperativeKernel(kern, dim3(t->grid), dim3(NTHREADS), args, t->smem, s);
+}
+
+int bb_tc_train_set_bn(TcTrainer* t, float* running_mean, float* running_var, long long* batches_tracked) {
+  if (!t || t->M.kind != 1 || !running_mean || !running_var || !batches_tracked) return BB_ERR_INVALID;
+  t->P.rm = running_mean; t->P.rv = running_var; t->P.nbt = batches_tracked;
+  return BB_OK;
+}
+
+int bb_tc_train_set_dropout(TcTrainer* t, unsigned long long seed, const unsigned char* const* masks_dev) {
+  if (!t || t->M.kind != 1) return BB_ERR_INVALID;
+  t->P.seed = seed;
+  for (int i = 0; i < 4; ++i) t->P.mask[i] = masks_dev ? masks_dev[i] : nullptr;
+  return BB_OK;
+}
+
+void bb_tc_train_set_mode(TcTrainer* t, int train, unsigned long long drop_step) {
+  if (!t) return;
+  t->P.train = train;
+  t->P.drop_step = drop_step;
 }
 
 int bb_tc_train_adam_flat(TcTrainer* t, const TcHyper* h, long long step, double* loss_accum, cudaStream_t s) {
@@ -1116,9 +1575,13 @@ int bb_tc_train_range_flag(TcTrainer* t, int reset, int* out) {
 }
 
 static size_t dp_flag_bytes(const TcTrainer*, int) { return 256; }  // reserved
-static size_t dp_total_bytes(const TcTrainer* t, int world) {
+static size_t dp_xchg_bytes(const TcTrainer* t, int world) {
   // [2 step parities][world source ranks][items][256 threads][4 {value, tag} packets of 8 bytes]
-  return dp_flag_bytes(t, world) + (size_t)2 * world * t->M.n_items * NTHREADS * 4 * sizeof(uint2);
+  return (size_t)2 * world * t->M.n_items * NTHREADS * 4 * sizeof(uint2);
+}
+static size_t dp_total_bytes(const TcTrainer* t, int world) {
+  // ... and, AE_Dropout_BN, [2 step parities][8 reduction points][world source ranks][BN_PW] 16-byte packets
+  return dp_flag_bytes(t, world) + dp_xchg_bytes(t, world) + (t->M.kind == 1 ? (size_t)2 * 8 * world * BN_PW * sizeof(uint4) : 0);
 }
 
 static void dp_release(TcTrainer* t) {
@@ -1159,6 +1622,7 @@ int bb_tc_train_dp_connect(TcTrainer* t, int rank, int world, const unsigned cha
   for (int r = 0; r < world; ++r) {
     t->P.xflag[r] = reinterpret_cast<unsigned*>(t->dp_peer[r]);
     t->P.xchg[r] = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(t->dp_peer[r]) + t->dp_flag_bytes);
+    t->P.bnx[r] = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(t->dp_peer[r]) + t->dp_flag_bytes + dp_xchg_bytes(t, world));
   }
   return BB_OK;
 }

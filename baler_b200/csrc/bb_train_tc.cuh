@@ -19,8 +19,18 @@ struct TcHyper {
   double lr, b1d, b2d;  // per-step bias corrections are derived on the host from the step number
 };
 
+// kind 0: AE (8 Linears); kind 1: AE_Dropout_BN (models.py:256-313), whose flat parameter vector continues after the
+// Linears with gamma / beta of the four decoder BatchNorms at bn_g_off / bn_b_off (n_params_total values in all)
 int bb_tc_train_create(bb_ctx* ctx, const int* dims /*9*/, const int* acts /*8*/, int max_batch, float* params, float* m,
-                       float* v, float* grads, TcTrainer** out);
+                       float* v, float* grads, int kind, const int* bn_g_off /*4*/, const int* bn_b_off /*4*/,
+                       int n_params_total, TcTrainer** out);
+// AE_Dropout_BN: running statistics (concatenated over the four BatchNorms) and num_batches_tracked[4], device memory
+int bb_tc_train_set_bn(TcTrainer* t, float* running_mean, float* running_var, long long* batches_tracked);
+// dropout stream: Philox seed, or four injected keep-mask arrays [global batch][width] (uint8, device) for parity tests
+int bb_tc_train_set_dropout(TcTrainer* t, unsigned long long seed, const unsigned char* const* masks_dev);
+// train = 1: dropout on, batch statistics (updates the running statistics); 0: eval.  drop_step: dropout stream position
+// of the first step of the next launch (one position per batch)
+void bb_tc_train_set_mode(TcTrainer* t, int train, unsigned long long drop_step);
 void bb_tc_train_destroy(TcTrainer* t);
 // rebuild the packed fp16 hi / lo weight images from the flat fp32 parameters (after creation, or after the fp32
 // kernels moved the parameters)

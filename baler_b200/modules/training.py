@@ -74,9 +74,12 @@ class DeviceAdam:
         if self.trainer is None:
             # wide rows (CFD_dense_AE on flattened 2-D snapshots): the layer-by-layer GEMM trainer
             self.trainer = engine.LayeredTrainer(w, b, ["leaky", "leaky", "leaky", "none"] * 2, max_batch)
-        if self.has_bn:
-            self.trainer.set_dropout(seed=dropout_seed + self.rank)  # every rank draws its own dropout stream
         self.dp = sharded.DataParallelTrainer(self.trainer, fused=not l1) if self.world > 1 else None
+        if self.has_bn:
+            # fused data parallel: one dropout stream keyed by the global batch row, the same on every rank; otherwise every
+            # rank draws its own
+            fused = self.dp is not None and self.dp.fused
+            self.trainer.set_dropout(seed=dropout_seed + (0 if fused else self.rank))
 
     def hyper(self, world_size=None):
         return engine.make_hyper(lr=self.lr, reg_param=self.reg_param, l1=self.l1,

@@ -65,19 +65,23 @@ class DataParallelTrainer:
     def __init__(self, trainer, group=None, fused=True):
         self.trainer, self.group = trainer, group
         self.grads = trainer.grads_view()  # n_params + 1 floats: gradient, then the batch loss
-        # the tensor-core step of the plain AE exchanges its gradient tiles itself (NVLink peer memory, fused with the
-        # weight-gradient phase): no collective and no host loop per step.  Everything else (fp32 step, BatchNorm models,
-        # the layered trainer, the CPU stand-in of the gloo tests) all-reduces the flat gradient between the two phases.
+        # the tensor-core step exchanges its gradient tiles itself (NVLink peer memory, fused with the weight-gradient
+        # phase): no collective and no host loop per step.  AE_Dropout_BN on that path also exchanges the BatchNorm sums
+        # at its 8 reduction points, i.e. it normalises with the statistics of the GLOBAL batch and keys the dropout
+        # stream by global row: the replicas compute exactly what one GPU computes at batch_size = global batch
+        # (models.py:256-313 under training.py:253-263).  Everything else (fp32 step, the layered trainer, the CPU
+        # stand-in of the gloo tests) all-reduces the flat gradient between the two phases.
         self.fused = False
-        if (fused and hasattr(trainer, "dp_connect") and getattr(trainer, "_bn", None) is None and dist.is_initialized()
+        if (fused and hasattr(trainer, "dp_connect") and dist.is_initialized()
                 and dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1
                 and getattr(trainer, "precision", None) == "split16"):
             trainer.dp_connect(group)
             self.fused = True
-        # AE_Dropout_BN: every rank normalises ITS slice of the batch (per-rank BatchNorm statistics, as torch
-        # DistributedDataParallel runs the reference model) and draws its own dropout stream; the running statistics
-        # are averaged over ranks at the end of an epoch so that the replicas save the same model.pt
-        self.bn_running = trainer.bn_running_views() if getattr(trainer, "_bn", None) is not None else None
+        # AE_Dropout_BN without the fused exchange (fused=False, the labelled local-statistics mode): every rank normalises
+        # ITS slice of the batch (per-rank BatchNorm statistics, as torch DistributedDataParallel runs the reference model)
+        # and draws its own dropout stream; the running statistics are averaged over ranks at the end of an epoch so that
+        # the replicas save the same model.pt
+        self.bn_running = trainer.bn_running_views() if getattr(trainer, "_bn", None) is not None and not self.fused else None
 
     def sync_running_stats(self):
         if self.bn_running is None or not (dist.is_available() and dist.is_initialized()):

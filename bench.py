@@ -516,15 +516,61 @@ def run_ours(args):
         dm = models.AE_Dropout_BN(24, 15)
         w, b = dm.linear_tensors()
         trd = engine.Trainer(w, b, 24, 15, 512, bn=dm.bn_tensors())
-        trd.set_dropout(seed=1234 + rank)
-        train_dbn = one_epoch(trd, "fp32")
+        trd.set_dropout(seed=1234)  # one stream keyed by the global batch row, the same on every rank
+        train_dbn = one_epoch(trd, trd.precision)
         train_dbn["model"] = "AE_Dropout_BN 24-200-100-50-15-50-100-200-24 (dropout .5/.4/.3/.2, 4 BatchNorm1d)"
-        train_dbn["batchnorm"] = "per-rank batch statistics" if world > 1 else "batch statistics"
+        train_dbn["batchnorm"] = ("statistics of the global batch: the 8 reduction points of a step exchanged over NVLink peer "
+                                  "memory inside the kernel" if world > 1 else "batch statistics")
+        train_dbn["loss"] = "sum-MSE / n_columns as training.fit evaluates it (validate=True: the L1 term never trains, SURVEY F2)"
+        if world == 1:
+            trd32 = engine.Trainer(w, b, 24, 15, 512, bn=dm.bn_tensors())
+            trd32.set_precision("fp32")
+            trd32.set_dropout(seed=1234)
+            train_dbn["fp32_step"] = {k: v for k, v in one_epoch(trd32, "fp32").items() if k in ("samples_per_s", "us_per_step", "epoch_loss")}
+            del trd32
         if cpu and cpu.get("fit_AE_Dropout_BN_samples_per_s"):
             train_dbn["cpu_baseline"] = {"samples_per_s": cpu["fit_AE_Dropout_BN_samples_per_s"], "cores": cpu["cores"],
                                          "kind": cpu["kind"],
                                          "sample": "training.fit of the unmodified reference, 200 steps of bs 512 (BASELINE.md C4)"}
             train_dbn["vs_cpu"] = train_dbn["samples_per_s"] / cpu["fit_AE_Dropout_BN_samples_per_s"]
+        if world > 1:
+            # BASELINE configs[2] parity, visible to the driver: replicas bit-identical (parameters and BatchNorm running
+            # statistics), and equal to ONE GPU training the same 20 global batches at batch_size = 512 x N with the same
+            # dropout seed (<= 1e-5 of max|w|)
+            rows_p = 20 * gb
+            hyper = engine.make_hyper(lr=1e-3, world_size=world)
+            trp = engine.Trainer(w, b, 24, 15, 512, bn=dm.bn_tensors())
+            trp.set_dropout(seed=99)
+            dpp = sharded.DataParallelTrainer(trp)
+            dpp.epoch_table(xt[:rows_p], gb, hyper, rank, world)
+            mine = torch.cat([trp.params_view()] + list(trp.bn_running_views())).clone()
+            ref0 = mine.clone()
+            dist.broadcast(ref0, src=0)
+            same = torch.tensor([1 if torch.equal(mine, ref0) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            train_dbn["dp_parity"] = {"replicas_identical": bool(same.item()), "global_steps": 20, "fused": dpp.fused}
+            if rank == 0:
+                ok = False
+                try:
+                    tr1 = engine.Trainer(w, b, 24, 15, gb, bn=dm.bn_tensors())
+                    if tr1.precision == "split16":  # (one GPU holds at most 148 x 16 rows of a BatchNorm batch)
+                        tr1.set_dropout(seed=99)
+                        tr1.epoch(xt[:rows_p], gb, engine.make_hyper(lr=1e-3))
+                        one = torch.cat([tr1.params_view()] + list(tr1.bn_running_views()))
+                        npar = tr1.n_params
+                        train_dbn["dp_parity"]["vs_single_gpu_same_global_batch_rel_max"] = \
+                            ((mine[:npar] - one[:npar]).abs().max() / one[:npar].abs().max()).item()
+                        train_dbn["dp_parity"]["running_stats_rel_max"] = \
+                            ((mine[npar:] - one[npar:]).abs().max() / one[npar:].abs().max()).item()
+                        ok = (bool(same.item()) and train_dbn["dp_parity"]["vs_single_gpu_same_global_batch_rel_max"] <= 1e-5
+                              and train_dbn["dp_parity"]["running_stats_rel_max"] <= 1e-5)
+                    else:
+                        train_dbn["dp_parity"]["note"] = "global batch of %d rows exceeds one GPU's tensor-core BatchNorm step" % gb
+                    del tr1
+                except Exception as e:  # noqa: BLE001
+                    train_dbn["dp_parity"]["note"] = "single-GPU comparison unavailable: %s" % e
+                train_dbn["dp_parity"]["ok"] = ok
+            del trp, dpp
         del trd
 
     # ---- CFD line (secondary, BASELINE configs[3]): Conv_AE on 5x5 blocks of synthetic 50x50 flow-field snapshots,

@@ -18,6 +18,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _norm_rows(synth, n):
+    t = synth.cms_table(n, seed=3)
+    return np.ascontiguousarray((t - t.min(axis=0)) / (t.max(axis=0) - t.min(axis=0)), dtype=np.float32)
+
+
 def _worker(rank, world, port, out_dir):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -59,13 +64,25 @@ def _worker(rank, world, port, out_dir):
         bn["num_batches_tracked"] = [int(sdb[b + ".num_batches_tracked"]) for b in bnn]
         trb = engine.Trainer([sdb[n + ".weight"] for n in lin], [sdb[n + ".bias"] for n in lin], 24, 15, 512, bn=bn)
         trb.set_dropout(seed=5 + rank)
-        dpb = sharded.DataParallelTrainer(trb)
+        dpb = sharded.DataParallelTrainer(trb, fused=False)  # the labelled local-statistics mode
         xb = torch.from_numpy(np.ascontiguousarray(gd["x_norm"][:1024])).cuda()
         sl = sharded.dp_batch_slices(1024, 512, rank, world)
         losses = [dpb.epoch([xb[lo:hi].contiguous() for lo, hi in sl], hyper) for _ in range(3)]
         rm, rv = trb.bn_running_views()
         np.save(os.path.join(out_dir, "dbn_%d.npy" % rank),
                 np.concatenate([trb.params_view().cpu().numpy(), rm.cpu().numpy(), rv.cpu().numpy(), np.array(losses, dtype=np.float32)]))
+        # AE_Dropout_BN through the library's own exchange: BatchNorm over the GLOBAL batch (the 8 reduction points of a step
+        # exchanged over peer memory), dropout keyed by global row, gradient tiles summed in the weight-gradient phase:
+        # three epochs over 1500 rows in global batches of 1024 (the second one ragged: 238 rows per rank)
+        trs = engine.Trainer([sdb[n + ".weight"] for n in lin], [sdb[n + ".bias"] for n in lin], 24, 15, 512, bn=bn)
+        trs.set_dropout(seed=77)
+        dps = sharded.DataParallelTrainer(trs)
+        assert dps.fused
+        xs_ = torch.from_numpy(_norm_rows(synth, 1500)).cuda()
+        sl_ = [dps.epoch_table(xs_, 1024, hyper, rank, world) for _ in range(3)]
+        rms, rvs = trs.bn_running_views()
+        np.save(os.path.join(out_dir, "dbn_sync_%d.npy" % rank),
+                np.concatenate([trs.params_view().cpu().numpy(), rms.cpu().numpy(), rvs.cpu().numpy(), np.array(sl_, dtype=np.float32)]))
         # Conv_AE, data parallel through the layer-by-layer trainer: per-rank BatchNorm2d statistics, SUM all-reduce of the
         # trainable (kernel-level) gradient, identical Adam step + dense re-expansion on every rank
         torch.manual_seed(0)
@@ -109,6 +126,26 @@ def test_data_parallel_equals_single_gpu(tmp_path):
     d0, d1 = np.load(tmp_path / "dbn_0.npy"), np.load(tmp_path / "dbn_1.npy")
     assert np.array_equal(d0, d1) and np.isfinite(d0).all()  # AE_Dropout_BN replicas: parameters, running statistics, losses
     assert d0[-1] < d0[-3]  # three epochs: the loss goes down
+    # exact-sync AE_Dropout_BN: replicas bit-identical, and equal to ONE GPU training at batch_size = global batch with the
+    # same dropout seed (parameters <= 1e-5 of max|w|, running statistics and epoch losses 1e-5)
+    s0, s1 = np.load(tmp_path / "dbn_sync_0.npy"), np.load(tmp_path / "dbn_sync_1.npy")
+    assert np.array_equal(s0, s1) and np.isfinite(s0).all()
+    gd = np.load(os.path.join(GOLDEN, "ae_dbn.npz"))
+    sdb = {k[4:]: np.asarray(gd[k], order="C") for k in gd.files if k.startswith("sd0/")}
+    lin = models.AE_Dropout_BN.enc_names + models.AE_Dropout_BN.dec_names
+    bnn = models.AE_Dropout_BN.bn_names
+    bn = {k: [sdb[b + "." + k] for b in bnn] for k in ("weight", "bias", "running_mean", "running_var")}
+    bn["num_batches_tracked"] = [int(sdb[b + ".num_batches_tracked"]) for b in bnn]
+    one = engine.Trainer([sdb[n + ".weight"] for n in lin], [sdb[n + ".bias"] for n in lin], 24, 15, 1024, bn=bn)
+    one.set_dropout(seed=77)
+    xs_ = torch.from_numpy(_norm_rows(synth, 1500)).cuda()
+    l1 = [one.epoch(xs_, 1024, engine.make_hyper(lr=1e-3)) for _ in range(3)]
+    rm1, rv1 = one.bn_running_views()
+    ref1 = np.concatenate([one.params_view().cpu().numpy(), rm1.cpu().numpy(), rv1.cpu().numpy()])
+    npar = one.n_params
+    assert np.abs(s0[:npar] - ref1[:npar]).max() <= 1e-5 * np.abs(ref1[:npar]).max(), np.abs(s0[:npar] - ref1[:npar]).max()
+    assert np.abs(s0[npar:-3] - ref1[npar:]).max() <= 1e-5 * np.abs(ref1[npar:]).max()
+    assert np.abs(s0[-3:] - np.array(l1)).max() <= 1e-5 * max(l1)
     c0, c1 = np.load(tmp_path / "conv_0.npy"), np.load(tmp_path / "conv_1.npy")
     assert np.array_equal(c0, c1) and np.isfinite(c0).all() and c0[-1] < c0[-3]  # Conv_AE replicas stay identical and learn
     gc = np.load(os.path.join(GOLDEN, "conv_train.npz"))

@@ -198,12 +198,15 @@ def dbn_flat(sd_like):
     return np.concatenate(lin + bn)
 
 
-def test_dropout_bn_train_step_with_injected_masks(golden):
+@pytest.mark.parametrize("precision", ["split16", "fp32"])
+def test_dropout_bn_train_step_with_injected_masks(golden, precision):
     """one reference train step of AE_Dropout_BN (loss, every gradient, BN running statistics, Adam update) with the
-    dropout masks torch drew, injected"""
+    dropout masks torch drew, injected; on the tensor-core step (default) and on the fp32 kernels"""
     g = golden("ae_dbn.npz")
     sd0, sd1 = sub_sd(g, "sd0"), sub_sd(g, "sd1")
     tr = dbn_trainer(sd0)
+    tr.set_precision(precision)
+    assert tr.precision == precision
     assert tr.n_params == 61839 + 2 * (50 + 100 + 200 + 24)
     masks = [torch.from_numpy(g["mask%d" % i].astype(np.uint8)).cuda() for i in range(4)]
     tr.set_dropout(masks=masks)
@@ -258,6 +261,59 @@ def test_dropout_bn_philox_keep_rates_and_training(golden):
         t_.set_dropout(seed=seed)
         t_.step(x[:512].contiguous(), h)
     assert torch.equal(a.params_view(), b.params_view()) and not torch.equal(a.params_view(), c.params_view())
+
+
+@pytest.mark.parametrize("rows", [2000, 1999, 37])
+def test_dropout_bn_large_batch_vs_oracle(golden, rows):
+    """tensor-core AE_Dropout_BN step on batches beyond the fp32 kernel's 592 rows (and ragged ones): loss, all gradients
+    and running statistics against the float64 oracle with the same (numpy-drawn) keep-masks"""
+    g = golden("ae_dbn.npz")
+    sd0 = sub_sd(g, "sd0")
+    x = orc.normalize(synth.cms_table(rows, seed=31))
+    rng = np.random.default_rng(5)
+    masks = [(rng.random((rows, w)) < keep).astype(np.uint8) for w, keep in ((200, 0.5), (100, 0.6), (50, 0.7), (15, 0.8))]
+    tr = dbn_trainer(sd0, max_batch=2048)
+    assert tr.precision == "split16"
+    tr.set_dropout(masks=[torch.from_numpy(m).cuda() for m in masks])
+    tr.step(torch.from_numpy(x).cuda(), engine.make_hyper(lr=1e-3), phase=1)
+    loss, _, grads, buf = orc.dbn_train_step({k: np.asarray(v, dtype=np.float64) for k, v in sd0.items()}, x.astype(np.float64),
+                                             [m.astype(np.float64) for m in masks])
+    got = tr.grads_view().cpu().numpy()
+    assert abs(got[-1] - loss) <= 1e-5 * loss, (got[-1], loss)
+    ref = dbn_flat(grads)
+    gscale = np.abs(ref).max()
+    # (a 37-row batch: 1 / sqrt(var + eps) of the small-population statistics amplifies the 22-bit operand rounding)
+    tol = 2e-5 if rows >= 512 else 5e-5
+    assert np.abs(got[:-1] - ref).max() <= tol * gscale and rel_l2(got[:-1], ref) <= 2e-5, (np.abs(got[:-1] - ref).max() / gscale, rel_l2(got[:-1], ref))
+    bn = tr.get_bn()
+    for i, b in enumerate(DBN_BN):
+        assert rel_max(bn["running_mean"][i], buf[b + ".running_mean"]) <= 1e-5, b
+        assert rel_max(bn["running_var"][i], buf[b + ".running_var"]) <= 1e-5, b
+
+
+def test_dropout_bn_paths_share_the_dropout_stream(golden):
+    """the tensor-core step and the fp32 kernels draw the same Philox keep-masks from (seed, step, layer, row, column):
+    one step from the same state with the same seed gives the same gradients up to arithmetic (2e-5), and an epoch of the
+    tensor-core path tracks the fp32 path"""
+    g = golden("ae_dbn.npz")
+    sd0 = sub_sd(g, "sd0")
+    x = torch.from_numpy(orc.normalize(synth.cms_table(4096, seed=23))).cuda()
+    h = engine.make_hyper(lr=1e-3)
+    out = {}
+    for prec in ("split16", "fp32"):
+        tr = dbn_trainer(sd0)
+        tr.set_precision(prec)
+        tr.set_dropout(seed=4321)
+        tr.step(x[:512].contiguous(), h, phase=1)
+        out[prec] = tr.grads_view().cpu().numpy()
+        tr2 = dbn_trainer(sd0)
+        tr2.set_precision(prec)
+        tr2.set_dropout(seed=4321)
+        out[prec + "_loss"] = [tr2.epoch(x, 512, h) for _ in range(2)]
+    gscale = np.abs(out["fp32"][:-1]).max()
+    assert np.abs(out["split16"] - out["fp32"])[:-1].max() <= 2e-5 * gscale
+    assert abs(out["split16"][-1] - out["fp32"][-1]) <= 1e-5 * out["fp32"][-1]
+    assert np.allclose(out["split16_loss"], out["fp32_loss"], rtol=1e-2)  # the north-star bar for loss curves: 1 %
 
 
 def test_dropout_bn_validate_equals_folded_codec(golden):
