@@ -63,6 +63,7 @@ constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 constexpr int MAX_WORLD = 16;
 constexpr int BN_PW = 208;         // row width (columns) of the per-tile BatchNorm partial-sum packets
 constexpr int BN_TW = 208;         // width of the backward totals scratch in shared memory
+constexpr int POLL = 8;            // BatchNorm packets a thread keeps in flight
 constexpr int RING_DBN = 3;        // AE_Dropout_BN: one ring stage less, its 32 KB hold the BatchNorm inputs
 constexpr float BN_EPS = 1e-5f, BN_MOMENTUM = 0.1f;  // nn.BatchNorm1d defaults (models.py:284-296)
 
@@ -111,8 +112,9 @@ struct TcModel {
   int kind, n_linear;            // 0 AE / 1 AE_Dropout_BN; Linear parameters in the flat vector (BatchNorm gamma / beta follow)
   // AE_Dropout_BN: flat offsets of gamma / beta, feature offset in the concatenated running statistics, width, the fp32
   // shared-memory copy U_i of every BatchNorm input (byte offset, row stride in floats), and the per-feature scratch
-  // [mean bn_f_total | 1/sqrt(var + eps) bn_f_total | T1 BN_TW | T2 BN_TW] (byte offset)
-  int bn_g_off[4], bn_b_off[4], bn_f_off[4], bn_n[4], u_off[4], u_ld[4], stat_off, bn_f_total;
+  // [mean bn_f_total | 1/sqrt(var + eps) bn_f_total | 4 transient arrays of BN_TW] and the slice partials of a reduction
+  // point (byte offsets)
+  int bn_g_off[4], bn_b_off[4], bn_f_off[4], bn_n[4], bn_slices[4], u_off[4], u_ld[4], stat_off, red_off, bn_f_total;
   unsigned keep_thr[4];          // dropout: keep when the 32-bit draw is below this (1 - p of models.py:263-275) ...
   float keep_scale[4];           // ... and scale the kept value by 1 / (1 - p)
   alignas(16) TcChunk chunk[MAX_CHUNKS];
@@ -326,9 +328,12 @@ struct StepCtx {
   int rows, n_tiles;         // this rank's rows of the batch / their 16-row tiles
   int row_base;              // position of this rank's first row in the global batch (dropout and injected masks are keyed by it)
   int B;                     // rows of the global batch: the BatchNorm population
+  float inv_rows, inv_B, inv_Bm1;  // 1 / rows, 1 / B, 1 / max(B - 1, 1)
+  int per[4];                // tiles per slice of a reduction point of BatchNorm i
   unsigned tag;              // packet tag of the step
   unsigned long long dstep;  // dropout stream position of the step
   bool fwd_only;
+  long long* prof;           // diagnostics (CTA 0, armed step): clock stamps of the reduction points at [520 + 8 pt + k]
 };
 
 // ------------------------------------------------------------------------------------------------ AE_Dropout_BN
@@ -347,13 +352,26 @@ struct StepCtx {
 template <int NJ>
 using Vals = float[NJ > 0 ? NJ * 2 : 1][2];
 
+// Packet loads are relaxed (strong) loads at the scope of the writer: gpu for the tiles of this GPU, sys for what peers
+// push over NVLink.  (Not volatile: ptxas completes a volatile access before it issues the next one.  And not weak
+// ld.global.cg / L1::no_allocate either: a weak load carries no inter-thread guarantee, and ptxas did rewrite a
+// `while (tag mismatch) reload` loop around one into a single unchecked reload.)  Independent relaxed loads are all in
+// flight together; the tag inside each 8-byte half makes a torn read harmless: it is simply retried.
 __device__ __forceinline__ uint4 ld_pkt(const uint4* p) {
   uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_pkt_sys(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_pkt(uint4* p, const float a, const float b, const unsigned tag) {
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(tag), "r"(__float_as_uint(b)), "r"(tag) : "memory");
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(tag), "r"(__float_as_uint(b)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void st_pkt_sys(uint4* p, const float a, const float b, const unsigned tag) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(tag), "r"(__float_as_uint(b)), "r"(tag) : "memory");
 }
 __device__ __forceinline__ float sum_over_rows(float s) {  // the 8 lanes that hold one column pair differ in lane bits 2..4
   s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -366,107 +384,184 @@ __device__ __forceinline__ int dp_rank_rows(const int B, const int world, const 
   return base + (r < B - base * world ? 1 : 0);
 }
 
-// Thread j sums column j of reduction point `pt`.  FWD: packets are (sum, sum of squares about the tile mean) and the
+// Sum of reduction point `pt` over the tiles of this rank (and, data parallel, over the ranks).  Column j is owned by
+// thread j; when the layer is narrower than half the CTA the idle threads take slices of the tile range (fixed
+// geometry, combined in slice order: reproducible).  FWD: packets are (sum, sum of squares about the tile mean) and the
 // result is the batch mean and 1 / sqrt(biased variance + eps) (Chan's pairwise combination, no E[x^2] - mean^2
-// cancellation in fp32); otherwise (sum dY, sum dY xhat) and the result is the two totals = d beta, d gamma.
+// cancellation in fp32); otherwise (sum dY, sum dY xhat) and the result is the two totals = d beta, d gamma.  Leaves in
+// shared memory what the warps need for their values: mean | inv (kept for the backward pass) and gamma | beta, or
+// T1 / B | T2 / B | gamma inv.
 template <bool FWD>
-__device__ __noinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, const StepCtx& sc, const int bi, const int pt,
+__device__ __forceinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, const StepCtx& sc, const int bi, const int pt,
                                        unsigned char* smem) {
-  const int j = threadIdx.x, N = M.bn_n[bi], fo = M.bn_f_off[bi];
+  // All of it in fp32 (FP64 instructions issue at a small fraction of the fp32 rate here: measured ~175 cycles per
+  // packet with double accumulators).  The forward sums are taken about a shift K = the mean of the rank's first
+  // tile, the same for every slice of a column: sum (x - K) and sum (x - K)^2 are additive over tiles and slices, and
+  // M2 = sum (x - K)^2 - (sum (x - K))^2 / n loses nothing to cancellation because |mean - K| is a fraction of sigma.
+  const int tid = threadIdx.x, N = M.bn_n[bi], fo = M.bn_f_off[bi];
   float* stat = reinterpret_cast<float*>(smem + M.stat_off);
-  if (j < N) {
-    double S1 = 0.0, S2 = 0.0;
-    const uint4* base = P.bn_part + (size_t)pt * M.max_tiles * BN_PW + j;
-    for (int t0 = 0; t0 < sc.n_tiles; t0 += 8) {
-      uint4 pk[8];
+  float* tr = stat + 2 * M.bn_f_total;  // transient: [gamma | beta | T1 / B | T2 / B or gamma inv] x BN_TW
+  float2* red = reinterpret_cast<float2*>(smem + M.red_off);
+  const int slices = M.bn_slices[bi];
+  int sl = 0, col = tid;
+  while (col >= N) { col -= N; ++sl; }
+  float gam = 0.f, bet = 0.f;
+  if (tid < N) {
+    gam = __ldcg(P.params + M.bn_g_off[bi] + tid);
+    if (FWD) bet = __ldcg(P.params + M.bn_b_off[bi] + tid);
+  }
+  const bool pk0 = sc.prof != nullptr && tid == 0;
+  if (pk0) sc.prof[520 + 8 * pt + 1] = clock64();
+  float S1 = 0.f, S2 = 0.f, K = 0.f;
+  if (sl < slices) {
+    const int per = sc.per[bi];
+    const int tb = sl * per, te = tb + per < sc.n_tiles ? tb + per : sc.n_tiles;
+    const uint4* base = P.bn_part + (size_t)pt * M.max_tiles * BN_PW + col;
+    const int last = sc.rows - (sc.n_tiles - 1) * TROWS;            // rows of the last tile
+    const float n_last = (float)last, inv_last = __frcp_rn(n_last);  // (1 / 16 is exact; 1 / last is used for one tile)
+    if (FWD) {
+      uint4 k0 = ld_pkt(base);
+      while (k0.y != sc.tag || k0.w != sc.tag) k0 = ld_pkt(base);
+      K = __uint_as_float(k0.x) * (sc.n_tiles == 1 ? inv_last : 1.f / TROWS);
+    }
+    for (int t0 = tb; t0 < te; t0 += POLL) {
+      uint4 pk[POLL];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (t0 + u < sc.n_tiles) pk[u] = ld_pkt(base + (size_t)(t0 + u) * BN_PW);
+      for (int u = 0; u < POLL; ++u)
+        if (t0 + u < te) pk[u] = ld_pkt(base + (size_t)(t0 + u) * BN_PW);
+      if (pk0) sc.prof[600 + 16 * pt + 2 * ((t0 - tb) / POLL)] = clock64();
+      bool missing;
+      do {  // re-issue the loads of the packets that have not landed yet, all of them together
+        missing = false;
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (t0 + u < sc.n_tiles) {
-          while (pk[u].y != sc.tag || pk[u].w != sc.tag) pk[u] = ld_pkt(base + (size_t)(t0 + u) * BN_PW);
-          const double a = (double)__uint_as_float(pk[u].x), b = (double)__uint_as_float(pk[u].z);
-          S1 += a;
+        for (int u = 0; u < POLL; ++u)
+          if (t0 + u < te && (pk[u].y != sc.tag || pk[u].w != sc.tag)) {
+            pk[u] = ld_pkt(base + (size_t)(t0 + u) * BN_PW);
+            missing = true;
+          }
+      } while (missing);
+      if (pk0) sc.prof[600 + 16 * pt + 2 * ((t0 - tb) / POLL) + 1] = clock64();
+#pragma unroll
+      for (int u = 0; u < POLL; ++u)
+        if (t0 + u < te) {
+          const float a = __uint_as_float(pk[u].x), b = __uint_as_float(pk[u].z);
           if (FWD) {
-            const int left = sc.rows - (t0 + u) * TROWS;
-            S2 += b + a * a / (double)(left < TROWS ? left : TROWS);
+            const bool is_last = t0 + u == sc.n_tiles - 1;
+            const float d = a - (is_last ? n_last : (float)TROWS) * K;
+            S1 += d;
+            S2 += fmaf(d * d, is_last ? inv_last : 1.f / TROWS, b);
           } else {
+            S1 += a;
             S2 += b;
           }
         }
     }
-    double r1, r2;  // FWD: mean, M2 of the global batch; else the totals
+  }
+  if (pk0) sc.prof[520 + 8 * pt + 2] = clock64();
+  if (slices > 1) {
+    if (sl > 0 && sl < slices) red[(sl - 1) * N + col] = make_float2(S1, S2);
+    __syncwarp();
+    __syncthreads();
+    if (sl == 0)
+      for (int q = 1; q < slices; ++q) {
+        const float2 o = red[(q - 1) * N + col];
+        S1 += o.x;
+        S2 += o.y;
+      }
+  }
+  if (pk0) sc.prof[520 + 8 * pt + 3] = clock64();
+  if (tid < N) {
+    const int j = tid;
+    float r1, r2;  // FWD: mean, M2 of the global batch; else the totals
     if (FWD) {
-      const double n = (double)sc.rows;
-      r1 = S1 / n;
-      r2 = S2 - S1 * S1 / n;
-      r2 = r2 > 0.0 ? r2 : 0.0;
+      const float dm = S1 * sc.inv_rows;
+      r1 = K + dm;
+      r2 = fmaxf(S2 - S1 * dm, 0.f);
     } else {
       r1 = S1;
       r2 = S2;
     }
     if (P.dp_slice) {
-      // this rank's sums travel (and are used locally) rounded to fp32, so every rank combines the same numbers
-      const float fa = (float)r1, fb = (float)r2;
+      // every rank combines the same fp32 numbers in the same (rank) order: identical statistics on all replicas
       const size_t blk = (((size_t)(sc.tag & 1u) * 8 + pt) * P.world) * BN_PW + j;
       if (blockIdx.x == 0)
         for (int r = 0; r < P.world; ++r)
-          if (r != P.rank) st_pkt(P.bnx[r] + blk + (size_t)P.rank * BN_PW, fa, fb, sc.tag);
-      double cn = 0.0, c1 = 0.0, c2 = 0.0;
-      for (int r = 0; r < P.world; ++r) {
-        const int nr = dp_rank_rows(sc.B, P.world, r);
-        if (nr == 0) continue;
-        float a = fa, b = fb;
-        if (r != P.rank) {
-          const uint4* src = P.bnx[P.rank] + blk + (size_t)r * BN_PW;
-          uint4 q = ld_pkt(src);
-          while (q.y != sc.tag || q.w != sc.tag) q = ld_pkt(src);
-          a = __uint_as_float(q.x);
-          b = __uint_as_float(q.z);
-        }
-        if (FWD) {
-          const double delta = (double)a - c1, nn = cn + nr;
-          c1 += delta * nr / nn;
-          c2 += (double)b + delta * delta * cn * nr / nn;
-          cn = nn;
-        } else {
-          c1 += (double)a;
-          c2 += (double)b;
+          if (r != P.rank) st_pkt_sys(P.bnx[r] + blk + (size_t)P.rank * BN_PW, r1, r2, sc.tag);
+      float cn = 0.f, c1 = 0.f, c2 = 0.f;
+      const uint4* mine = P.bnx[P.rank] + blk;
+      for (int r0 = 0; r0 < P.world; r0 += 4) {
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (r0 + u < P.world && r0 + u != P.rank) q[u] = ld_pkt_sys(mine + (size_t)(r0 + u) * BN_PW);
+        bool missing;
+        do {
+          missing = false;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (r0 + u < P.world && r0 + u != P.rank && dp_rank_rows(sc.B, P.world, r0 + u) > 0 &&
+                (q[u].y != sc.tag || q[u].w != sc.tag)) {
+              q[u] = ld_pkt_sys(mine + (size_t)(r0 + u) * BN_PW);
+              missing = true;
+            }
+        } while (missing);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u;
+          const int nr = r < P.world ? dp_rank_rows(sc.B, P.world, r) : 0;
+          if (nr > 0) {
+            const float a = r == P.rank ? r1 : __uint_as_float(q[u].x), b = r == P.rank ? r2 : __uint_as_float(q[u].z);
+            if (FWD) {  // Chan's pairwise update of (count, mean, M2)
+              const float delta = a - c1, nn = cn + (float)nr;
+              const float w = __fdiv_rn((float)nr, nn);
+              c1 = fmaf(delta, w, c1);
+              c2 += fmaf(delta * delta, cn * w, b);
+              cn = nn;
+            } else {
+              c1 += a;
+              c2 += b;
+            }
+          }
         }
       }
       r1 = c1;
       r2 = c2;
     }
     if (FWD) {
-      const double var = r2 / (double)sc.B;
-      stat[fo + j] = (float)r1;
-      stat[M.bn_f_total + fo + j] = (float)(1.0 / sqrt(var + (double)BN_EPS));
+      stat[fo + j] = r1;
+      stat[M.bn_f_total + fo + j] = __frcp_rn(__fsqrt_rn(fmaf(r2, sc.inv_B, BN_EPS)));  // IEEE roundings: ~1 ulp
+      tr[j] = gam;
+      tr[BN_TW + j] = bet;
       if (blockIdx.x == 0) {  // running statistics: momentum 0.1, unbiased variance (torch.nn.BatchNorm1d)
-        const double unb = r2 / (double)(sc.B > 1 ? sc.B - 1 : 1);
-        P.rm[fo + j] = (1.f - BN_MOMENTUM) * P.rm[fo + j] + BN_MOMENTUM * (float)r1;
-        P.rv[fo + j] = (1.f - BN_MOMENTUM) * P.rv[fo + j] + BN_MOMENTUM * (float)unb;
+        P.rm[fo + j] = (1.f - BN_MOMENTUM) * P.rm[fo + j] + BN_MOMENTUM * r1;
+        P.rv[fo + j] = (1.f - BN_MOMENTUM) * P.rv[fo + j] + BN_MOMENTUM * (r2 * sc.inv_Bm1);
         if (j == 0) P.nbt[bi] += 1;
       }
     } else {
-      stat[2 * M.bn_f_total + j] = (float)r1;
-      stat[2 * M.bn_f_total + BN_TW + j] = (float)r2;
+      tr[2 * BN_TW + j] = r1 * sc.inv_B;
+      tr[3 * BN_TW + j] = r2 * sc.inv_B;
+      tr[j] = gam * stat[M.bn_f_total + fo + j];
       if (blockIdx.x == 0) {
-        P.grads[M.bn_b_off[bi] + j] = (float)r1;
-        P.grads[M.bn_g_off[bi] + j] = (float)r2;
+        P.grads[M.bn_b_off[bi] + j] = r1;
+        P.grads[M.bn_g_off[bi] + j] = r2;
       }
     }
   }
+  if (pk0) sc.prof[520 + 8 * pt + 4] = clock64();
+  __syncwarp();
   __syncthreads();
+  if (pk0) sc.prof[520 + 8 * pt + 5] = clock64();
 }
 
 // eval mode: the running statistics
-__device__ __noinline__ void bn_eval_stats(const TcModel& M, const TcPtrs& P, const int bi, unsigned char* smem) {
+__device__ __forceinline__ void bn_eval_stats(const TcModel& M, const TcPtrs& P, const int bi, unsigned char* smem) {
   const int j = threadIdx.x, N = M.bn_n[bi], fo = M.bn_f_off[bi];
   float* stat = reinterpret_cast<float*>(smem + M.stat_off);
   if (j < N) {
     stat[fo + j] = __ldcg(P.rm + fo + j);
     stat[M.bn_f_total + fo + j] = 1.f / sqrtf(__ldcg(P.rv + fo + j) + BN_EPS);
+    stat[2 * M.bn_f_total + j] = __ldcg(P.params + M.bn_g_off[bi] + j);
+    stat[2 * M.bn_f_total + BN_TW + j] = __ldcg(P.params + M.bn_b_off[bi] + j);
   }
   __syncthreads();
 }
@@ -480,111 +575,275 @@ __device__ __forceinline__ void dbn_dropout(Vals<NJ>& v, const TcModel& M, const
   const float ks = M.keep_scale[l];
   const unsigned thr = M.keep_thr[l];
   const unsigned char* mk = P.mask[l];
+  if (mk != nullptr) {
 #pragma unroll
-  for (int q = 0; q < NJ * 2; ++q) {
-    const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = row0 + g + 8 * (q & 1);
-    bool k0 = false, k1 = false;
-    if (r < sc.rows && col < N) {
-      const unsigned grow = (unsigned)(sc.row_base + r);
-      if (mk != nullptr) {
-        k0 = mk[(size_t)grow * N + col] != 0;
-        k1 = col + 1 < N && mk[(size_t)grow * N + col + 1] != 0;
-      } else {
-        const uint4 d = curand_Philox4x32_10(make_uint4((unsigned)(col >> 2), grow, (unsigned)l, (unsigned)sc.dstep),
-                                             make_uint2((unsigned)P.seed, (unsigned)(P.seed >> 32) ^ (unsigned)(sc.dstep >> 32)));
-        k0 = ((col & 2) ? d.z : d.x) < thr;
-        k1 = col + 1 < N && ((col & 2) ? d.w : d.y) < thr;
+    for (int q = 0; q < NJ * 2; ++q) {
+      const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = row0 + g + 8 * (q & 1);
+      bool k0 = false, k1 = false;
+      if (r < sc.rows && col < N) {
+        const size_t grow = (size_t)(sc.row_base + r);
+        k0 = mk[grow * N + col] != 0;
+        k1 = col + 1 < N && mk[grow * N + col + 1] != 0;
       }
+      v[q][0] = k0 ? v[q][0] * ks : 0.f;
+      v[q][1] = k1 ? v[q][1] * ks : 0.f;
     }
-    v[q][0] = k0 ? v[q][0] * ks : 0.f;
-    v[q][1] = k1 ? v[q][1] * ks : 0.f;
+    return;
   }
-}
-
-// BatchNorm forward on this thread's values a (the BatchNorm input): keeps a copy U for the backward pass, publishes the
-// tile's column sums, waits for the batch statistics and returns xhat in `xh` (0 outside the valid rows / columns).
-template <int NJ>
-__device__ __forceinline__ void dbn_bn_forward(const Vals<NJ>& a, Vals<NJ>& xh, const TcModel& M, const TcPtrs& P,
-                                               const StepCtx& sc, const int bi, const int tile, const int warp, const int g,
-                                               const int t, const int row0, unsigned char* smem) {
-  const int N = M.bn_n[bi], uld = M.u_ld[bi], fo = M.bn_f_off[bi];
-  float* U = reinterpret_cast<float*>(smem + M.u_off[bi]);
-  const bool vr[2] = {row0 + g < sc.rows, row0 + g + 8 < sc.rows};
-#pragma unroll
-  for (int q = 0; q < NJ * 2; ++q) {
-    const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = g + 8 * (q & 1);
-    if (col < N) *reinterpret_cast<float2*>(U + r * uld + col) = make_float2(a[q][0], a[q][1]);
-  }
-  if (P.train) {
-    const int left = sc.rows - row0;
-    const float inv_nt = 1.f / (float)(left < TROWS ? left : TROWS);
-    uint4* part = P.bn_part + ((size_t)bi * M.max_tiles + tile) * BN_PW;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int col = (warp + NWARPS * j) * 8 + 2 * t;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float a0 = vr[0] ? a[2 * j][e] : 0.f, a1 = vr[1] ? a[2 * j + 1][e] : 0.f;
-        const float s = sum_over_rows(a0 + a1);
-        const float mean = s * inv_nt;
-        const float d0 = vr[0] ? a0 - mean : 0.f, d1 = vr[1] ? a1 - mean : 0.f;
-        const float m2 = sum_over_rows(d0 * d0 + d1 * d1);
-        if (g == 0 && col + e < N) st_pkt(part + col + e, s, m2, sc.tag);
-      }
-    }
-    bn_reduce<true>(M, P, sc, bi, bi, smem);
-  } else {
-    bn_eval_stats(M, P, bi, smem);
-  }
-  const float* stat = reinterpret_cast<const float*>(smem + M.stat_off);
-#pragma unroll
-  for (int q = 0; q < NJ * 2; ++q) {
-    const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      float x = 0.f;
-      if (vr[q & 1] && col + e < N) x = (a[q][e] - stat[fo + col + e]) * stat[M.bn_f_total + fo + col + e];
-      xh[q][e] = x;
-    }
-  }
-}
-
-// BatchNorm backward on this thread's values: dy (gradient w.r.t. the BatchNorm output, 0 outside the valid rows /
-// columns) and xhat -> gradient w.r.t. the BatchNorm input, dx = gamma inv / B (B dy - sum dy - xhat sum dy xhat)
-template <int NJ>
-__device__ __forceinline__ void dbn_bn_backward(Vals<NJ>& dy, const Vals<NJ>& xh, const TcModel& M, const TcPtrs& P,
-                                                const StepCtx& sc, const int bi, const int pt, const int tile, const int warp,
-                                                const int g, const int t, const int row0, unsigned char* smem) {
-  const int N = M.bn_n[bi], fo = M.bn_f_off[bi];
-  uint4* part = P.bn_part + ((size_t)pt * M.max_tiles + tile) * BN_PW;
-#pragma unroll
+  // One Philox call yields the draws of 4 consecutive columns of a row.  The two lanes of a pair (t, t ^ 1) hold columns
+  // 4c..4c+1 and 4c+2..4c+3 of rows g and g + 8: the even lane draws row g, the odd lane row g + 8, and they swap halves.
+  const bool odd = (t & 1) != 0;
+  const uint2 key = make_uint2((unsigned)P.seed, (unsigned)(P.seed >> 32) ^ (unsigned)(sc.dstep >> 32));
+#pragma unroll 2
   for (int j = 0; j < NJ; ++j) {
     const int col = (warp + NWARPS * j) * 8 + 2 * t;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float s1 = sum_over_rows(dy[2 * j][e] + dy[2 * j + 1][e]);
-      const float s2 = sum_over_rows(fmaf(dy[2 * j][e], xh[2 * j][e], dy[2 * j + 1][e] * xh[2 * j + 1][e]));
-      if (g == 0 && col + e < N) st_pkt(part + col + e, s1, s2, sc.tag);
-    }
+    const unsigned grow = (unsigned)(sc.row_base + row0 + g + (odd ? 8 : 0));
+    const uint4 d = curand_Philox4x32_10(make_uint4((unsigned)(col >> 2), grow, (unsigned)l, (unsigned)sc.dstep), key);
+    const unsigned o0 = __shfl_xor_sync(0xffffffffu, odd ? d.x : d.z, 1);
+    const unsigned o1 = __shfl_xor_sync(0xffffffffu, odd ? d.y : d.w, 1);
+    // draws of (row g, col), (row g, col + 1), (row g + 8, col), (row g + 8, col + 1)
+    const unsigned a0 = odd ? o0 : d.x, a1 = odd ? o1 : d.y, b0 = odd ? d.z : o0, b1 = odd ? d.w : o1;
+    const bool va = row0 + g < sc.rows, vb = row0 + g + 8 < sc.rows;
+    v[2 * j][0] = va && col < N && a0 < thr ? v[2 * j][0] * ks : 0.f;
+    v[2 * j][1] = va && col + 1 < N && a1 < thr ? v[2 * j][1] * ks : 0.f;
+    v[2 * j + 1][0] = vb && col < N && b0 < thr ? v[2 * j + 1][0] * ks : 0.f;
+    v[2 * j + 1][1] = vb && col + 1 < N && b1 < thr ? v[2 * j + 1][1] * ks : 0.f;
   }
-  bn_reduce<false>(M, P, sc, bi, pt, smem);
-  const float* stat = reinterpret_cast<const float*>(smem + M.stat_off);
-  const float inv_b = 1.f / (float)sc.B;
+}
+
+// A BatchNorm epilogue runs in phases around the reduction (phase1_tile): publish -> reduce -> apply.  Nothing stays in
+// registers across a reduction: the BatchNorm input a is parked in the fp32 copy U (which the backward pass needs
+// anyway) and a gradient dY in the pass's own output slots (the hi / lo words of a column pair hold the two floats), each
+// value read back by the thread that wrote it.  The reduction is then one piece of code per direction instead of one per
+// epilogue variant, and it has the whole register file for its packets (with this kernel's shared-memory footprint the
+// L1 that would back register spills is ~28 KB: a spill is an L2 round trip).
+struct Own {  // this thread's position in the epilogue layout
+  int warp, g, t, row0;
+};
+template <int NJ>
+__device__ __forceinline__ int own_col(const Own& o, const int q) { return (o.warp + NWARPS * (q >> 1)) * 8 + 2 * o.t; }
+
+// publish (sum, sum of squares about the tile mean) of this tile's columns of BatchNorm input `a` and park a in U
+template <int NJ>
+__device__ __forceinline__ void bn_publish_fwd(const Vals<NJ>& a, const TcModel& M, const TcPtrs& P, const StepCtx& sc, const int bi,
+                                               const int tile, const Own& o, unsigned char* smem) {
+  const int N = M.bn_n[bi], uld = M.u_ld[bi];
+  float* U = reinterpret_cast<float*>(smem + M.u_off[bi]);
+  const bool vr[2] = {o.row0 + o.g < sc.rows, o.row0 + o.g + 8 < sc.rows};
 #pragma unroll
   for (int q = 0; q < NJ * 2; ++q) {
-    const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t;
-    const bool vr = row0 + g + 8 * (q & 1) < sc.rows;
+    const int col = own_col<NJ>(o, q), r = o.g + 8 * (q & 1);
+    if (col < N) *reinterpret_cast<float2*>(U + r * uld + col) = make_float2(a[q][0], a[q][1]);
+  }
+  if (!P.train) return;
+  if (sc.prof != nullptr && threadIdx.x == 0) sc.prof[520 + 8 * bi] = clock64();
+  const int left = sc.rows - o.row0;
+  const float inv_nt = 1.f / (float)(left < TROWS ? left : TROWS);
+  uint4* part = P.bn_part + ((size_t)bi * M.max_tiles + tile) * BN_PW;
+#if 0
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int col = own_col<NJ>(o, 2 * j);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      float dx = 0.f;
-      if (vr && col + e < N) {
-        const int c = col + e;
-        const float gam = __ldcg(P.params + M.bn_g_off[bi] + c), inv = stat[M.bn_f_total + fo + c];
-        dx = inv * gam * (dy[q][e] - inv_b * stat[2 * M.bn_f_total + c] - xh[q][e] * inv_b * stat[2 * M.bn_f_total + BN_TW + c]);
-      }
-      dy[q][e] = dx;
+      const float a0 = vr[0] ? a[2 * j][e] : 0.f, a1 = vr[1] ? a[2 * j + 1][e] : 0.f;
+      const float s = sum_over_rows(a0 + a1);
+      const float mean = s * inv_nt;
+      const float d0 = vr[0] ? a0 - mean : 0.f, d1 = vr[1] ? a1 - mean : 0.f;
+      const float m2 = sum_over_rows(d0 * d0 + d1 * d1);
+      if (o.g == 0 && col + e < N) st_pkt(part + col + e, s, m2, sc.tag);
     }
   }
+}
+#else
+  // the column sums over the 16 rows: independent shuffles issued back to back, one butterfly stage at a time (a warp
+  // issues in order: a dependent shuffle right behind its source waits out the ~25-cycle latency)
+  Vals<NJ> s, m2;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) s[j][e] = (vr[0] ? a[2 * j][e] : 0.f) + (vr[1] ? a[2 * j + 1][e] : 0.f);
+#pragma unroll
+  for (int st = 4; st <= 16; st <<= 1)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) s[j][e] += __shfl_xor_sync(0xffffffffu, s[j][e], st);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float mean = s[j][e] * inv_nt;
+      const float d0 = vr[0] ? a[2 * j][e] - mean : 0.f, d1 = vr[1] ? a[2 * j + 1][e] - mean : 0.f;
+      m2[j][e] = d0 * d0 + d1 * d1;
+    }
+#pragma unroll
+  for (int st = 4; st <= 16; st <<= 1)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) m2[j][e] += __shfl_xor_sync(0xffffffffu, m2[j][e], st);
+  if (o.g == 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int col = own_col<NJ>(o, 2 * j);
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (col + e < N) st_pkt(part + col + e, s[j][e], m2[j][e], sc.tag);
+    }
+  }
+}
+#endif
+
+// xhat of this thread's values from the parked BatchNorm input (0 outside the valid rows / columns); u = the input itself
+template <int NJ>
+__device__ __forceinline__ void bn_load_xhat(Vals<NJ>& xh, Vals<NJ>& u, const TcModel& M, const StepCtx& sc, const int bi,
+                                             const Own& o, unsigned char* smem) {
+  const int N = M.bn_n[bi], uld = M.u_ld[bi], fo = M.bn_f_off[bi];
+  const float* U = reinterpret_cast<const float*>(smem + M.u_off[bi]);
+  const float* stat = reinterpret_cast<const float*>(smem + M.stat_off);
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    const int col = own_col<NJ>(o, q), r = o.g + 8 * (q & 1);
+    const bool vr = o.row0 + r < sc.rows;
+    float2 uu = make_float2(0.f, 0.f);
+    if (col < N) uu = *reinterpret_cast<const float2*>(U + r * uld + col);
+    u[q][0] = uu.x; u[q][1] = uu.y;
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      xh[q][e] = vr && col + e < N ? (u[q][e] - stat[fo + col + e]) * stat[M.bn_f_total + fo + col + e] : 0.f;
+  }
+}
+
+// publish (sum dY, sum dY xhat) of this tile's columns and park dY in the output slots
+template <int NJ>
+__device__ __forceinline__ void bn_publish_bwd(const Vals<NJ>& dy, const Vals<NJ>& xh, const TcModel& M, const TcPtrs& P,
+                                               const StepCtx& sc, const int bi, const int pt, const int tile, const Own& o,
+                                               const uint32_t o_hi, const uint32_t o_lo, const uint32_t o_ld) {
+  const int N = M.bn_n[bi];
+  if (sc.prof != nullptr && threadIdx.x == 0) sc.prof[520 + 8 * pt] = clock64();
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    const uint32_t off = (o.g + 8 * (q & 1)) * o_ld + own_col<NJ>(o, q) * 2;
+    sts32(o_hi + off, __float_as_uint(dy[q][0]));
+    sts32(o_lo + off, __float_as_uint(dy[q][1]));
+  }
+  uint4* part = P.bn_part + ((size_t)pt * M.max_tiles + tile) * BN_PW;
+  Vals<NJ> s1, s2;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      s1[j][e] = dy[2 * j][e] + dy[2 * j + 1][e];
+      s2[j][e] = fmaf(dy[2 * j][e], xh[2 * j][e], dy[2 * j + 1][e] * xh[2 * j + 1][e]);
+    }
+#pragma unroll
+  for (int st = 4; st <= 16; st <<= 1)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s1[j][e] += __shfl_xor_sync(0xffffffffu, s1[j][e], st);
+        s2[j][e] += __shfl_xor_sync(0xffffffffu, s2[j][e], st);
+      }
+  if (o.g == 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int col = own_col<NJ>(o, 2 * j);
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (col + e < N) st_pkt(part + col + e, s1[j][e], s2[j][e], sc.tag);
+    }
+  }
+}
+
+// after the backward reduction: dx = gamma inv / B (B dy - sum dy - xhat sum dy xhat), times the LeakyReLU slope of the
+// BatchNorm input when the activation sits in front of the BatchNorm; split to hi | lo in place of the parked dY
+template <int NJ>
+__device__ __forceinline__ void bn_apply_bwd(const TcModel& M, const StepCtx& sc, const int bi, const bool leaky, const Own& o,
+                                             const uint32_t o_hi, const uint32_t o_lo, const uint32_t o_ld, unsigned char* smem) {
+  const int N = M.bn_n[bi];
+  const float* tr = reinterpret_cast<const float*>(smem + M.stat_off) + 2 * M.bn_f_total;
+  Vals<NJ> xh, u;
+  bn_load_xhat<NJ>(xh, u, M, sc, bi, o, smem);
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    const int col = own_col<NJ>(o, q);
+    const bool vr = o.row0 + o.g + 8 * (q & 1) < sc.rows;
+    const uint32_t off = (o.g + 8 * (q & 1)) * o_ld + col * 2;
+    const float dy[2] = {__uint_as_float(lds32(o_hi + off)), __uint_as_float(lds32(o_lo + off))};
+    float dx[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      dx[e] = 0.f;
+      if (vr && col + e < N) {
+        const int c = col + e;
+        dx[e] = tr[c] * (dy[e] - tr[2 * BN_TW + c] - xh[q][e] * tr[3 * BN_TW + c]);
+        if (leaky && !(u[q][e] > 0.f)) dx[e] *= BB_LEAKY;
+      }
+    }
+    uint32_t hi, lo;
+    split16x2(dx[0], dx[1], hi, lo);
+    sts32(o_hi + off, hi);
+    sts32(o_lo + off, lo);
+  }
+}
+
+// after the forward reduction of a hidden decoder layer: X_{l+1} = gamma xhat + beta, the bias column of ones, zero padding
+template <int NJ>
+__device__ __forceinline__ void bn_apply_fwd(const TcModel& M, const StepCtx& sc, const int bi, const Own& o, const uint32_t o_hi,
+                                             const uint32_t o_lo, const uint32_t o_ld, unsigned char* smem) {
+  const int N = M.bn_n[bi];
+  const float* tr = reinterpret_cast<const float*>(smem + M.stat_off) + 2 * M.bn_f_total;  // gamma | beta
+  Vals<NJ> xh, u;
+  bn_load_xhat<NJ>(xh, u, M, sc, bi, o, smem);
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    const int col = own_col<NJ>(o, q);
+    const bool vr = o.row0 + o.g + 8 * (q & 1) < sc.rows;
+    float y[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      y[e] = 0.f;
+      if (vr && col + e < N) y[e] = fmaf(xh[q][e], tr[col + e], tr[BN_TW + col + e]);
+      if (vr && col + e == N) y[e] = 1.f;
+    }
+    uint32_t hi, lo;
+    split16x2(y[0], y[1], hi, lo);
+    const uint32_t off = (o.g + 8 * (q & 1)) * o_ld + col * 2;
+    sts32(o_hi + off, hi);
+    sts32(o_lo + off, lo);
+  }
+}
+
+// last layer after the forward reduction: reconstruction = ReLU(gamma xhat + beta), loss = sum (recon - x)^2 / F, the seed
+// gradient back through the ReLU; publishes the sums of the BatchNorm backward (train) - the values land in dZ_7's slots
+template <int NJ>
+__device__ __forceinline__ void bn_loss(const TcModel& M, const TcPtrs& P, const StepCtx& sc, const int tile, const Own& o,
+                                        const uint32_t o_hi, const uint32_t o_lo, const uint32_t o_ld, const float* xs, float& loss,
+                                        unsigned char* smem) {
+  const int F = M.F;
+  const float inv_f = 1.f / (float)F;
+  const float* tr = reinterpret_cast<const float*>(smem + M.stat_off) + 2 * M.bn_f_total;  // gamma | beta
+  Vals<NJ> xh, u;
+  bn_load_xhat<NJ>(xh, u, M, sc, 3, o, smem);
+#pragma unroll
+  for (int q = 0; q < NJ * 2; ++q) {
+    const int col = own_col<NJ>(o, q), r = o.g + 8 * (q & 1);
+    const bool valid = o.row0 + r < sc.rows;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float gz = 0.f;
+      if (valid && col + e < F) {
+        const float y = fmaf(xh[q][e], tr[col + e], tr[BN_TW + col + e]);
+        const float diff = fmaxf(y, 0.f) - xs[r * F + col + e];
+        loss = fmaf(diff * diff, inv_f, loss);
+        gz = y > 0.f ? 2.f * diff * inv_f : 0.f;
+      }
+      u[q][e] = gz;
+    }
+  }
+  if (!sc.fwd_only) bn_publish_bwd<NJ>(u, xh, M, P, sc, 3, 4, tile, o, o_hi, o_lo, o_ld);
 }
 
 // ------------------------------------------------------------------------------------------------ phase 1
@@ -700,20 +959,8 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
         v[q][0] = act_apply(v[q][0], act);
         v[q][1] = act_apply(v[q][1], act);
       }
-      Vals<NJ> xh;
-      dbn_bn_forward<NJ>(v, xh, M, P, sc, ps.bn, tile, warp, g, t, row0, smem);
-#pragma unroll
-      for (int q = 0; q < NJ * 2; ++q) {
-        const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t;
-        const bool vr = row0 + g + 8 * (q & 1) < rows;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          float y = 0.f;
-          if (vr && col + e < N) y = fmaf(xh[q][e], __ldcg(P.params + M.bn_g_off[ps.bn] + col + e), __ldcg(P.params + M.bn_b_off[ps.bn] + col + e));
-          if (vr && col + e == N) y = 1.f;
-          v[q][e] = y;
-        }
-      }
+      bn_publish_fwd<NJ>(v, M, P, sc, ps.bn, tile, Own{warp, g, t, row0}, smem);
+      return;  // phase1_tile: reduction, then bn_apply_fwd
     } else {
 #pragma unroll
       for (int q = 0; q < NJ * 2; ++q) {
@@ -726,25 +973,8 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
   } else if (kind == 1 && DBN) {
     // reconstruction = ReLU(BatchNorm(X_7 W_7^T + b_7)); loss = sum (recon - x)^2 / F; the seed gradient goes back through
     // the ReLU and the BatchNorm to dZ_7
-    Vals<NJ> xh;
-    dbn_bn_forward<NJ>(v, xh, M, P, sc, 3, tile, warp, g, t, row0, smem);
-#pragma unroll
-    for (int q = 0; q < NJ * 2; ++q) {
-      const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = g + 8 * (q & 1);
-      const bool valid = row0 + r < rows;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float gz = 0.f;
-        if (valid && col + e < F) {
-          const float y = fmaf(xh[q][e], __ldcg(P.params + M.bn_g_off[3] + col + e), __ldcg(P.params + M.bn_b_off[3] + col + e));
-          const float diff = fmaxf(y, 0.f) - xs[r * F + col + e];
-          loss = fmaf(diff * diff, inv_f, loss);
-          gz = y > 0.f ? 2.f * diff * inv_f : 0.f;
-        }
-        v[q][e] = gz;
-      }
-    }
-    if (!sc.fwd_only) dbn_bn_backward<NJ>(v, xh, M, P, sc, 3, 4, tile, warp, g, t, row0, smem);
+    bn_publish_fwd<NJ>(v, M, P, sc, 3, tile, Own{warp, g, t, row0}, smem);
+    return;  // phase1_tile: reduction, bn_loss, reduction, bn_apply_bwd
   } else if (kind == 1) {
     // reconstruction: loss = sum (recon - x)^2 / F, seed gradient dZ_7 = 2 (recon - x) / F
 #pragma unroll
@@ -766,31 +996,19 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
   } else if (DBN && ps.bn >= 0) {
     // v = gradient w.r.t. the output of BatchNorm ps.bn (= dZ_{l} W_{l}); back through the BatchNorm and the LeakyReLU
     // in front of it.  The BatchNorm input U is this thread's own copy from the forward pass.
-    const int bi = ps.bn, Nb = M.bn_n[bi], uld = M.u_ld[bi], fo = M.bn_f_off[bi];
-    const float* U = reinterpret_cast<const float*>(smem + M.u_off[bi]);
-    const float* stat = reinterpret_cast<const float*>(smem + M.stat_off);
+    const Own o{warp, g, t, row0};
+    const int Nb = M.bn_n[ps.bn];
     Vals<NJ> xh, u;
+    bn_load_xhat<NJ>(xh, u, M, sc, ps.bn, o, smem);
 #pragma unroll
     for (int q = 0; q < NJ * 2; ++q) {
-      const int col = (warp + NWARPS * (q >> 1)) * 8 + 2 * t, r = g + 8 * (q & 1);
-      const bool vr = row0 + r < rows;
-      float2 uu = make_float2(0.f, 0.f);
-      if (col < Nb) uu = *reinterpret_cast<const float2*>(U + r * uld + col);
-      u[q][0] = uu.x; u[q][1] = uu.y;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float x = 0.f;
-        if (vr && col + e < Nb) x = (u[q][e] - stat[fo + col + e]) * stat[M.bn_f_total + fo + col + e];
-        else v[q][e] = 0.f;
-        xh[q][e] = x;
-      }
+      const int col = own_col<NJ>(o, q);
+      const bool vr = row0 + g + 8 * (q & 1) < rows;
+      if (!(vr && col < Nb)) v[q][0] = 0.f;
+      if (!(vr && col + 1 < Nb)) v[q][1] = 0.f;
     }
-    dbn_bn_backward<NJ>(v, xh, M, P, sc, bi, 7 - bi, tile, warp, g, t, row0, smem);
-#pragma unroll
-    for (int q = 0; q < NJ * 2; ++q) {
-      if (!(u[q][0] > 0.f)) v[q][0] *= BB_LEAKY;
-      if (!(u[q][1] > 0.f)) v[q][1] *= BB_LEAKY;
-    }
+    bn_publish_bwd<NJ>(v, xh, M, P, sc, ps.bn, 7 - ps.bn, tile, o, o_hi, o_lo, o_ld);
+    return;  // phase1_tile: reduction, then bn_apply_bwd
   } else {
     if (pact != BB_ACT_NONE) {
       // dZ_{l-1} = (dZ_l W_l) * act'_{l-1}; the sign of the pre-activation is the sign of X_l (slope > 0)
@@ -825,7 +1043,7 @@ __device__ __forceinline__ void run_pass(const TcModel& M, const TcPtrs& P, Smem
 
 // forward + loss + backward of one 16-row tile, all 8 warps alike
 template <bool DBN>
-__device__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __restrict__ xg, const StepCtx& sc, const int tile,
+__device__ __forceinline__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __restrict__ xg, const StepCtx& sc, const int tile,
                             const int loss_slot, unsigned char* smem, SmemBars* bars, PipeState& ps, long long* prof) {
   constexpr int RN = DBN ? RING_DBN : RING;
   const int tid = threadIdx.x, warp = uni(tid >> 5), lane = tid & 31;
@@ -871,7 +1089,7 @@ __device__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __re
   float loss = 0.f;
   for (int pass = 0; pass < n_pass; ++pass) {
     __syncthreads();  // the previous pass's epilogue (this pass's A operand) is complete and visible
-    const TcPass pd = M.pass[pass];
+    const TcPass& pd = M.pass[pass];  // (a reference into shared memory: a copy would keep two dozen registers live across the pass)
     if (prof && lane == 0) prof[16 + (pass * NWARPS + warp) * 4] = clock64();
     // the A operand of this pass goes to phase 2 feature-major (shared by the warps, a few 512-byte runs each)
     write_tile_major(sbase + pd.a_hi_off, sbase + pd.a_lo_off, pd.a_ld_b, pd.a_feat, pd.a_which ? P.zt_hi : P.xt_hi,
@@ -883,6 +1101,39 @@ __device__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __re
     else if (nj == 2) run_pass<2, DBN>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, sc, tile, smem, xs, loss, prof, pass);
     else if (nj == 1) run_pass<1, DBN>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, sc, tile, smem, xs, loss, prof, pass);
     else run_pass<0, DBN>(M, P, bars, ring, sbase, pd, c_base, n_chunks, warp, lane, row0, sc, tile, smem, xs, loss, prof, pass);
+    if (DBN && (pd.bn >= 0 || pd.kind == 1)) {
+      // BatchNorm epilogue: the pass published this tile's column sums; reduce over the batch, then apply
+#define BB_BY_NJ(call)            \
+  do {                            \
+    if (nj >= 4) { constexpr int NJ = 4; call; }       \
+    else if (nj == 3) { constexpr int NJ = 3; call; }  \
+    else if (nj == 2) { constexpr int NJ = 2; call; }  \
+    else if (nj == 1) { constexpr int NJ = 1; call; }  \
+  } while (0)
+      const Own o{warp, lane >> 2, lane & 3, row0};
+      const uint32_t o_hi = sbase + pd.o_hi_off, o_lo = sbase + pd.o_lo_off, o_ld = pd.o_ld_b;
+      int bwd_bi = -1, bwd_pt = 0;
+      bool leaky = false;
+      if (pd.kind != 2) {
+        const int bi = pd.kind == 1 ? 3 : pd.bn;
+        if (P.train) bn_reduce<true>(M, P, sc, bi, bi, smem);
+        else bn_eval_stats(M, P, bi, smem);
+        if (pd.kind == 0) {
+          BB_BY_NJ(bn_apply_fwd<NJ>(M, sc, bi, o, o_hi, o_lo, o_ld, smem));
+        } else {
+          BB_BY_NJ(bn_loss<NJ>(M, P, sc, tile, o, o_hi, o_lo, o_ld, xs, loss, smem));
+          if (!fwd_only) { bwd_bi = 3; bwd_pt = 4; }
+        }
+      } else {
+        bwd_bi = pd.bn; bwd_pt = 7 - pd.bn; leaky = true;
+      }
+      if (bwd_bi >= 0) {
+        bn_reduce<false>(M, P, sc, bwd_bi, bwd_pt, smem);
+        BB_BY_NJ(bn_apply_bwd<NJ>(M, sc, bwd_bi, leaky, o, o_hi, o_lo, o_ld, smem));
+      }
+#undef BB_BY_NJ
+      if (prof && lane == 0) prof[16 + (pass * NWARPS + warp) * 4 + 2] = clock64();
+    }
   }
   __syncthreads();
   if (!fwd_only) {  // dZ_0 (ping-pong buffer (7 - 0) & 1)
@@ -903,7 +1154,7 @@ __device__ void phase1_tile(const TcModel& M, const TcPtrs& P, const float* __re
 
 // ------------------------------------------------------------------------------------------------ phase 2
 // one 32 x 32 block of dW_l = dZ_l^T [X_l | 1] over all rows of the batch, then (exchange,) Adam and re-packing
-__device__ void phase2_item(const TcModel& M, const TcPtrs& P, const int item_idx, const int rows, const int flags,
+__device__ __forceinline__ void phase2_item(const TcModel& M, const TcPtrs& P, const int item_idx, const int rows, const int flags,
                             const float lr_bc1, const float inv_sqrt_bc2, const float beta1, const float beta2, const float eps,
                             const unsigned step_tag, const int parity, unsigned char* smem, SmemBars* bars, PipeState& ps,
                             long long* prof) {
@@ -1130,26 +1381,39 @@ tc_train_kernel(const __grid_constant__ TcModel Mparam, const __grid_constant__ 
   __syncthreads();
   PipeState ps = {0u, 0u};
   unsigned target = 0;
-  StepCtx sc;
-  sc.fwd_only = (flags & TC_FWD_ONLY) != 0;
+  // per-step facts live in shared memory, not in registers: the layer passes run at the register cap, and with this
+  // kernel's shared-memory footprint only ~28 KB of L1 would back spills
+  __shared__ StepCtx sc;
   for (int step = 0; step < n_steps; ++step) {
     long long r_begin = (long long)step * batch;
     int rows = (int)(n_rows - r_begin < batch ? n_rows - r_begin : batch);
-    sc.B = rows;
-    sc.row_base = 0;
+    const int B = rows;
+    int row_base = 0;
     if (P.dp_slice) {
       // data parallel: `batch` is the GLOBAL batch (the reference's batch_size) of the full table every rank holds; this
       // rank takes its contiguous share of it, the first (rows % world) ranks one row more (sharded.row_range)
       const int base = rows / P.world, extra = rows - base * P.world;
-      sc.row_base = P.rank * base + (P.rank < extra ? P.rank : extra);
-      r_begin += sc.row_base;
+      row_base = P.rank * base + (P.rank < extra ? P.rank : extra);
+      r_begin += row_base;
       rows = base + (P.rank < extra ? 1 : 0);
     }
     const int n_tiles = (rows + TROWS - 1) / TROWS;
     const int slot = step & 1;
     const unsigned tag = P.xbase + (unsigned)step + 1u;
-    sc.rows = rows; sc.n_tiles = n_tiles; sc.tag = tag; sc.dstep = P.drop_step + (unsigned long long)step;
     long long* prof = (P.prof && blockIdx.x == 0 && step == P.prof_step) ? P.prof : nullptr;
+    if (threadIdx.x == 0) {
+      sc.rows = rows; sc.n_tiles = n_tiles; sc.row_base = row_base; sc.B = B; sc.tag = tag;
+      sc.dstep = P.drop_step + (unsigned long long)step;
+      sc.fwd_only = (flags & TC_FWD_ONLY) != 0;
+      sc.prof = prof;
+      if (DBN) {
+        sc.inv_rows = 1.f / (float)(rows > 0 ? rows : 1);
+        sc.inv_B = 1.f / (float)(B > 0 ? B : 1);
+        sc.inv_Bm1 = 1.f / (float)(B > 1 ? B - 1 : 1);
+        for (int i = 0; i < 4; ++i) sc.per[i] = (n_tiles + M.bn_slices[i] - 1) / M.bn_slices[i];
+      }
+    }
+    __syncthreads();
     if (prof && threadIdx.x == 0) prof[0] = clock64();
     if (flags & (TC_P1 | TC_FWD_ONLY)) {
       // (AE_Dropout_BN in train mode: the tiles of a batch meet at the BatchNorm reduction points, so every tile needs its
@@ -1290,6 +1554,7 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
       M.keep_scale[i] = 1.f / keep_p[i];
       M.bn_g_off[i] = bn_g_off[i]; M.bn_b_off[i] = bn_b_off[i];
       M.bn_n[i] = dims[5 + i];
+      M.bn_slices[i] = NTHREADS / dims[5 + i] > 0 ? NTHREADS / dims[5 + i] : 1;  // threads beyond the columns take slices of the tile range
       M.bn_f_off[i] = M.bn_f_total;
       M.bn_f_total += dims[5 + i];
       if (dims[5 + i] > BN_PW || dims[5 + i] > NTHREADS) { delete t; return BB_ERR_UNSUPPORTED; }
@@ -1365,7 +1630,10 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
       smem1 += (size_t)TROWS * M.u_ld[i] * 4;
     }
     M.stat_off = (int)smem1;
-    smem1 += (size_t)(2 * M.bn_f_total + 2 * BN_TW) * 4;
+    smem1 += (size_t)(2 * M.bn_f_total + 4 * BN_TW) * 4;
+    smem1 = (smem1 + 15) / 16 * 16;
+    M.red_off = (int)smem1;
+    smem1 += (size_t)NTHREADS * sizeof(float2);
   }
   const size_t smem2 = (size_t)4 * P2_PANEL + 32 * 33 * 4;
   t->bars_off = (int)(((smem1 > smem2 ? smem1 : smem2) + 127) / 128 * 128);

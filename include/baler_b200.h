@@ -121,9 +121,11 @@ int bb_renormalize_f32(bb_ctx* ctx, const float* y_dev, int64_t n_rows, int n_co
 
 /*
  * z = encode((x - min) / range)  for n_rows rows of the row-major table x (n_rows x n_features).
- * Replaces helper.normalize (helper.py:261-274, data_processing.py:133-153; same float32
- * subtract + IEEE divide, bit-equal) fused with the `model.encode` loop of helper.compress
- * (helper.py:583-611).  min_dev/range_dev may both be NULL (apply_normalization = False).
+ * Replaces helper.normalize (helper.py:261-274, data_processing.py:133-153) fused with the
+ * `model.encode` loop of helper.compress (helper.py:583-611).  The fused form computes
+ * (x - min) * rcp(range) (one multiply by the correctly rounded reciprocal: <= 1 ulp from the
+ * reference's IEEE divide, inside the 1e-5 bar); the stand-alone bb_normalize_f32 above is the
+ * bit-equal subtract + divide.  min_dev/range_dev may both be NULL (apply_normalization = False).
  * z_dtype: BB_F32 or BB_F16 (row-major n_rows x z_dim).
  */
 int bb_encode_f32(bb_model* m, const float* x_dev, int64_t n_rows,
@@ -181,8 +183,13 @@ int bb_trainer_create(bb_ctx* ctx, int n_features, int z_dim,
  * AE_Dropout_BN (models.py:256-313) in train mode: the 8 Linear tensors as above plus, for the 4 decoder
  * BatchNorm1d layers (dec_nn.2, .5, .8, .10), weight / bias / running_mean / running_var (float64 host) and
  * num_batches_tracked.  Dropout p = .5/.4/.3/.2 after the encoder Linears, BatchNorm with whole-batch statistics
- * (biased variance, eps 1e-5, momentum 0.1).  Restrictions: MSE loss only (what training.fit evaluates), single
- * GPU (the batch statistics are not exchanged), batch <= 4 rows x resident CTAs (592 on B200).
+ * (biased variance, eps 1e-5, momentum 0.1).  Runs on the tensor-core step (BB_PREC_SPLIT16, the default): batches of
+ * up to 16 rows x resident CTAs per GPU (2368 on B200: the tiles of a batch meet at the 8 BatchNorm reduction points
+ * of a step); data parallel through bb_trainer_dp_connect with the statistics of the GLOBAL batch (the per-rank sums
+ * of every reduction point are exchanged over NVLink peer memory inside the kernel) and a dropout stream keyed by
+ * the global batch row, i.e. the replicas compute what one GPU computes at batch_size = global batch.  The fp32
+ * kernels (BB_PREC_FP32) remain as the reference-accuracy path: one GPU's statistics, batch <= 592 rows.
+ * MSE loss only: what training.fit evaluates (it calls the loss with validate=True, so the L1 term never trains).
  */
 int bb_trainer_create_dbn(bb_ctx* ctx, int n_features, int z_dim,
                           const double* const* weights_host, const double* const* biases_host,
@@ -192,8 +199,9 @@ int bb_trainer_create_dbn(bb_ctx* ctx, int n_features, int z_dim,
 /* dropout: in-kernel Philox4x32-10 keyed by (seed, step, layer, row, column); `masks_dev` (4 device pointers to
  * [batch x width] uint8 keep-masks, or NULL) injects torch-generated masks for parity tests */
 int bb_trainer_set_dropout(bb_trainer* t, unsigned long long seed, const unsigned char* const* masks_dev);
-/* device views of the concatenated BatchNorm running statistics (4 layers, 200 + 100 + 50 + n_features values each):
- * data-parallel runs average them over ranks (torch DDP broadcasts rank 0's buffers instead; models.py:275-296) */
+/* device views of the concatenated BatchNorm running statistics (4 layers, 50 + 100 + 200 + n_features values each).
+ * Data parallel inside the library keeps them identical on every rank; host-loop data parallel (per-rank statistics)
+ * averages them over ranks (torch DDP broadcasts rank 0's buffers instead; models.py:275-296) */
 int bb_trainer_bn_running_dev(bb_trainer* t, float** running_mean_dev, float** running_var_dev, int* n);
 int bb_trainer_get_bn(bb_trainer* t, double* const* bn_weight_host, double* const* bn_bias_host,
                       double* const* bn_mean_host, double* const* bn_var_host, long long* bn_batches_tracked);
@@ -202,8 +210,9 @@ int bb_trainer_destroy(bb_trainer* t);
  * Arithmetic of the training step (the reference trains in float64 on torch, training.py:64-97; both choices here meet
  * the 1e-5 per-step bar on loss, gradients and the Adam update):
  *   BB_PREC_SPLIT16  tensor cores (mma.sync m16n8k16, fp16 hi / lo 3-product split, fp32 accumulate), one persistent
- *                    kernel per epoch; the default (BB_PREC_AUTO) for `AE` / `CFD_dense_AE` with the MSE loss.
- *   BB_PREC_FP32     fp32 FFMA kernels; always used for the opt-in L1 chain and for AE_Dropout_BN.
+ *                    kernel per epoch; the default (BB_PREC_AUTO) for `AE` / `CFD_dense_AE` / `AE_Dropout_BN` with the
+ *                    MSE loss.
+ *   BB_PREC_FP32     fp32 FFMA kernels; always used for the opt-in L1 chain.
  * bb_trainer_precision returns what the next MSE step will run on.  Values beyond +-65504 (un-normalised tables) leave
  * the fp16 range on the SPLIT16 path: the batch loss turns non-finite, a sticky flag is raised and
  * bb_trainer_range_flag reports it (synchronises the device); the caller restarts with BB_PREC_FP32.
@@ -250,7 +259,9 @@ int bb_trainer_step(bb_trainer* t, const float* x_dev, int batch_rows, const bb_
  * pushes every 32 x 32 gradient tile into all ranks' buffers over NVLink as 8-byte {value, step tag} packets and sums the
  * world's tiles in rank order as they land, before Adam - a fused SUM all-reduce (the loss is a sum: utils.py:195),
  * bit-identical replicas, no collective call on the host inside an epoch.  The epoch loss each rank gets back is ITS share
- * (sum of its rows' terms / number of batches): the caller adds the ranks' values.  SPLIT16 step only (AE family, MSE).
+ * (sum of its rows' terms / number of batches): the caller adds the ranks' values.  SPLIT16 step only (MSE loss).
+ * AE_Dropout_BN additionally exchanges, at each of its 8 BatchNorm reduction points, the per-rank column sums as 16-byte
+ * {a, tag, b, tag} packets and combines them in rank order: BatchNorm over the global batch, identical on every rank.
  */
 int bb_trainer_dp_export(bb_trainer* t, int world_size, unsigned char* handle_out_64);
 int bb_trainer_dp_connect(bb_trainer* t, int rank, int world_size, const unsigned char* handles);
