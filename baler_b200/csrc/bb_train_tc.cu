@@ -1262,37 +1262,61 @@ __device__ __forceinline__ void phase2_item(const TcModel& M, const TcPtrs& P, c
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = hh[i] + (cross[i] + cross2[i]) * LO_INV;
   if (P.world > 1 && (flags & TC_XCHG)) {
-    // Fused all-reduce (SUM) of this tile over NVLink peer memory.  Every value travels as an 8-byte {value, tag}
-    // packet (one atomic store; the tag is the step number): the receiver spins on the packet itself, so there is no
-    // fence, no flag and no CTA barrier on the path - one NVLink store latency.  Slots are double-buffered by step
-    // parity; a slot is rewritten two steps later, which the sender can only reach after the receiver has consumed it
-    // (it needs the receiver's packets of the step in between).  The sum runs in rank order on every rank: replicas
-    // stay bit-identical.
-    const size_t slot = ((size_t)item_idx * NTHREADS + tid) * 4;                      // uint2 index inside one rank's block
-    const size_t per_rank = (size_t)M.n_items * NTHREADS * 4;
+    // Fused all-reduce (SUM) of this tile over NVLink peer memory.  The thread's four values travel as two 16-byte
+    // {value, tag, value, tag} packets (each 8-byte half carries the step tag: the receiver spins on the data itself, so
+    // there is no fence, no flag and no CTA barrier on the path - one NVLink store latency).  Relaxed sys-scope accesses,
+    // not volatile ones: the stores to all peers leave back to back and the loads of a group of peers are in flight
+    // together (ptxas completes a volatile access before it issues the next one: 28 dependent round trips per thread at
+    // 8 GPUs).  Slots are double-buffered by step parity; a slot is rewritten two steps later, which the sender can only
+    // reach after the receiver has consumed it (it needs the receiver's packets of the step in between).  The sum runs in
+    // rank order on every rank: replicas stay bit-identical.
+    // [item][packet 0 | 1][thread]: the 32 lanes of a store instruction write 512 contiguous bytes = whole 128-byte lines
+    // on the wire
+    const size_t slot = (size_t)item_idx * 2 * NTHREADS + tid;                        // uint4 index inside one rank's block
+    const size_t per_rank = (size_t)M.n_items * NTHREADS * 2;
     const size_t mine = ((size_t)parity * P.world + P.rank) * per_rank + slot;
     for (int r = 0; r < P.world; ++r) {
       if (r == P.rank) continue;
-      uint2* dst = reinterpret_cast<uint2*>(P.xchg[r]) + mine;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + i), "r"(__float_as_uint(v[i])), "r"(step_tag) : "memory");
+      uint4* dst = reinterpret_cast<uint4*>(P.xchg[r]) + mine;
+      st_pkt_sys(dst, v[0], v[1], step_tag);
+      st_pkt_sys(dst + NTHREADS, v[2], v[3], step_tag);
     }
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = 0; r < P.world; ++r) {
-      if (r == P.rank) {
+    const uint4* inbox = reinterpret_cast<const uint4*>(P.xchg[P.rank]) + (size_t)parity * P.world * per_rank + slot;
+    for (int r0 = 0; r0 < P.world; r0 += 4) {
+      uint4 q[4][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[i] += v[i];
-        continue;
-      }
-      const uint2* src = reinterpret_cast<const uint2*>(P.xchg[P.rank]) + ((size_t)parity * P.world + r) * per_rank + slot;
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u < P.world && r0 + u != P.rank) {
+          q[u][0] = ld_pkt_sys(inbox + (size_t)(r0 + u) * per_rank);
+          q[u][1] = ld_pkt_sys(inbox + (size_t)(r0 + u) * per_rank + NTHREADS);
+        }
+      bool missing;
+      do {
+        missing = false;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t val, tag;
-        do {
-          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(val), "=r"(tag) : "l"(src + i) : "memory");
-        } while (tag != step_tag);
-        s[i] += __uint_as_float(val);
+        for (int u = 0; u < 4; ++u)
+          if (r0 + u < P.world && r0 + u != P.rank) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (q[u][h].y != step_tag || q[u][h].w != step_tag) {
+                q[u][h] = ld_pkt_sys(inbox + (size_t)(r0 + u) * per_rank + h * NTHREADS);
+                missing = true;
+              }
+          }
+      } while (missing);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r0 + u >= P.world) continue;
+        if (r0 + u == P.rank) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) s[i] += v[i];
+        } else {
+          s[0] += __uint_as_float(q[u][0].x);
+          s[1] += __uint_as_float(q[u][0].z);
+          s[2] += __uint_as_float(q[u][1].x);
+          s[3] += __uint_as_float(q[u][1].z);
+        }
       }
     }
     v[0] = s[0]; v[1] = s[1]; v[2] = s[2]; v[3] = s[3];
