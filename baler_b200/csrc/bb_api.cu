@@ -81,11 +81,16 @@ void free_chain(Chain* c) {
   if (c->blob_dev) cudaFree(c->blob_dev);
   if (c->tc_blob_dev) cudaFree(c->tc_blob_dev);
   if (c->lay_blob_dev) cudaFree(c->lay_blob_dev);
+  if (c->lay_tc_blob_dev) cudaFree(c->lay_tc_blob_dev);
   bb_tc_release(c);
 }
 
+// the chain has a tensor-core form: one of the fused tcgen05 kernels, or the layered mma.sync GEMMs for shapes too
+// large for any fused kernel
+bool chain_has_tc(const Chain* c) { return c->tc_ok || (!c->f32_ok && c->lay_tc_ok); }
+
 int resolve_precision(const bb_model* m, const Chain* c, int precision) {
-  if (precision == BB_PREC_AUTO) return c->tc_ok ? BB_PREC_SPLIT16 : BB_PREC_FP32;
+  if (precision == BB_PREC_AUTO) return chain_has_tc(c) ? BB_PREC_SPLIT16 : BB_PREC_FP32;
   return precision;
 }
 
@@ -100,10 +105,13 @@ int run_chain(bb_model* m, const Chain* c, const void* in, int in_dtype, int64_t
   if (p == BB_PREC_FP32) {
     if (!c->f32_ok)  // weights do not fit shared memory: one GEMM launch per layer
       return bb_chain_layered_launch(m->ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range, out,
-                                     out_dtype, stream);
+                                     out_dtype, 0, nullptr, stream);
     return bb_chain_f32_launch(m->ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range,
                                out, out_dtype, stream);
   }
+  if (p == BB_PREC_SPLIT16 && !c->tc_ok && chain_has_tc(c))
+    return bb_chain_layered_launch(m->ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range, out, out_dtype, 1,
+                                   m->flag_dev, stream);
   if (p == BB_PREC_SPLIT16 || p == BB_PREC_FAST16) {
     if (!c->tc_ok) return BB_ERR_UNSUPPORTED;
     return bb_tc_launch(m->ctx, c, in, in_dtype, n_rows, pre_min, pre_range, post_min, post_range, out,
@@ -322,7 +330,7 @@ int bb_model_range_flag(bb_model* m, int reset, int* out) {
 int bb_model_n_features(const bb_model* m) { return m ? m->enc.desc.in_dim : 0; }
 int bb_model_z_dim(const bb_model* m) { return m ? m->enc.desc.out_dim : 0; }
 int bb_model_auto_precision(const bb_model* m) {
-  return (m && m->enc.tc_ok && m->dec.tc_ok) ? BB_PREC_SPLIT16 : BB_PREC_FP32;
+  return (m && chain_has_tc(&m->enc) && chain_has_tc(&m->dec)) ? BB_PREC_SPLIT16 : BB_PREC_FP32;
 }
 
 int bb_colminmax_f32(bb_ctx* ctx, const float* x_dev, int64_t n_rows, int n_cols, float* min_dev,
@@ -433,7 +441,7 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
   for (int64_t k = std::max<int64_t>(0, n_chunks - 2); k < n_chunks && rc == BB_OK; ++k) rc = finish_chunk(k);
   cudaStreamSynchronize(m->s_compute);
   cudaStreamSynchronize(m->s_copy_out);
-  if (rc == BB_OK && precision == BB_PREC_AUTO && m->enc.tc_ok) {
+  if (rc == BB_OK && precision == BB_PREC_AUTO && chain_has_tc(&m->enc)) {
     int tripped = 0;  // fp16 range guard of the split path: redo on the fp32 kernel (features are already known)
     rc = bb_model_range_flag(m, 1, &tripped);
     if (rc == BB_OK && tripped) return bb_compress_host(m, x_host, n_rows, features_host, 0, z_host, z_dtype, BB_PREC_FP32);
@@ -515,7 +523,7 @@ int bb_decompress_host(bb_model* m, const void* z_host, int z_dtype, int64_t n_r
   cudaStreamSynchronize(m->s_compute);
   cudaStreamSynchronize(m->s_copy_out);
   cleanup();
-  if (rc == BB_OK && precision == BB_PREC_AUTO && m->dec.tc_ok) {
+  if (rc == BB_OK && precision == BB_PREC_AUTO && chain_has_tc(&m->dec)) {
     int tripped = 0;
     rc = bb_model_range_flag(m, 1, &tripped);
     if (rc == BB_OK && tripped) return bb_decompress_host(m, z_host, z_dtype, n_rows, features_host, y_host, y_dtype, BB_PREC_FP32);

@@ -7,6 +7,16 @@
 // 128-bit vectors), 8 x 4 outputs per thread, register prefetch of the next K slab.  All leading dimensions are
 // padded to multiples of 4 floats (zero weights / zero bias in the padding) so every global access is a 16-byte
 // vector.  Normalisation, dtype conversion and un-normalisation run as thin elementwise kernels around the GEMMs.
+//
+// BB_PREC_SPLIT16 (the default when the shape is not served by the fused kernels): the same GEMM on the tensor cores,
+// dense_layer_tc_kernel - warp-level MMA (mma.sync m16n8k16, SASS HMMA) with the fp16 hi / lo 3-product split of the
+// fused kernels (x = hi + lo / 2048; hi*hi + (hi*lo + lo*hi) / 2048, fp32 accumulate).  96 % of Conv_AE's FLOPs are its
+// 128 -> 2000 -> z Linears (models.py:320-321,343).  Why mma.sync and not tcgen05 here: the weight images (6 MB for
+// Conv_AE) stream through shared memory tile by tile like in any GEMM, the activations arrive as fp32 from the previous
+// layer and are split on the way into shared memory; this is the layer-at-a-time fallback path, one kernel serves every
+// layer shape, inference and (bb_train_layered.cu) training alike.
+#include <cstdlib>
+
 #include "bb_common.cuh"
 
 namespace {
@@ -89,6 +99,158 @@ dense_layer_kernel(const float* __restrict__ X, const int ldx, const float* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ tensor-core GEMM
+constexpr int TBM = 128, TBN = 64, TBK = 32, TLD = 40, TNT = 256;  // TLD: row stride in halves (80 B: ldmatrix rows hit distinct banks)
+constexpr float T_LO = 2048.f, T_LO_INV = 1.f / 2048.f;
+constexpr int T_SMEM = 2 * 2 * (TBM + TBN) * TLD * 2;  // [2 stages][hi | lo][A 128 rows + B 64 rows][40 halves]
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void hmma(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(const uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// 4 floats -> packed fp16 hi (2 words) and packed scaled lo (2 words)
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn((v.x - f0.x) * T_LO, (v.y - f0.y) * T_LO);
+  const __half2 l1 = __floats2half2_rn((v.z - f1.x) * T_LO, (v.w - f1.y) * T_LO);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
+// Y[n x Np4] = act(X[n x K] . W[N x K]^T + b).  X fp32 rows of pitch ldx (valid and zero padded up to kx columns), W as
+// two fp16 images [rows padded to 64][Kp] (hi, and lo scaled by 2048; zero padding), 128 x 64 tiles, 8 warps of 32 x 32.
+__global__ void __launch_bounds__(TNT, 2)
+dense_layer_tc_kernel(const float* __restrict__ X, const int ldx, const int kx, const __half* __restrict__ Whi,
+                      const __half* __restrict__ Wlo, const int Kp, const float* __restrict__ bias, float* __restrict__ Y,
+                      const int ldy, const int n, const int Np4, const int act, int* __restrict__ flag) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  // stage s: [A hi | A lo | B hi | B lo]
+  constexpr int A_B = TBM * TLD * 2, B_B = TBN * TLD * 2, STAGE = 2 * A_B + 2 * B_B;
+  const uint32_t sb = smem_addr(tsm);
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  // loaders: A 4 x float4 per thread (rows lr + 32 i, 4 consecutive k), B one 16-byte chunk per image
+  const int lr = tid >> 3, lc = (tid & 7) * 4;
+  const int br = tid >> 2, bc = (tid & 3) * 8;
+  float hh[2][4][4], cr[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hh[i][j][q] = cr[i][j][q] = 0.f;
+  float4 av[4];
+  auto load_a = [&](const int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = m0 + lr + 32 * i;
+      av[i] = (r < n && k0 + lc < kx) ? __ldg(reinterpret_cast<const float4*>(X + (size_t)r * ldx + k0 + lc))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stash_a = [&](const int st) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint2 hi, lo;
+      split4(av[i], hi, lo);
+      const uint32_t off = (uint32_t)(st * STAGE + ((lr + 32 * i) * TLD + lc) * 2);
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sb + off), "r"(hi.x), "r"(hi.y) : "memory");
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sb + off + A_B), "r"(lo.x), "r"(lo.y) : "memory");
+    }
+  };
+  auto load_b = [&](const int st, const int k0) {
+    const size_t src = (size_t)(n0 + br) * Kp + k0 + bc;
+    const uint32_t dst = sb + st * STAGE + 2 * A_B + (br * TLD + bc) * 2;
+    cp_async16(dst, Whi + src);
+    cp_async16(dst + B_B, Wlo + src);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_a(0);
+  load_b(0, 0);
+  stash_a(0);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // ldmatrix lane addresses inside a stage
+  const uint32_t a_lane = (uint32_t)(((wm + (lane & 7) + ((lane >> 3) & 1) * 8) * TLD + (lane >> 4) * 8) * 2);
+  const uint32_t b_lane = (uint32_t)(2 * A_B + ((wn + (lane & 7) + ((lane >> 4) & 1) * 8) * TLD + ((lane >> 3) & 1) * 8) * 2);
+  int st = 0;
+  for (int k0 = 0; k0 < Kp; k0 += TBK) {
+    const bool more = k0 + TBK < Kp;
+    if (more) {
+      load_a(k0 + TBK);
+      load_b(st ^ 1, k0 + TBK);
+    }
+    const uint32_t base = sb + st * STAGE;
+#pragma unroll
+    for (int ks = 0; ks < TBK / 16; ++ks) {
+      uint32_t ah[2][4], al[2][4], bh[2][4], bl[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        ldsm4(ah[i], base + a_lane + (i * 16 * TLD + ks * 16) * 2);
+        ldsm4(al[i], base + a_lane + A_B + (i * 16 * TLD + ks * 16) * 2);
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        ldsm4(bh[p], base + b_lane + (p * 16 * TLD + ks * 16) * 2);
+        ldsm4(bl[p], base + b_lane + B_B + (p * 16 * TLD + ks * 16) * 2);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hmma(hh[i][j], ah[i], bh[j >> 1][(j & 1) * 2], bh[j >> 1][(j & 1) * 2 + 1]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hmma(cr[i][j], ah[i], bl[j >> 1][(j & 1) * 2], bl[j >> 1][(j & 1) * 2 + 1]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hmma(cr[i][j], al[i], bh[j >> 1][(j & 1) * 2], bh[j >> 1][(j & 1) * 2 + 1]);
+    }
+    if (more) {
+      stash_a(st ^ 1);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+      st ^= 1;
+    }
+  }
+  const int g = lane >> 2, t = lane & 3;
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = n0 + wn + j * 8 + 2 * t;
+    if (c < Np4) {
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + c));
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = m0 + wm + i * 16 + g + 8 * h;
+          if (r < n) {
+            float2 o;
+            o.x = act_l(fmaf(cr[i][j][2 * h], T_LO_INV, hh[i][j][2 * h]) + b.x, act);
+            o.y = act_l(fmaf(cr[i][j][2 * h + 1], T_LO_INV, hh[i][j][2 * h + 1]) + b.y, act);
+            bad = bad || !(fabsf(o.x) <= 3.0e38f) || !(fabsf(o.y) <= 3.0e38f);
+            *reinterpret_cast<float2*>(Y + (size_t)r * ldy + c) = o;
+          }
+        }
+    }
+  }
+  if (bad && flag != nullptr) *flag = 1;  // a value left the fp16 range on the way (inf / NaN): BB_PREC_AUTO callers re-run in fp32
+}
+
 // in (f32 | f16, compact rows of `dim`) -> scratch rows of pitch `ld` (zero padded), optionally (x - min) / range
 __global__ void __launch_bounds__(256) stage_in_kernel(const void* __restrict__ in, const int in_dtype, const int64_t n,
                                                        const int dim, const int ld, const float* __restrict__ mn,
@@ -153,16 +315,44 @@ int bb_chain_layered_prepare(bb_ctx*, Chain* c) {
   BB_CUDA(cudaMemcpy(c->lay_blob_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   c->lay_max_ld = max_ld;
   c->lay_ok = true;
+  // tensor-core images: per layer W as fp16 hi and lo * 2048, rows padded to the 64-column tile, K to the 32-wide slab
+  size_t halves = 0;
+  for (int l = 0; l < d.n_layers; ++l) {
+    c->lay_tc_off[l] = halves;
+    halves += 2 * (size_t)((d.layer[l].N + TBN - 1) / TBN * TBN) * ((d.layer[l].K + TBK - 1) / TBK * TBK);
+  }
+  std::vector<__half> img(halves, __float2half(0.f));
+  for (int l = 0; l < d.n_layers; ++l) {
+    const int K = d.layer[l].K, N = d.layer[l].N, Kp = (K + TBK - 1) / TBK * TBK, Nr = (N + TBN - 1) / TBN * TBN;
+    __half* hi = img.data() + c->lay_tc_off[l];
+    __half* lo = hi + (size_t)Nr * Kp;
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) {
+        const double w = c->w_host[l][(size_t)n * K + k];
+        const __half h = __float2half_rn((float)w);
+        hi[(size_t)n * Kp + k] = h;
+        lo[(size_t)n * Kp + k] = __float2half_rn((float)((w - (double)__half2float(h)) * (double)T_LO));
+      }
+  }
+  if (c->lay_tc_blob_dev) cudaFree(c->lay_tc_blob_dev);
+  c->lay_tc_blob_dev = nullptr;
+  BB_CUDA(cudaMalloc(&c->lay_tc_blob_dev, img.size() * sizeof(__half)));
+  BB_CUDA(cudaMemcpy(c->lay_tc_blob_dev, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  BB_CUDA(cudaFuncSetAttribute(dense_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+  c->lay_tc_ok = true;
   return BB_OK;
 }
 
 int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
                             const float* pre_min, const float* pre_range, const float* post_min,
-                            const float* post_range, void* out, int out_dtype, cudaStream_t stream) {
-  if (!c->lay_ok) return BB_ERR_UNSUPPORTED;
+                            const float* post_range, void* out, int out_dtype, int tensor_cores, int* flag_dev,
+                            cudaStream_t stream) {
+  if (!c->lay_ok || (tensor_cores && !c->lay_tc_ok)) return BB_ERR_UNSUPPORTED;
   if (n_rows == 0) return BB_OK;
   const ChainDesc& d = c->desc;
-  const int64_t chunk = n_rows < CHUNK_ROWS ? n_rows : CHUNK_ROWS;
+  int64_t chunk_rows = CHUNK_ROWS;
+  if (const char* e = getenv("BALER_B200_LAYER_CHUNK")) chunk_rows = atoll(e) > 0 ? atoll(e) : CHUNK_ROWS;  // (tuning)
+  const int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
   const size_t need = 2 * (size_t)chunk * c->lay_max_ld * sizeof(float);
   if (ctx->lay_scratch_bytes < need) {
     // grown only (never shrunk); stream-ordered work that still uses the old buffer has been enqueued before the free
@@ -182,10 +372,19 @@ int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_
     int cur = 0;
     for (int l = 0; l < d.n_layers; ++l) {
       const int K = d.layer[l].K, N = d.layer[l].N, Kp = pad4(K), Np = pad4(N);
-      const dim3 grid((Np + BN - 1) / BN, (unsigned)((rows + BM - 1) / BM));
-      dense_layer_kernel<<<grid, LT, 0, stream>>>(buf[cur], ld, c->lay_blob_dev + c->lay_w_off[l], Kp,
-                                                 c->lay_blob_dev + c->lay_b_off[l], buf[cur ^ 1], Np, (int)rows, Kp, Np,
-                                                 d.layer[l].act);
+      if (tensor_cores) {
+        const int Kt = (K + TBK - 1) / TBK * TBK, Nr = (N + TBN - 1) / TBN * TBN;
+        const __half* whi = reinterpret_cast<const __half*>(c->lay_tc_blob_dev) + c->lay_tc_off[l];
+        const dim3 grid((Np + TBN - 1) / TBN, (unsigned)((rows + TBM - 1) / TBM));
+        dense_layer_tc_kernel<<<grid, TNT, T_SMEM, stream>>>(buf[cur], ld, ld, whi, whi + (size_t)Nr * Kt, Kt,
+                                                            c->lay_blob_dev + c->lay_b_off[l], buf[cur ^ 1], Np, (int)rows, Np,
+                                                            d.layer[l].act, flag_dev);
+      } else {
+        const dim3 grid((Np + BN - 1) / BN, (unsigned)((rows + BM - 1) / BM));
+        dense_layer_kernel<<<grid, LT, 0, stream>>>(buf[cur], ld, c->lay_blob_dev + c->lay_w_off[l], Kp,
+                                                   c->lay_blob_dev + c->lay_b_off[l], buf[cur ^ 1], Np, (int)rows, Kp, Np,
+                                                   d.layer[l].act);
+      }
       cur ^= 1;
       ld = Np;
     }

@@ -68,6 +68,9 @@ struct Chain {
   bool lay_ok = false;
   float* lay_blob_dev = nullptr;
   size_t lay_w_off[BB_MAX_LAYERS] = {0}, lay_b_off[BB_MAX_LAYERS] = {0};
+  bool lay_tc_ok = false;      // ... and its tensor-core form: fp16 hi / lo weight images per layer
+  void* lay_tc_blob_dev = nullptr;
+  size_t lay_tc_off[BB_MAX_LAYERS] = {0};
   int lay_max_ld = 0;
   std::vector<double> w_host[BB_MAX_LAYERS];  // kept for re-packing
   std::vector<double> b_host[BB_MAX_LAYERS];
@@ -100,7 +103,8 @@ int bb_chain_f32_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtyp
 int bb_chain_layered_prepare(bb_ctx* ctx, Chain* c);
 int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t n_rows,
                             const float* pre_min, const float* pre_range, const float* post_min,
-                            const float* post_range, void* out, int out_dtype, cudaStream_t stream);
+                            const float* post_range, void* out, int out_dtype, int tensor_cores, int* flag_dev,
+                            cudaStream_t stream);
 int bb_colminmax_launch(bb_ctx* ctx, const float* x, int64_t n_rows, int n_cols, float* min_dev,
                         float* max_dev, int reset, cudaStream_t stream);
 int bb_tc_prepare(bb_ctx* ctx, Chain* c);

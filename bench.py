@@ -597,16 +597,31 @@ def run_ours(args):
         snaps = synth.cfd_snapshots((nb + 99) // 100)  # 50x50 snapshots -> 100 blocks of 5x5 each (convert_to_blocks=[1,5,5])
         snaps = (snaps - snaps.min()) / (snaps.max() - snaps.min())
         blocks = torch.from_numpy(np.ascontiguousarray(snaps.reshape(-1, 1, 5, 5)[:nb])).cuda()
-        zc = cm.encode(blocks); cm.decode(zc)  # warm-up (packs the dense-equivalent matrices)
-        torch.cuda.synchronize()
-        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        c0.record(); zc = cm.encode(blocks); c1.record(); yc = cm.decode(zc); c2.record()
-        torch.cuda.synchronize()
         flop = 1593216  # per block and direction
-        cfd = {"model": "Conv_AE 5x5 -> 250", "blocks": nb, "encode_blocks_per_s": nb / (c0.elapsed_time(c1) * 1e-3),
-               "decode_blocks_per_s": nb / (c1.elapsed_time(c2) * 1e-3),
-               "encode_tflops_fp32": nb * flop / (c0.elapsed_time(c1) * 1e-3) / 1e12,
-               "note": "layered fp32 GEMM path (CUDA cores); nominal FFMA peak 74.5 TFLOP/s"}
+
+        def cfd_pass(prec):
+            zc = cm.encode(blocks, precision=prec); cm.decode(zc, precision=prec)  # warm-up (packs the dense-equivalent matrices)
+            torch.cuda.synchronize()
+            c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            c0.record(); zc = cm.encode(blocks, precision=prec); c1.record(); yc = cm.decode(zc, precision=prec); c2.record()
+            torch.cuda.synchronize()
+            return zc, yc, c0.elapsed_time(c1) * 1e-3, c1.elapsed_time(c2) * 1e-3
+
+        zc, yc, te, td = cfd_pass("auto")
+        z32, y32, te32, td32 = cfd_pass("fp32")
+        cfd_prec = cm.codec(5, 5).auto_precision
+        cfd = {"model": "Conv_AE 5x5 -> 250", "blocks": nb, "precision": cfd_prec,
+               "encode_blocks_per_s": nb / te, "decode_blocks_per_s": nb / td,
+               "encode_tflops": nb * flop / te / 1e12, "decode_tflops": nb * flop / td / 1e12,
+               "latent_err_vs_fp32": ((zc - z32).abs().max() / z32.abs().max()).item(),
+               "recon_err_vs_fp32": ((yc - y32).abs().max() / y32.abs().max()).item(),
+               "roofline": {"bound": "tensor", "achieved": nb * flop / te / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                            "frac": nb * flop / te / 1e12 / peaks["tflops"],
+                            "kernel": "dense_layer_tc_kernel (one mma.sync split16 GEMM launch per layer; useful single-count FLOPs)"},
+               "fp32_path": {"encode_blocks_per_s": nb / te32, "decode_blocks_per_s": nb / td32,
+                             "encode_tflops": nb * flop / te32 / 1e12,
+                             "note": "layered fp32 GEMM path (CUDA cores); nominal FFMA peak 74.5 TFLOP/s"}}
+        del z32, y32
         # one training pass over 60k blocks, batch 600 (train-mode BatchNorm2d, sum-MSE, Adam): the layer-by-layer trainer
         # with the convolutions as weight-sharing dense layers
         sp = cm.training_spec(5, 5)

@@ -31,19 +31,22 @@ def check_sums(model, g):
         assert abs(float(v.double().abs().sum()) - ref) <= 1e-6 * max(ref, 1.0), k
 
 
-def test_conv_ae_eval_matches_reference(golden):
+@pytest.mark.parametrize("precision", ["auto", "fp32"])
+def test_conv_ae_eval_matches_reference(golden, precision):
+    """the reference module's outputs on the tensor-core GEMM path (auto = split16: mma.sync hi / lo) and on the fp32 one"""
     g = golden("conv_ae.npz")
     torch.manual_seed(0)
     m = models.Conv_AE(5, 250)
     m.load_state_dict(randomise_bn2d(m.state_dict()))
     check_sums(m, g)  # same initial weights and BatchNorm statistics as the reference instance
     m.eval()
+    assert m.codec(5, 5).auto_precision == "split16"
     x = torch.from_numpy(g["blocks"]).view(-1, 1, 5, 5)
-    z = m.encode(x)
+    z = m.encode(x, precision=precision)
     assert z.shape == (600, 250) and z.dtype == torch.float32
     assert tuple(m.get_final_layer_dims()) == (600, 32, 4, 1)
     assert rel_max(z.cpu().numpy(), g["latent_eval"]) <= 1e-5 and rel_l2(z.cpu().numpy(), g["latent_eval"]) <= 1e-5
-    y = m.decode(torch.from_numpy(g["latent_eval"]))
+    y = m.decode(torch.from_numpy(g["latent_eval"]), precision=precision)
     assert y.shape == (600, 1, 5, 5)
     assert rel_max(y.cpu().numpy(), g["recon_eval"]) <= 1e-5 and rel_l2(y.cpu().numpy(), g["recon_eval"]) <= 1e-5
     with pytest.raises(RuntimeError, match="flattens"):
@@ -52,18 +55,19 @@ def test_conv_ae_eval_matches_reference(golden):
         m.train().encode(x)
 
 
-def test_cfd_dense_ae_2500_features(golden):
+@pytest.mark.parametrize("precision", ["auto", "fp32"])
+def test_cfd_dense_ae_2500_features(golden, precision):
     g = golden("cfd_dense.npz")
     torch.manual_seed(0)
     m = models.CFD_dense_AE(2500, 25)
     check_sums(m, g)
     m.eval()
-    assert m.codec().auto_precision == "fp32"  # W1 is 2 MB: layered GEMM path, not the fused kernels
+    assert m.codec().auto_precision == "split16"  # W1 is 2 MB: layered GEMM path (tensor cores), not the fused kernels
     x = torch.from_numpy(synth.cfd_snapshots(60).reshape(60, 2500))
-    z = m.encode(x)
+    z = m.encode(x, precision=precision)
     assert z.dtype == torch.float32
     assert rel_max(z.cpu().numpy(), g["latent"]) <= 1e-5 and rel_l2(z.cpu().numpy(), g["latent"]) <= 1e-5
-    y = m.decode(torch.from_numpy(g["latent"]))
+    y = m.decode(torch.from_numpy(g["latent"]), precision=precision)
     assert rel_max(y.cpu().numpy(), g["recon"]) <= 1e-5 and rel_l2(y.cpu().numpy(), g["recon"]) <= 1e-5
 
 
@@ -77,10 +81,22 @@ def test_layered_path_ragged_rows_and_chunks(golden):
     base = g["blocks"].reshape(600, 25)
     n = 32768 * 2 + 77
     idx = np.arange(n) % 600
-    z = m.codec(5, 5).encode(torch.from_numpy(np.ascontiguousarray(base[idx])).cuda())
-    ref = g["latent_eval"][idx]
-    assert rel_max(z.cpu().numpy(), ref) <= 1e-5
-    assert torch.equal(z[:600], z[600:1200])  # independent rows: identical blocks give identical bits
+    for precision in ("auto", "fp32"):
+        z = m.codec(5, 5).encode(torch.from_numpy(np.ascontiguousarray(base[idx])).cuda(), precision=precision)
+        ref = g["latent_eval"][idx]
+        assert rel_max(z.cpu().numpy(), ref) <= 1e-5
+        assert torch.equal(z[:600], z[600:1200])  # independent rows: identical blocks give identical bits
+
+
+def test_layered_tensor_core_range_guard():
+    """values beyond the fp16 range on the layered tensor-core path raise the sticky flag; AUTO callers re-run in fp32"""
+    torch.manual_seed(0)
+    m = models.CFD_dense_AE(2500, 25).eval()
+    x = torch.from_numpy(synth.cfd_snapshots(8).reshape(8, 2500)).cuda() * 1.0e6
+    codec = m.codec()
+    z = codec.encode(x)                      # auto: trips, re-runs on the fp32 GEMMs
+    z32 = codec.encode(x, precision="fp32")
+    assert torch.isfinite(z).all() and torch.equal(z, z32)
 
 
 def test_conv_cli_compress_decompress(golden, tmp_path, monkeypatch):
