@@ -40,19 +40,20 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
 // C[m][n] = sum_k A(m, k) * B(k, n) with A(m, k) = A[m * sam + k * sak], B(k, n) = B[k * sbk + n * sbn];
 // epilogue: + bias[n], activation; fixed summation order (k ascending: the same bits whatever the tile size), one thread
 // per (TM_ / 16) x (TN_ / 16) outputs.  64 x 64 tiles by default, 32 x 32 when those would leave most SMs without a CTA.
+// The small tile takes 64-wide k slabs (a quarter of the barriers; the per-output k order, hence the bits, are unchanged).
 // The next k slab is fetched into registers while the current one is multiplied (the batches here are a few hundred
 // rows: one CTA per SM at best, nothing else hides the global-memory latency).  Split-K (gridDim.z > 1): CTA z takes the
 // k range [z * k_per, (z + 1) * k_per) and writes its partial tile to C + z * split_stride without the epilogue;
 // splitk_reduce_kernel adds the partials in z order.  The K = 2000 products of Conv_AE (N = 128 or 250: 40 - 150 CTAs with
 // a 125-iteration k loop) and the weight-gradient products (k = batch rows) run that way.
-template <int TM_, int TN_>
+template <int TM_, int TN_, int TK_>
 __global__ void __launch_bounds__(GT)
 gemm_strided_kernel(const float* __restrict__ A, const int64_t sam, const int64_t sak, const float* __restrict__ B,
                     const int64_t sbk, const int64_t sbn, float* __restrict__ C, const int64_t ldc, const int M, const int N,
                     const int K, const float* __restrict__ bias, const int act, const int k_per, const int64_t split_stride) {
-  constexpr int RM = TM_ / 16, RN = TN_ / 16, EA = TK * TM_ / GT, EB = TK * TN_ / GT;
-  __shared__ float As[TK][TM_ + 1];
-  __shared__ float Bs[TK][TN_ + 1];
+  constexpr int RM = TM_ / 16, RN = TN_ / 16, EA = TK_ * TM_ / GT, EB = TK_ * TN_ / GT;
+  __shared__ float As[TK_][TM_ + 1];
+  __shared__ float Bs[TK_][TN_ + 1];
   const int m0 = blockIdx.y * TM_, n0 = blockIdx.x * TN_;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int k_begin = blockIdx.z * k_per, k_end = k_begin + k_per < K ? k_begin + k_per : K;
@@ -73,7 +74,7 @@ gemm_strided_kernel(const float* __restrict__ A, const int64_t sam, const int64_
     }
   };
   fetch(k_begin);
-  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+  for (int k0 = k_begin; k0 < k_end; k0 += TK_) {
 #pragma unroll
     for (int i = 0; i < EA; ++i) {
       const int e = tid + i * GT, kk = e / TM_;
@@ -85,9 +86,9 @@ gemm_strided_kernel(const float* __restrict__ A, const int64_t sam, const int64_
       Bs[kk][e - kk * TN_] = rb[i];
     }
     __syncthreads();
-    if (k0 + TK < k_end) fetch(k0 + TK);
+    if (k0 + TK_ < k_end) fetch(k0 + TK_);
 #pragma unroll
-    for (int kk = 0; kk < TK; ++kk) {
+    for (int kk = 0; kk < TK_; ++kk) {
       float a[RM], b[RN];
 #pragma unroll
       for (int i = 0; i < RM; ++i) a[i] = As[kk][ty * RM + i];
@@ -431,14 +432,14 @@ void lgemm(bb_ltrainer* t, cudaStream_t s, const float* A, int64_t sam, int64_t 
   }
   int k_per = K;
   if (S > 1) {
-    k_per = ((K + S - 1) / S + TK - 1) / TK * TK;
+    k_per = ((K + S - 1) / S + 63) / 64 * 64;  // whole k slabs of either tile shape
     S = (K + k_per - 1) / k_per;
   }
   float* out = S > 1 ? t->splitk : C;
   const int64_t stride = (int64_t)M * ldc;
   grid.z = S;
-  if (!small) gemm_strided_kernel<TM, TN><<<grid, GT, 0, s>>>(A, sam, sak, B, sbk, sbn, out, ldc, M, N, K, bias, act, k_per, stride);
-  else gemm_strided_kernel<32, 32><<<grid, GT, 0, s>>>(A, sam, sak, B, sbk, sbn, out, ldc, M, N, K, bias, act, k_per, stride);
+  if (!small) gemm_strided_kernel<TM, TN, TK><<<grid, GT, 0, s>>>(A, sam, sak, B, sbk, sbn, out, ldc, M, N, K, bias, act, k_per, stride);
+  else gemm_strided_kernel<32, 32, 64><<<grid, GT, 0, s>>>(A, sam, sak, B, sbk, sbn, out, ldc, M, N, K, bias, act, k_per, stride);
   if (S > 1) {
     const int64_t total = (int64_t)M * N;
     const int blocks = (int)((total + 255) / 256 < 4 * t->ctx->sm_count ? (total + 255) / 256 : 4 * t->ctx->sm_count);
