@@ -4,6 +4,9 @@
 #include <cstring>
 #include <new>
 #include <thread>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 
 #include <cstdlib>
 
@@ -209,6 +212,142 @@ int pinned_init(bb_model* m, int io, size_t bytes) {
   return BB_OK;
 }
 
+// Column min / max of a host table on host threads (data_processing.find_minmax, data_processing.py:113-130), for the
+// resident path of bb_compress_host: the scan reads host memory at several times the PCIe rate, so the features are known
+// long before the upload of the table ends and the latent download overlaps the rest of the upload (full duplex) instead
+// of following it.  Same results as colminmax_kernel: order-preserving integer keys (-0 < +0), NaN propagates per column.
+// key(u) = u ^ ((u >> 31) & 0x7fffffff) as a SIGNED int is monotonic in the float value.
+inline int32_t mm_key(uint32_t u) { return (int32_t)(u ^ ((uint32_t)((int32_t)u >> 31) & 0x7fffffffu)); }
+inline float mm_unkey(int32_t k) {
+  const uint32_t u = k >= 0 ? (uint32_t)k : ((uint32_t)k ^ 0x7fffffffu);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// scalar scan of elements [e0, e1) of the flat table; column = element index % F
+void mm_scan_scalar(const uint32_t* p, int64_t e0, int64_t e1, int F, int32_t* mn, int32_t* mx, uint32_t* nan) {
+  int c = (int)(e0 % F);
+  for (int64_t e = e0; e < e1; ++e) {
+    const uint32_t u = p[e];
+    if ((u & 0x7fffffffu) > 0x7f800000u) {
+      nan[c] = 1u;
+    } else {
+      const int32_t k = mm_key(u);
+      mn[c] = k < mn[c] ? k : mn[c];
+      mx[c] = k > mx[c] ? k : mx[c];
+    }
+    if (++c == F) c = 0;
+  }
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+// AVX2: the column pattern of 8 consecutive elements repeats every L = lcm(F, 8) elements, so L / 8 vector accumulators
+// cover a period; lane j of accumulator v belongs to column (8 v + j) % F
+// (accumulators as plain int arrays of 8 L8 entries; kept in registers for the scan when L8 <= 4: the CMS table has L8 = 3)
+__attribute__((target("avx2"))) void mm_scan_avx2(const uint32_t* p, int64_t n_periods, int L8, int32_t* mn, int32_t* mx, int32_t* nanv) {
+  const __m256i mag = _mm256_set1_epi32(0x7fffffff), inf = _mm256_set1_epi32(0x7f800000);
+  const __m256i imax = _mm256_set1_epi32(0x7fffffff), imin = _mm256_set1_epi32((int)0x80000000u);
+#define BB_MM_STEP(U, MN, MX, NV)                                                              \
+  do {                                                                                         \
+    const __m256i key_ = _mm256_xor_si256(U, _mm256_and_si256(_mm256_srai_epi32(U, 31), mag)); \
+    const __m256i isnan_ = _mm256_cmpgt_epi32(_mm256_and_si256(U, mag), inf);                  \
+    NV = _mm256_or_si256(NV, isnan_);                                                          \
+    MN = _mm256_min_epi32(MN, _mm256_blendv_epi8(key_, imax, isnan_));                         \
+    MX = _mm256_max_epi32(MX, _mm256_blendv_epi8(key_, imin, isnan_));                         \
+  } while (0)
+  if (L8 <= 4) {
+    __m256i rmn[4], rmx[4], rnv[4];
+    for (int v = 0; v < L8; ++v) {
+      rmn[v] = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(mn + 8 * v));
+      rmx[v] = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(mx + 8 * v));
+      rnv[v] = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(nanv + 8 * v));
+    }
+    for (int64_t q = 0; q < n_periods; ++q, p += (size_t)L8 * 8)
+      for (int v = 0; v < L8; ++v) {
+        const __m256i u = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 8 * v));
+        BB_MM_STEP(u, rmn[v], rmx[v], rnv[v]);
+      }
+    for (int v = 0; v < L8; ++v) {
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(mn + 8 * v), rmn[v]);
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(mx + 8 * v), rmx[v]);
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(nanv + 8 * v), rnv[v]);
+    }
+    return;
+  }
+  for (int64_t q = 0; q < n_periods; ++q, p += (size_t)L8 * 8)
+    for (int v = 0; v < L8; ++v) {
+      const __m256i u = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 8 * v));
+      __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(mn + 8 * v));
+      __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(mx + 8 * v));
+      __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(nanv + 8 * v));
+      BB_MM_STEP(u, a, b, c);
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(mn + 8 * v), a);
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(mx + 8 * v), b);
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(nanv + 8 * v), c);
+    }
+#undef BB_MM_STEP
+}
+#endif
+
+void host_colminmax(const float* x, int64_t n_rows, int F, float* mn_out, float* mx_out) {
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  int g = F, b = 8;
+  while (b) { const int r = g % b; g = b; b = r; }
+  const int period_rows = 8 / g, L8 = F / g;  // rows / 8-lane vectors of one period
+  bool avx2 = false;
+#if defined(__x86_64__) && defined(__GNUC__)
+  avx2 = __builtin_cpu_supports("avx2") && L8 <= 1024;
+#endif
+  const int64_t periods = n_rows / period_rows;
+  const int64_t per = (periods + hw - 1) / hw;
+  std::vector<std::vector<int32_t>> pmn(hw, std::vector<int32_t>((size_t)F, 0x7fffffff)), pmx(hw, std::vector<int32_t>((size_t)F, (int32_t)0x80000000u));
+  std::vector<std::vector<uint32_t>> pnan(hw, std::vector<uint32_t>((size_t)F, 0u));
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(x);
+  auto work = [&](unsigned t) {
+    const int64_t q0 = std::min<int64_t>(periods, (int64_t)t * per), q1 = std::min<int64_t>(periods, q0 + per);
+    int32_t* mn = pmn[t].data();
+    int32_t* mx = pmx[t].data();
+    uint32_t* nan = pnan[t].data();
+    int64_t e0 = q0 * period_rows * F;
+    const int64_t e1 = (t + 1 == hw ? n_rows : q1 * period_rows) * (int64_t)F;  // the last thread also takes the ragged tail
+#if defined(__x86_64__) && defined(__GNUC__)
+    if (avx2 && q1 > q0) {
+      std::vector<int32_t> acc(3 * (size_t)L8 * 8);
+      int32_t* vmn = acc.data();
+      int32_t* vmx = vmn + (size_t)L8 * 8;
+      int32_t* vnan = vmx + (size_t)L8 * 8;
+      for (int i = 0; i < L8 * 8; ++i) { vmn[i] = 0x7fffffff; vmx[i] = (int32_t)0x80000000u; vnan[i] = 0; }
+      mm_scan_avx2(p + e0, q1 - q0, L8, vmn, vmx, vnan);
+      for (int i = 0; i < L8 * 8; ++i) {
+        const int c = i % F;
+        mn[c] = vmn[i] < mn[c] ? vmn[i] : mn[c];
+        mx[c] = vmx[i] > mx[c] ? vmx[i] : mx[c];
+        nan[c] |= vnan[i] ? 1u : 0u;
+      }
+      e0 = q1 * period_rows * F;
+    }
+#endif
+    mm_scan_scalar(p, e0, e1, F, mn, mx, nan);
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < hw; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& h : th) h.join();
+  for (int c = 0; c < F; ++c) {
+    int32_t mn = 0x7fffffff, mx = (int32_t)0x80000000u;
+    uint32_t nan = 0u;
+    for (unsigned t = 0; t < hw; ++t) {
+      mn = std::min(mn, pmn[t][c]); mx = std::max(mx, pmx[t][c]); nan |= pnan[t][c];
+    }
+    const uint32_t qnan = 0x7fc00000u;
+    float fn;
+    memcpy(&fn, &qnan, 4);
+    mn_out[c] = nan ? fn : mm_unkey(mn);
+    mx_out[c] = nan ? fn : mm_unkey(mx);
+  }
+}
+
 // device copy of the whole table between the two passes of bb_compress_host, when it fits in half of the free memory
 float* resident_get(bb_model* m, size_t bytes) {
   if (getenv("BALER_B200_NO_RESIDENT")) return nullptr;  // test hook: take the two-pass streaming path of tables that do not fit
@@ -374,26 +513,58 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
   // Column statistics of THIS table (helper.py:500-502): either a first streaming pass that keeps
   // the table resident when it fits, or the features handed in.
   float* resident = nullptr;
+  std::vector<cudaEvent_t> ev_up;  // resident path: upload of chunk k complete
   if (norm && recompute_minmax && n_rows) {
     resident = resident_get(m, (size_t)n_rows * F * sizeof(float));
-    for (int64_t k = 0; k < n_chunks; ++k) {
-      const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
-      const int s = (int)(k & 1);
-      float* dst = resident ? resident + (size_t)r0 * F : (float*)m->stage_dev[0][s];
-      if (!resident && k >= 2) BB_CUDA(cudaStreamWaitEvent(m->s_copy_in, m->ev_done[s], 0));
-      BB_CUDA(cudaMemcpyAsync(dst, x_host + (size_t)r0 * F, (size_t)rows * F * sizeof(float), cudaMemcpyHostToDevice, m->s_copy_in));
-      BB_CUDA(cudaEventRecord(m->ev_in[s], m->s_copy_in));
-      BB_CUDA(cudaStreamWaitEvent(m->s_compute, m->ev_in[s], 0));
-      rc = bb_colminmax_launch(m->ctx, dst, rows, F, fmin, fmax, k == 0, m->s_compute);
-      if (rc != BB_OK) return rc;
-      BB_CUDA(cudaEventRecord(m->ev_done[s], m->s_compute));
+    if (resident) {
+      // the table fits: queue the whole upload now, find the column min / max on host threads meanwhile, and let the
+      // encode + latent download of the chunks that have landed run against the rest of the upload
+      // (the scan starts first, on its own threads: queuing copies from pageable memory blocks the calling thread)
+      std::vector<float> mm(2 * (size_t)F);
+      std::thread scan(host_colminmax, x_host, n_rows, F, mm.data(), mm.data() + F);
+      ev_up.resize((size_t)n_chunks, nullptr);
+      cudaError_t up_rc = cudaSuccess;
+      for (int64_t k = 0; k < n_chunks && up_rc == cudaSuccess; ++k) {
+        const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
+        up_rc = cudaMemcpyAsync(resident + (size_t)r0 * F, x_host + (size_t)r0 * F, (size_t)rows * F * sizeof(float), cudaMemcpyHostToDevice, m->s_copy_in);
+        if (up_rc == cudaSuccess) up_rc = cudaEventCreateWithFlags(&ev_up[(size_t)k], cudaEventDisableTiming);
+        if (up_rc == cudaSuccess) up_rc = cudaEventRecord(ev_up[(size_t)k], m->s_copy_in);
+      }
+      scan.join();
+      if (up_rc != cudaSuccess) {
+        for (cudaEvent_t e : ev_up) if (e) cudaEventDestroy(e);
+        return (int)up_rc;
+      }
+      BB_CUDA(cudaMemcpyAsync(fmin, mm.data(), F * sizeof(float), cudaMemcpyHostToDevice, m->s_compute));
+      BB_CUDA(cudaMemcpyAsync(fmax, mm.data() + F, F * sizeof(float), cudaMemcpyHostToDevice, m->s_compute));
+      range_kernel<<<(F + 127) / 128, 128, 0, m->s_compute>>>(fmin, fmax, frange, F);
+      BB_CUDA(cudaMemcpyAsync(features_host, fmin, 2 * F * sizeof(float), cudaMemcpyDeviceToHost, m->s_compute));
+      BB_CUDA(cudaStreamSynchronize(m->s_compute));  // (mm goes out of scope; features_host is final)
+    } else {
+      // too large to keep: a first streaming pass for the statistics, a second one (below) for the encode
+      for (int64_t k = 0; k < n_chunks; ++k) {
+        const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
+        const int s = (int)(k & 1);
+        float* dst = (float*)m->stage_dev[0][s];
+        if (k >= 2) BB_CUDA(cudaStreamWaitEvent(m->s_copy_in, m->ev_done[s], 0));
+        BB_CUDA(cudaMemcpyAsync(dst, x_host + (size_t)r0 * F, (size_t)rows * F * sizeof(float), cudaMemcpyHostToDevice, m->s_copy_in));
+        BB_CUDA(cudaEventRecord(m->ev_in[s], m->s_copy_in));
+        BB_CUDA(cudaStreamWaitEvent(m->s_compute, m->ev_in[s], 0));
+        rc = bb_colminmax_launch(m->ctx, dst, rows, F, fmin, fmax, k == 0, m->s_compute);
+        if (rc != BB_OK) return rc;
+        BB_CUDA(cudaEventRecord(m->ev_done[s], m->s_compute));
+      }
+      range_kernel<<<(F + 127) / 128, 128, 0, m->s_compute>>>(fmin, fmax, frange, F);
+      BB_CUDA(cudaMemcpyAsync(features_host, fmin, 2 * F * sizeof(float), cudaMemcpyDeviceToHost, m->s_compute));
+      BB_CUDA(cudaStreamSynchronize(m->s_compute));
     }
-    range_kernel<<<(F + 127) / 128, 128, 0, m->s_compute>>>(fmin, fmax, frange, F);
-    BB_CUDA(cudaMemcpyAsync(features_host, fmin, 2 * F * sizeof(float), cudaMemcpyDeviceToHost, m->s_compute));
-    BB_CUDA(cudaStreamSynchronize(m->s_compute));
   } else if (norm) {
     BB_CUDA(cudaMemcpyAsync(fmin, features_host, 2 * F * sizeof(float), cudaMemcpyHostToDevice, m->s_compute));
   }
+  struct EvGuard {  // the per-chunk upload events live for this call only
+    std::vector<cudaEvent_t>& v;
+    ~EvGuard() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+  } ev_guard{ev_up};
 
   std::vector<float> widen_tmp;
   float* pinned_out[2] = {nullptr, nullptr};
@@ -417,6 +588,7 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
     const float* src;
     if (resident) {
       src = resident + (size_t)r0 * F;
+      BB_CUDA(cudaStreamWaitEvent(m->s_compute, ev_up[(size_t)k], 0));
     } else {
       if (k >= 2) BB_CUDA(cudaStreamWaitEvent(m->s_copy_in, m->ev_done[s], 0));  // slot's previous kernel finished
       BB_CUDA(cudaMemcpyAsync(m->stage_dev[0][s], x_host + (size_t)r0 * F, (size_t)rows * F * sizeof(float), cudaMemcpyHostToDevice, m->s_copy_in));

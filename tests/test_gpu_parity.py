@@ -184,6 +184,33 @@ def test_compress_decompress_host_roundtrip(ae):
     close(y_plain, orc.ae_decode(sd, zr))
 
 
+@pytest.mark.parametrize("n", [1, 7, 1000, 30011])
+def test_compress_host_statistics_match_the_kernel(ae, n, monkeypatch):
+    """the column min / max that bb_compress_host finds on host threads while the table uploads (resident path) equals the
+    device kernel's - bit for bit, incl. -0 < +0 and NaN propagation per column - and the streaming two-pass path"""
+    m, _, _ = ae
+    codec = m.codec()
+    rng = np.random.default_rng(n)
+    table = synth.cms_table(n, seed=5)
+    table[rng.integers(0, n, size=max(1, n // 50)), rng.integers(0, 24, size=max(1, n // 50))] = 0.0
+    table[rng.integers(0, n, size=max(1, n // 80)), rng.integers(0, 24, size=max(1, n // 80))] = -0.0
+    _, feats = codec.compress_host(table, recompute_minmax=True, z_dtype=np.float32)
+    mn, mx = engine.colminmax(torch.from_numpy(table).cuda())
+    ref = np.stack([mn.cpu().numpy(), (mx - mn).cpu().numpy()])
+    assert feats.tobytes() == ref.tobytes()
+    monkeypatch.setenv("BALER_B200_NO_RESIDENT", "1")
+    _, feats2 = codec.compress_host(table, recompute_minmax=True, z_dtype=np.float32)
+    assert feats2.tobytes() == feats.tobytes()
+    monkeypatch.delenv("BALER_B200_NO_RESIDENT")
+    if n >= 1000:  # numpy semantics: a NaN makes that column's min and max NaN, and only that column's
+        table[n // 3, 5] = np.nan
+        table[n - 1, 23] = np.nan
+        _, fn = codec.compress_host(table, recompute_minmax=True, z_dtype=np.float32)
+        bad = np.zeros(24, dtype=bool)
+        bad[[5, 23]] = True
+        assert np.isnan(fn[:, bad]).all() and fn[:, ~bad].tobytes() == feats[:, ~bad].tobytes()
+
+
 def test_host_pipeline_multi_chunk(ae):
     """more rows than one pipeline chunk (2^21): slots, events and ragged tail; checked on sampled rows"""
     m, sd, _ = ae
