@@ -4,6 +4,9 @@
 #include <cstring>
 #include <new>
 #include <thread>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
 #endif
@@ -290,8 +293,21 @@ __attribute__((target("avx2"))) void mm_scan_avx2(const uint32_t* p, int64_t n_p
 }
 #endif
 
+// host threads this process may use for the scan: the CPUs it is allowed on (a launcher may have bound the rank to its
+// GPU's NUMA node), shared with the other ranks of the node (LOCAL_WORLD_SIZE, set by torchrun), at most 16
+unsigned host_scan_threads() {
+  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = std::min<unsigned>(hw, (unsigned)CPU_COUNT(&set));
+#endif
+  unsigned ranks = 1;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(e));
+  return std::max(1u, std::min(16u, hw / ranks));
+}
+
 void host_colminmax(const float* x, int64_t n_rows, int F, float* mn_out, float* mx_out) {
-  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const unsigned hw = host_scan_threads();
   int g = F, b = 8;
   while (b) { const int r = g % b; g = b; b = r; }
   const int period_rows = 8 / g, L8 = F / g;  // rows / 8-lane vectors of one period
@@ -516,7 +532,9 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
   std::vector<cudaEvent_t> ev_up;  // resident path: upload of chunk k complete
   if (norm && recompute_minmax && n_rows) {
     resident = resident_get(m, (size_t)n_rows * F * sizeof(float));
-    if (resident) {
+    // the host scan pays when enough host threads are free for it (at 8 ranks on a 32-CPU node they are not: the device
+    // pass below costs nothing on the host)
+    if (resident && host_scan_threads() >= 8 && !getenv("BALER_B200_DEVICE_MINMAX")) {
       // the table fits: queue the whole upload now, find the column min / max on host threads meanwhile, and let the
       // encode + latent download of the chunks that have landed run against the rest of the upload
       // (the scan starts first, on its own threads: queuing copies from pageable memory blocks the calling thread)
@@ -541,12 +559,13 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
       BB_CUDA(cudaMemcpyAsync(features_host, fmin, 2 * F * sizeof(float), cudaMemcpyDeviceToHost, m->s_compute));
       BB_CUDA(cudaStreamSynchronize(m->s_compute));  // (mm goes out of scope; features_host is final)
     } else {
-      // too large to keep: a first streaming pass for the statistics, a second one (below) for the encode
+      // a first streaming pass for the statistics on the device (column min / max kernel per chunk as it lands), which
+      // keeps the table resident when it fits; otherwise the second pass below uploads it again
       for (int64_t k = 0; k < n_chunks; ++k) {
         const int64_t r0 = k * chunk, rows = std::min(chunk, n_rows - r0);
         const int s = (int)(k & 1);
-        float* dst = (float*)m->stage_dev[0][s];
-        if (k >= 2) BB_CUDA(cudaStreamWaitEvent(m->s_copy_in, m->ev_done[s], 0));
+        float* dst = resident ? resident + (size_t)r0 * F : (float*)m->stage_dev[0][s];
+        if (!resident && k >= 2) BB_CUDA(cudaStreamWaitEvent(m->s_copy_in, m->ev_done[s], 0));
         BB_CUDA(cudaMemcpyAsync(dst, x_host + (size_t)r0 * F, (size_t)rows * F * sizeof(float), cudaMemcpyHostToDevice, m->s_copy_in));
         BB_CUDA(cudaEventRecord(m->ev_in[s], m->s_copy_in));
         BB_CUDA(cudaStreamWaitEvent(m->s_compute, m->ev_in[s], 0));
@@ -588,7 +607,7 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
     const float* src;
     if (resident) {
       src = resident + (size_t)r0 * F;
-      BB_CUDA(cudaStreamWaitEvent(m->s_compute, ev_up[(size_t)k], 0));
+      if (!ev_up.empty()) BB_CUDA(cudaStreamWaitEvent(m->s_compute, ev_up[(size_t)k], 0));
     } else {
       if (k >= 2) BB_CUDA(cudaStreamWaitEvent(m->s_copy_in, m->ev_done[s], 0));  // slot's previous kernel finished
       BB_CUDA(cudaMemcpyAsync(m->stage_dev[0][s], x_host + (size_t)r0 * F, (size_t)rows * F * sizeof(float), cudaMemcpyHostToDevice, m->s_copy_in));

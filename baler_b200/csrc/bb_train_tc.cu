@@ -143,6 +143,7 @@ struct TcPtrs {
   float *rm, *rv;                   // running mean / variance, bn_f_total each
   long long* nbt;                   // num_batches_tracked[4]
   uint4* bn_part;                   // [8 reduction points][max_tiles][BN_PW] packets {a, tag, b, tag} of per-tile column sums
+  uint4* bn_fin;                    // [8 reduction points][BN_PW] final packets of the columns (statistics / totals of the batch)
   uint4* bnx[MAX_WORLD];            // data parallel: every rank's [2 parities][8 points][world][BN_PW] packets of per-rank sums
   const unsigned char* mask[4];     // injected dropout keep-masks [global batch][width] (parity tests) or nullptr (Philox)
   unsigned long long seed;
@@ -384,27 +385,25 @@ __device__ __forceinline__ int dp_rank_rows(const int B, const int world, const 
   return base + (r < B - base * world ? 1 : 0);
 }
 
-// Sum of reduction point `pt` over the tiles of this rank (and, data parallel, over the ranks).  Column j is owned by
-// thread j; when the layer is narrower than half the CTA the idle threads take slices of the tile range (fixed
-// geometry, combined in slice order: reproducible).  FWD: packets are (sum, sum of squares about the tile mean) and the
-// result is the batch mean and 1 / sqrt(biased variance + eps) (Chan's pairwise combination, no E[x^2] - mean^2
-// cancellation in fp32); otherwise (sum dY, sum dY xhat) and the result is the two totals = d beta, d gamma.  Leaves in
-// shared memory what the warps need for their values: mean | inv (kept for the backward pass) and gamma | beta, or
-// T1 / B | T2 / B | gamma inv.
+// Reduction point `pt` over the tiles of this rank (and, data parallel, over the ranks) as reduce-scatter + all-gather,
+// so that a thread has ONE packet in flight per hop instead of one per tile (reading every tile's packet of every column in
+// every CTA measured 1.4 k cycles per 8 packets, 4 rounds for the 200-wide layers: 4 - 12 k cycles per point).
+//   hop 1  column j belongs to the CTA of tile j % n_tiles.  Warp w of that CTA takes its q-th column, lane l the packets
+//          of tiles l, l + 32, ...; a butterfly over the lanes adds them (fixed pattern: reproducible).  Forward sums are
+//          taken about a shift K = the mean of tile 0, the same for all lanes: sum (x - K) and sum (x - K)^2 are additive
+//          and M2 = sum (x - K)^2 - (sum (x - K))^2 / n loses nothing to cancellation (|mean - K| is a fraction of sigma).
+//          All of it in fp32: FP64 instructions issue at a small fraction of the fp32 rate here.
+//          Data parallel: lane r pushes the rank's (mean, M2) or (sum dY, sum dY xhat) of the column to rank r and polls
+//          rank r's packet; the ranks are combined in rank order (Chan), so every rank holds the same bits.
+//          Lane 0 publishes the result - (mean, 1 / sqrt(var + eps)) or (T1 / B, T2 / B) - as the column's final packet.
+//   hop 2  thread j of every CTA reads the final packet of column j and leaves in shared memory what the warps need for
+//          their values: mean | inv (kept for the backward pass) and gamma | beta, or T1 / B | T2 / B | gamma inv.
 template <bool FWD>
 __device__ __forceinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, const StepCtx& sc, const int bi, const int pt,
-                                       unsigned char* smem) {
-  // All of it in fp32 (FP64 instructions issue at a small fraction of the fp32 rate here: measured ~175 cycles per
-  // packet with double accumulators).  The forward sums are taken about a shift K = the mean of the rank's first
-  // tile, the same for every slice of a column: sum (x - K) and sum (x - K)^2 are additive over tiles and slices, and
-  // M2 = sum (x - K)^2 - (sum (x - K))^2 / n loses nothing to cancellation because |mean - K| is a fraction of sigma.
-  const int tid = threadIdx.x, N = M.bn_n[bi], fo = M.bn_f_off[bi];
+                                       const int tile, unsigned char* smem) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, N = M.bn_n[bi], fo = M.bn_f_off[bi];
   float* stat = reinterpret_cast<float*>(smem + M.stat_off);
   float* tr = stat + 2 * M.bn_f_total;  // transient: [gamma | beta | T1 / B | T2 / B or gamma inv] x BN_TW
-  float2* red = reinterpret_cast<float2*>(smem + M.red_off);
-  const int slices = M.bn_slices[bi];
-  int sl = 0, col = tid;
-  while (col >= N) { col -= N; ++sl; }
   float gam = 0.f, bet = 0.f;
   if (tid < N) {
     gam = __ldcg(P.params + M.bn_g_off[bi] + tid);
@@ -412,67 +411,50 @@ __device__ __forceinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, con
   }
   const bool pk0 = sc.prof != nullptr && tid == 0;
   if (pk0) sc.prof[520 + 8 * pt + 1] = clock64();
-  float S1 = 0.f, S2 = 0.f, K = 0.f;
-  if (sl < slices) {
-    const int per = sc.per[bi];
-    const int tb = sl * per, te = tb + per < sc.n_tiles ? tb + per : sc.n_tiles;
-    const uint4* base = P.bn_part + (size_t)pt * M.max_tiles * BN_PW + col;
-    const int last = sc.rows - (sc.n_tiles - 1) * TROWS;            // rows of the last tile
-    const float n_last = (float)last, inv_last = __frcp_rn(n_last);  // (1 / 16 is exact; 1 / last is used for one tile)
-    if (FWD) {
-      uint4 k0 = ld_pkt(base);
-      while (k0.y != sc.tag || k0.w != sc.tag) k0 = ld_pkt(base);
-      K = __uint_as_float(k0.x) * (sc.n_tiles == 1 ? inv_last : 1.f / TROWS);
-    }
-    for (int t0 = tb; t0 < te; t0 += POLL) {
-      uint4 pk[POLL];
+  const int n_tiles = sc.n_tiles;
+  const uint4* part = P.bn_part + (size_t)pt * M.max_tiles * BN_PW;
+  uint4* fin = P.bn_fin + (size_t)pt * BN_PW;
+  const int last = sc.rows - (n_tiles - 1) * TROWS;               // rows of the last tile
+  const float n_last = (float)last, inv_last = __frcp_rn(n_last);  // (1 / 16 is exact; 1 / last is used for one tile)
+  // ---- hop 1: the columns this CTA owns
+  for (int j = tile + warp * n_tiles; j < N; j += NWARPS * n_tiles) {
+    uint4 pk[5];
 #pragma unroll
-      for (int u = 0; u < POLL; ++u)
-        if (t0 + u < te) pk[u] = ld_pkt(base + (size_t)(t0 + u) * BN_PW);
-      if (pk0) sc.prof[600 + 16 * pt + 2 * ((t0 - tb) / POLL)] = clock64();
-      bool missing;
-      do {  // re-issue the loads of the packets that have not landed yet, all of them together
-        missing = false;
+    for (int u = 0; u < 5; ++u)
+      if (lane + 32 * u < n_tiles) pk[u] = ld_pkt(part + (size_t)(lane + 32 * u) * BN_PW + j);
+    bool missing;
+    do {
+      missing = false;
 #pragma unroll
-        for (int u = 0; u < POLL; ++u)
-          if (t0 + u < te && (pk[u].y != sc.tag || pk[u].w != sc.tag)) {
-            pk[u] = ld_pkt(base + (size_t)(t0 + u) * BN_PW);
-            missing = true;
-          }
-      } while (missing);
-      if (pk0) sc.prof[600 + 16 * pt + 2 * ((t0 - tb) / POLL) + 1] = clock64();
-#pragma unroll
-      for (int u = 0; u < POLL; ++u)
-        if (t0 + u < te) {
-          const float a = __uint_as_float(pk[u].x), b = __uint_as_float(pk[u].z);
-          if (FWD) {
-            const bool is_last = t0 + u == sc.n_tiles - 1;
-            const float d = a - (is_last ? n_last : (float)TROWS) * K;
-            S1 += d;
-            S2 += fmaf(d * d, is_last ? inv_last : 1.f / TROWS, b);
-          } else {
-            S1 += a;
-            S2 += b;
-          }
+      for (int u = 0; u < 5; ++u)
+        if (lane + 32 * u < n_tiles && (pk[u].y != sc.tag || pk[u].w != sc.tag)) {
+          pk[u] = ld_pkt(part + (size_t)(lane + 32 * u) * BN_PW + j);
+          missing = true;
         }
-    }
-  }
-  if (pk0) sc.prof[520 + 8 * pt + 2] = clock64();
-  if (slices > 1) {
-    if (sl > 0 && sl < slices) red[(sl - 1) * N + col] = make_float2(S1, S2);
-    __syncwarp();
-    __syncthreads();
-    if (sl == 0)
-      for (int q = 1; q < slices; ++q) {
-        const float2 o = red[(q - 1) * N + col];
-        S1 += o.x;
-        S2 += o.y;
+    } while (missing);
+    float K = 0.f;
+    if (FWD) K = __shfl_sync(0xffffffffu, __uint_as_float(pk[0].x) * (n_tiles == 1 ? inv_last : 1.f / TROWS), 0);
+    float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < 5; ++u)
+      if (lane + 32 * u < n_tiles) {
+        const float a = __uint_as_float(pk[u].x), b = __uint_as_float(pk[u].z);
+        if (FWD) {
+          const bool is_last = lane + 32 * u == n_tiles - 1;
+          const float d = a - (is_last ? n_last : (float)TROWS) * K;
+          S1 += d;
+          S2 += fmaf(d * d, is_last ? inv_last : 1.f / TROWS, b);
+        } else {
+          S1 += a;
+          S2 += b;
+        }
       }
-  }
-  if (pk0) sc.prof[520 + 8 * pt + 3] = clock64();
-  if (tid < N) {
-    const int j = tid;
-    float r1, r2;  // FWD: mean, M2 of the global batch; else the totals
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      S1 += __shfl_xor_sync(0xffffffffu, S1, o);
+      S2 += __shfl_xor_sync(0xffffffffu, S2, o);
+    }
+    float r1, r2;  // FWD: mean, M2 of this rank's rows; else its totals
     if (FWD) {
       const float dm = S1 * sc.inv_rows;
       r1 = K + dm;
@@ -482,73 +464,72 @@ __device__ __forceinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, con
       r2 = S2;
     }
     if (P.dp_slice) {
-      // every rank combines the same fp32 numbers in the same (rank) order: identical statistics on all replicas
+      // lane r talks to rank r; every rank combines the same fp32 numbers in rank order: identical statistics everywhere
       const size_t blk = (((size_t)(sc.tag & 1u) * 8 + pt) * P.world) * BN_PW + j;
-      if (blockIdx.x == 0)
-        for (int r = 0; r < P.world; ++r)
-          if (r != P.rank) st_pkt_sys(P.bnx[r] + blk + (size_t)P.rank * BN_PW, r1, r2, sc.tag);
+      float a = r1, b = r2;
+      const int nr = lane < P.world ? dp_rank_rows(sc.B, P.world, lane) : 0;
+      if (lane < P.world && lane != P.rank) {
+        st_pkt_sys(P.bnx[lane] + blk + (size_t)P.rank * BN_PW, r1, r2, sc.tag);
+        if (nr > 0) {
+          const uint4* src = P.bnx[P.rank] + blk + (size_t)lane * BN_PW;
+          uint4 q = ld_pkt_sys(src);
+          while (q.y != sc.tag || q.w != sc.tag) q = ld_pkt_sys(src);
+          a = __uint_as_float(q.x);
+          b = __uint_as_float(q.z);
+        }
+      }
       float cn = 0.f, c1 = 0.f, c2 = 0.f;
-      const uint4* mine = P.bnx[P.rank] + blk;
-      for (int r0 = 0; r0 < P.world; r0 += 4) {
-        uint4 q[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (r0 + u < P.world && r0 + u != P.rank) q[u] = ld_pkt_sys(mine + (size_t)(r0 + u) * BN_PW);
-        bool missing;
-        do {
-          missing = false;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (r0 + u < P.world && r0 + u != P.rank && dp_rank_rows(sc.B, P.world, r0 + u) > 0 &&
-                (q[u].y != sc.tag || q[u].w != sc.tag)) {
-              q[u] = ld_pkt_sys(mine + (size_t)(r0 + u) * BN_PW);
-              missing = true;
-            }
-        } while (missing);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = r0 + u;
-          const int nr = r < P.world ? dp_rank_rows(sc.B, P.world, r) : 0;
-          if (nr > 0) {
-            const float a = r == P.rank ? r1 : __uint_as_float(q[u].x), b = r == P.rank ? r2 : __uint_as_float(q[u].z);
-            if (FWD) {  // Chan's pairwise update of (count, mean, M2)
-              const float delta = a - c1, nn = cn + (float)nr;
-              const float w = __fdiv_rn((float)nr, nn);
-              c1 = fmaf(delta, w, c1);
-              c2 += fmaf(delta * delta, cn * w, b);
-              cn = nn;
-            } else {
-              c1 += a;
-              c2 += b;
-            }
-          }
+      for (int r = 0; r < P.world; ++r) {
+        const float ar = __shfl_sync(0xffffffffu, a, r), br = __shfl_sync(0xffffffffu, b, r);
+        const int nrr = __shfl_sync(0xffffffffu, nr, r);
+        if (nrr == 0) continue;
+        if (FWD) {  // Chan's pairwise update of (count, mean, M2)
+          const float delta = ar - c1, nn = cn + (float)nrr;
+          const float w = __fdiv_rn((float)nrr, nn);
+          c1 = fmaf(delta, w, c1);
+          c2 += fmaf(delta * delta, cn * w, br);
+          cn = nn;
+        } else {
+          c1 += ar;
+          c2 += br;
         }
       }
       r1 = c1;
       r2 = c2;
     }
-    if (FWD) {
-      stat[fo + j] = r1;
-      stat[M.bn_f_total + fo + j] = __frcp_rn(__fsqrt_rn(fmaf(r2, sc.inv_B, BN_EPS)));  // IEEE roundings: ~1 ulp
-      tr[j] = gam;
-      tr[BN_TW + j] = bet;
-      if (blockIdx.x == 0) {  // running statistics: momentum 0.1, unbiased variance (torch.nn.BatchNorm1d)
+    if (lane == 0) {
+      if (FWD) {
+        const float inv = __frcp_rn(__fsqrt_rn(fmaf(r2, sc.inv_B, BN_EPS)));  // IEEE roundings: ~1 ulp
+        st_pkt(fin + j, r1, inv, sc.tag);
+        // running statistics: momentum 0.1, unbiased variance (torch.nn.BatchNorm1d)
         P.rm[fo + j] = (1.f - BN_MOMENTUM) * P.rm[fo + j] + BN_MOMENTUM * r1;
         P.rv[fo + j] = (1.f - BN_MOMENTUM) * P.rv[fo + j] + BN_MOMENTUM * (r2 * sc.inv_Bm1);
         if (j == 0) P.nbt[bi] += 1;
-      }
-    } else {
-      tr[2 * BN_TW + j] = r1 * sc.inv_B;
-      tr[3 * BN_TW + j] = r2 * sc.inv_B;
-      tr[j] = gam * stat[M.bn_f_total + fo + j];
-      if (blockIdx.x == 0) {
+      } else {
+        st_pkt(fin + j, r1 * sc.inv_B, r2 * sc.inv_B, sc.tag);
         P.grads[M.bn_b_off[bi] + j] = r1;
         P.grads[M.bn_g_off[bi] + j] = r2;
       }
     }
   }
+  if (pk0) sc.prof[520 + 8 * pt + 2] = clock64();
+  // ---- hop 2: every CTA gathers the final packets
+  if (tid < N) {
+    uint4 q = ld_pkt(fin + tid);
+    while (q.y != sc.tag || q.w != sc.tag) q = ld_pkt(fin + tid);
+    const float v1 = __uint_as_float(q.x), v2 = __uint_as_float(q.z);
+    if (FWD) {
+      stat[fo + tid] = v1;
+      stat[M.bn_f_total + fo + tid] = v2;
+      tr[tid] = gam;
+      tr[BN_TW + tid] = bet;
+    } else {
+      tr[2 * BN_TW + tid] = v1;
+      tr[3 * BN_TW + tid] = v2;
+      tr[tid] = gam * stat[M.bn_f_total + fo + tid];
+    }
+  }
   if (pk0) sc.prof[520 + 8 * pt + 4] = clock64();
-  __syncwarp();
   __syncthreads();
   if (pk0) sc.prof[520 + 8 * pt + 5] = clock64();
 }
@@ -1116,7 +1097,7 @@ __device__ __forceinline__ void phase1_tile(const TcModel& M, const TcPtrs& P, c
       bool leaky = false;
       if (pd.kind != 2) {
         const int bi = pd.kind == 1 ? 3 : pd.bn;
-        if (P.train) bn_reduce<true>(M, P, sc, bi, bi, smem);
+        if (P.train) bn_reduce<true>(M, P, sc, bi, bi, tile, smem);
         else bn_eval_stats(M, P, bi, smem);
         if (pd.kind == 0) {
           BB_BY_NJ(bn_apply_fwd<NJ>(M, sc, bi, o, o_hi, o_lo, o_ld, smem));
@@ -1128,7 +1109,7 @@ __device__ __forceinline__ void phase1_tile(const TcModel& M, const TcPtrs& P, c
         bwd_bi = pd.bn; bwd_pt = 7 - pd.bn; leaky = true;
       }
       if (bwd_bi >= 0) {
-        bn_reduce<false>(M, P, sc, bwd_bi, bwd_pt, smem);
+        bn_reduce<false>(M, P, sc, bwd_bi, bwd_pt, tile, smem);
         BB_BY_NJ(bn_apply_bwd<NJ>(M, sc, bwd_bi, leaky, o, o_hi, o_lo, o_ld, smem));
       }
 #undef BB_BY_NJ
@@ -1517,6 +1498,7 @@ struct TcTrainer {
   size_t dp_flag_bytes = 0;
   int xt_feat[NL], zt_feat[NL];
   uint4* bn_part = nullptr;      // AE_Dropout_BN: per-tile BatchNorm packets
+  uint4* bn_fin = nullptr;       // ... and the final packet of every column
   size_t dp_bnx_off = 0;         // ... and where the per-rank packets start inside the data-parallel block
   int ring = RING;
 };
@@ -1682,6 +1664,7 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
   alloc((void**)&t->flag, sizeof(int));
   alloc((void**)&t->prof, sizeof(long long) * 1024);
   if (kind == 1) alloc((void**)&t->bn_part, sizeof(uint4) * 8 * (size_t)M.max_tiles * BN_PW);
+  if (kind == 1) alloc((void**)&t->bn_fin, sizeof(uint4) * 8 * BN_PW);
   if (rc == BB_OK) rc = (int)cudaMemcpy(t->items, items.data(), sizeof(TcItem) * items.size(), cudaMemcpyHostToDevice);
   const void* kern = kind == 1 ? (const void*)tc_train_kernel<true> : (const void*)tc_train_kernel<false>;
   if (rc == BB_OK) rc = (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem);
@@ -1703,6 +1686,7 @@ int bb_tc_train_create(bb_ctx* ctx, const int* dims, const int* acts, int max_ba
   P.loss_part = t->loss_part; P.items = t->items; P.bar = t->bar; P.flag = t->flag;
   P.rank = 0; P.world = 1;
   P.bn_part = t->bn_part;
+  P.bn_fin = t->bn_fin;
   P.train = 1;
   *out = t;
   return BB_OK;
@@ -1712,7 +1696,7 @@ void bb_tc_train_destroy(TcTrainer* t) {
   if (!t) return;
   dp_release(t);
   void* ptrs[] = {t->img, t->xt_hi, t->xt_lo, t->zt_hi, t->zt_lo, t->loss_part, t->items, t->bar, t->flag, t->stephyper, t->prof,
-                  t->bn_part};
+                  t->bn_part, t->bn_fin};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete t;

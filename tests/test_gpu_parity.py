@@ -194,14 +194,15 @@ def test_compress_host_statistics_match_the_kernel(ae, n, monkeypatch):
     table = synth.cms_table(n, seed=5)
     table[rng.integers(0, n, size=max(1, n // 50)), rng.integers(0, 24, size=max(1, n // 50))] = 0.0
     table[rng.integers(0, n, size=max(1, n // 80)), rng.integers(0, 24, size=max(1, n // 80))] = -0.0
-    _, feats = codec.compress_host(table, recompute_minmax=True, z_dtype=np.float32)
+    z1, feats = codec.compress_host(table, recompute_minmax=True, z_dtype=np.float32)
     mn, mx = engine.colminmax(torch.from_numpy(table).cuda())
     ref = np.stack([mn.cpu().numpy(), (mx - mn).cpu().numpy()])
     assert feats.tobytes() == ref.tobytes()
-    monkeypatch.setenv("BALER_B200_NO_RESIDENT", "1")
-    _, feats2 = codec.compress_host(table, recompute_minmax=True, z_dtype=np.float32)
-    assert feats2.tobytes() == feats.tobytes()
-    monkeypatch.delenv("BALER_B200_NO_RESIDENT")
+    for hook in ("BALER_B200_NO_RESIDENT", "BALER_B200_DEVICE_MINMAX"):  # the two device-side statistics paths
+        monkeypatch.setenv(hook, "1")
+        z2, feats2 = codec.compress_host(table, recompute_minmax=True, z_dtype=np.float32)
+        assert feats2.tobytes() == feats.tobytes() and z2.tobytes() == z1.tobytes()
+        monkeypatch.delenv(hook)
     if n >= 1000:  # numpy semantics: a NaN makes that column's min and max NaN, and only that column's
         table[n // 3, 5] = np.nan
         table[n - 1, 23] = np.nan
