@@ -37,13 +37,8 @@ for q in range(15):
     rec = st[16 + q * 32: 16 + q * 32 + 32].reshape(8, 4)
     print("  pass %2d:" % q, " ".join("%d|%d/%d/%d" % (r[0] - t0, r[3] - r[0], r[1] - r[3], r[2] - r[1]) for r in rec))
 if kind != "ae":
-    print("BatchNorm reduction points (cycles from the start of the point's epilogue): packets stored | polled | slices combined | "
-          "statistics written | barrier passed")
+    print("BatchNorm reduction points (cycles from the start of the point's epilogue): packets stored | hop 1 (owned columns "
+          "reduced, final packets published) | hop 2 (final packets gathered) | barrier passed")
     for pt in range(8):
         q = st[520 + 8 * pt: 520 + 8 * pt + 6]
-        print("  point %d: start %d |" % (pt, q[0] - t0), " ".join(str(int(v - q[0])) for v in q[1:]))
-    print("poll batches of thread 0 (cycles from the point's start: loads issued | all landed)")
-    for pt in range(8):
-        q0 = st[520 + 8 * pt]
-        print("  point %d:" % pt, " ".join("%d|%d" % (st[600 + 16 * pt + 2 * b] - q0, st[600 + 16 * pt + 2 * b + 1] - q0)
-                                           for b in range(4) if st[600 + 16 * pt + 2 * b]))
+        print("  point %d: start %d |" % (pt, q[0] - t0), " ".join(str(int(q[k] - q[0])) for k in (1, 2, 4, 5)))
