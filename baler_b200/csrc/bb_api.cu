@@ -128,37 +128,79 @@ int run_chain(bb_model* m, const Chain* c, const void* in, int in_dtype, int64_t
 
 size_t dtype_size(int dt) { return dt == BB_F64 ? 8 : (dt == BB_F16 ? 2 : 4); }
 
-// fp32 -> fp64 widening of a finished chunk on host threads (the reference stores float64 latents)
-void widen_f32_f64(const float* src, double* dst, size_t n) {
-  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  const size_t per = (n + hw - 1) / hw;
-  if (n < (1u << 16)) {
-    for (size_t i = 0; i < n; ++i) dst[i] = (double)src[i];
+// host threads this process may use for the scan: the CPUs it is allowed on (a launcher may have bound the rank to its
+// GPU's NUMA node), shared with the other ranks of the node (LOCAL_WORLD_SIZE, set by torchrun), at most 16
+unsigned host_scan_threads() {
+  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = std::min<unsigned>(hw, (unsigned)CPU_COUNT(&set));
+#endif
+  unsigned ranks = 1;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(e));
+  return std::max(1u, std::min(16u, hw / ranks));
+}
+
+// fp32 <-> fp64 conversion of a chunk on host threads (the reference stores float64 latents and reconstructions:
+// helper.py:565).  AVX2 with non-temporal stores where the destination allows it: the output is written once and not
+// read here, so the cache lines need not be fetched first (a plain store of a 3.8 GB reconstruction reads 3.8 GB too).
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) void widen_range_avx2(const float* src, double* dst, size_t lo, size_t hi) {
+  size_t i = lo;
+  for (; i < hi && (reinterpret_cast<uintptr_t>(dst + i) & 31u); ++i) dst[i] = (double)src[i];
+  for (; i + 8 <= hi; i += 8) {
+    const __m256 v = _mm256_loadu_ps(src + i);
+    _mm256_stream_pd(dst + i, _mm256_cvtps_pd(_mm256_castps256_ps128(v)));
+    _mm256_stream_pd(dst + i + 4, _mm256_cvtps_pd(_mm256_extractf128_ps(v, 1)));
+  }
+  for (; i < hi; ++i) dst[i] = (double)src[i];
+  _mm_sfence();
+}
+__attribute__((target("avx2"))) void narrow_range_avx2(const double* src, float* dst, size_t lo, size_t hi) {
+  size_t i = lo;
+  for (; i < hi && (reinterpret_cast<uintptr_t>(dst + i) & 31u); ++i) dst[i] = (float)src[i];
+  for (; i + 8 <= hi; i += 8) {
+    const __m128 a = _mm256_cvtpd_ps(_mm256_loadu_pd(src + i)), b = _mm256_cvtpd_ps(_mm256_loadu_pd(src + i + 4));
+    _mm256_stream_ps(dst + i, _mm256_set_m128(b, a));
+  }
+  for (; i < hi; ++i) dst[i] = (float)src[i];
+  _mm_sfence();
+}
+#endif
+
+template <typename Fn>
+void host_parallel_ranges(size_t n, Fn fn) {
+  const unsigned hw = host_scan_threads();
+  const size_t per = ((n + hw - 1) / hw + 7) & ~(size_t)7;
+  if (n < (1u << 16) || hw == 1) {
+    fn((size_t)0, n);
     return;
   }
   std::vector<std::thread> th;
   for (unsigned t = 0; t < hw; ++t) {
     const size_t lo = t * per, hi = std::min(n, lo + per);
     if (lo >= hi) break;
-    th.emplace_back([=] { for (size_t i = lo; i < hi; ++i) dst[i] = (double)src[i]; });
+    th.emplace_back([=] { fn(lo, hi); });
   }
   for (auto& t : th) t.join();
 }
 
+void widen_f32_f64(const float* src, double* dst, size_t n) {
+  host_parallel_ranges(n, [=](size_t lo, size_t hi) {
+#if defined(__x86_64__) && defined(__GNUC__)
+    if (__builtin_cpu_supports("avx2")) { widen_range_avx2(src, dst, lo, hi); return; }
+#endif
+    for (size_t i = lo; i < hi; ++i) dst[i] = (double)src[i];
+  });
+}
+
 void narrow_f64_f32(const double* src, float* dst, size_t n) {
-  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  const size_t per = (n + hw - 1) / hw;
-  if (n < (1u << 16)) {
-    for (size_t i = 0; i < n; ++i) dst[i] = (float)src[i];
-    return;
-  }
-  std::vector<std::thread> th;
-  for (unsigned t = 0; t < hw; ++t) {
-    const size_t lo = t * per, hi = std::min(n, lo + per);
-    if (lo >= hi) break;
-    th.emplace_back([=] { for (size_t i = lo; i < hi; ++i) dst[i] = (float)src[i]; });
-  }
-  for (auto& t : th) t.join();
+  host_parallel_ranges(n, [=](size_t lo, size_t hi) {
+#if defined(__x86_64__) && defined(__GNUC__)
+    if (__builtin_cpu_supports("avx2")) { narrow_range_avx2(src, dst, lo, hi); return; }
+#endif
+    for (size_t i = lo; i < hi; ++i) dst[i] = (float)src[i];
+  });
 }
 
 constexpr int64_t PIPE_CHUNK_ROWS = 1 << 21;  // rows per pipeline chunk (2 Mi rows: 192 MiB in, 120 MiB out for 24 -> 15)
@@ -292,19 +334,6 @@ __attribute__((target("avx2"))) void mm_scan_avx2(const uint32_t* p, int64_t n_p
 #undef BB_MM_STEP
 }
 #endif
-
-// host threads this process may use for the scan: the CPUs it is allowed on (a launcher may have bound the rank to its
-// GPU's NUMA node), shared with the other ranks of the node (LOCAL_WORLD_SIZE, set by torchrun), at most 16
-unsigned host_scan_threads() {
-  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-#if defined(__linux__)
-  cpu_set_t set;
-  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = std::min<unsigned>(hw, (unsigned)CPU_COUNT(&set));
-#endif
-  unsigned ranks = 1;
-  if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(e));
-  return std::max(1u, std::min(16u, hw / ranks));
-}
 
 void host_colminmax(const float* x, int64_t n_rows, int F, float* mn_out, float* mx_out) {
   const unsigned hw = host_scan_threads();
