@@ -108,8 +108,9 @@ def main():
             a, b = losses["single"][0], losses["dp2"][0]
             print(model, "single", a, "dp2", b, "rel diff", np.abs(a - b) / a)
             assert np.all(np.isfinite(b)) and b[-1] < b[0]
-            if model == "AE":
-                assert np.all(np.abs(a - b) <= 0.01 * a)  # same global batch, summed gradients: the reference curve within 1 %
+            # same global batch, summed gradients (AE_Dropout_BN: BatchNorm statistics of the global batch and one dropout stream
+            # keyed by the global row, exchanged inside the training kernel): the single-process curve within 1 %
+            assert np.all(np.abs(a - b) <= 0.01 * a)
     print("dp cli check ok")
 
 if __name__ == "__main__":
