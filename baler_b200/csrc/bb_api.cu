@@ -88,6 +88,8 @@ void free_chain(Chain* c) {
   if (c->tc_blob_dev) cudaFree(c->tc_blob_dev);
   if (c->lay_blob_dev) cudaFree(c->lay_blob_dev);
   if (c->lay_tc_blob_dev) cudaFree(c->lay_tc_blob_dev);
+  if (c->g5_blob_dev) cudaFree(c->g5_blob_dev);
+  if (c->g5_bias_dev) cudaFree(c->g5_bias_dev);
   bb_tc_release(c);
 }
 

@@ -340,6 +340,9 @@ int bb_chain_layered_prepare(bb_ctx*, Chain* c) {
   BB_CUDA(cudaMemcpy(c->lay_tc_blob_dev, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
   BB_CUDA(cudaFuncSetAttribute(dense_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
   c->lay_tc_ok = true;
+  // the tcgen05 form of the same GEMMs (optional per shape)
+  const int g5 = bb_gemm_tc5_prepare(nullptr, c);
+  if (g5 != BB_OK && g5 != BB_ERR_UNSUPPORTED) return g5;
   return BB_OK;
 }
 
@@ -353,13 +356,30 @@ int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_
   int64_t chunk_rows = CHUNK_ROWS;
   if (const char* e = getenv("BALER_B200_LAYER_CHUNK")) chunk_rows = atoll(e) > 0 ? atoll(e) : CHUNK_ROWS;  // (tuning)
   const int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
-  const size_t need = 2 * (size_t)chunk * c->lay_max_ld * sizeof(float);
+  // tensor cores: the tcgen05 GEMM (bb_gemm_tc5.cu) when the shape has it, else the mma.sync one below
+  const bool tc5 = tensor_cores && c->g5_ok && !getenv("BALER_B200_LAYERED_MMA");
+  const size_t buf_bytes = tc5 ? bb_gemm_tc5_buf_bytes(c, chunk) : (size_t)chunk * c->lay_max_ld * sizeof(float);
+  const size_t need = 2 * buf_bytes;
   if (ctx->lay_scratch_bytes < need) {
     // grown only (never shrunk); stream-ordered work that still uses the old buffer has been enqueued before the free
     if (ctx->lay_scratch) BB_CUDA(cudaFree(ctx->lay_scratch));
     ctx->lay_scratch = nullptr;
     BB_CUDA(cudaMalloc(&ctx->lay_scratch, need));
     ctx->lay_scratch_bytes = need;
+  }
+  if (tc5) {
+    const size_t in_esz5 = in_dtype == BB_F16 ? 2 : 4, out_esz5 = out_dtype == BB_F16 ? 2 : 4;
+    char* b0 = reinterpret_cast<char*>(ctx->lay_scratch);
+    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+      const int64_t rows = n_rows - r0 < chunk ? n_rows - r0 : chunk;
+      int ob = 0, ldo = 0;
+      const int rc = bb_gemm_tc5_chunk(ctx, c, (const char*)in + (size_t)r0 * d.in_dim * in_esz5, in_dtype, rows, pre_min, pre_range, b0,
+                                       b0 + buf_bytes, flag_dev, &ob, &ldo, stream);
+      if (rc != BB_OK) return rc;
+      stage_out_kernel<<<ctx->sm_count * 8, 256, 0, stream>>>(reinterpret_cast<const float*>(b0 + (size_t)ob * buf_bytes), rows, d.out_dim, ldo,
+                                                             post_min, post_range, (char*)out + (size_t)r0 * d.out_dim * out_esz5, out_dtype);
+    }
+    return (int)cudaGetLastError();
   }
   float* buf[2] = {ctx->lay_scratch, ctx->lay_scratch + (size_t)chunk * c->lay_max_ld};
   const size_t in_esz = in_dtype == BB_F16 ? 2 : 4, out_esz = out_dtype == BB_F16 ? 2 : 4;

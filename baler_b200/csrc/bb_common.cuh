@@ -71,6 +71,12 @@ struct Chain {
   bool lay_tc_ok = false;      // ... and its tensor-core form: fp16 hi / lo weight images per layer
   void* lay_tc_blob_dev = nullptr;
   size_t lay_tc_off[BB_MAX_LAYERS] = {0};
+  // ... and its tcgen05 form (bb_gemm_tc5.cu): weights packed per column tile in the UMMA core-matrix layout
+  bool g5_ok = false;
+  void* g5_blob_dev = nullptr;
+  float* g5_bias_dev = nullptr;
+  size_t g5_w_off[BB_MAX_LAYERS] = {0}, g5_b_off[BB_MAX_LAYERS] = {0};
+  float g5_unscale[BB_MAX_LAYERS] = {0};
   int lay_max_ld = 0;
   std::vector<double> w_host[BB_MAX_LAYERS];  // kept for re-packing
   std::vector<double> b_host[BB_MAX_LAYERS];
@@ -105,6 +111,11 @@ int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_
                             const float* pre_min, const float* pre_range, const float* post_min,
                             const float* post_range, void* out, int out_dtype, int tensor_cores, int* flag_dev,
                             cudaStream_t stream);
+int bb_gemm_tc5_prepare(bb_ctx* ctx, Chain* c);
+size_t bb_gemm_tc5_buf_bytes(const Chain* c, int64_t rows);
+int bb_gemm_tc5_chunk(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype, int64_t rows, const float* pre_min,
+                      const float* pre_range, void* buf0, void* buf1, int* flag_dev, int* out_buf, int* ld_out,
+                      cudaStream_t stream);
 int bb_colminmax_launch(bb_ctx* ctx, const float* x, int64_t n_rows, int n_cols, float* min_dev,
                         float* max_dev, int reset, cudaStream_t stream);
 int bb_tc_prepare(bb_ctx* ctx, Chain* c);

@@ -16,7 +16,8 @@ snaps = synth.cfd_snapshots((nb + 99) // 100)
 snaps = (snaps - snaps.min()) / (snaps.max() - snaps.min())
 blocks = torch.from_numpy(np.ascontiguousarray(snaps.reshape(-1, 1, 5, 5)[:nb])).cuda()
 for prec in ("auto", "fp32"):
-    z = cm.encode(blocks, precision=prec); cm.decode(z, precision=prec)
+    z = cm.encode(blocks, precision=prec); y = cm.decode(z, precision=prec)
+    del z, y
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record(); z = cm.encode(blocks, precision=prec); ev[1].record(); y = cm.decode(z, precision=prec); ev[2].record()
