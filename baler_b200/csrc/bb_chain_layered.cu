@@ -353,11 +353,12 @@ int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_
   if (!c->lay_ok || (tensor_cores && !c->lay_tc_ok)) return BB_ERR_UNSUPPORTED;
   if (n_rows == 0) return BB_OK;
   const ChainDesc& d = c->desc;
-  int64_t chunk_rows = CHUNK_ROWS;
-  if (const char* e = getenv("BALER_B200_LAYER_CHUNK")) chunk_rows = atoll(e) > 0 ? atoll(e) : CHUNK_ROWS;  // (tuning)
-  const int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
   // tensor cores: the tcgen05 GEMM (bb_gemm_tc5.cu) when the shape has it, else the mma.sync one below
   const bool tc5 = tensor_cores && c->g5_ok && !getenv("BALER_B200_LAYERED_MMA");
+  // (tcgen05: persistent CTAs walk 128-row tiles; 2 tiles per SM and chunk leave no partial wave on the one-column-tile layers)
+  int64_t chunk_rows = tc5 ? (int64_t)2 * ctx->sm_count * 128 : CHUNK_ROWS;
+  if (const char* e = getenv("BALER_B200_LAYER_CHUNK")) chunk_rows = atoll(e) > 0 ? atoll(e) : chunk_rows;  // (tuning)
+  const int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
   const size_t buf_bytes = tc5 ? bb_gemm_tc5_buf_bytes(c, chunk) : (size_t)chunk * c->lay_max_ld * sizeof(float);
   const size_t need = 2 * buf_bytes;
   if (ctx->lay_scratch_bytes < need) {

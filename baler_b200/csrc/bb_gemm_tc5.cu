@@ -25,7 +25,8 @@
 
 namespace {
 
-constexpr int GM = 128, GK = 64, GSTAGES = 2, GTHREADS = 320;
+constexpr int GM = 128, GK = 64, GSTAGES = 4, GTHREADS = 320;  // GSTAGES: most stages a layer may use (as many as fit)
+constexpr int G_SMEM_MAX = 200 * 1024;
 constexpr int G_A_BYTES = GM * GK * 2;  // one image (hi or lo) of an A stage
 // Activations travel multiplied by 2^8: the lo half of a small activation (|x| < 0.1: lo < 6e-5) would be a subnormal fp16
 // with an absolute step of 6e-8, i.e. 1e-5 relative at |x| = 0.01 (measured: latent error 1.3e-5 without the scaling).
@@ -113,7 +114,8 @@ struct G5Layer {
   float* y_f32;         // last layer: fp32 rows of pitch ldy
   int ldy;
   int kp, ntw, n_tiles, m_tiles, n, kp_next;
-  int n_split, n_bufs;  // partial accumulators per tile (k slabs round-robin), accumulator sets in flight
+  int n_split, n_bufs;  // accumulators per tile (2: hi * hi | cross products), accumulator sets in flight
+  int n_stages;         // operand stages in shared memory
   int rows;             // valid rows of the chunk
   int act;
   float unscale;        // 2^-sw of the layer's weight scaling x 1 / G_ACT_SCALE of its input
@@ -163,8 +165,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
         const int mt = item / L.n_tiles, nt = item - mt * L.n_tiles;
         const size_t a_tile = (size_t)mt * (L.kp / 8) * GM * 8, w_tile = (size_t)nt * (L.kp / 8) * L.ntw * 8;
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
-          const int s = it % GSTAGES;
-          g_mbar_wait(bar_empty(s), ((it / GSTAGES) & 1u) ^ 1u);
+          const int s = it % L.n_stages;
+          g_mbar_wait(bar_empty(s), ((it / L.n_stages) & 1u) ^ 1u);
           g_mbar_expect_tx(bar_full(s), stage_bytes);
           const uint32_t dst = sbase + s * stage_bytes;
           const size_t a_off = a_tile + (size_t)kc * (GK / 8) * GM * 8, w_off = w_tile + (size_t)kc * (GK / 8) * L.ntw * 8;
@@ -187,23 +189,26 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
       g_fence_after();
       const uint32_t d0 = tmem0 + (uint32_t)(a * L.n_split * L.ntw);
       for (int kc = 0; kc < n_kc; ++kc, ++it) {
-        const int s = it % GSTAGES;
-        g_mbar_wait(bar_full(s), (it / GSTAGES) & 1u);
+        const int s = it % L.n_stages;
+        g_mbar_wait(bar_full(s), (it / L.n_stages) & 1u);
         g_fence_after();
         if (g_elect_one()) {
           const uint32_t st = sbase + s * stage_bytes;
-          // k slab kc accumulates into partial accumulator kc % n_split: the tensor core truncates when it adds to the
-          // fp32 accumulator, a bias that grows with the number of additions (measured 1.2e-5 on the latent for K = 2000
-          // in one accumulator); the epilogue adds the partials with rounded fp32 adds
-          const uint32_t d = d0 + (uint32_t)((kc % L.n_split) * L.ntw);
+          // Long contractions keep the hi * hi products and the two cross products in separate accumulators: the tensor
+          // core truncates when it adds to the fp32 accumulator, a bias that grows with the number of additions
+          // (measured 1.2e-5 on the latent for K = 2000 with all 375 additions in one accumulator); the cross products
+          // are 2^-11 of the sum, so their additions (two thirds of all) need not touch it.  The epilogue adds the two
+          // with a rounded fp32 add.
+          const uint32_t d_hh = d0, d_cr = d0 + (uint32_t)((L.n_split - 1) * L.ntw);
 #pragma unroll
           for (int ks = 0; ks < GK / 16; ++ks) {
             const uint64_t ah = g_desc(st + ks * 2 * lbo_a, lbo_a), al = g_desc(st + G_A_BYTES + ks * 2 * lbo_a, lbo_a);
             const uint64_t bh = g_desc(st + 2 * G_A_BYTES + ks * 2 * lbo_b, lbo_b);
             const uint64_t bl = g_desc(st + 2 * G_A_BYTES + b_bytes + ks * 2 * lbo_b, lbo_b);
-            g_mma(d, ah, bh, idesc, (kc >= L.n_split || ks > 0) ? 1u : 0u);
-            g_mma(d, ah, bl, idesc, 1u);
-            g_mma(d, al, bh, idesc, 1u);
+            const uint32_t first = (kc > 0 || ks > 0) ? 1u : 0u;
+            g_mma(d_hh, ah, bh, idesc, first);
+            g_mma(d_cr, ah, bl, idesc, L.n_split > 1 ? first : 1u);
+            g_mma(d_cr, al, bh, idesc, 1u);
           }
           g_commit(bar_empty(s));                      // the stage is free once these MMAs have read it
           if (kc == n_kc - 1) g_commit(bar_accf(a));   // ... and the accumulators are complete
@@ -224,20 +229,20 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
       g_mbar_wait(bar_accf(a), (tile_i / L.n_bufs) & 1u);
       g_fence_after();
       const uint32_t tbase = tmem0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * L.n_split * L.ntw);
-      const int n_part = n_kc < L.n_split ? n_kc : L.n_split;  // partial accumulators that received a k slab
+      const int n_part = L.n_split;  // hi * hi | cross products, or everything in one
       const bool row_ok = mt * GM + row < L.rows;
+      // the TMEM load of the next 16 columns is in flight while the current ones are converted and stored
+      uint32_t vn[2][16];
+      g_tmem_ld16(tbase + (uint32_t)(h * half_w), vn[0]);
+      if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + h * half_w), vn[1]);
       for (int c0 = h * half_w; c0 < (h + 1) * half_w; c0 += 16) {
-        uint32_t v[16];
-        g_tmem_ld16(tbase + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float acc[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
-        for (int p = 1; p < n_part; ++p) {
-          g_tmem_ld16(tbase + (uint32_t)(p * L.ntw + c0), v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(vn[0][j]) + (n_part > 1 ? __uint_as_float(vn[1][j]) : 0.f);
+        if (c0 + 16 < (h + 1) * half_w) {
+          g_tmem_ld16(tbase + (uint32_t)(c0 + 16), vn[0]);
+          if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + c0 + 16), vn[1]);
         }
         const int col = nt * L.ntw + c0;  // global output column of acc[0]
         float o[16];
@@ -330,17 +335,16 @@ inline int g5_round(int x, int m) { return (x + m - 1) / m * m; }
 }  // namespace
 
 // ---- host side: per-layer geometry, weight packing, launch
-struct G5Geom { int K, N, kp, ntw, n_tiles, n_split, n_bufs; };
+struct G5Geom { int K, N, kp, ntw, n_tiles, n_split, n_bufs, n_stages; };
 static G5Geom g5_geom(int K, int N) {
   G5Geom g;
   g.K = K; g.N = N;
   g.kp = g5_round(K, GK);
-  // long contractions: column tiles of at most 128 so that four partial accumulators fit the 512 TMEM columns
-  const int max_w = g.kp >= 1024 ? 128 : 256;
-  g.n_tiles = (N + max_w - 1) / max_w;
+  g.n_tiles = (N + 255) / 256;
   g.ntw = g5_round((N + g.n_tiles - 1) / g.n_tiles, 32);
-  g.n_split = g.kp >= 1024 ? 4 : 1;
+  g.n_split = g.kp >= 512 ? 2 : 1;  // long contractions: hi * hi and the cross products in separate accumulators
   g.n_bufs = 2 * g.n_split * g.ntw <= 512 ? 2 : 1;
+  g.n_stages = std::max(2, std::min(GSTAGES, G_SMEM_MAX / (2 * G_A_BYTES + 2 * g.ntw * GK * 2)));
   return g;
 }
 
@@ -392,7 +396,7 @@ int bb_gemm_tc5_prepare(bb_ctx*, Chain* c) {
   BB_CUDA(cudaMemcpy(c->g5_blob_dev, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
   BB_CUDA(cudaMalloc(&c->g5_bias_dev, bias.size() * sizeof(float)));
   BB_CUDA(cudaMemcpy(c->g5_bias_dev, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
-  const int smem = GSTAGES * (2 * G_A_BYTES + 2 * 256 * GK * 2);
+  const int smem = G_SMEM_MAX;
   BB_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   c->g5_ok = true;
   return BB_OK;
@@ -437,7 +441,7 @@ int bb_gemm_tc5_chunk(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype,
     L.w_lo = L.w_hi + (size_t)g.n_tiles * g.kp * g.ntw;
     L.bias = c->g5_bias_dev + c->g5_b_off[l];
     L.kp = g.kp; L.ntw = g.ntw; L.n_tiles = g.n_tiles; L.m_tiles = m_tiles; L.n = g.N;
-    L.n_split = g.n_split; L.n_bufs = g.n_bufs;
+    L.n_split = g.n_split; L.n_bufs = g.n_bufs; L.n_stages = g.n_stages;
     L.rows = (int)rows; L.act = d.layer[l].act; L.unscale = c->g5_unscale[l]; L.flag = flag_dev;
     if (!last) {
       L.kp_next = g5_round(g.N, GK);
@@ -453,7 +457,7 @@ int bb_gemm_tc5_chunk(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype,
     }
     const int items = m_tiles * g.n_tiles;
     const int grid = items < ctx->sm_count ? items : ctx->sm_count;
-    const int smem = GSTAGES * (2 * G_A_BYTES + 2 * g.ntw * GK * 2);
+    const int smem = g.n_stages * (2 * G_A_BYTES + 2 * g.ntw * GK * 2);
     gemm_tc5_kernel<<<grid, GTHREADS, smem, stream>>>(L);
     cur ^= 1;
   }
