@@ -41,6 +41,7 @@ _SIGNATURES = {
     "bb_model_n_features": (C.c_int, [_P]),
     "bb_model_z_dim": (C.c_int, [_P]),
     "bb_model_auto_precision": (C.c_int, [_P]),
+    "bb_model_chain_precision": (C.c_int, [_P, C.c_int]),
     "bb_model_range_flag": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "bb_colminmax_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, _P]),
     "bb_normalize_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, _P, _P]),

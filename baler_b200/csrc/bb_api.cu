@@ -52,7 +52,6 @@ int bb_ctx_create(int device, bb_ctx** out) {
 int bb_ctx_destroy(bb_ctx* ctx) {
   if (!ctx) return BB_OK;
   if (ctx->minmax_scratch) cudaFree(ctx->minmax_scratch);
-  if (ctx->lay_scratch) cudaFree(ctx->lay_scratch);
   delete ctx;
   return BB_OK;
 }
@@ -87,6 +86,7 @@ void free_chain(Chain* c) {
   if (c->blob_dev) cudaFree(c->blob_dev);
   if (c->tc_blob_dev) cudaFree(c->tc_blob_dev);
   if (c->lay_blob_dev) cudaFree(c->lay_blob_dev);
+  if (c->lay_scratch) cudaFree(c->lay_scratch);
   if (c->lay_tc_blob_dev) cudaFree(c->lay_tc_blob_dev);
   if (c->g5_blob_dev) cudaFree(c->g5_blob_dev);
   if (c->g5_bias_dev) cudaFree(c->g5_bias_dev);
@@ -515,6 +515,11 @@ int bb_model_range_flag(bb_model* m, int reset, int* out) {
 
 int bb_model_n_features(const bb_model* m) { return m ? m->enc.desc.in_dim : 0; }
 int bb_model_z_dim(const bb_model* m) { return m ? m->enc.desc.out_dim : 0; }
+int bb_model_chain_precision(const bb_model* m, int direction) {
+  if (!m || direction < 0 || direction > 1) return BB_ERR_INVALID;
+  return chain_has_tc(direction == 0 ? &m->enc : &m->dec) ? BB_PREC_SPLIT16 : BB_PREC_FP32;
+}
+
 int bb_model_auto_precision(const bb_model* m) {
   return (m && chain_has_tc(&m->enc) && chain_has_tc(&m->dec)) ? BB_PREC_SPLIT16 : BB_PREC_FP32;
 }

@@ -361,16 +361,16 @@ int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_
   const int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
   const size_t buf_bytes = tc5 ? bb_gemm_tc5_buf_bytes(c, chunk) : (size_t)chunk * c->lay_max_ld * sizeof(float);
   const size_t need = 2 * buf_bytes;
-  if (ctx->lay_scratch_bytes < need) {
+  if (c->lay_scratch_bytes < need) {
     // grown only (never shrunk); stream-ordered work that still uses the old buffer has been enqueued before the free
-    if (ctx->lay_scratch) BB_CUDA(cudaFree(ctx->lay_scratch));
-    ctx->lay_scratch = nullptr;
-    BB_CUDA(cudaMalloc(&ctx->lay_scratch, need));
-    ctx->lay_scratch_bytes = need;
+    if (c->lay_scratch) BB_CUDA(cudaFree(c->lay_scratch));
+    c->lay_scratch = nullptr;
+    BB_CUDA(cudaMalloc(&c->lay_scratch, need));
+    c->lay_scratch_bytes = need;
   }
   if (tc5) {
     const size_t in_esz5 = in_dtype == BB_F16 ? 2 : 4, out_esz5 = out_dtype == BB_F16 ? 2 : 4;
-    char* b0 = reinterpret_cast<char*>(ctx->lay_scratch);
+    char* b0 = reinterpret_cast<char*>(c->lay_scratch);
     for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
       const int64_t rows = n_rows - r0 < chunk ? n_rows - r0 : chunk;
       int ob = 0, ldo = 0;
@@ -382,7 +382,7 @@ int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_
     }
     return (int)cudaGetLastError();
   }
-  float* buf[2] = {ctx->lay_scratch, ctx->lay_scratch + (size_t)chunk * c->lay_max_ld};
+  float* buf[2] = {c->lay_scratch, c->lay_scratch + (size_t)chunk * c->lay_max_ld};
   const size_t in_esz = in_dtype == BB_F16 ? 2 : 4, out_esz = out_dtype == BB_F16 ? 2 : 4;
   const int ew_grid = ctx->sm_count * 8;
   for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {

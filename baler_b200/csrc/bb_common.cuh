@@ -23,8 +23,6 @@ struct bb_ctx {
   float* minmax_scratch = nullptr;  // [2][blocks][cols] partials of the column min/max pass
   size_t minmax_scratch_bytes = 0;
   unsigned int* minmax_counter = nullptr;
-  float* lay_scratch = nullptr;     // ping-pong activation scratch of the layered GEMM path
-  size_t lay_scratch_bytes = 0;
 };
 
 // One dense layer of a fused chain as the fp32 kernel sees it.
@@ -68,6 +66,10 @@ struct Chain {
   bool lay_ok = false;
   float* lay_blob_dev = nullptr;
   size_t lay_w_off[BB_MAX_LAYERS] = {0}, lay_b_off[BB_MAX_LAYERS] = {0};
+  // ping-pong activation scratch of the layered path: per chain (not per context: two models, or an encode on the caller's
+  // stream next to a host pipeline on the model's own stream, must not share it); grown on demand, kept
+  mutable float* lay_scratch = nullptr;
+  mutable size_t lay_scratch_bytes = 0;
   bool lay_tc_ok = false;      // ... and its tensor-core form: fp16 hi / lo weight images per layer
   void* lay_tc_blob_dev = nullptr;
   size_t lay_tc_off[BB_MAX_LAYERS] = {0};

@@ -10,8 +10,8 @@
 // in that layout in global memory, so a stage is four plain bulk copies:
 //   activations  [128-row tile][k / 8][row 128][8 halves]      hi array, lo array      (written by the producing layer)
 //   weights      [column tile][k / 8][column NTW][8 halves]    hi image, lo image      (packed once per model)
-// Kernel: persistent, one CTA per SM, warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..9 = epilogue (TMEM lane
-// quarter = warp % 4, column half = (warp - 2) / 4).  Two 96 KB stages of 64 k columns, two accumulators of up to 256
+// Kernel: persistent, one CTA per SM, warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..17 = epilogue (TMEM lane
+// quarter = warp % 4, column group = (warp - 2) / 4: 16-column chunks g, g + 4, ...).  Two 96 KB stages of 64 k columns, two accumulators of up to 256
 // TMEM columns (the epilogue of one tile runs under the main loop of the next).  The epilogue adds the bias, applies the
 // activation and writes the next layer's operand directly in the layout above (16-byte pieces, 512 contiguous bytes per
 // warp), or fp32 rows for the last layer.
@@ -25,7 +25,7 @@
 
 namespace {
 
-constexpr int GM = 128, GK = 64, GSTAGES = 4, GTHREADS = 320;  // GSTAGES: most stages a layer may use (as many as fit)
+constexpr int GM = 128, GK = 64, GSTAGES = 4, G_EPI_GROUPS = 4, GTHREADS = (2 + 4 * G_EPI_GROUPS) * 32;  // GSTAGES: most stages a layer may use (as many as fit)
 constexpr int G_SMEM_MAX = 200 * 1024;
 constexpr int G_A_BYTES = GM * GK * 2;  // one image (hi or lo) of an A stage
 // Activations travel multiplied by 2^8: the lo half of a small activation (|x| < 0.1: lo < 6e-5) would be a subnormal fp16
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
       g_mbar_init(bar_full(s), 1);
       g_mbar_init(bar_empty(s), 1);
       g_mbar_init(bar_accf(s), 1);
-      g_mbar_init(bar_acce(s), 8);
+      g_mbar_init(bar_acce(s), 4 * G_EPI_GROUPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -218,8 +218,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
     }
   } else {
     // ---- epilogue: TMEM -> registers -> bias, activation -> next operand (packed hi | lo) or fp32 rows
-    const int q = warp & 3, h = (warp - 2) >> 2;        // TMEM lane quarter, column half
-    const int half_w = L.ntw / 2;                        // columns of a half (ntw is a multiple of 32)
+    const int q = warp & 3, h = (warp - 2) >> 2;        // TMEM lane quarter, column group (16-column chunks h, h + groups, ...)
     const int row = q * 32 + lane;
     uint32_t tile_i = 0;
     bool bad = false;
@@ -233,16 +232,18 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
       const bool row_ok = mt * GM + row < L.rows;
       // the TMEM load of the next 16 columns is in flight while the current ones are converted and stored
       uint32_t vn[2][16];
-      g_tmem_ld16(tbase + (uint32_t)(h * half_w), vn[0]);
-      if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + h * half_w), vn[1]);
-      for (int c0 = h * half_w; c0 < (h + 1) * half_w; c0 += 16) {
+      if (h * 16 < L.ntw) {
+        g_tmem_ld16(tbase + (uint32_t)(h * 16), vn[0]);
+        if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + h * 16), vn[1]);
+      }
+      for (int c0 = h * 16; c0 < L.ntw; c0 += 16 * G_EPI_GROUPS) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float acc[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(vn[0][j]) + (n_part > 1 ? __uint_as_float(vn[1][j]) : 0.f);
-        if (c0 + 16 < (h + 1) * half_w) {
-          g_tmem_ld16(tbase + (uint32_t)(c0 + 16), vn[0]);
-          if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + c0 + 16), vn[1]);
+        if (c0 + 16 * G_EPI_GROUPS < L.ntw) {
+          g_tmem_ld16(tbase + (uint32_t)(c0 + 16 * G_EPI_GROUPS), vn[0]);
+          if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + c0 + 16 * G_EPI_GROUPS), vn[1]);
         }
         const int col = nt * L.ntw + c0;  // global output column of acc[0]
         float o[16];
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
       }
       // the last column tile also zero-fills the k padding of the next operand beyond its own columns
       if (L.y_hi != nullptr && nt == L.n_tiles - 1) {
-        for (int k8 = (L.n_tiles * L.ntw) / 8 + h; k8 < L.kp_next / 8; k8 += 2) {
+        for (int k8 = (L.n_tiles * L.ntw) / 8 + h; k8 < L.kp_next / 8; k8 += G_EPI_GROUPS) {
           const size_t off = (((size_t)mt * (L.kp_next / 8) + k8) * GM + row) * 8;
           *reinterpret_cast<uint4*>(L.y_hi + off) = make_uint4(0u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(L.y_lo + off) = make_uint4(0u, 0u, 0u, 0u);

@@ -146,11 +146,13 @@ class DenseCodec:
         check(_lib.lib().bb_model_range_flag(self.handle, int(reset), C.byref(flag)), "bb_model_range_flag")
         return bool(flag.value)
 
-    def _guarded(self, launch, precision, check_range):
-        """run `launch(precision)`; with precision "auto" on the tensor-core path, re-run on the fp32 kernel if a
-        value left the fp16 range (costs one 4-byte device->host read; pass check_range=False to stay async)"""
+    def _guarded(self, launch, precision, check_range, direction):
+        """run `launch(precision)`; with precision "auto" on a chain (direction 0 encoder, 1 decoder) that resolves to the
+        tensor-core path, re-run on the fp32 kernel if a value left the fp16 range (costs one 4-byte device->host read;
+        pass check_range=False to stay async)"""
         launch(_prec(precision))
-        if check_range and _prec(precision) == _lib.BB_PREC_AUTO and self.auto_precision == "split16" and self.range_flag():
+        if (check_range and _prec(precision) == _lib.BB_PREC_AUTO
+                and _lib.lib().bb_model_chain_precision(self.handle, direction) == _lib.BB_PREC_SPLIT16 and self.range_flag()):
             launch(_lib.BB_PREC_FP32)
 
     # ---- device-resident tensors
@@ -160,7 +162,7 @@ class DenseCodec:
         z = out if out is not None else torch.empty((n, self.z_dim), dtype=out_dtype, device=x.device)
         self._guarded(lambda p: check(_lib.lib().bb_encode_f32(
             self.handle, _ptr(x), n, _ptr(fmin), _ptr(frange), _ptr(z), _T2BB[z.dtype], p, _stream(self.ctx)),
-            "bb_encode_f32"), precision, check_range)
+            "bb_encode_f32"), precision, check_range, 0)
         return z
 
     def decode(self, z, fmin=None, frange=None, precision="auto", out=None, check_range=True):
@@ -169,7 +171,7 @@ class DenseCodec:
         y = out if out is not None else torch.empty((n, self.n_features), dtype=torch.float32, device=z.device)
         self._guarded(lambda p: check(_lib.lib().bb_decode_f32(
             self.handle, _ptr(z), _T2BB[z.dtype], n, _ptr(fmin), _ptr(frange), _ptr(y), p, _stream(self.ctx)),
-            "bb_decode_f32"), precision, check_range)
+            "bb_decode_f32"), precision, check_range, 1)
         return y
 
     # ---- host buffers (numpy), chunked copy/compute pipeline inside the library

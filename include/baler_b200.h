@@ -90,6 +90,9 @@ int bb_model_n_features(const bb_model* m);
 int bb_model_z_dim(const bb_model* m);
 /* which arithmetic BB_PREC_AUTO resolves to for this model (BB_PREC_FP32 or BB_PREC_SPLIT16) */
 int bb_model_auto_precision(const bb_model* m);
+/* Per direction: which arithmetic BB_PREC_AUTO resolves to for the encoder (direction 0) / the decoder (1) alone -
+ * BB_PREC_SPLIT16 when that chain has a tensor-core form, else BB_PREC_FP32 (bb_model_auto_precision: both have one). */
+int bb_model_chain_precision(const bb_model* m, int direction);
 /*
  * Range guard of BB_PREC_SPLIT16 / FAST16: activations are carried as fp16 hi + lo, so a value beyond
  * +-65504 anywhere in the chain poisons that row (inf/NaN).  The kernels raise a sticky device flag when
