@@ -568,9 +568,10 @@ int bb_compress_host(bb_model* m, const float* x_host, int64_t n_rows, float* fe
   std::vector<cudaEvent_t> ev_up;  // resident path: upload of chunk k complete
   if (norm && recompute_minmax && n_rows) {
     resident = resident_get(m, (size_t)n_rows * F * sizeof(float));
-    // the host scan pays when enough host threads are free for it (at 8 ranks on a 32-CPU node they are not: the device
-    // pass below costs nothing on the host)
-    if (resident && host_scan_threads() >= 8 && !getenv("BALER_B200_DEVICE_MINMAX")) {
+    // the host scan pays when 16 host threads are free for it (measured on a 32-CPU node: 2 ranks 483 M rows/s against 414
+    // with the device pass, 4 ranks of 8 threads each 385 against 557: the scans then compete with four uploads for the host's
+    // memory bandwidth; the device pass below costs nothing on the host)
+    if (resident && host_scan_threads() >= 16 && !getenv("BALER_B200_DEVICE_MINMAX")) {
       // the table fits: queue the whole upload now, find the column min / max on host threads meanwhile, and let the
       // encode + latent download of the chunks that have landed run against the rest of the upload
       // (the scan starts first, on its own threads: queuing copies from pageable memory blocks the calling thread)

@@ -229,6 +229,13 @@ __device__ __forceinline__ void split16x2(const float a, const float b, uint32_t
 // inner loops (measured: ~300 cycles per k-step).  A shuffle from lane 0 is uniform by construction.
 __device__ __forceinline__ int uni(const int v) { return __shfl_sync(0xffffffffu, v, 0); }
 
+// A spin that never ends must not hang the GPU (a peer rank that died, a protocol bug): trap - the launch fails with an
+// error instead - after 2^28 polls (a poll is an L2 round trip: about a minute; a data-parallel peer may legitimately be
+// seconds late into an epoch while rank 0 writes files).
+__device__ __forceinline__ void spin_guard(unsigned& spins) {
+  if (++spins > (1u << 28)) __trap();
+}
+
 // every CTA of the (cooperatively launched, co-resident) grid arrives; `target` counts arrivals since the launch
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
   __syncthreads();
@@ -236,7 +243,8 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(bar, 1u);
-    while (*reinterpret_cast<volatile unsigned*>(bar) < target) {}
+    unsigned spins = 0;
+    while (*reinterpret_cast<volatile unsigned*>(bar) < target) spin_guard(spins);
     __threadfence();
   }
   __syncthreads();
@@ -423,6 +431,7 @@ __device__ __forceinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, con
     for (int u = 0; u < 5; ++u)
       if (lane + 32 * u < n_tiles) pk[u] = ld_pkt(part + (size_t)(lane + 32 * u) * BN_PW + j);
     bool missing;
+    unsigned spins = 0;
     do {
       missing = false;
 #pragma unroll
@@ -431,6 +440,7 @@ __device__ __forceinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, con
           pk[u] = ld_pkt(part + (size_t)(lane + 32 * u) * BN_PW + j);
           missing = true;
         }
+      spin_guard(spins);
     } while (missing);
     float K = 0.f;
     if (FWD) K = __shfl_sync(0xffffffffu, __uint_as_float(pk[0].x) * (n_tiles == 1 ? inv_last : 1.f / TROWS), 0);
@@ -473,7 +483,8 @@ __device__ __forceinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, con
         if (nr > 0) {
           const uint4* src = P.bnx[P.rank] + blk + (size_t)lane * BN_PW;
           uint4 q = ld_pkt_sys(src);
-          while (q.y != sc.tag || q.w != sc.tag) q = ld_pkt_sys(src);
+          unsigned spins_x = 0;
+          while (q.y != sc.tag || q.w != sc.tag) { q = ld_pkt_sys(src); spin_guard(spins_x); }
           a = __uint_as_float(q.x);
           b = __uint_as_float(q.z);
         }
@@ -516,7 +527,8 @@ __device__ __forceinline__ void bn_reduce(const TcModel& M, const TcPtrs& P, con
   // ---- hop 2: every CTA gathers the final packets
   if (tid < N) {
     uint4 q = ld_pkt(fin + tid);
-    while (q.y != sc.tag || q.w != sc.tag) q = ld_pkt(fin + tid);
+    unsigned spins_f = 0;
+    while (q.y != sc.tag || q.w != sc.tag) { q = ld_pkt(fin + tid); spin_guard(spins_f); }
     const float v1 = __uint_as_float(q.x), v2 = __uint_as_float(q.z);
     if (FWD) {
       stat[fo + tid] = v1;
@@ -1273,8 +1285,10 @@ __device__ __forceinline__ void phase2_item(const TcModel& M, const TcPtrs& P, c
           q[u][1] = ld_pkt_sys(inbox + (size_t)(r0 + u) * per_rank + NTHREADS);
         }
       bool missing;
+      unsigned spins = 0;
       do {
         missing = false;
+        spin_guard(spins);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (r0 + u < P.world && r0 + u != P.rank) {
