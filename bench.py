@@ -318,6 +318,54 @@ def run_ours(args):
     value = n * world / (ms_per_step * 1e-3)
     gpu_launches = launches["n"]
 
+    # ---- BASELINE configs[4]: one 1B-row x 24-col table row-sharded over the N GPUs (strong scaling).  It does not fit one
+    # GPU next to its latent and reconstruction (252 GB), so every rank walks its contiguous share in chunks regenerated from
+    # their seeds, in the two passes the file-level path takes: column min / max of the WHOLE table (chunk results combined,
+    # then one 2 x 24 exchange), then encode + decode of every chunk with the global features.  Timed: the kernels
+    # (CUDA events around min/max, encode, decode; generating the synthetic chunks is not part of the path).
+    sweep = None
+    if not args.no_sweep:
+        total_rows = 1_000_000_000
+        lo, hi = sharded.row_range(total_rows, rank, world)
+        rows_r = hi - lo
+        chunks = [(c0, min(n, rows_r - c0)) for c0 in range(0, rows_r, n)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_ms = 0.0
+        mn_g = torch.full((24,), float("inf"), device=dev)
+        mx_g = -mn_g
+        del x
+        for ci, (c0, rows) in enumerate(chunks):
+            xc = synth.cms_table_device(rows, seed=synth.CMS_SEED + 5000 + rank * 64 + ci, device=dev)
+            e0.record(); mn, mx = engine.colminmax(xc); e1.record()
+            torch.cuda.synchronize()
+            t_ms += e0.elapsed_time(e1)
+            mn_g, mx_g = torch.minimum(mn_g, mn), torch.maximum(mx_g, mx)
+            del xc
+        if world > 1:
+            sharded.combine_minmax_(mn_g, mx_g)
+        rg_g = mx_g - mn_g
+        worst = 0.0
+        for ci, (c0, rows) in enumerate(chunks):
+            xc = synth.cms_table_device(rows, seed=synth.CMS_SEED + 5000 + rank * 64 + ci, device=dev)
+            e0.record()
+            codec.encode(xc, mn_g, rg_g, precision=precision, out=z[:rows], check_range=False)
+            codec.decode(z[:rows], mn_g, rg_g, precision=precision, out=y[:rows], check_range=False)
+            e1.record()
+            torch.cuda.synchronize()
+            t_ms += e0.elapsed_time(e1)
+            # size-independent sanity of every chunk: the reconstruction stays inside the table's range envelope
+            worst = max(worst, ((y[:rows:1009] - xc[::1009]).abs() / rg_g).max().item())
+            del xc
+        tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sweep = {"rows": total_rows, "rows_per_rank": rows_r, "chunks_per_rank": len(chunks), "kernel_seconds": tt.item() * 1e-3,
+                 "rows_per_s": total_rows / (tt.item() * 1e-3), "scaling": "strong",
+                 "max_sampled_recon_error_over_range": worst,
+                 "note": "min/max of the whole table (pass 1), then encode + decode of every chunk with the global features (pass 2); "
+                         "kernel time, max over ranks; chunks regenerated from their seeds in HBM"}
+        x = synth.cms_table_device(n, seed=synth.CMS_SEED + rank, device=dev)  # the table of the lines below
+
     # ---- the CPU legs first (a child process with the GPUs hidden): the training / CFD lines quote them
     cpu = cpu_baseline_subprocess(args) if (world == 1 and not args.no_cpu) else None
 
@@ -686,6 +734,7 @@ def run_ours(args):
                             "hbm": {"achieved_gbs": n * BYTES_PER_ROW / (dec_ms * 1e-3) / 1e9,
                                     "frac": n * BYTES_PER_ROW / (dec_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
         "modes": modes,
+        "sweep_1b": sweep,
         "e2e": e2e, "train": train, "train_dbn": train_dbn, "cfd": cfd,
     }
     if cpu is not None:
@@ -713,6 +762,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cfd", action="store_true")
     ap.add_argument("--no-modes", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 1B-row strong-scaling sweep (BASELINE configs[4])")
     ap.add_argument("--cfd-blocks", type=int, default=600_000)
     args = ap.parse_args()
     if args.impl == "reference":
