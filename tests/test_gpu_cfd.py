@@ -88,6 +88,42 @@ def test_layered_path_ragged_rows_and_chunks(golden):
         assert torch.equal(z[:600], z[600:1200])  # independent rows: identical blocks give identical bits
 
 
+@pytest.mark.parametrize("rows", [1, 127, 129, 5000])
+@pytest.mark.parametrize("mode", ["tcgen05", "mma"])
+def test_layered_gemm_odd_shapes_vs_float64(rows, mode, monkeypatch):
+    """the per-layer tensor-core GEMMs (tcgen05 gemm_tc5_kernel; mma.sync dense_layer_tc_kernel) on a chain with widths that
+    are multiples of nothing, a long contraction (3001: partial accumulators) and ragged row counts, against float64 numpy"""
+    from baler_b200 import engine
+    if mode == "mma":
+        monkeypatch.setenv("BALER_B200_LAYERED_MMA", "1")
+    rng = np.random.default_rng(17)
+    dims_e, dims_d = [333, 3001, 17, 9], [9, 70, 1111, 333]
+    acts = ["leaky", "relu", "none"]
+
+    def layers(dims):
+        return [(rng.standard_normal((dims[i + 1], dims[i])) / np.sqrt(dims[i]), 0.1 * rng.standard_normal(dims[i + 1]), acts[i])
+                for i in range(len(dims) - 1)]
+
+    enc, dec = layers(dims_e), layers(dims_d)
+    codec = engine.DenseCodec(enc, dec)
+    assert codec.auto_precision == "split16"
+    x = rng.standard_normal((rows, 333)).astype(np.float32)
+
+    def ref(v, ls):
+        v = v.astype(np.float64)
+        for w, b, a in ls:
+            v = v @ w.T + b
+            v = np.where(v > 0, v, 0.01 * v) if a == "leaky" else np.maximum(v, 0) if a == "relu" else v
+        return v
+
+    z = codec.encode(torch.from_numpy(x).cuda())
+    zr = ref(x, enc)
+    assert rel_max(z.cpu().numpy(), zr) <= 1e-5 and rel_l2(z.cpu().numpy(), zr) <= 1e-5
+    y = codec.decode(z)
+    yr = ref(z.cpu().numpy(), dec)
+    assert rel_max(y.cpu().numpy(), yr) <= 1e-5 and rel_l2(y.cpu().numpy(), yr) <= 1e-5
+
+
 def test_layered_tensor_core_range_guard():
     """values beyond the fp16 range on the layered tensor-core path raise the sticky flag; AUTO callers re-run in fp32"""
     torch.manual_seed(0)
