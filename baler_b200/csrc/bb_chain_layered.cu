@@ -255,10 +255,10 @@ dense_layer_tc_kernel(const float* __restrict__ X, const int ldx, const int kx, 
 __global__ void __launch_bounds__(256) stage_in_kernel(const void* __restrict__ in, const int in_dtype, const int64_t n,
                                                        const int dim, const int ld, const float* __restrict__ mn,
                                                        const float* __restrict__ rg, float* __restrict__ out) {
-  const int64_t total = n * ld, G = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += G) {
-    const int64_t r = e / ld;
-    const int c = (int)(e - r * ld);
+  const uint32_t total = (uint32_t)(n * ld), G = gridDim.x * blockDim.x;  // (< 2^31 per chunk, as in stage_out_kernel)
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += G) {
+    const int64_t r = e / (uint32_t)ld;
+    const int c = (int)(e - (uint32_t)r * (uint32_t)ld);
     float v = 0.f;
     if (c < dim) {
       v = in_dtype == BB_F16 ? __half2float(reinterpret_cast<const __half*>(in)[r * dim + c]) : reinterpret_cast<const float*>(in)[r * dim + c];
@@ -273,14 +273,29 @@ __global__ void __launch_bounds__(256) stage_out_kernel(const float* __restrict_
                                                         const int ld, const float* __restrict__ mn,
                                                         const float* __restrict__ rg, void* __restrict__ out,
                                                         const int out_dtype) {
-  const int64_t total = n * dim, G = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += G) {
-    const int64_t r = e / dim;
-    const int c = (int)(e - r * dim);
-    float v = in[r * ld + c];
-    if (mn != nullptr) v = fmaf(v, __ldg(rg + c), __ldg(mn + c));
-    if (out_dtype == BB_F16) reinterpret_cast<__half*>(out)[e] = __float2half_rn(v);
-    else reinterpret_cast<float*>(out)[e] = v;
+  // (chunks hold < 2^31 values - checked by the launcher: 32-bit index arithmetic, a 64-bit division per element costs
+  // more than the copy)
+  const uint32_t total = (uint32_t)(n * dim), G = gridDim.x * blockDim.x;
+  // four independent elements per trip: the loads are all issued before the first store
+  for (uint32_t e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += 4 * G) {
+    float v[4];
+    int c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t e = e0 + u * G;
+      const uint32_t r = e / (uint32_t)dim;
+      c[u] = (int)(e - r * (uint32_t)dim);
+      v[u] = e < total ? in[(size_t)r * ld + c[u]] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t e = e0 + u * G;
+      if (e >= total) break;
+      float y = v[u];
+      if (mn != nullptr) y = fmaf(y, __ldg(rg + c[u]), __ldg(mn + c[u]));
+      if (out_dtype == BB_F16) reinterpret_cast<__half*>(out)[e] = __float2half_rn(y);
+      else reinterpret_cast<float*>(out)[e] = y;
+    }
   }
 }
 
@@ -359,6 +374,7 @@ int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_
   int64_t chunk_rows = tc5 ? (int64_t)2 * ctx->sm_count * 128 : CHUNK_ROWS;
   if (const char* e = getenv("BALER_B200_LAYER_CHUNK")) chunk_rows = atoll(e) > 0 ? atoll(e) : chunk_rows;  // (tuning)
   const int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
+  if (chunk * (int64_t)(c->lay_max_ld > d.out_dim ? c->lay_max_ld : d.out_dim) >= (1ll << 31)) return BB_ERR_INVALID;  // staging: 32-bit indices
   const size_t buf_bytes = tc5 ? bb_gemm_tc5_buf_bytes(c, chunk) : (size_t)chunk * c->lay_max_ld * sizeof(float);
   const size_t need = 2 * buf_bytes;
   if (c->lay_scratch_bytes < need) {

@@ -27,6 +27,8 @@ namespace {
 
 constexpr int GM = 128, GK = 64, GSTAGES = 4, G_EPI_GROUPS = 4, GTHREADS = (2 + 4 * G_EPI_GROUPS) * 32;  // GSTAGES: most stages a layer may use (as many as fit)
 constexpr int G_SMEM_MAX = 200 * 1024;
+constexpr int G_SCR_LD = 12;                                   // floats per row of an epilogue warp's transpose patch
+constexpr int G_SCR_BYTES = 16 * 32 * G_SCR_LD * 4;            // ... of all 16 epilogue warps (last layer only)
 constexpr int G_A_BYTES = GM * GK * 2;  // one image (hi or lo) of an A stage
 // Activations travel multiplied by 2^8: the lo half of a small activation (|x| < 0.1: lo < 6e-5) would be a subnormal fp16
 // with an absolute step of 6e-8, i.e. 1e-5 relative at |x| = 0.01 (measured: latent error 1.3e-5 without the scaling).
@@ -230,18 +232,20 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
       const uint32_t tbase = tmem0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * L.n_split * L.ntw);
       const int n_part = L.n_split;  // hi * hi | cross products, or everything in one
       const bool row_ok = mt * GM + row < L.rows;
+      // columns of this tile that exist (whole 16-column chunks): the last tile can be wider than what is left of the layer
+      const int c_end = min(L.ntw, (L.n - nt * L.ntw + 15) & ~15);
       // the TMEM load of the next 16 columns is in flight while the current ones are converted and stored
       uint32_t vn[2][16];
-      if (h * 16 < L.ntw) {
+      if (h * 16 < c_end) {
         g_tmem_ld16(tbase + (uint32_t)(h * 16), vn[0]);
         if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + h * 16), vn[1]);
       }
-      for (int c0 = h * 16; c0 < L.ntw; c0 += 16 * G_EPI_GROUPS) {
+      for (int c0 = h * 16; c0 < c_end; c0 += 16 * G_EPI_GROUPS) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float acc[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(vn[0][j]) + (n_part > 1 ? __uint_as_float(vn[1][j]) : 0.f);
-        if (c0 + 16 * G_EPI_GROUPS < L.ntw) {
+        if (c0 + 16 * G_EPI_GROUPS < c_end) {
           g_tmem_ld16(tbase + (uint32_t)(c0 + 16 * G_EPI_GROUPS), vn[0]);
           if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + c0 + 16 * G_EPI_GROUPS), vn[1]);
         }
@@ -270,17 +274,35 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
               *reinterpret_cast<uint4*>(L.y_lo + off) = lo;
             }
           }
-        } else if (row_ok) {
+        } else {
+          // fp32 rows: a thread holds 16 consecutive values of ONE row, so storing them directly makes every store
+          // instruction touch 32 rows (4 useful bytes per sector: 145 us for the 2000 -> 250 Linear of Conv_AE against 61
+          // for the same contraction with the packed output).  Eight columns at a time go through a 32 x 8 patch of shared
+          // memory (48-byte row stride) and leave as 16-byte stores, two lanes per row.
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            bad = bad || !(fabsf(o[j]) <= 3.0e38f);
-            if (col + j < L.ldy) L.y_f32[(size_t)(mt * GM + row) * L.ldy + col + j] = o[j];
+          for (int j = 0; j < 16; ++j) bad = bad || !(fabsf(o[j]) <= 3.0e38f);
+          float* scr = reinterpret_cast<float*>(gsm + (size_t)L.n_stages * stage_bytes) + (warp - 2) * (32 * G_SCR_LD);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            __syncwarp();
+            *reinterpret_cast<float4*>(scr + lane * G_SCR_LD) = make_float4(o[8 * half], o[8 * half + 1], o[8 * half + 2], o[8 * half + 3]);
+            *reinterpret_cast<float4*>(scr + lane * G_SCR_LD + 4) =
+                make_float4(o[8 * half + 4], o[8 * half + 5], o[8 * half + 6], o[8 * half + 7]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int r = 16 * i + (lane >> 1), cq = (lane & 1) * 4;
+              const float4 v = *reinterpret_cast<const float4*>(scr + r * G_SCR_LD + cq);
+              const int grow = mt * GM + q * 32 + r, gcol = col + 8 * half + cq;
+              if (grow < L.rows && gcol < L.ldy)  // ldy is a multiple of 4: a quad is inside the row or outside
+                *reinterpret_cast<float4*>(L.y_f32 + (size_t)grow * L.ldy + gcol) = v;
+            }
           }
         }
       }
       // the last column tile also zero-fills the k padding of the next operand beyond its own columns
       if (L.y_hi != nullptr && nt == L.n_tiles - 1) {
-        for (int k8 = (L.n_tiles * L.ntw) / 8 + h; k8 < L.kp_next / 8; k8 += G_EPI_GROUPS) {
+        for (int k8 = (nt * L.ntw + c_end) / 8 + h; k8 < L.kp_next / 8; k8 += G_EPI_GROUPS) {
           const size_t off = (((size_t)mt * (L.kp_next / 8) + k8) * GM + row) * 8;
           *reinterpret_cast<uint4*>(L.y_hi + off) = make_uint4(0u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(L.y_lo + off) = make_uint4(0u, 0u, 0u, 0u);
@@ -302,12 +324,19 @@ __global__ void __launch_bounds__(256) g5_stage_in_kernel(const void* __restrict
                                                           const int dim, const int kp, const int m_tiles,
                                                           const float* __restrict__ mn, const float* __restrict__ rg,
                                                           __half* __restrict__ hi, __half* __restrict__ lo, int* __restrict__ flag) {
-  const int64_t total = (int64_t)m_tiles * (kp / 8) * GM, G = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += G) {
-    const int r = (int)(e % GM);
-    const int64_t t = e / GM;
-    const int k8 = (int)(t % (kp / 8));
-    const int64_t row = (t / (kp / 8)) * GM + r;
+  // One thread per 16-byte unit (8 k values of one row).  A warp covers 4 rows x 8 units: it reads four 256-byte runs of
+  // the row-major input and writes eight 64-byte runs of each packed image (with one row per lane every load touched 32
+  // rows).  32-bit index arithmetic: a chunk is at most a few million units (checked by the launcher).
+  const uint32_t kq = (uint32_t)(kp / 8);  // units per row, a multiple of 8
+  const uint32_t total = (uint32_t)m_tiles * kq * GM, G = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += G) {
+    const uint32_t w = i >> 5, ln = i & 31u;              // warp-sized group, lane in it
+    const uint32_t rg4 = w % (GM / 4), t = w / (GM / 4);  // 4-row group of the tile
+    const uint32_t kg = t % (kq / 8), mt = t / (kq / 8);  // 8-unit group of the row, row tile
+    const int r = (int)(rg4 * 4 + (ln & 3u));
+    const int k8 = (int)(kg * 8 + (ln >> 2));
+    const int64_t row = (int64_t)mt * GM + r;
+    const uint32_t e = (mt * kq + (uint32_t)k8) * GM + (uint32_t)r;  // unit index in the packed images
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -397,7 +426,7 @@ int bb_gemm_tc5_prepare(bb_ctx*, Chain* c) {
   BB_CUDA(cudaMemcpy(c->g5_blob_dev, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
   BB_CUDA(cudaMalloc(&c->g5_bias_dev, bias.size() * sizeof(float)));
   BB_CUDA(cudaMemcpy(c->g5_bias_dev, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
-  const int smem = G_SMEM_MAX;
+  const int smem = G_SMEM_MAX + G_SCR_BYTES;
   BB_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   c->g5_ok = true;
   return BB_OK;
@@ -423,6 +452,7 @@ int bb_gemm_tc5_chunk(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype,
   if (!c->g5_ok) return BB_ERR_UNSUPPORTED;
   const ChainDesc& d = c->desc;
   const int m_tiles = (int)((rows + GM - 1) / GM);
+  if ((int64_t)m_tiles * GM * (g5_round(d.in_dim, GK) / 8) >= (1ll << 31)) return BB_ERR_INVALID;  // staging kernel: 32-bit indices
   void* buf[2] = {buf0, buf1};
   int cur = 0;
   int kp = g5_round(d.in_dim, GK);
@@ -458,7 +488,7 @@ int bb_gemm_tc5_chunk(bb_ctx* ctx, const Chain* c, const void* in, int in_dtype,
     }
     const int items = m_tiles * g.n_tiles;
     const int grid = items < ctx->sm_count ? items : ctx->sm_count;
-    const int smem = g.n_stages * (2 * G_A_BYTES + 2 * g.ntw * GK * 2);
+    const int smem = g.n_stages * (2 * G_A_BYTES + 2 * g.ntw * GK * 2) + (last ? G_SCR_BYTES : 0);
     gemm_tc5_kernel<<<grid, GTHREADS, smem, stream>>>(L);
     cur ^= 1;
   }
