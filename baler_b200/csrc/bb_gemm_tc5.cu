@@ -91,11 +91,6 @@ __device__ __forceinline__ void g_mma(uint32_t d, uint64_t a, uint64_t b, uint32
 __device__ __forceinline__ void g_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ float g_act(float v, int act) {
-  if (act == BB_ACT_LEAKY) return v > 0.f ? v : BB_LEAKY * v;
-  if (act == BB_ACT_RELU) return fmaxf(v, 0.f);
-  return v;
-}
 // two fp32 values -> packed fp16 hi (top 11 significant bits, truncated: x - hi is exact) and lo = fp16_rn(x - hi)
 __device__ __forceinline__ void g_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
@@ -224,6 +219,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
     const int row = q * 32 + lane;
     uint32_t tile_i = 0;
     bool bad = false;
+    const float slope = L.act == BB_ACT_LEAKY ? BB_LEAKY : (L.act == BB_ACT_RELU ? 0.f : 1.f);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
       const int mt = item / L.n_tiles, nt = item - mt * L.n_tiles;
       const int a = tile_i % L.n_bufs;
@@ -231,34 +227,53 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
       g_fence_after();
       const uint32_t tbase = tmem0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * L.n_split * L.ntw);
       const int n_part = L.n_split;  // hi * hi | cross products, or everything in one
-      const bool row_ok = mt * GM + row < L.rows;
       // columns of this tile that exist (whole 16-column chunks): the last tile can be wider than what is left of the layer
       const int c_end = min(L.ntw, (L.n - nt * L.ntw + 15) & ~15);
-      // the TMEM load of the next 16 columns is in flight while the current ones are converted and stored
+      // the TMEM load and the bias of the next 16 columns are in flight while the current ones are converted and stored
+      // (the bias used to be loaded where it is added: a third of the kernel's stall samples sat on that first FFMA)
       uint32_t vn[2][16];
+      float4 bn[4];
+      const float4* bias4 = reinterpret_cast<const float4*>(L.bias + nt * L.ntw);  // 16-byte aligned: ntw is a multiple of 32
       if (h * 16 < c_end) {
         g_tmem_ld16(tbase + (uint32_t)(h * 16), vn[0]);
         if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + h * 16), vn[1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + h * 4 + i);
       }
+      bool released = false;
       for (int c0 = h * 16; c0 < c_end; c0 += 16 * G_EPI_GROUPS) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float acc[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(vn[0][j]) + (n_part > 1 ? __uint_as_float(vn[1][j]) : 0.f);
-        if (c0 + 16 * G_EPI_GROUPS < c_end) {
+        const bool more = c0 + 16 * G_EPI_GROUPS < c_end;
+        if (more) {
           g_tmem_ld16(tbase + (uint32_t)(c0 + 16 * G_EPI_GROUPS), vn[0]);
           if (n_part > 1) g_tmem_ld16(tbase + (uint32_t)(L.ntw + c0 + 16 * G_EPI_GROUPS), vn[1]);
+        } else {
+          // this warp has read its last columns of the accumulator set: the MMA warp may refill it while they are stored
+          g_fence_before();
+          __syncwarp();
+          if (lane == 0) g_mbar_arrive(bar_acce(a));
+          released = true;
         }
         const int col = nt * L.ntw + c0;  // global output column of acc[0]
         float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          o[j] = g_act(fmaf(acc[j], L.unscale, __ldg(L.bias + col + j)), L.act);
-          if (!row_ok) o[j] = 0.f;
+        for (int i = 0; i < 4; ++i) {
+          o[4 * i + 0] = fmaf(acc[4 * i + 0], L.unscale, bn[i].x);
+          o[4 * i + 1] = fmaf(acc[4 * i + 1], L.unscale, bn[i].y);
+          o[4 * i + 2] = fmaf(acc[4 * i + 2], L.unscale, bn[i].z);
+          o[4 * i + 3] = fmaf(acc[4 * i + 3], L.unscale, bn[i].w);
         }
-        if (L.y_hi != nullptr) {
+        if (more) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] *= G_ACT_SCALE;
+          for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + (c0 + 16 * G_EPI_GROUPS) / 4 + i);
+        }
+        // activation, branch-free: slope 1 (none), 0 (ReLU), BB_LEAKY - max(v, 0) + slope * min(v, 0) is v, relu(v), leaky(v)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = fmaf(slope, fminf(o[j], 0.f), fmaxf(o[j], 0.f));
+        if (L.y_hi != nullptr) {
 #pragma unroll
           for (int k8 = 0; k8 < 2; ++k8) {
             if (col + 8 * k8 < L.kp_next) {
@@ -308,9 +323,11 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_tc5_kernel(const __grid_cons
           *reinterpret_cast<uint4*>(L.y_lo + off) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
-      g_fence_before();
-      __syncwarp();
-      if (lane == 0) g_mbar_arrive(bar_acce(a));
+      if (!released) {  // (a warp without columns in this tile)
+        g_fence_before();
+        __syncwarp();
+        if (lane == 0) g_mbar_arrive(bar_acce(a));
+      }
     }
     if (bad && L.flag != nullptr) *L.flag = 1;
   }
@@ -400,7 +417,11 @@ int bb_gemm_tc5_prepare(bb_ctx*, Chain* c) {
     int sw = 0;  // scale so that max |w| lands in [512, 1024): lo = w - hi of all but the tiniest weights stays a normal fp16
     if (mx > 0.0) sw = (int)std::floor(std::log2(1024.0 / mx) - 1e-9);
     sw = std::max(-14, std::min(24, sw));
-    c->g5_unscale[l] = (float)(std::ldexp(1.0, -sw) / (double)G_ACT_SCALE);
+    // the accumulator carries 2^sw (weights) x G_ACT_SCALE (input operand); all but the last layer's output is the next
+    // operand and leaves scaled by G_ACT_SCALE again: folded into this factor and into the bias (powers of two, and the
+    // activations are positively homogeneous, so the values are the ones a separate multiplication would give)
+    const double out_scale = l + 1 < d.n_layers ? (double)G_ACT_SCALE : 1.0;
+    c->g5_unscale[l] = (float)(std::ldexp(1.0, -sw) / (double)G_ACT_SCALE * out_scale);
     __half* hi = img.data() + c->g5_w_off[l];
     __half* lo = hi + (size_t)g.n_tiles * g.kp * g.ntw;
     for (int n = 0; n < N; ++n) {
@@ -416,7 +437,7 @@ int bb_gemm_tc5_prepare(bb_ctx*, Chain* c) {
         hi[idx] = __float2half_rn(wh);
         lo[idx] = __float2half_rn(w - wh);
       }
-      bias[c->g5_b_off[l] + n] = (float)c->b_host[l][n];
+      bias[c->g5_b_off[l] + n] = (float)(c->b_host[l][n] * out_scale);
     }
   }
   if (c->g5_blob_dev) cudaFree(c->g5_blob_dev);

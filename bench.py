@@ -375,9 +375,13 @@ def run_ours(args):
     if world == 1 and not args.no_modes:
         modes = {}
         ns = min(n, 2_000_000)
-        z_ref, y_ref = z[:ns].clone(), y[:ns].clone()
         mn, mx = engine.colminmax(x)
         rg = mx - mn
+        # the exact mode's own output on the first ns rows (z / y were reused by the 1B-row sweep above)
+        z_ref = torch.empty((ns, 15), dtype=torch.float32, device=dev)
+        y_ref = torch.empty((ns, 24), dtype=torch.float32, device=dev)
+        codec.encode(x[:ns], mn, rg, precision=precision, out=z_ref, check_range=False)
+        codec.decode(z_ref, mn, rg, precision=precision, out=y_ref, check_range=False)
         for name, prec, zdt in (("exact_f16_latent", precision, torch.float16), ("fast", "fast", torch.float32),
                                 ("fast_f16_latent", "fast", torch.float16)):
             zz = torch.empty((n, 15), dtype=zdt, device=dev)
