@@ -86,13 +86,18 @@ def test_layered_path_ragged_rows_and_chunks(golden):
         ref = g["latent_eval"][idx]
         assert rel_max(z.cpu().numpy(), ref) <= 1e-5
         assert torch.equal(z[:600], z[600:1200])  # independent rows: identical blocks give identical bits
+        # ... and back (>= 148 row tiles per chunk: the tcgen05 GEMM keeps the A tile of the 2000-wide layers resident)
+        y = m.codec(5, 5).decode(z, precision=precision)
+        assert rel_max(y.cpu().numpy(), g["recon_eval"].reshape(600, 25)[idx]) <= 1e-5
+        assert torch.equal(y[:600], y[600:1200])
 
 
-@pytest.mark.parametrize("rows", [1, 127, 129, 5000])
+@pytest.mark.parametrize("rows", [1, 127, 129, 5000, 20000])
 @pytest.mark.parametrize("mode", ["tcgen05", "mma"])
 def test_layered_gemm_odd_shapes_vs_float64(rows, mode, monkeypatch):
     """the per-layer tensor-core GEMMs (tcgen05 gemm_tc5_kernel; mma.sync dense_layer_tc_kernel) on a chain with widths that
-    are multiples of nothing, a long contraction (3001: partial accumulators) and ragged row counts, against float64 numpy"""
+    are multiples of nothing, a long contraction (3001: partial accumulators) and ragged row counts (20000: enough row
+    tiles for the resident-A mode of the 70 -> 1111 layer), against float64 numpy"""
     from baler_b200 import engine
     if mode == "mma":
         monkeypatch.setenv("BALER_B200_LAYERED_MMA", "1")
