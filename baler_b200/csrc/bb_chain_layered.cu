@@ -370,8 +370,15 @@ int bb_chain_layered_launch(bb_ctx* ctx, const Chain* c, const void* in, int in_
   const ChainDesc& d = c->desc;
   // tensor cores: the tcgen05 GEMM (bb_gemm_tc5.cu) when the shape has it, else the mma.sync one below
   const bool tc5 = tensor_cores && c->g5_ok && !getenv("BALER_B200_LAYERED_MMA");
-  // (tcgen05: persistent CTAs walk 128-row tiles; 2 tiles per SM and chunk leave no partial wave on the one-column-tile layers)
-  int64_t chunk_rows = tc5 ? (int64_t)2 * ctx->sm_count * 128 : CHUNK_ROWS;
+  // (tcgen05: persistent CTAs walk 128-row tiles; a whole number of tiles per SM leaves no partial wave on the
+  // one-column-tile layers, and 8 per SM amortise the fill / drain of the ~7 launches per chunk: Conv_AE encode / decode
+  // 148 / 153 M blocks/s with 2 tiles per SM, 157 / 165 with 4, 163 / 172 with 8 - 2 x 1.24 GB of scratch for 2000-wide layers)
+  int64_t chunk_rows = CHUNK_ROWS;
+  if (tc5) {
+    int tiles = 8;  // ... halved while one ping-pong buffer would pass 2 GiB (wider models)
+    while (tiles > 1 && bb_gemm_tc5_buf_bytes(c, (int64_t)tiles * ctx->sm_count * 128) > ((size_t)2 << 30)) tiles /= 2;
+    chunk_rows = (int64_t)tiles * ctx->sm_count * 128;
+  }
   if (const char* e = getenv("BALER_B200_LAYER_CHUNK")) chunk_rows = atoll(e) > 0 ? atoll(e) : chunk_rows;  // (tuning)
   const int64_t chunk = n_rows < chunk_rows ? n_rows : chunk_rows;
   if (chunk * (int64_t)(c->lay_max_ld > d.out_dim ? c->lay_max_ld : d.out_dim) >= (1ll << 31)) return BB_ERR_INVALID;  // staging: 32-bit indices

@@ -71,8 +71,12 @@ def test_cfd_dense_ae_2500_features(golden, precision):
     assert rel_max(y.cpu().numpy(), g["recon"]) <= 1e-5 and rel_l2(y.cpu().numpy(), g["recon"]) <= 1e-5
 
 
-def test_layered_path_ragged_rows_and_chunks(golden):
-    """more rows than one scratch chunk (32768) and a ragged tail on the GEMM path; Conv_AE blocks"""
+@pytest.mark.parametrize("chunk", [None, "37888"])
+def test_layered_path_ragged_rows_and_chunks(golden, chunk, monkeypatch):
+    """more rows than one scratch chunk (32768 on the fp32 path; the tcgen05 path takes 8 row tiles per SM, or the 37888
+    rows the tuning variable asks for) and a ragged tail on the GEMM path; Conv_AE blocks"""
+    if chunk is not None:
+        monkeypatch.setenv("BALER_B200_LAYER_CHUNK", chunk)
     g = golden("conv_ae.npz")
     torch.manual_seed(0)
     m = models.Conv_AE(5, 250)
