@@ -132,7 +132,8 @@ def perform_decompression(output_path, config, verbose):
         print("Un-normalizing...")
         features = np.load(os.path.join(output_path, "training", "normalization_features.npy"))
     blocks = hasattr(config, "convert_to_blocks") and config.convert_to_blocks
-    flat_features = None if features is None else np.asarray(features, dtype=np.float32).reshape(2, -1)
+    # (kept in the file's dtype: float64 features of a table whose offset dwarfs its spread are applied in float64)
+    flat_features = None if features is None else np.asarray(features).reshape(2, -1)
     decompressed, names, _ = helper.decompress(
         model_path=os.path.join(output_path, "compressed_output", "model.pt"),
         input_path=os.path.join(output_path, "compressed_output", "compressed.npz"),

@@ -184,10 +184,27 @@ def compress(model_path, config):
     model = data_processing.load_model(data_processing.initialise_model(config.model_name), model_path,
                                        n_features=n_features, z_dim=config.latent_space_size)
     model.eval()
-    table = np.ascontiguousarray(data_before.reshape(data_before.shape[0], -1), dtype=np.float32)
     normalise = bool(config.apply_normalization) and not config.custom_norm
     if config.apply_normalization:
         print("Normalizing...")
+    table = None
+    if normalise and data_before.dtype == np.float64 and data_before.size:
+        # a float64 file whose offset dwarfs its spread is normalised here in float64, as the reference's numpy does
+        # (data_processing.F32_OFFSET_LIMIT); the kernels then take the normalised float32 table as it is
+        flat64 = data_before.reshape(data_before.shape[0], -1)
+        shard_stats = None
+        if world > 1:  # every rank holds the file: same decision everywhere, statistics from the row shards
+            lo64, hi64 = sharded.row_range(len(flat64), rank, world)
+
+            def shard_stats(_flat):
+                f = sharded.global_minmax(_flat[lo64:hi64])
+                return f[0], f[0] + f[1]
+        st = data_processing.float64_stats(flat64, shard_stats)
+        if st is not None:
+            table = np.ascontiguousarray(data_processing.normalize_float64_host(flat64, st[0], st[1], np.float32))
+            normalise = False
+    if table is None:
+        table = np.ascontiguousarray(data_before.reshape(data_before.shape[0], -1), dtype=np.float32)
     codec = model.codec(data_before.shape[1], data_before.shape[2]) if conv else model.codec()
     if getattr(config, "save_error_bounded_deltas", False):
         return _compress_with_deltas(codec, model, table, normalise, config, rank, world)
@@ -307,6 +324,13 @@ def decompress(model_path, input_path, input_path_deltas, input_batch_index, mod
         codec = model.codec(h, w)
     else:
         codec = model.codec()
+    host_renorm = None
+    if renormalize_features is not None and out_dtype == np.float64:
+        f64 = np.asarray(renormalize_features, dtype=np.float64).reshape(2, -1)
+        if data_processing._ill_conditioned(f64[0], f64[0] + f64[1]):
+            # float32 could not hold y * range + min (data_processing.F32_OFFSET_LIMIT): decode to normalised values and
+            # un-normalise in float64 on the host, as the reference's renormalize_func does
+            host_renorm, renormalize_features = f64, None
     if world == 1:
         decompressed = codec.decompress_host(data, features=renormalize_features, y_dtype=out_dtype,
                                              precision=getattr(config, "precision", "auto"))
@@ -318,6 +342,9 @@ def decompress(model_path, input_path, input_path_deltas, input_batch_index, mod
         decompressed = sharded.gather_rows_to_rank0(part, len(data))
         if decompressed is None:
             return None, names, normalization_features
+    if host_renorm is not None:
+        decompressed = decompressed * host_renorm[1] + host_renorm[0]
+        renormalize_features = host_renorm
     if getattr(config, "save_error_bounded_deltas", False):  # host step; under torchrun rank 0 holds the gathered rows
         decompressed = _apply_deltas(decompressed, input_path_deltas, input_batch_index, int(config.batch_size),
                                      None if renormalize_features is None else renormalize_features[1])

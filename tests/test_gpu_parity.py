@@ -341,6 +341,45 @@ def test_cli_roundtrip_matches_reference_files(golden, tmp_path, monkeypatch):
     baler.print_info(out, type("c", (), {"input_path": path}))
 
 
+def test_cli_float64_table_with_large_offsets(ae, tmp_path, monkeypatch):
+    """a float64 file with an event-counter column (offset 1e9, spread ~1e3) and a shifted column: the reference normalises
+    and un-normalises it in float64 (numpy); float32 would keep 64 / 977 of the counter's resolution.  --mode compress /
+    decompress must match the oracle's float64 pipeline: the latent to 1e-5, the reconstruction to 1e-5 of each column's
+    range (data_processing.F32_OFFSET_LIMIT: host float64 (re)normalisation around the float32 kernels)."""
+    from baler_b200 import baler
+    from baler_b200.modules import helper
+
+    m, sd, _ = ae
+    n = 4096
+    table = synth.cms_table(n, seed=29).astype(np.float64)
+    table[:, 5] = 1.0e9 + np.arange(n) % 977
+    table[:, 11] = -4.0e7 + 0.25 * table[:, 11]
+    feats = orc.find_minmax(table)
+    monkeypatch.chdir(tmp_path)
+    helper.create_new_project("CMS_workspace", "CMS_project_v1")
+    path = os.path.join("workspaces", "CMS_workspace", "data", "example_CMS_data.npz")
+    np.savez(path, data=table, names=synth.CMS_NAMES)
+    out = os.path.join("workspaces", "CMS_workspace", "CMS_project_v1", "output")
+    torch.save(m.state_dict(), os.path.join(out, "compressed_output", "model.pt"))
+    np.save(os.path.join(out, "training", "normalization_features.npy"), feats)
+
+    class cfg(helper.Config):
+        input_path = path
+        data_dimension, compression_ratio, apply_normalization, model_name = 1, 1.6, True, "AE"
+        batch_size, custom_norm, extra_compression, separate_model_saving = 512, False, False, False
+        save_error_bounded_deltas, convert_to_blocks = False, False
+
+    baler.perform_compression(out, cfg, False)
+    z = np.load(os.path.join(out, "compressed_output", "compressed.npz"))["data"]
+    z_ref = orc.compress(sd, table)
+    close(z, z_ref)
+    baler.perform_decompression(out, cfg, False)
+    dec = np.load(os.path.join(out, "decompressed_output", "decompressed.npz"))["data"]
+    ref = orc.decompress(sd, z_ref, feats)
+    assert dec.dtype == np.float64 and dec.shape == ref.shape
+    assert (np.abs(dec - ref) / feats[1]).max() <= 1e-5
+
+
 def test_host_pipeline_streaming_path(ae, monkeypatch):
     """tables that do not fit next to their latent in HBM (BASELINE configs[4]: 1B rows = 96 GB) are read from the host
     twice - once for the column min / max, once for the encode - instead of staying resident between the passes; the
