@@ -417,6 +417,12 @@ void model_trim(bb_model* m) {
     }
     m->pinned_bytes[io] = 0;
   }
+  // the activation scratch of the layered GEMM path (up to 2 x 1.24 GB per direction for 2000-wide layers; cudaFree waits
+  // for the device, so work still using it on any stream has finished)
+  for (Chain* c : {&m->enc, &m->dec}) {
+    if (c->lay_scratch) cudaFree(c->lay_scratch);
+    c->lay_scratch = nullptr; c->lay_scratch_bytes = 0;
+  }
 }
 
 // range = max - min on device (float32 subtraction, like numpy on a float32 table)

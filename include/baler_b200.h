@@ -83,7 +83,8 @@ int bb_model_create_dense(bb_ctx* ctx,
                           bb_model** out);
 int bb_model_destroy(bb_model* m);
 /* The host pipelines keep their device / pinned scratch between calls (the resident copy of the table between the two
- * passes of bb_compress_host can be as large as the table).  This releases it; the next call allocates again.  The
+ * passes of bb_compress_host can be as large as the table), and the layered GEMM path of wide models (Conv_AE,
+ * CFD_dense_AE) keeps its activation scratch (up to 2 x 1.24 GB per direction).  This releases both; the next call allocates again.  The
  * reference has no counterpart: helper.compress (helper.py:473-616) holds the whole table in host memory instead. */
 int bb_model_trim(bb_model* m);
 int bb_model_n_features(const bb_model* m);
