@@ -402,6 +402,13 @@ int bb_gemm_tc5_prepare(bb_ctx*, Chain* c) {
   for (int l = 0; l < d.n_layers; ++l) {
     const G5Geom g = g5_geom(d.layer[l].K, d.layer[l].N);
     if (g.ntw > 256 || g.ntw % 32) return BB_ERR_UNSUPPORTED;
+    // a model with a non-finite parameter is left to the mma.sync GEMM, whose range guard sees the nan / inf and sends
+    // BB_PREC_AUTO callers to the fp32 kernels, where it propagates as it does upstream (the min / max form of the
+    // activation in this kernel's epilogue would turn a nan into 0)
+    for (size_t i = 0; i < (size_t)d.layer[l].N * d.layer[l].K; ++i)
+      if (!std::isfinite(c->w_host[l][i])) return BB_ERR_UNSUPPORTED;
+    for (int n = 0; n < d.layer[l].N; ++n)
+      if (!std::isfinite(c->b_host[l][n])) return BB_ERR_UNSUPPORTED;
     c->g5_w_off[l] = halves;
     halves += 2 * (size_t)g.n_tiles * g.kp * g.ntw;
     c->g5_b_off[l] = nb;
