@@ -357,6 +357,12 @@ class Conv_AE:
             sv, tv = s.repeat_interleave(rep).numpy(), t.repeat_interleave(rep).numpy()
             return mat * sv[:, None], bias * sv + tv
 
+        # the conv stack's output shape, before any matrix is built (a 50x50 snapshot would ask for a 100 GB identity basis):
+        # (2,5) kernel pad 1 -> (h + 1, w - 2); 3x3 pad 1 keeps it; 3x3 pad 0 -> (h - 1, w - 4), 32 channels
+        flat = 32 * max(h - 1, 0) * max(w - 4, 0)
+        if flat != self.q_z_output_dim:
+            raise RuntimeError("Conv_AE: a %dx%d block flattens to %d values, the model's Linear expects %d "
+                               "(reference models.py:320-343)" % (h, w, flat, self.q_z_output_dim))
         enc, shape = [], (1, h, w)
         m, b, shape = self._as_matrix(lambda x: F.conv2d(x, self._t("q_z_conv.0.weight"), self._t("q_z_conv.0.bias"), padding=1), shape)
         enc.append((m, b, "relu"))
@@ -366,9 +372,7 @@ class Conv_AE:
         m, b, shape = self._as_matrix(lambda x: F.conv2d(x, self._t("q_z_conv.5.weight"), self._t("q_z_conv.5.bias"), padding=0), shape)
         enc.append((m, b, "relu"))
         conv_out = shape
-        if int(np.prod(shape)) != self.q_z_output_dim:
-            raise RuntimeError("Conv_AE: a %dx%d block flattens to %d values, the model's Linear expects %d "
-                               "(reference models.py:320-343)" % (h, w, int(np.prod(shape)), self.q_z_output_dim))
+        assert int(np.prod(shape)) == flat
         enc.append((self._t("q_z_lin.0.weight").numpy(), self._t("q_z_lin.0.bias").numpy(), "relu"))
         enc.append((self._t("q_z_lin.2.weight").numpy(), self._t("q_z_lin.2.bias").numpy(), "relu"))
         dec = [(self._t("p_x_lin.0.weight").numpy(), self._t("p_x_lin.0.bias").numpy(), "relu"),
@@ -396,6 +400,10 @@ class Conv_AE:
         through torch's own (transposed) convolution with the kernel entries replaced by their 1-based flat indices: at
         stride 1 every (output, input) pair meets at most one kernel entry."""
         F = torch.nn.functional
+        flat = 32 * max(h - 1, 0) * max(w - 4, 0)  # as in _chains: refuse before any identity basis is built
+        if flat != self.q_z_output_dim:
+            raise RuntimeError("Conv_AE: a %dx%d block flattens to %d values, the model's Linear expects %d "
+                               "(reference models.py:320-343)" % (h, w, flat, self.q_z_output_dim))
         dims, acts, weights, biases, maps, bn = [h * w], [], [], [], [], []
         shape = (1, h, w)
         for i, (name, kind, pad, bn_name) in enumerate(self._CONV):

@@ -19,6 +19,7 @@ Fixtures (all float64 unless noted; state-dict tensors stored under "<prefix>/<k
   cli_roundtrip.npz perform_training/compression/decompression in a temp workspace (4096 rows)
   schedules.npz     LRScheduler / EarlyStopping decision sequences
   conv_ae.npz       Conv_AE(5, 250) on 5x5 blocks: eval encode / decode (weights by seed + checksums)
+  conv_shapes.npz   Conv_AE on the other two valid block shapes (3x6 with z = 9, 2x8 with z = 4): eval encode / decode
   cfd_dense.npz     CFD_dense_AE(2500, 25) on 50x50 snapshots: encode / decode (weights by seed + checksums)
   conv_train.npz    Conv_AE(5, 250) training on 600 5x5 blocks, batch 300: loss, gradients and parameters after 1 and 3 Adam
                     steps (the four 2000-wide Linear weights as every 101st entry + l2 norm), BatchNorm2d running statistics,
@@ -335,6 +336,30 @@ def randomise_bn2d(model, seed=2):
                 m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
 
 
+def gen_conv_shapes():
+    """the other two block shapes whose conv stack flattens to the hard-coded 128 values: 3x6 blocks of 48x48
+    snapshots with Conv_AE(6, 9), 2x8 blocks with Conv_AE(8, 4); eval encode / decode, weights by seed + checksums"""
+    d = {}
+    for tag, (h, w), z_dim in (("b36", (3, 6), 9), ("b28", (2, 8), 4)):
+        snaps = synth.cfd_snapshots(2, h=48, w=48)  # 2 x 48 x 48 -> 256 blocks of 3x6 / 288 of 2x8
+        blocks = ref_helper.data_processing.convert_to_blocks_util([1, h, w], snaps)
+        xs = torch.tensor(blocks, dtype=torch.float32).view(blocks.shape[0], 1, h, w)
+        torch.manual_seed(0)
+        model = ref_models.Conv_AE(w, z_dim)
+        randomise_bn2d(model)
+        d[f"{tag}/blocks"] = blocks.astype(np.float32)
+        d.update({f"{tag}/{k}": v for k, v in _checksums(model).items()})
+        model.eval()
+        with torch.no_grad():
+            z = model.encode(xs)
+            y = model.decode(z)
+        d[f"{tag}/latent_eval"], d[f"{tag}/recon_eval"] = z.numpy(), y.numpy()
+        d[f"{tag}/final_layer"] = np.array(model.get_final_layer_dims())
+        print("conv_shapes", tag, z.shape, y.shape)
+    np.savez_compressed(os.path.join(OUT, "conv_shapes.npz"), **d)
+    print("conv_shapes", os.path.getsize(os.path.join(OUT, "conv_shapes.npz")) / 1e6, "MB")
+
+
 def gen_conv_ae():
     """Conv_AE(5, 250) on 5x5 blocks (the only block shapes the reference model accepts).  The 6 MB of
     weights are not stored: they are torch.manual_seed(0) initial weights (reproduced by the drop-in class, checked
@@ -516,6 +541,6 @@ def gen_eb_deltas():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules", "conv_ae", "conv_train", "cfd_dense", "swae", "eb_deltas"]
+    which = sys.argv[1:] or ["ae_cms", "ae_train", "ae_fit", "ae_dbn", "cli_roundtrip", "schedules", "conv_ae", "conv_shapes", "conv_train", "cfd_dense", "swae", "eb_deltas"]
     for name in which:
         globals()["gen_" + name]()

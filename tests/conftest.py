@@ -2,6 +2,7 @@ import os
 import sys
 
 import numpy as np
+import torch
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -46,3 +47,15 @@ def golden():
         return cache[name]
 
     return get
+
+
+def randomise_bn2d(sd, seed=2):
+    """same draws as oracle/gen_golden.py::randomise_bn2d, in module order"""
+    g = torch.Generator().manual_seed(seed)
+    for name in ("q_z_conv.3", "p_x_conv.1", "p_x_conv.4"):
+        n = sd[name + ".weight"].shape
+        sd[name + ".weight"] = 0.5 + torch.rand(n, generator=g)
+        sd[name + ".bias"] = 0.2 * torch.randn(n, generator=g)
+        sd[name + ".running_mean"] = 0.1 * torch.randn(n, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(n, generator=g)
+    return sd

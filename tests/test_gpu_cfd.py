@@ -6,23 +6,11 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_l2, rel_max
+from conftest import randomise_bn2d, rel_l2, rel_max
 from baler_b200 import synth
 from baler_b200.modules import helper, models
 
 pytestmark = pytest.mark.gpu
-
-
-def randomise_bn2d(sd, seed=2):
-    """same draws as oracle/gen_golden.py::randomise_bn2d, in module order"""
-    g = torch.Generator().manual_seed(seed)
-    for name in ("q_z_conv.3", "p_x_conv.1", "p_x_conv.4"):
-        n = sd[name + ".weight"].shape
-        sd[name + ".weight"] = 0.5 + torch.rand(n, generator=g)
-        sd[name + ".bias"] = 0.2 * torch.randn(n, generator=g)
-        sd[name + ".running_mean"] = 0.1 * torch.randn(n, generator=g)
-        sd[name + ".running_var"] = 0.5 + torch.rand(n, generator=g)
-    return sd
 
 
 def check_sums(model, g):
@@ -53,6 +41,28 @@ def test_conv_ae_eval_matches_reference(golden, precision):
         m.encode(torch.zeros(4, 1, 50, 50))  # the shipped 50x50 CFD_project_still shape is invalid upstream too
     with pytest.raises(NotImplementedError):
         m.train().encode(x)
+
+
+@pytest.mark.parametrize("tag,h,w,z_dim", [("b36", 3, 6, 9), ("b28", 2, 8, 4)])
+def test_conv_ae_other_block_shapes(golden, tag, h, w, z_dim):
+    """the other two block shapes the reference model accepts (their conv stack flattens to the hard-coded 128 values,
+    SURVEY F7b): 3x6 blocks with z = 9, 2x8 blocks with z = 4, against the reference module's eval outputs"""
+    g = golden("conv_shapes.npz")
+    torch.manual_seed(0)
+    m = models.Conv_AE(w, z_dim)
+    m.load_state_dict(randomise_bn2d(m.state_dict()))
+    for k, v in m.state_dict().items():
+        ref = float(g[f"{tag}/chk/{k}"])
+        assert abs(float(v.double().abs().sum()) - ref) <= 1e-6 * max(ref, 1.0), k
+    m.eval()
+    x = torch.from_numpy(g[f"{tag}/blocks"]).view(-1, 1, h, w)
+    for precision in ("auto", "fp32"):
+        z = m.encode(x, precision=precision)
+        assert tuple(m.get_final_layer_dims()) == tuple(g[f"{tag}/final_layer"])
+        assert rel_max(z.cpu().numpy(), g[f"{tag}/latent_eval"]) <= 1e-5
+        y = m.decode(torch.from_numpy(g[f"{tag}/latent_eval"]), precision=precision)
+        assert y.shape == g[f"{tag}/recon_eval"].shape
+        assert rel_max(y.cpu().numpy(), g[f"{tag}/recon_eval"]) <= 1e-5
 
 
 @pytest.mark.parametrize("precision", ["auto", "fp32"])
