@@ -83,13 +83,19 @@ int fill_chain(Chain* c, int n_layers, const int* dims, const int* acts, const d
 }
 
 void free_chain(Chain* c) {
-  if (c->blob_dev) cudaFree(c->blob_dev);
-  if (c->tc_blob_dev) cudaFree(c->tc_blob_dev);
-  if (c->lay_blob_dev) cudaFree(c->lay_blob_dev);
-  if (c->lay_scratch) cudaFree(c->lay_scratch);
-  if (c->lay_tc_blob_dev) cudaFree(c->lay_tc_blob_dev);
-  if (c->g5_blob_dev) cudaFree(c->g5_blob_dev);
-  if (c->g5_bias_dev) cudaFree(c->g5_bias_dev);
+  // (pointers are cleared: bb_model_destroy also runs model_trim, which releases the scratch of a live model)
+  auto release = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  release(c->blob_dev);
+  release(c->tc_blob_dev);
+  release(c->lay_blob_dev);
+  release(c->lay_scratch);
+  c->lay_scratch_bytes = 0;
+  release(c->lay_tc_blob_dev);
+  release(c->g5_blob_dev);
+  release(c->g5_bias_dev);
   bb_tc_release(c);
 }
 
