@@ -143,6 +143,37 @@ def test_layered_gemm_odd_shapes_vs_float64(rows, mode, monkeypatch):
     assert rel_max(y.cpu().numpy(), yr) <= 1e-5 and rel_l2(y.cpu().numpy(), yr) <= 1e-5
 
 
+def test_trim_and_destroy_of_a_layered_model_leave_no_pending_cuda_error():
+    """bb_model_trim releases the layered path's activation scratch of a live model (the next call allocates again and gives
+    the same bits); bb_model_destroy must not release it a second time - a double cudaFree is not fatal, but it leaves an
+    `invalid argument` for the next call that reads cudaGetLastError"""
+    import gc
+    from baler_b200 import engine
+    rng = np.random.default_rng(1)
+
+    def layers(dims):
+        return [(rng.standard_normal((dims[i + 1], dims[i])) / np.sqrt(dims[i]), 0.1 * rng.standard_normal(dims[i + 1]), "relu")
+                for i in range(len(dims) - 1)]
+
+    codec = engine.DenseCodec(layers([333, 3001, 17, 9]), layers([9, 70, 1111, 333]))  # (too wide for the fused kernels)
+    x = torch.randn(1000, 333, device="cuda")
+    free0 = torch.cuda.mem_get_info()[0]
+    y1 = codec.decode(codec.encode(x))
+    torch.cuda.synchronize()
+    held = free0 - torch.cuda.mem_get_info()[0]
+    codec.trim()
+    assert free0 - torch.cuda.mem_get_info()[0] < held  # the scratch went back
+    y2 = codec.decode(codec.encode(x))
+    assert torch.equal(y1, y2)
+    del codec
+    gc.collect()
+    mn, mx = engine.colminmax(x)  # a launch that reports cudaGetLastError
+    assert torch.equal(mn, x.min(dim=0).values) and torch.equal(mx, x.max(dim=0).values)
+    # ... and the layered trainer, the call that tripped over the stale error
+    tr = engine.LayeredTrainer([w for w, _, _ in layers([32, 64, 32])], [np.zeros(64), np.zeros(32)], ["relu", "none"], 64)
+    tr.step(torch.rand(64, 32, device="cuda"), engine.make_hyper(lr=1e-3))
+
+
 def test_layered_tensor_core_range_guard():
     """values beyond the fp16 range on the layered tensor-core path raise the sticky flag; AUTO callers re-run in fp32"""
     torch.manual_seed(0)
