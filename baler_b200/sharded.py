@@ -46,10 +46,14 @@ def dp_batch_slices(n_rows, global_batch, rank, world):
 
 
 def combine_minmax_(mn, mx, group=None):
-    """in-place global column min / max over all ranks"""
+    """in-place global column min / max over all ranks: ONE MIN all-reduce of [min | -max] (2 x C values; negation is
+    exact, so max = -min(-max) bit for bit)"""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        c = mn.numel()
+        both = torch.cat([mn.reshape(-1), -mx.reshape(-1)])
+        dist.all_reduce(both, op=dist.ReduceOp.MIN, group=group)
+        mn.copy_(both[:c].reshape(mn.shape))
+        mx.copy_((-both[c:]).reshape(mx.shape))
     return mn, mx
 
 
