@@ -38,6 +38,8 @@ _SIGNATURES = {
     "bb_model_create_dense": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _PP]),
     "bb_model_destroy": (C.c_int, [_P]),
     "bb_model_trim": (C.c_int, [_P]),
+    "bb_host_convert": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int64]),
+    "bb_host_colminmax_f32": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P]),
     "bb_model_n_features": (C.c_int, [_P]),
     "bb_model_z_dim": (C.c_int, [_P]),
     "bb_model_auto_precision": (C.c_int, [_P]),

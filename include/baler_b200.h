@@ -146,6 +146,17 @@ int bb_decode_f32(bb_model* m, const void* z_dev, int z_dtype, int64_t n_rows,
                   float* y_dev, int precision, bb_stream_t stream);
 
 /*
+ * The host-side steps of the two pipelines below, callable on their own (no device needed):
+ *   bb_host_convert        float32 -> float64 (exact) or float64 -> float32 (round to nearest even) of n values on the
+ *                          library's worker threads with non-temporal stores - the astype() of helper.py:565 / 653 that
+ *                          turns the latent / reconstruction into the dtypes the reference writes;
+ *   bb_host_colminmax_f32  per-column min and max of a row-major float32 table (data_processing.py:113-130), the scan
+ *                          bb_compress_host overlaps with the upload; a column holding a nan gives nan, as numpy does.
+ */
+int bb_host_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n);
+int bb_host_colminmax_f32(const float* x_host, int64_t n_rows, int n_cols, float* min_out, float* max_out);
+
+/*
  * Whole-table compress / decompress with HOST buffers: chunked, double-buffered H2D copy ->
  * kernels -> D2H copy on internal streams; returns when the output is complete in host memory.
  * These are what the reference-facing `helper.compress` / `helper.decompress` drop-ins call and

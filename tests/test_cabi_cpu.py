@@ -258,3 +258,54 @@ def test_apply_deltas_host_step_matches_reference(golden, tmp_path):
     mn = np.linspace(-1.0, 1.0, decoded.shape[1])
     out2 = helper._apply_deltas(decoded * rng + mn, paths[0], paths[1], bs, rng)
     assert np.abs(out2 - (fixed * rng + mn)).max() <= 1e-12 * np.abs(fixed * rng + mn).max()
+
+
+def test_host_helpers_convert_and_colminmax_without_a_device(lib):
+    """the host-side steps of bb_compress_host / bb_decompress_host (worker-thread pool, AVX2 paths and their scalar tails):
+    widening is exact, narrowing rounds like ndarray.astype, the column scan equals numpy's min / max (nan columns -> nan)"""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 7, 65535, 65536 + 13, 3_000_001):  # below / above the threshold of the thread pool, ragged tails
+        a32 = (rng.standard_normal(n) * 10.0 ** rng.uniform(-30, 30, n)).astype(np.float32)
+        if n > 10:
+            a32[:6] = [np.inf, -np.inf, np.nan, 0.0, -0.0, 1e-45]
+        out64 = np.full(n + 1, 7.0)  # one guard value behind the destination
+        assert lib.bb_host_convert(a32.ctypes.data, 0, out64.ctypes.data, 2, n) == 0
+        assert np.array_equal(out64[:n], a32.astype(np.float64), equal_nan=True) and out64[n] == 7.0
+        a64 = rng.standard_normal(n) * 10.0 ** rng.uniform(-50, 50, n)  # overflow to inf and underflow to 0 included
+        if n > 10:
+            a64[:5] = [np.inf, -np.inf, np.nan, 1.0 + 2.0 ** -24, 1.0 + 3 * 2.0 ** -24]  # ties: to even
+        out32 = np.full(n + 1, 7.0, dtype=np.float32)
+        assert lib.bb_host_convert(a64.ctypes.data, 2, out32.ctypes.data, 0, n) == 0
+        with np.errstate(over="ignore"):
+            ref = a64.astype(np.float32)
+        assert np.array_equal(out32[:n].view(np.uint32), ref.view(np.uint32)) and out32[n] == 7.0
+    assert lib.bb_host_convert(None, 0, None, 2, 5) != 0 and lib.bb_host_convert(a32.ctypes.data, 0, out64.ctypes.data, 1, 1) != 0
+    # unaligned destination (a view one element into the buffer)
+    buf = np.zeros(100_001)
+    src = rng.standard_normal(100_000).astype(np.float32)
+    assert lib.bb_host_convert(src.ctypes.data, 0, buf[1:].ctypes.data, 2, 100_000) == 0
+    assert buf[0] == 0.0 and np.array_equal(buf[1:], src.astype(np.float64))
+    for n, c in ((1, 24), (7, 24), (100_003, 24), (4099, 25), (513, 3), (20, 200), (300_000, 5)):
+        x = rng.standard_normal((n, c)).astype(np.float32)
+        x[rng.integers(0, n), 0] = -0.0
+        if n > 100:
+            x[n // 2, c - 1] = np.nan
+        mn, mx = np.empty(c, np.float32), np.empty(c, np.float32)
+        assert lib.bb_host_colminmax_f32(x.ctypes.data, n, c, mn.ctypes.data, mx.ctypes.data) == 0
+        assert np.array_equal(mn, x.min(axis=0), equal_nan=True) and np.array_equal(mx, x.max(axis=0), equal_nan=True)
+    # many dispatches through the pool in a row, from two threads at once (jobs queue on the pool)
+    import threading
+    big = rng.standard_normal(1 << 20).astype(np.float32)
+    errs = []
+
+    def hammer():
+        out = np.empty(big.size)
+        for _ in range(50):
+            if lib.bb_host_convert(big.ctypes.data, 0, out.ctypes.data, 2, big.size) != 0 or not np.array_equal(out, big):
+                errs.append(1)
+
+    th = [threading.Thread(target=hammer) for _ in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
