@@ -35,7 +35,7 @@ def _table(data):
     """(n, c) float32 view of 1-D / 2-D / 3-D input: statistics are per position over axis 0"""
     arr = np.asarray(data)
     flat = arr.reshape(arr.shape[0], -1) if arr.ndim > 1 else arr.reshape(-1, 1)
-    return arr, np.ascontiguousarray(flat, dtype=np.float32)
+    return arr, engine.host_convert(flat, np.float32)
 
 
 # float64 tables whose offset dwarfs their spread (IDs, timestamps ~1e9 with a range of a few units): in float32, x alone
@@ -115,7 +115,7 @@ def normalize(data, custom_norm):
     x, mn, mx = _minmax_dev(flat)
     out = engine.normalize_table(x, mn, mx - mn).cpu().numpy()  # max - min: one float32 subtraction per column
     out = out.reshape(arr.shape)
-    return out if arr.dtype == np.float32 else out.astype(np.float64)
+    return out if arr.dtype == np.float32 else engine.host_convert(out, np.float64)
 
 
 def renormalize_std(input_data, true_min, feature_range):
@@ -136,4 +136,4 @@ def renormalize_func(norm_data, min_list, range_list):
     mn = torch.as_tensor(np.asarray(min_list, dtype=np.float32).reshape(-1)).cuda()
     rg = torch.as_tensor(np.asarray(range_list, dtype=np.float32).reshape(-1)).cuda()
     out = engine.normalize_table(x, mn, rg, inverse=True).cpu().numpy()
-    return out.reshape(arr.shape).astype(np.float64)
+    return engine.host_convert(out, np.float64).reshape(arr.shape)

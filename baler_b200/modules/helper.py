@@ -204,7 +204,7 @@ def compress(model_path, config):
             table = np.ascontiguousarray(data_processing.normalize_float64_host(flat64, st[0], st[1], np.float32))
             normalise = False
     if table is None:
-        table = np.ascontiguousarray(data_before.reshape(data_before.shape[0], -1), dtype=np.float32)
+        table = engine.host_convert(data_before.reshape(data_before.shape[0], -1), np.float32)
     codec = model.codec(data_before.shape[1], data_before.shape[2]) if conv else model.codec()
     if getattr(config, "save_error_bounded_deltas", False):
         return _compress_with_deltas(codec, model, table, normalise, config, rank, world)

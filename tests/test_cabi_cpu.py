@@ -309,3 +309,19 @@ def test_host_helpers_convert_and_colminmax_without_a_device(lib):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs
+
+
+def test_engine_host_convert_matches_astype(lib):
+    from baler_b200 import engine
+    rng = np.random.default_rng(2)
+    a64 = rng.standard_normal((70_000, 24)) * 1e3
+    out = engine.host_convert(a64, np.float32)
+    assert out.dtype == np.float32 and out.flags.c_contiguous and np.array_equal(out, a64.astype(np.float32))
+    back = engine.host_convert(out, np.float64)
+    assert back.dtype == np.float64 and np.array_equal(back, out.astype(np.float64))
+    assert engine.host_convert(out, np.float32) is out or np.shares_memory(engine.host_convert(out, np.float32), out)
+    # fall-backs: strided source, small array, integer table
+    assert np.array_equal(engine.host_convert(a64[:, ::2], np.float32), a64[:, ::2].astype(np.float32))
+    assert np.array_equal(engine.host_convert(a64[:10], np.float32), a64[:10].astype(np.float32))
+    ints = rng.integers(-5, 5, (70_000, 3))
+    assert np.array_equal(engine.host_convert(ints, np.float32), ints.astype(np.float32))
