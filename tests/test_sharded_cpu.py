@@ -86,6 +86,23 @@ def _worker(rank, world, port, out_dir):
             assert (full is None) == (rank != 0)
             if rank == 0:
                 assert full.dtype == np.float64 and np.array_equal(full, t[:, :15].astype(np.float64))
+        # --- a float64 file whose offset dwarfs its spread (data_processing.F32_OFFSET_LIMIT): every rank reaches the same
+        # decision from the row sample and gets the exact float64 statistics of the WHOLE table from the shard exchange,
+        # the way helper.compress wires it under torchrun
+        from baler_b200.modules import data_processing as dp
+        t64 = synth.cms_table(10_001, seed=8).astype(np.float64)
+        t64[:, 3] = 2.0e9 + np.arange(len(t64)) % 701
+        lo, hi = sharded.row_range(len(t64), rank, world)
+
+        def shard_stats(flat):
+            f = sharded.global_minmax(flat[lo:hi])
+            return f[0], f[0] + f[1]
+
+        st = dp.float64_stats(t64, shard_stats)
+        ref64 = orc.find_minmax(t64)
+        assert st is not None and np.array_equal(st[0], ref64[0]) and np.allclose(st[1], ref64[1], rtol=0, atol=1e-6)
+        assert np.allclose(dp.normalize_float64_host(t64, *st), orc.normalize(t64), rtol=0, atol=1e-9)
+        assert dp.float64_stats(synth.cms_table(10_001, seed=8).astype(np.float64), shard_stats) is None  # no exchange needed
         # --- sharded.DataParallelTrainer itself (the class the GPU trainers run under) on a CPU stand-in trainer built on the
         # oracle: phase 1 fills [grads | loss], SUM all-reduce, phase 2 applies Adam; a rank with an empty slice of the last
         # batch contributes zeros; BatchNorm running statistics (one tensor, as the layer-by-layer trainer exposes them)
