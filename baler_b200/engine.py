@@ -195,7 +195,7 @@ class DenseCodec:
     def compress_host(self, x, features=None, recompute_minmax=False, z_dtype=np.float32, precision="auto", out=None):
         """x: (n, F) float32 ndarray.  features: None (no normalisation) or (2, F) float32 [min; range]
         (overwritten when recompute_minmax).  Returns (z, features)."""
-        x = np.ascontiguousarray(x, dtype=np.float32)
+        x = host_convert(x, np.float32)  # (float64 tables: narrowed on the worker threads)
         n = x.shape[0]
         z = out if out is not None else np.empty((n, self.z_dim), dtype=z_dtype)
         feats = None
